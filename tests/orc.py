@@ -1,0 +1,291 @@
+"""ctypes face of the CPU oracle (oracle/liborc.so) and of the reference's own
+noise.cpp (oracle/_ref/libref_noise.so).  TEST INFRASTRUCTURE: imported only by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+ORC_SO = os.path.join(ORC_DIR, "liborc.so")
+REF_SO = os.path.join(ORC_DIR, "_ref", "libref_noise.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int)
+c_u8_p = C.POINTER(C.c_uint8)
+
+
+def build():
+    """(Re)build the oracle; also rebuilds oracle/_ref when /root/reference exists."""
+    subprocess.check_call(["make", "-s", "-C", ORC_DIR], stdout=subprocess.DEVNULL)
+
+
+class ElevParams(C.Structure):
+    _fields_ = [("W", C.c_int), ("level", C.c_int), ("pixel_size", C.c_float),
+                ("grid", C.c_int), ("flip", C.c_int), ("dx", C.c_int), ("dy", C.c_int),
+                ("has_resid", C.c_int), ("rx", C.c_int), ("ry", C.c_int),
+                ("resid_stride", C.c_int), ("noiseR", C.c_int), ("noiseL", C.c_int),
+                ("rs", C.c_float), ("noise_mode", C.c_int), ("no_clamp", C.c_int)]
+
+
+class NormParams(C.Structure):
+    _fields_ = [("W", C.c_int), ("grid", C.c_int), ("format", C.c_int),
+                ("elev_W", C.c_int), ("elev_border", C.c_int), ("elev_filter", C.c_int),
+                ("has_parent", C.c_int), ("ptx", C.c_int), ("pty", C.c_int),
+                ("parent_filter", C.c_int),
+                ("deform", C.c_float * 4), ("corners", C.c_float * 16),
+                ("verticals", C.c_float * 16), ("norms", C.c_float * 4),
+                ("w2t", C.c_float * 9), ("p2t", C.c_float * 9)]
+
+
+class ResidFile(C.Structure):
+    pass
+
+
+ResidFile._fields_ = [("minLevel", C.c_int), ("maxLevel", C.c_int), ("tileSize", C.c_int),
+                      ("rootLevel", C.c_int), ("rootTx", C.c_int), ("rootTy", C.c_int),
+                      ("scale", C.c_float), ("deltaLevel", C.c_int), ("ntiles", C.c_int),
+                      ("header", C.c_uint32), ("offsets", C.c_void_p), ("data", C.c_void_p),
+                      ("size", C.c_size_t), ("nchildren", C.c_int),
+                      ("children", C.POINTER(C.POINTER(ResidFile)))]
+
+
+class Scene(C.Structure):
+    _fields_ = [("W", C.c_int), ("gridMeshSize", C.c_int), ("rootQuadSize", C.c_float),
+                ("face", C.c_int), ("flip", C.c_int), ("noise_mode", C.c_int),
+                ("no_clamp", C.c_int), ("nAmp", C.c_int), ("noiseAmp", C.c_float * 32),
+                ("sphere", C.c_int), ("elev_filter", C.c_int),
+                ("resid", C.POINTER(ResidFile))]
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORC_SO):
+            build()
+        L = C.CDLL(ORC_SO)
+        L.orc_lrandom.restype = C.c_long
+        L.orc_lrandom.argtypes = [C.POINTER(C.c_long)]
+        L.orc_frandom.restype = C.c_float
+        L.orc_frandom.argtypes = [C.POINTER(C.c_long)]
+        L.orc_cnoise2.restype = C.c_float
+        L.orc_cnoise2.argtypes = [C.c_float, C.c_float]
+        L.orc_round_half.restype = C.c_float
+        L.orc_round_half.argtypes = [C.c_float]
+        L.orc_float_to_half_bits.restype = C.c_uint16
+        L.orc_float_to_half_bits.argtypes = [C.c_float]
+        L.orc_unorm8.restype = C.c_uint8
+        L.orc_unorm8.argtypes = [C.c_float]
+        L.orc_tiff_inflate.restype = C.c_long
+        L.orc_resid_blob.restype = C.c_void_p
+        L.orc_produce_quadtree.restype = C.c_long
+        _lib = L
+    return _lib
+
+
+def ref():
+    """The reference's own noise.cpp, or None when oracle/_ref was not built."""
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            return None
+        R = C.CDLL(REF_SO)
+        R.ref_lrandom.restype = C.c_long
+        R.ref_lrandom.argtypes = [C.POINTER(C.c_long)]
+        R.ref_frandom.restype = C.c_float
+        R.ref_frandom.argtypes = [C.POINTER(C.c_long)]
+        R.ref_cnoise2.restype = C.c_float
+        R.ref_cnoise2.argtypes = [C.c_float, C.c_float]
+        _ref = R
+    return _ref
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_float_p)
+
+
+# ---------------------------------------------------------------- noise ----
+
+def dem_noise(W=101, r16f=True):
+    out = np.empty((6, W, W), np.float32)
+    (lib().orc_dem_noise_r16f if r16f else lib().orc_dem_noise)(C.c_int(W), _fp(out))
+    return out
+
+
+def cnoise_tables():
+    p = np.empty(514, np.int32)
+    g2 = np.empty((514, 2), np.float32)
+    lib().orc_cnoise_tables(p.ctypes.data_as(c_int_p), _fp(g2))
+    return p, g2
+
+
+def noise_select(level, tx, ty, face):
+    r, l = C.c_int(), C.c_int()
+    lib().orc_noise_select(level, tx, ty, face, C.byref(r), C.byref(l))
+    return r.value, l.value
+
+
+# ------------------------------------------------------------ elevation ----
+
+def elev_uniforms(level, tx, ty, *, W=101, gridMeshSize=24, rootQuadSize=100000.0, flip=0,
+                  noiseAmp=(), face=0, has_resid=0, resid_W=0, noise_mode=1, no_clamp=0):
+    p = ElevParams()
+    amp = np.asarray(noiseAmp, np.float32)
+    lib().orc_elev_uniforms(W, gridMeshSize, C.c_float(rootQuadSize), flip, _fp(amp), len(amp),
+                            face, level, tx, ty, has_resid, resid_W, noise_mode, no_clamp,
+                            C.byref(p))
+    return p
+
+
+def upsample_tile(p, parent, resid, noise):
+    W = p.W
+    out = np.empty((W, W, 3), np.float32)
+    par = _fp(np.ascontiguousarray(parent, np.float32)) if parent is not None else None
+    res = _fp(np.ascontiguousarray(resid, np.float32)) if resid is not None else None
+    lib().orc_upsample_tile(C.byref(p), par, res, _fp(noise), _fp(out))
+    return out
+
+
+def cpu_elevation_tile(W, level, tx, ty, parent, resid, resid_W, rx, ry):
+    out = np.empty((W, W), np.float32)
+    par = _fp(np.ascontiguousarray(parent, np.float32)) if parent is not None else None
+    res = _fp(np.ascontiguousarray(resid, np.float32)) if resid is not None else None
+    lib().orc_cpu_elevation_tile(W, level, tx, ty, par, res, resid_W, rx, ry, _fp(out))
+    return out
+
+
+def tile_minmax(elev):
+    W = elev.shape[0]
+    a, b = C.c_float(), C.c_float()
+    lib().orc_tile_minmax(W, _fp(np.ascontiguousarray(elev, np.float32)), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+# -------------------------------------------------------------- normals ----
+
+def normal_uniforms(level, tx, ty, *, W=97, gridMeshSize=24, components=2, signed_comp=0,
+                    elev_W=101, elev_border=2, elev_filter=1, parent_filter=1,
+                    rootQuadSize=100000.0, sphere=0):
+    p = NormParams()
+    lib().orc_normal_uniforms(W, gridMeshSize, components, signed_comp, elev_W, elev_border,
+                              elev_filter, parent_filter, C.c_double(rootQuadSize), sphere,
+                              level, tx, ty, C.byref(p))
+    return p
+
+
+def normal_tile(p, elev, parent=None):
+    out = np.empty((p.W, p.W, 4), np.float32)
+    par = _fp(np.ascontiguousarray(parent, np.float32)) if parent is not None else None
+    lib().orc_normal_tile(C.byref(p), _fp(np.ascontiguousarray(elev, np.float32)), par, _fp(out))
+    return out
+
+
+def pack_unorm8(data, channels):
+    W = data.shape[0]
+    out = np.empty((W, W, channels), np.uint8)
+    lib().orc_pack_unorm8(W, channels, _fp(np.ascontiguousarray(data, np.float32)),
+                          out.ctypes.data_as(c_u8_p))
+    return out
+
+
+# ------------------------------------------------------------ residuals ----
+
+class Resid:
+    """An opened residual container (keeps the file bytes alive)."""
+
+    def __init__(self, data: bytes, delta=0, zscale=1.0):
+        self.buf = np.frombuffer(data, np.uint8).copy()
+        self.f = ResidFile()
+        rc = lib().orc_resid_open(self.buf.ctypes.data_as(c_u8_p), C.c_size_t(len(self.buf)),
+                                  delta, C.c_float(zscale), C.byref(self.f))
+        if rc != 0:
+            raise ValueError("bad residual container rc=%d" % rc)
+        self._children = []
+
+    def add_child(self, child):
+        self._children.append(child)
+        arr = (C.POINTER(ResidFile) * len(self._children))(
+            *[C.pointer(c.f) for c in self._children])
+        self._arr = arr
+        self.f.children = C.cast(arr, C.POINTER(C.POINTER(ResidFile)))
+        self.f.nchildren = len(self._children)
+
+    @property
+    def width(self):
+        return self.f.tileSize + 5
+
+    def has_tile(self, level, tx, ty):
+        return bool(lib().orc_resid_has_tile(C.byref(self.f), level, tx, ty))
+
+    def tile_id(self, l, tx, ty):
+        return lib().orc_resid_tile_id(C.byref(self.f), l, tx, ty)
+
+    def tile_size(self, l):
+        return lib().orc_resid_tile_size(C.byref(self.f), l)
+
+    def blob(self, tileid):
+        n = C.c_uint32()
+        p = lib().orc_resid_blob(C.byref(self.f), tileid, C.byref(n))
+        off = p - self.buf.ctypes.data
+        return self.buf[off:off + n.value].tobytes()
+
+    def inflate(self, tileid):
+        b = np.frombuffer(self.blob(tileid), np.uint8)
+        cap = self.width * self.width * 2
+        raw = np.empty(cap, np.uint8)
+        w, h = C.c_int(), C.c_int()
+        n = lib().orc_tiff_inflate(b.ctypes.data_as(c_u8_p), C.c_uint32(len(b)),
+                                   raw.ctypes.data_as(c_u8_p), C.c_size_t(cap),
+                                   C.byref(w), C.byref(h))
+        if n < 0:
+            raise ValueError("inflate failed rc=%d" % n)
+        return raw[:n].tobytes(), w.value, h.value
+
+    def create_tile(self, level, tx, ty):
+        n = self.width
+        out = np.zeros((n, n), np.float32)
+        rc = lib().orc_resid_create_tile(C.byref(self.f), level, tx, ty, _fp(out))
+        if rc != 0:
+            raise ValueError("create_tile rc=%d" % rc)
+        return out
+
+
+# --------------------------------------------------------------- driver ----
+
+def make_scene(*, W=101, gridMeshSize=24, rootQuadSize=100000.0, face=0, flip=0, noise_mode=1,
+               no_clamp=0, noiseAmp=(), sphere=0, elev_filter=1, resid=None):
+    s = Scene()
+    s.W, s.gridMeshSize, s.rootQuadSize, s.face = W, gridMeshSize, rootQuadSize, face
+    s.flip, s.noise_mode, s.no_clamp = flip, noise_mode, no_clamp
+    s.nAmp = len(noiseAmp)
+    for i, a in enumerate(noiseAmp):
+        s.noiseAmp[i] = a
+    s.sphere, s.elev_filter = sphere, elev_filter
+    s.resid = C.pointer(resid.f) if resid is not None else None
+    s._keep = resid
+    return s
+
+
+def produce_pair(scene, noise, level, tx, ty, parent, resid_tile=None, want_normals=True):
+    W = scene.W
+    elev = np.empty((W, W, 3), np.float32)
+    norm = np.empty((W - 4, W - 4, 2), np.uint8) if want_normals else None
+    par = _fp(np.ascontiguousarray(parent, np.float32)) if parent is not None else None
+    res = _fp(np.ascontiguousarray(resid_tile, np.float32)) if resid_tile is not None else None
+    lib().orc_produce_pair(C.byref(scene), _fp(noise), level, tx, ty, par, res, _fp(elev),
+                           norm.ctypes.data_as(c_u8_p) if want_normals else None)
+    return elev, norm
+
+
+def produce_quadtree(scene, max_level, nthreads=0):
+    cs, lo, hi = C.c_double(), C.c_float(), C.c_float()
+    n = lib().orc_produce_quadtree(C.byref(scene), max_level, nthreads, C.byref(cs),
+                                   C.byref(lo), C.byref(hi))
+    return n, cs.value, lo.value, hi.value
