@@ -1,0 +1,203 @@
+/*
+ * proland_b200.h -- C ABI of the B200-native terrain tile-production path
+ * (ElevationProducer -> NormalProducer, fed by ResidualProducer).
+ *
+ * Plain C, plain pointers and sizes.  This is the boundary a Proland build
+ * binds instead of its GLSL draw calls; INTEGRATION.md shows the C++ side.
+ * Reference paths below are relative to the reference checkout.
+ *
+ * Every function returns a pl_status (0 = ok) unless stated otherwise.  The
+ * library never falls back to the CPU: without a CUDA device every entry point
+ * that needs one returns PL_ERR_NO_DEVICE.
+ */
+#ifndef PROLAND_B200_H
+#define PROLAND_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PL_ABI_VERSION 1
+
+/* Error convention: the reference asserts / logs / returns NULL
+ * (TileSampler.cpp:441-444, ResidualProducer.cpp:86-91); here each
+ * condition has a code and pl_last_error() gives the text that would be logged. */
+typedef enum pl_status {
+    PL_OK = 0,
+    PL_ERR_ARG = 1,        /* bad argument (an assert in the reference)          */
+    PL_ERR_POOL_FULL = 2,  /* "Insufficient tile cache size"                     */
+    PL_ERR_CUDA = 3,       /* a CUDA runtime / driver call failed                */
+    PL_ERR_CORRUPT = 4,    /* residual container / blob does not parse           */
+    PL_ERR_NO_DEVICE = 5,  /* no CUDA device: there is no CPU fallback           */
+    PL_ERR_IO = 6          /* residual file cannot be opened (maxLevel = -1)     */
+} pl_status;
+
+const char *pl_last_error(void);
+int pl_abi_version(void);
+
+/* ------------------------------------------------------------------ context */
+
+typedef struct pl_ctx pl_ctx;
+typedef struct pl_pool pl_pool;
+
+/* One context per GPU / per producer thread (replaces the GL context + FBO of
+ * ElevationProducer.cpp:136-155).  Work is ordered on the context's stream. */
+int pl_ctx_create(int device, pl_ctx **out);
+void pl_ctx_destroy(pl_ctx *ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) instead of the
+ * context's own; NULL restores the own stream. */
+int pl_ctx_set_stream(pl_ctx *ctx, void *cuda_stream);
+void *pl_ctx_stream(pl_ctx *ctx);
+int pl_sync(pl_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t pl_ctx_launch_count(const pl_ctx *ctx);
+int pl_device_sm_count(pl_ctx *ctx);
+
+/* ------------------------------------------------- tile pools (TileStorage) */
+
+/* Replaces GPUTileStorage (producer/GPUTileStorage.cpp:129-199) and, for
+ * residuals, the CPUTileStorage<float> slots ElevationProducer reads
+ * (ElevationProducer.cpp:326-337): one device slab, a slot is an index.
+ * Slot bookkeeping (free list, LRU) stays on the host (TileStorage/TileCache). */
+typedef enum pl_pool_kind {
+    PL_POOL_ELEV_F32x3 = 0, /* RGB32F elevation (zf,zc,zm); planar, padded pitch  */
+    PL_POOL_NORM_UN8x2 = 1, /* RG8 normals                                        */
+    PL_POOL_NORM_UN8x4 = 2, /* RGBA8 normals (fine + coarse)                      */
+    PL_POOL_RESID_F32 = 3,  /* float residual tiles (CPUTileStorage<float>)       */
+    PL_POOL_RESID_I16 = 4   /* raw int16 residual tiles as stored in the file     */
+} pl_pool_kind;
+
+int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, pl_pool **out);
+void pl_pool_destroy(pl_pool *pool);
+int pl_pool_capacity(const pl_pool *pool);
+int pl_pool_tile_w(const pl_pool *pool);
+/* bytes of one tile in the REFERENCE's layout (what download/upload move):
+ * tile_w*tile_w*{12, 2, 4, 4, 2} */
+size_t pl_pool_tile_bytes(const pl_pool *pool);
+/* bytes of one slot in HBM (padded) and the device base pointer */
+size_t pl_pool_slot_bytes(const pl_pool *pool);
+void *pl_pool_device_ptr(pl_pool *pool);
+/* copy one slot to / from host memory in the reference's layout: interleaved
+ * (zf,zc,zm) floats, row-major, row 0 first (GPUSlot::copyPixels order);
+ * interleaved bytes for normals; dense floats / int16 for residuals. */
+int pl_pool_download(pl_pool *pool, int slot, void *host, size_t bytes);
+int pl_pool_upload(pl_pool *pool, int slot, const void *host, size_t bytes);
+
+/* ------------------------------------------------------------------- noise */
+
+/* createDemNoise (ElevationProducer.cpp:50-133): builds the six W x W layers
+ * with the reference's LCG, rounds to fp16 (the R16F upload) and stores the 4
+ * rotations of each layer on the device.  host_out (optional, 6*W*W floats)
+ * receives the fp16-rounded layers. */
+int pl_noise_init(pl_ctx *ctx, int tile_w, float *host_out);
+/* ElevationProducer.cpp:345-373: noise layer / rotation of a tile (host). */
+void pl_noise_select(int level, int tx, int ty, int face, int *noiseR, int *noiseL);
+/* noise.cpp:117-165 (2D) -- exported so the host mirror and tests share it */
+float pl_cnoise2(float x, float y);
+
+/* --------------------------------------------------------------- elevation */
+
+enum { PL_NOISE_PLAIN = 0,   /* upsampleShader variants A, C: zf += |rs|*n        */
+       PL_NOISE_SLOPE = 1 }; /* variants B, D: slope / curvature modulated        */
+
+/* per-producer constants = the tile-independent uniforms + shader variant */
+typedef struct pl_elev_scene {
+    int32_t tile_w;      /* tileWSDF.x, e.g. 101                                  */
+    int32_t grid;        /* tileWSDF.z = (tile_w-5)/gridSize                      */
+    int32_t flip;        /* tileWSDF.w (and the variant honours it)               */
+    int32_t noise_mode;  /* PL_NOISE_*                                            */
+    int32_t no_clamp;    /* #define NO_CLAMP (upsampleShader-noClamp.xml)         */
+    int32_t want_stats;  /* also write per-slot (zmin,zmax) of zm, TileSamplerZ   */
+    float resid_scale;   /* int16 -> metres factor when the residual pool is I16
+                            (ResidualProducer.cpp:333: the file's scale * zscale) */
+    int32_t pad_;
+} pl_elev_scene;
+
+/* per-tile uniforms, ElevationProducer.cpp:305-376 */
+typedef struct pl_elev_req {
+    int32_t out_slot;     /* GPUSlot::l of the tile being produced                */
+    int32_t parent_slot;  /* coarseLevelOSL.w, -1 at level 0                      */
+    int32_t resid_slot;   /* slot in the residual pool, -1: residualOSH.w = 0     */
+    int32_t dx, dy;       /* coarseLevelOSL.xy in texels: (t%2)*(tile_w-5)/2      */
+    int32_t rx, ry;       /* residual window origin, ElevationProducer.cpp:324    */
+    int32_t noise_r;      /* noiseUVLH.x                                          */
+    int32_t noise_l;      /* noiseUVLH.z                                          */
+    float rs;             /* noiseUVLH.w                                          */
+    float pixel_size;     /* tileWSDF.y                                           */
+    int32_t level, tx, ty;/* informational (kept for device-generated batches)    */
+    int32_t pad_[2];
+} pl_elev_req;            /* 64 bytes */
+
+/* Fill one request exactly as ElevationProducer::doCreateTile does (host). */
+void pl_elev_make_req(int tile_w, float root_quad_size, const float *noise_amp, int n_amp,
+                      int face, int level, int tx, int ty, int resid_tile_w, int has_resid,
+                      pl_elev_req *req);
+
+/* The batched upsampleShader: n tiles, one CTA per tile.  reqs is HOST memory
+ * (copied to the device inside the call).  resid may be NULL. */
+int pl_elevation_batch(pl_ctx *ctx, const pl_elev_scene *scene, pl_pool *elev,
+                       pl_pool *resid, int n, const pl_elev_req *reqs);
+/* same, requests already on the device */
+int pl_elevation_batch_dev(pl_ctx *ctx, const pl_elev_scene *scene, pl_pool *elev,
+                           pl_pool *resid, int n, const pl_elev_req *dev_reqs);
+/* per-slot (zmin,zmax) written by want_stats batches; out = 2*n floats */
+int pl_elev_stats_download(pl_ctx *ctx, pl_pool *elev, int n, const int32_t *slots, float *out);
+
+/* ----------------------------------------------------------------- normals */
+
+enum { PL_FILTER_NEAREST = 0, PL_FILTER_LINEAR = 1 };
+
+typedef struct pl_norm_scene {
+    int32_t tile_w;        /* tileSDF.x, e.g. 97                                  */
+    int32_t grid;          /* tileSDF.y                                           */
+    int32_t elev_border;   /* elevationTiles->getBorder() = 2                     */
+    int32_t elev_filter;   /* min/mag filter of the elevation storage             */
+    int32_t parent_filter; /* min/mag filter of the normal storage                */
+    int32_t sphere;        /* deform="sphere"                                     */
+} pl_norm_scene;
+
+/* per-tile uniforms, NormalProducer.cpp:196-283 (fp64 on the host -> fp32) */
+typedef struct pl_norm_req {
+    int32_t out_slot;
+    int32_t elev_slot;
+    int32_t parent_slot;   /* parent normal tile, -1: normalOSL = -1              */
+    int32_t ptx, pty;      /* tx%2, ty%2                                          */
+    int32_t level;
+    float deform[4];       /* x0, y0, quad size, R (0 = flat)                     */
+    float corners[12];     /* patchCorners rows x,y,z (row w is 1,1,1,1)          */
+    float verticals[12];   /* patchVerticals rows x,y,z (row w is 0)              */
+    float norms[4];        /* patchCornerNorms                                    */
+    float w2t[9];          /* worldToTangentFrame, row-major                      */
+    float p2t[9];          /* parentToTangentFrame, row-major                     */
+    float smooth;          /* smoothstep(R/32, R/64, deform.z)                    */
+    int32_t pad_[3];
+} pl_norm_req;             /* 240 bytes */
+
+void pl_norm_make_req(const pl_norm_scene *scene, double root_quad_size, int components,
+                      int level, int tx, int ty, pl_norm_req *req);
+
+int pl_normal_batch(pl_ctx *ctx, const pl_norm_scene *scene, pl_pool *norm, pl_pool *elev,
+                    int n, const pl_norm_req *reqs);
+int pl_normal_batch_dev(pl_ctx *ctx, const pl_norm_scene *scene, pl_pool *norm, pl_pool *elev,
+                        int n, const pl_norm_req *dev_reqs);
+
+/* --------------------------------------------------------------- residuals */
+
+/* ResidualProducer::readTile (ResidualProducer.cpp:268-340): n blobs, each a
+ * little-endian TIFF with one DEFLATE strip of w*w little-endian int16.
+ * blobs/offsets/sizes are HOST memory; tile j is written at the lower-left of
+ * slot out_slots[j] of an I16 pool (raw) or an F32 pool (int16 * scale, added
+ * to what add_slots[j] of the same pool holds when add_slots != NULL and
+ * add_slots[j] >= 0).  widths[j] = w of tile j (<= pool tile_w). */
+int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs,
+                             const uint64_t *offsets, const uint32_t *sizes,
+                             const int32_t *widths, const int32_t *out_slots,
+                             const int32_t *add_slots, float scale);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -9,13 +9,15 @@
  *   terrain/sources/proland/dem/CPUElevationProducer.cpp:194-245
  *   core/sources/proland/terrain/TileSamplerZ.cpp:43-133 (min/max region)
  *
- * Evaluation is plain IEEE fp32, left to right, no FMA contraction
- * (-ffp-contract=off), mat4 sums in the order GLSL's `mdot` spells them.
+ * Evaluation follows the canonical fp32 order of orc_fp.h (dot products are
+ * left-to-right fma chains, a*b+c is one fma; -DORC_STRICT: no contraction),
+ * mat4 sums in the order GLSL's `mdot` spells them.
  * Texture fetches are NEAREST on exact texel centres (the shader's own
  * coordinate maths resolves to the integer texels used here; checked by
  * tests/test_oracle.py::test_texcoord_identities) with CLAMP_TO_EDGE.
  */
 #include "orc.h"
+#include "orc_fp.h"
 #include <math.h>
 #include <string.h>
 
@@ -53,11 +55,8 @@ static const mat4 UPSAMPLE[4] = {
     { {V1, V9, V9, V1}, {V9, V81, V81, V9}, {V9, V81, V81, V9}, {V1, V9, V9, V1} },
 };
 
-/* GLSL dot(vec4,vec4), left to right */
-static inline float dot4(const float *a, const float *b)
-{
-    return a[0] * b[0] + a[1] * b[1] + a[2] * b[2] + a[3] * b[3];
-}
+/* GLSL dot(vec4,vec4): canonical fma chain (orc_fp.h R1) */
+static inline float dot4(const float *a, const float *b) { return orc_dot4(a, b); }
 /* upsampleShader.glsl:136-138 */
 static inline float mdot(const mat4 a, const mat4 b)
 {
@@ -146,19 +145,20 @@ void orc_upsample_tile(const orc_elev_params *p, const float *parent,
             const float n = nlayer[nxi + nyi * W];
 
             if (p->noise_mode == ORC_NOISE_PLAIN) {
-                zf += fabsf(p->rs) * n;
+                zf = orc_fma(fabsf(p->rs), n, zf);
             } else {
                 float nvx = mdot(cz, SLOPEX[i]);
                 float nvy = mdot(cz, SLOPEY[i]);
                 float nvz = 2.0f * p->pixel_size;
-                float slope = sqrtf(nvx * nvx + nvy * nvy) / nvz;
+                float nv[2] = { nvx, nvy };
+                float slope = sqrtf(orc_dot2(nv, nv)) / nvz;   /* length(n.xy) / n.z */
                 float curvature = mdot(cz, CURV[i]) / p->pixel_size;
                 float amp = fmaxf(clampf(4.0f * curvature, 0.0f, 1.5f),
-                                  clampf(2.0f * slope - 0.5f, 0.1f, 4.0f));
+                                  clampf(orc_fma(2.0f, slope, -0.5f), 0.1f, 4.0f));
                 if (p->rs < 0.0f) {
-                    zf -= p->rs * n;
+                    zf = orc_fma(-p->rs, n, zf);
                 } else {
-                    zf += amp * p->rs * n;
+                    zf = orc_fma(amp * p->rs, n, zf);
                 }
             }
 

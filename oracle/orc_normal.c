@@ -13,8 +13,11 @@
  * tile at texel coordinate (i + 0.25); with a NEAREST storage that is texel i,
  * with a LINEAR storage it is 0.25*T[i-1] + 0.75*T[i] on each axis.
  * Ork (absent) supplies vec3d::normalize; restated as v * (1/|v|).
+ * fp32 shader maths follows the canonical order of orc_fp.h (fma chains for
+ * dot / matrix*vector / a*b+c; -DORC_STRICT: no contraction).
  */
 #include "orc.h"
+#include "orc_fp.h"
 #include <math.h>
 #include <string.h>
 
@@ -147,7 +150,8 @@ static float fetch_zm(const orc_norm_params *p, const float *elev, int i, int j)
      * tau = (1-a)(1-b) t00 + a(1-b) t10 + (1-a) b t01 + a b t11 (spec eq. 3.26) */
     const float a = 0.75f, b = 0.75f;
     float t00 = ZM(i - 1, j - 1), t10 = ZM(i, j - 1), t01 = ZM(i - 1, j), t11 = ZM(i, j);
-    return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+    return orc_fma(a * b, t11, orc_fma((1.0f - a) * b, t01,
+           orc_fma(a * (1.0f - b), t10, ((1.0f - a) * (1.0f - b)) * t00)));
 #undef ZM
 }
 
@@ -166,8 +170,8 @@ static void fetch_parent_xy(const orc_norm_params *p, const float *parent, float
     int i0 = (int) floorf(fx), j0 = (int) floorf(fy);
     float a = fx - (float) i0, b = fy - (float) j0;
     for (int ch = 0; ch < 2; ++ch) {
-        o[ch] = (1.0f - a) * (1.0f - b) * PN(i0, j0, ch) + a * (1.0f - b) * PN(i0 + 1, j0, ch)
-              + (1.0f - a) * b * PN(i0, j0 + 1, ch) + a * b * PN(i0 + 1, j0 + 1, ch);
+        o[ch] = orc_fma(a * b, PN(i0 + 1, j0 + 1, ch), orc_fma((1.0f - a) * b, PN(i0, j0 + 1, ch),
+                orc_fma(a * (1.0f - b), PN(i0 + 1, j0, ch), ((1.0f - a) * (1.0f - b)) * PN(i0, j0, ch))));
     }
 #undef PN
 }
@@ -177,13 +181,13 @@ static void fetch_parent_xy(const orc_norm_params *p, const float *parent, float
 static inline void m4v(const float *m, const float *v, float *o)
 {
     for (int r = 0; r < 4; ++r) {
-        o[r] = m[r * 4 + 0] * v[0] + m[r * 4 + 1] * v[1] + m[r * 4 + 2] * v[2] + m[r * 4 + 3] * v[3];
+        o[r] = orc_dot4(m + r * 4, v);
     }
 }
 static inline void m3v(const float *m, const float *v, float *o)
 {
     for (int r = 0; r < 3; ++r) {
-        o[r] = m[r * 3 + 0] * v[0] + m[r * 3 + 1] * v[1] + m[r * 3 + 2] * v[2];
+        o[r] = orc_dot3(m + r * 3, v);
     }
 }
 
@@ -193,8 +197,8 @@ static void world_position(const orc_norm_params *p, float ux, float uy, float h
     float u = ux / ((float) p->W - 1.0f);
     float v = uy / ((float) p->W - 1.0f);
     if (p->deform[3] == 0.0f) {
-        pos[0] = p->deform[0] + p->deform[2] * u;
-        pos[1] = p->deform[1] + p->deform[2] * v;
+        pos[0] = orc_fma(p->deform[2], u, p->deform[0]);
+        pos[1] = orc_fma(p->deform[2], v, p->deform[1]);
         pos[2] = h;
         return;
     }
@@ -203,7 +207,7 @@ static void world_position(const orc_norm_params *p, float ux, float uy, float h
     float U = 1.0f - u, V = 1.0f - v;
     float alpha[4] = { U * V, u * V, U * v, u * v };       /* uvUV.zxzx * uvUV.wwyy */
     float al[4] = { alpha[0] * L[0], alpha[1] * L[1], alpha[2] * L[2], alpha[3] * L[3] };
-    float den = alpha[0] * L[0] + alpha[1] * L[1] + alpha[2] * L[2] + alpha[3] * L[3];
+    float den = orc_dot4(alpha, L);
     float ap[4] = { al[0] / den, al[1] / den, al[2] / den, al[3] / den };
 
     float up[4], base[4];
@@ -212,14 +216,14 @@ static void world_position(const orc_norm_params *p, float ux, float uy, float h
     float e0 = R / 32.0f, e1 = R / 64.0f;
     float t = (p->deform[2] - e0) / (e1 - e0);
     t = fminf(fmaxf(t, 0.0f), 1.0f);
-    float s = t * t * (3.0f - 2.0f * t);
-    float len = sqrtf(up[0] * up[0] + up[1] * up[1] + up[2] * up[2]);
-    float k = len * (1.0f - s) + 1.0f * s;                  /* mix(len, 1, s) */
-    float hPrime = (h + R * (1.0f - k)) / k;
+    float s = t * t * orc_fma(-2.0f, t, 3.0f);
+    float len = sqrtf(orc_dot3(up, up));
+    float k = orc_fma(1.0f, s, len * (1.0f - s));           /* mix(len, 1, s) */
+    float hPrime = orc_fma(R, 1.0f - k, h) / k;
     m4v(p->corners, ap, base);
-    pos[0] = base[0] + hPrime * up[0];
-    pos[1] = base[1] + hPrime * up[1];
-    pos[2] = base[2] + hPrime * up[2];
+    pos[0] = orc_fma(hPrime, up[0], base[0]);
+    pos[1] = orc_fma(hPrime, up[1], base[1]);
+    pos[2] = orc_fma(hPrime, up[2], base[2]);
 }
 
 /* normalShader.glsl:84-125 */
@@ -245,8 +249,9 @@ void orc_normal_tile(const orc_norm_params *p, const float *elev,
 
             float a[3] = { p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2] };
             float c[3] = { p3[0] - p2[0], p3[1] - p2[1], p3[2] - p2[2] };
-            float n[3] = { a[1] * c[2] - a[2] * c[1], a[2] * c[0] - a[0] * c[2], a[0] * c[1] - a[1] * c[0] };
-            float inv = 1.0f / sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+            float n[3] = { orc_fma(a[1], c[2], -(a[2] * c[1])), orc_fma(a[2], c[0], -(a[0] * c[2])),
+                           orc_fma(a[0], c[1], -(a[1] * c[0])) };
+            float inv = 1.0f / sqrtf(orc_dot3(n, n));
             n[0] *= inv; n[1] *= inv; n[2] *= inv;
             float nt[3];
             m3v(p->w2t, n, nt);
@@ -268,11 +273,11 @@ void orc_normal_tile(const orc_norm_params *p, const float *elev,
                 nc[0] = (nc0[0] + nc1[0]) * 0.5f;
                 nc[1] = (nc0[1] + nc1[1]) * 0.5f;
                 if (p->format == 1) {
-                    nc[0] = nc[0] * 2.0f - 1.0f;
-                    nc[1] = nc[1] * 2.0f - 1.0f;
+                    nc[0] = orc_fma(nc[0], 2.0f, -1.0f);
+                    nc[1] = orc_fma(nc[1], 2.0f, -1.0f);
                 }
                 if (p->deform[3] != 0.0f) {
-                    float v3[3] = { nc[0], nc[1], sqrtf(1.0f - (nc[0] * nc[0] + nc[1] * nc[1])) };
+                    float v3[3] = { nc[0], nc[1], sqrtf(1.0f - orc_dot2(nc, nc)) };
                     float r3[3];
                     m3v(p->p2t, v3, r3);
                     nc[0] = r3[0];
@@ -283,10 +288,10 @@ void orc_normal_tile(const orc_norm_params *p, const float *elev,
             float *o = out + (size_t) (x + y * W) * 4;
             switch (p->format) {
             case 0: o[0] = nf[0]; o[1] = nf[1]; o[2] = nc[0]; o[3] = nc[1]; break;
-            case 1: o[0] = nf[0] * 0.5f + 0.5f; o[1] = nf[1] * 0.5f + 0.5f;
-                    o[2] = nc[0] * 0.5f + 0.5f; o[3] = nc[1] * 0.5f + 0.5f; break;
+            case 1: o[0] = orc_fma(nf[0], 0.5f, 0.5f); o[1] = orc_fma(nf[1], 0.5f, 0.5f);
+                    o[2] = orc_fma(nc[0], 0.5f, 0.5f); o[3] = orc_fma(nc[1], 0.5f, 0.5f); break;
             case 2: o[0] = nf[0]; o[1] = nf[1]; o[2] = 0.0f; o[3] = 0.0f; break;
-            default: o[0] = nf[0] * 0.5f + 0.5f; o[1] = nf[1] * 0.5f + 0.5f; o[2] = 0.5f; o[3] = 0.5f; break;
+            default: o[0] = orc_fma(nf[0], 0.5f, 0.5f); o[1] = orc_fma(nf[1], 0.5f, 0.5f); o[2] = 0.5f; o[3] = 0.5f; break;
             }
         }
     }

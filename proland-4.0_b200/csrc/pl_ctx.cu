@@ -1,0 +1,476 @@
+/*
+ * pl_ctx.cu -- context, device tile pools, noise texture, request staging: the
+ * host half of the C ABI in include/proland_b200.h.
+ *
+ * Replaces producer/GPUTileStorage.cpp:129-199 (a Texture2DArray per pool, a
+ * slot = one layer) by one cudaMalloc slab per pool, and the R16F noise
+ * Texture2DArray of ElevationProducer.cpp:129-130 by 24 fp16 planes (6 layers x
+ * 4 rotations) so that every kernel read of the noise is a coalesced row read.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "pl_internal.h"
+
+static thread_local char g_err[512] = "";
+
+int pl_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *pl_last_error(void) { return g_err; }
+extern "C" int pl_abi_version(void) { return PL_ABI_VERSION; }
+
+/* ------------------------------------------------------------------ context */
+
+extern "C" int pl_ctx_create(int device, pl_ctx **out)
+{
+    if (!out) return pl_set_error(PL_ERR_ARG, "pl_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return pl_set_error(PL_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                            e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return pl_set_error(PL_ERR_ARG, "device %d out of range", device);
+    PL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return pl_set_error(PL_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only",
+                            device, prop.major, prop.minor);
+    pl_ctx *ctx = new pl_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    PL_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return PL_OK;
+}
+
+extern "C" void pl_ctx_destroy(pl_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->noise_rot) cudaFree(ctx->noise_rot);
+    if (ctx->req_dev) cudaFree(ctx->req_dev);
+    if (ctx->req_pinned) cudaFreeHost(ctx->req_pinned);
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" int pl_ctx_set_stream(pl_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->own_stream;
+    return PL_OK;
+}
+
+extern "C" void *pl_ctx_stream(pl_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+
+extern "C" int pl_sync(pl_ctx *ctx)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PL_OK;
+}
+
+extern "C" uint64_t pl_ctx_launch_count(const pl_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int pl_device_sm_count(pl_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev)
+{
+    PL_CUDA(cudaSetDevice(ctx->device));
+    if (bytes > ctx->req_dev_bytes) {
+        /* the previous batch may still be reading the old buffer */
+        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->req_dev) cudaFree(ctx->req_dev);
+        if (ctx->req_pinned) cudaFreeHost(ctx->req_pinned);
+        ctx->req_dev = nullptr;
+        ctx->req_pinned = nullptr;
+        size_t cap = bytes + bytes / 2 + 4096;
+        PL_CUDA(cudaMalloc(&ctx->req_dev, cap));
+        PL_CUDA(cudaMallocHost(&ctx->req_pinned, cap));
+        ctx->req_dev_bytes = ctx->req_pinned_bytes = cap;
+    } else {
+        /* the pinned staging buffer is reused: wait until the last copy left it */
+        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    memcpy(ctx->req_pinned, host, bytes);
+    PL_CUDA(cudaMemcpyAsync(ctx->req_dev, ctx->req_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = ctx->req_dev;
+    return PL_OK;
+}
+
+/* -------------------------------------------------------------------- pools */
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_tiled()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn) p;
+    }
+    return fn;
+}
+
+static int elem_bytes(int kind)
+{
+    switch (kind) {
+    case PL_POOL_ELEV_F32x3: return 12;
+    case PL_POOL_NORM_UN8x2: return 2;
+    case PL_POOL_NORM_UN8x4: return 4;
+    case PL_POOL_RESID_F32: return 4;
+    case PL_POOL_RESID_I16: return 2;
+    default: return 0;
+    }
+}
+
+extern "C" int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, pl_pool **out)
+{
+    if (!ctx || !out) return pl_set_error(PL_ERR_ARG, "pl_pool_create: NULL argument");
+    *out = nullptr;
+    if (elem_bytes(kind) == 0) return pl_set_error(PL_ERR_ARG, "unknown pool kind %d", kind);
+    if (tile_w < 8 || tile_w > 1024 || capacity <= 0)
+        return pl_set_error(PL_ERR_ARG, "bad pool geometry tile_w=%d capacity=%d", tile_w, capacity);
+    PL_CUDA(cudaSetDevice(ctx->device));
+    pl_pool *p = new pl_pool();
+    memset(p, 0, sizeof(*p));
+    p->ctx = ctx;
+    p->kind = kind;
+    p->tile_w = tile_w;
+    p->capacity = capacity;
+    p->tile_bytes = (size_t) tile_w * tile_w * elem_bytes(kind);
+    switch (kind) {
+    case PL_POOL_ELEV_F32x3:
+        if ((tile_w - 5) % 2 != 0 || tile_w < 9) {
+            delete p;
+            return pl_set_error(PL_ERR_ARG, "elevation tile_w must be odd (tileSize + 5), got %d", tile_w);
+        }
+        p->pitch = pl_round_up(tile_w, 4);
+        p->plane_elems = (size_t) tile_w * p->pitch;
+        p->slot_bytes = 3 * p->plane_elems * sizeof(float);
+        break;
+    case PL_POOL_NORM_UN8x2:
+    case PL_POOL_NORM_UN8x4:
+        p->pitch = tile_w * elem_bytes(kind);
+        p->slot_bytes = (size_t) pl_round_up((int) (((size_t) tile_w * p->pitch + 15) / 16 * 16), 32);
+        break;
+    case PL_POOL_RESID_F32:
+        p->pitch = pl_round_up(tile_w, 4);
+        p->slot_bytes = (size_t) pl_round_up(tile_w * p->pitch * 4, 128);
+        break;
+    case PL_POOL_RESID_I16:
+        p->pitch = pl_round_up(tile_w, 8);
+        p->slot_bytes = (size_t) pl_round_up(tile_w * p->pitch * 2, 128);
+        break;
+    }
+    cudaError_t e = cudaMalloc(&p->base, p->slot_bytes * capacity);
+    if (e != cudaSuccess) {
+        const size_t want = p->slot_bytes * capacity;
+        delete p;
+        cudaGetLastError();
+        return pl_set_error(PL_ERR_POOL_FULL, "cudaMalloc of %zu bytes for %d slots failed: %s", want, capacity,
+                            cudaGetErrorString(e));
+    }
+    /* pad columns / bytes are part of whole-sector writes later; start from zero */
+    PL_CUDA(cudaMemsetAsync(p->base, 0, p->slot_bytes * capacity, ctx->stream));
+
+    if (kind == PL_POOL_ELEV_F32x3) {
+        PL_CUDA(cudaMalloc(&p->stats, sizeof(float2) * capacity));
+        PL_CUDA(cudaMemsetAsync(p->stats, 0, sizeof(float2) * capacity, ctx->stream));
+        /* parent window staged by TMA: (tileSize/2 + 6) texels each way, the
+         * inner extent rounded up to 4 floats (16-byte box rows) */
+        p->box_h = (tile_w - 5) / 2 + 6;
+        p->box_w = pl_round_up(p->box_h, 4);
+        EncodeTiledFn enc = get_encode_tiled();
+        if (!enc) {
+            pl_pool_destroy(p);
+            return pl_set_error(PL_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+        }
+        /* x: tile_w texels (pitch-padded rows), y: tile_w rows, z: plane index
+         * (3 planes per slot, slots are contiguous) */
+        cuuint64_t dims[3] = { (cuuint64_t) tile_w, (cuuint64_t) tile_w, (cuuint64_t) capacity * 3 };
+        cuuint64_t strides[2] = { (cuuint64_t) p->pitch * 4, (cuuint64_t) p->plane_elems * 4 };
+        cuuint32_t box[3] = { (cuuint32_t) p->box_w, (cuuint32_t) p->box_h, 1 };
+        cuuint32_t estr[3] = { 1, 1, 1 };
+        CUresult r = enc(&p->tm_parent, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p->base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            pl_pool_destroy(p);
+            return pl_set_error(PL_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int) r);
+        }
+    }
+    *out = p;
+    return PL_OK;
+}
+
+extern "C" void pl_pool_destroy(pl_pool *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    if (p->base) cudaFree(p->base);
+    if (p->stats) cudaFree(p->stats);
+    delete p;
+}
+
+extern "C" int pl_pool_capacity(const pl_pool *p) { return p ? p->capacity : 0; }
+extern "C" int pl_pool_tile_w(const pl_pool *p) { return p ? p->tile_w : 0; }
+extern "C" size_t pl_pool_tile_bytes(const pl_pool *p) { return p ? p->tile_bytes : 0; }
+extern "C" size_t pl_pool_slot_bytes(const pl_pool *p) { return p ? p->slot_bytes : 0; }
+extern "C" void *pl_pool_device_ptr(pl_pool *p) { return p ? p->base : nullptr; }
+
+static int check_slot(const pl_pool *p, int slot, size_t bytes)
+{
+    if (!p) return pl_set_error(PL_ERR_ARG, "pool is NULL");
+    if (slot < 0 || slot >= p->capacity) return pl_set_error(PL_ERR_ARG, "slot %d out of range [0,%d)", slot, p->capacity);
+    if (bytes != p->tile_bytes) return pl_set_error(PL_ERR_ARG, "expected %zu bytes per tile, got %zu", p->tile_bytes, bytes);
+    return PL_OK;
+}
+
+extern "C" int pl_pool_download(pl_pool *p, int slot, void *host, size_t bytes)
+{
+    int rc = check_slot(p, slot, bytes);
+    if (rc) return rc;
+    if (!host) return pl_set_error(PL_ERR_ARG, "host is NULL");
+    PL_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    const uint8_t *src = p->base + (size_t) slot * p->slot_bytes;
+    const int W = p->tile_w;
+    switch (p->kind) {
+    case PL_POOL_ELEV_F32x3: {
+        std::vector<float> planes(3 * p->plane_elems);
+        PL_CUDA(cudaMemcpyAsync(planes.data(), src, p->slot_bytes, cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        float *o = (float *) host;
+        for (int y = 0; y < W; ++y)
+            for (int x = 0; x < W; ++x)
+                for (int c = 0; c < 3; ++c)
+                    o[(size_t) (x + y * W) * 3 + c] = planes[c * p->plane_elems + (size_t) y * p->pitch + x];
+        break;
+    }
+    case PL_POOL_NORM_UN8x2:
+    case PL_POOL_NORM_UN8x4:
+        PL_CUDA(cudaMemcpyAsync(host, src, p->tile_bytes, cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        break;
+    case PL_POOL_RESID_F32:
+    case PL_POOL_RESID_I16: {
+        const size_t eb = p->kind == PL_POOL_RESID_F32 ? 4 : 2;
+        PL_CUDA(cudaMemcpy2DAsync(host, W * eb, src, p->pitch * eb, W * eb, W, cudaMemcpyDeviceToHost, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        break;
+    }
+    }
+    return PL_OK;
+}
+
+extern "C" int pl_pool_upload(pl_pool *p, int slot, const void *host, size_t bytes)
+{
+    int rc = check_slot(p, slot, bytes);
+    if (rc) return rc;
+    if (!host) return pl_set_error(PL_ERR_ARG, "host is NULL");
+    PL_CUDA(cudaSetDevice(p->ctx->device));
+    cudaStream_t s = p->ctx->stream;
+    uint8_t *dst = p->base + (size_t) slot * p->slot_bytes;
+    const int W = p->tile_w;
+    switch (p->kind) {
+    case PL_POOL_ELEV_F32x3: {
+        std::vector<float> planes(3 * p->plane_elems, 0.0f);
+        const float *in = (const float *) host;
+        for (int y = 0; y < W; ++y)
+            for (int x = 0; x < W; ++x)
+                for (int c = 0; c < 3; ++c)
+                    planes[c * p->plane_elems + (size_t) y * p->pitch + x] = in[(size_t) (x + y * W) * 3 + c];
+        PL_CUDA(cudaMemcpyAsync(dst, planes.data(), p->slot_bytes, cudaMemcpyHostToDevice, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        break;
+    }
+    case PL_POOL_NORM_UN8x2:
+    case PL_POOL_NORM_UN8x4:
+        PL_CUDA(cudaMemcpyAsync(dst, host, p->tile_bytes, cudaMemcpyHostToDevice, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        break;
+    case PL_POOL_RESID_F32:
+    case PL_POOL_RESID_I16: {
+        const size_t eb = p->kind == PL_POOL_RESID_F32 ? 4 : 2;
+        PL_CUDA(cudaMemcpy2DAsync(dst, p->pitch * eb, host, W * eb, W * eb, W, cudaMemcpyHostToDevice, s));
+        PL_CUDA(cudaStreamSynchronize(s));
+        break;
+    }
+    }
+    return PL_OK;
+}
+
+/* -------------------------------------------------------------------- noise */
+
+extern "C" int pl_noise_init(pl_ctx *ctx, int tile_w, float *host_out)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    if (tile_w < 11 || tile_w > 1024) return pl_set_error(PL_ERR_ARG, "bad noise tile_w %d", tile_w);
+    PL_CUDA(cudaSetDevice(ctx->device));
+    const int W = tile_w;
+    std::vector<float> n6((size_t) 6 * W * W);
+    pl_host_dem_noise(W, n6.data());
+    /* the reference uploads the array as R16F: round to nearest even */
+    std::vector<__half> h6(n6.size());
+    for (size_t i = 0; i < n6.size(); ++i) {
+        h6[i] = __float2half_rn(n6[i]);
+        if (host_out) host_out[i] = __half2float(h6[i]);
+    }
+    const int pitch = pl_round_up(W + 1, 8);
+    std::vector<__half> rot((size_t) 24 * W * pitch, __float2half_rn(0.0f));
+    for (int r = 0; r < 4; ++r)
+        for (int l = 0; l < 6; ++l)
+            for (int y = 0; y < W; ++y)
+                for (int x = 0; x < W; ++x) {
+                    /* uvs = (nx, ny, 1-nx, 1-ny)[r], [(r+1)%4]  (upsampleShader.glsl:172-174) */
+                    int sx, sy;
+                    switch (r) {
+                    case 0: sx = x; sy = y; break;
+                    case 1: sx = y; sy = W - 1 - x; break;
+                    case 2: sx = W - 1 - x; sy = W - 1 - y; break;
+                    default: sx = W - 1 - y; sy = x; break;
+                    }
+                    rot[((size_t) (r * 6 + l) * W + y) * pitch + x] = h6[(size_t) l * W * W + sx + (size_t) sy * W];
+                }
+    if (ctx->noise_rot) {
+        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->noise_rot);
+        ctx->noise_rot = nullptr;
+    }
+    PL_CUDA(cudaMalloc(&ctx->noise_rot, rot.size() * sizeof(__half)));
+    PL_CUDA(cudaMemcpyAsync(ctx->noise_rot, rot.data(), rot.size() * sizeof(__half), cudaMemcpyHostToDevice,
+                            ctx->stream));
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->noise_w = W;
+    ctx->noise_pitch = pitch;
+    return PL_OK;
+}
+
+/* ----------------------------------------------------------- batch wrappers */
+
+static int check_elev_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n)
+{
+    if (!ctx || !sc || !elev) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (n < 0) return pl_set_error(PL_ERR_ARG, "n < 0");
+    if (elev->kind != PL_POOL_ELEV_F32x3) return pl_set_error(PL_ERR_ARG, "elev is not an ELEV_F32x3 pool");
+    if (elev->tile_w != sc->tile_w) return pl_set_error(PL_ERR_ARG, "scene tile_w %d != pool tile_w %d", sc->tile_w, elev->tile_w);
+    if (resid && resid->kind != PL_POOL_RESID_F32 && resid->kind != PL_POOL_RESID_I16)
+        return pl_set_error(PL_ERR_ARG, "resid is not a residual pool");
+    if (resid && (resid->tile_w - 5) % (sc->tile_w - 5) != 0)
+        return pl_set_error(PL_ERR_ARG, "residual tile size %d is not a multiple of %d", resid->tile_w - 5, sc->tile_w - 5);
+    if (sc->grid <= 0) return pl_set_error(PL_ERR_ARG, "grid must be > 0");
+    if (ctx->noise_w != sc->tile_w)
+        return pl_set_error(PL_ERR_ARG, "pl_noise_init(ctx, %d) has not been called", sc->tile_w);
+    return PL_OK;
+}
+
+extern "C" int pl_elevation_batch_dev(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n,
+                                      const pl_elev_req *dev_reqs)
+{
+    int rc = check_elev_args(ctx, sc, elev, resid, n);
+    if (rc) return rc;
+    if (n == 0) return PL_OK;
+    if (!dev_reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    return pl_launch_elevation(ctx, sc, elev, resid, n, dev_reqs);
+}
+
+extern "C" int pl_elevation_batch(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n,
+                                  const pl_elev_req *reqs)
+{
+    int rc = check_elev_args(ctx, sc, elev, resid, n);
+    if (rc) return rc;
+    if (n == 0) return PL_OK;
+    if (!reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    const int rcap = resid ? resid->capacity : 0;
+    for (int i = 0; i < n; ++i) {
+        const pl_elev_req &q = reqs[i];
+        if (q.out_slot < 0 || q.out_slot >= elev->capacity || q.parent_slot >= elev->capacity ||
+            q.resid_slot >= rcap || q.noise_r < 0 || q.noise_r > 3 || q.noise_l < 0 || q.noise_l > 5 ||
+            q.parent_slot == q.out_slot)
+            return pl_set_error(PL_ERR_ARG, "request %d: slot / noise index out of range", i);
+    }
+    void *dev = nullptr;
+    rc = pl_stage_requests(ctx, reqs, sizeof(pl_elev_req) * (size_t) n, &dev);
+    if (rc) return rc;
+    return pl_launch_elevation(ctx, sc, elev, resid, n, (const pl_elev_req *) dev);
+}
+
+extern "C" int pl_elev_stats_download(pl_ctx *ctx, pl_pool *elev, int n, const int32_t *slots, float *out)
+{
+    if (!ctx || !elev || !slots || !out || n < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (elev->kind != PL_POOL_ELEV_F32x3) return pl_set_error(PL_ERR_ARG, "not an elevation pool");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    std::vector<float2> all(elev->capacity);
+    PL_CUDA(cudaMemcpyAsync(all.data(), elev->stats, sizeof(float2) * elev->capacity, cudaMemcpyDeviceToHost, ctx->stream));
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= elev->capacity) return pl_set_error(PL_ERR_ARG, "slot out of range");
+        out[2 * i] = all[slots[i]].x;
+        out[2 * i + 1] = all[slots[i]].y;
+    }
+    return PL_OK;
+}
+
+static int check_norm_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, int n)
+{
+    if (!ctx || !sc || !norm || !elev) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (n < 0) return pl_set_error(PL_ERR_ARG, "n < 0");
+    if (norm->kind != PL_POOL_NORM_UN8x2 && norm->kind != PL_POOL_NORM_UN8x4)
+        return pl_set_error(PL_ERR_ARG, "norm is not a normal pool");
+    if (elev->kind != PL_POOL_ELEV_F32x3) return pl_set_error(PL_ERR_ARG, "elev is not an elevation pool");
+    if (norm->tile_w != sc->tile_w) return pl_set_error(PL_ERR_ARG, "scene tile_w != normal pool tile_w");
+    if (elev->tile_w != sc->tile_w + 2 * sc->elev_border)
+        return pl_set_error(PL_ERR_ARG, "elevation tile_w %d != normal tile_w %d + 2*border %d", elev->tile_w, sc->tile_w, sc->elev_border);
+    if (sc->elev_border < 1) return pl_set_error(PL_ERR_ARG, "elev_border must be >= 1");
+    return PL_OK;
+}
+
+extern "C" int pl_normal_batch_dev(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, int n,
+                                   const pl_norm_req *dev_reqs)
+{
+    int rc = check_norm_args(ctx, sc, norm, elev, n);
+    if (rc) return rc;
+    if (n == 0) return PL_OK;
+    if (!dev_reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    return pl_launch_normal(ctx, sc, norm, elev, n, dev_reqs);
+}
+
+extern "C" int pl_normal_batch(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, int n,
+                               const pl_norm_req *reqs)
+{
+    int rc = check_norm_args(ctx, sc, norm, elev, n);
+    if (rc) return rc;
+    if (n == 0) return PL_OK;
+    if (!reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    for (int i = 0; i < n; ++i) {
+        const pl_norm_req &q = reqs[i];
+        if (q.out_slot < 0 || q.out_slot >= norm->capacity || q.elev_slot < 0 || q.elev_slot >= elev->capacity ||
+            q.parent_slot >= norm->capacity || (q.parent_slot >= 0 && q.parent_slot == q.out_slot))
+            return pl_set_error(PL_ERR_ARG, "request %d: slot out of range", i);
+    }
+    void *dev = nullptr;
+    rc = pl_stage_requests(ctx, reqs, sizeof(pl_norm_req) * (size_t) n, &dev);
+    if (rc) return rc;
+    return pl_launch_normal(ctx, sc, norm, elev, n, (const pl_norm_req *) dev);
+}

@@ -1,0 +1,80 @@
+/*
+ * pl_internal.h -- shared between the translation units of libproland_b200.so.
+ * Not part of the C ABI (include/proland_b200.h is).
+ */
+#ifndef PL_INTERNAL_H
+#define PL_INTERNAL_H
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include "proland_b200.h"
+
+/* ---- HBM layout of the pools (DESIGN.md "Data layout") ----------------------
+ * ELEV_F32x3 : per slot 3 planes (zf, zc, zm); a plane is tile_w rows of `pitch`
+ *              floats, pitch = tile_w rounded up to 4 (16-byte rows: TMA tensor
+ *              maps need 16-byte strides, 101*4 is not).  Pad columns hold 0.
+ * NORM_UN8xC : dense rows of tile_w*C bytes; slot stride rounded up so the
+ *              last 16-byte bulk store of a tile stays inside its slot.
+ * RESID_F32  : tile_w rows of pitch floats (pitch = tile_w rounded up to 4).
+ * RESID_I16  : tile_w rows of pitch int16  (pitch = tile_w rounded up to 8).
+ */
+struct pl_pool {
+    pl_ctx *ctx;
+    int kind;
+    int tile_w;
+    int capacity;
+    int pitch;          /* elements per row (floats / int16) or bytes per row (normals) */
+    size_t plane_elems; /* ELEV: tile_w * pitch */
+    size_t slot_bytes;
+    size_t tile_bytes;  /* reference layout */
+    uint8_t *base;      /* device */
+    float2 *stats;      /* ELEV only: per-slot (zmin, zmax) */
+    CUtensorMap tm_parent; /* ELEV only: 3-D map over the zf/zc/zm planes, box = parent window */
+    int box_w, box_h;
+};
+
+struct pl_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    uint64_t launches;
+    /* noise (createDemNoise), 4 rotations x 6 layers of fp16 */
+    int noise_w;
+    int noise_pitch;
+    __half *noise_rot;
+    /* request staging */
+    void *req_dev;
+    size_t req_dev_bytes;
+    void *req_pinned;
+    size_t req_pinned_bytes;
+};
+
+int pl_set_error(int code, const char *fmt, ...);
+#define PL_CUDA(call)                                                                       \
+    do {                                                                                    \
+        cudaError_t e_ = (call);                                                            \
+        if (e_ != cudaSuccess)                                                              \
+            return pl_set_error(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver \
+                                    ? PL_ERR_NO_DEVICE : PL_ERR_CUDA,                       \
+                                "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+/* stage n*bytes of host requests on the device (returns device pointer) */
+int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev);
+
+/* kernel launchers (defined next to their kernels) */
+int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid,
+                        int n, const pl_elev_req *dev_reqs);
+int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev,
+                     int n, const pl_norm_req *dev_reqs);
+
+/* host maths shared with the request builders (pl_hostmath.cpp) */
+void pl_host_dem_noise(int W, float *out6);      /* fp32, before the R16F rounding */
+
+static inline int pl_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+#endif

@@ -1,0 +1,303 @@
+"""ctypes binding of libproland_b200.so (include/proland_b200.h).
+
+This is the Python face of the C ABI used by the tests, bench.py and
+__graft_entry__.py.  It holds no arithmetic: everything is computed by the CUDA
+library.  There is no fallback: a missing library or a missing GPU raises.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libproland_b200.so")
+
+PL_OK, PL_ERR_ARG, PL_ERR_POOL_FULL, PL_ERR_CUDA, PL_ERR_CORRUPT, PL_ERR_NO_DEVICE, PL_ERR_IO = range(7)
+POOL_ELEV, POOL_NORM2, POOL_NORM4, POOL_RESID_F32, POOL_RESID_I16 = range(5)
+NOISE_PLAIN, NOISE_SLOPE = 0, 1
+FILTER_NEAREST, FILTER_LINEAR = 0, 1
+
+# every symbol include/proland_b200.h declares (tests check the .so exports them all)
+EXPORTS = [
+    "pl_last_error", "pl_abi_version", "pl_ctx_create", "pl_ctx_destroy", "pl_ctx_set_stream",
+    "pl_ctx_stream", "pl_sync", "pl_ctx_launch_count", "pl_device_sm_count", "pl_pool_create",
+    "pl_pool_destroy", "pl_pool_capacity", "pl_pool_tile_w", "pl_pool_tile_bytes",
+    "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload",
+    "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
+    "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_norm_make_req", "pl_normal_batch",
+    "pl_normal_batch_dev", "pl_residual_decode_batch",
+]
+
+
+class PlError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pl error %d: %s" % (code, msg))
+        self.code = code
+
+
+class ElevScene(C.Structure):
+    _fields_ = [("tile_w", C.c_int32), ("grid", C.c_int32), ("flip", C.c_int32),
+                ("noise_mode", C.c_int32), ("no_clamp", C.c_int32), ("want_stats", C.c_int32),
+                ("resid_scale", C.c_float), ("pad_", C.c_int32)]
+
+
+class ElevReq(C.Structure):
+    _fields_ = [("out_slot", C.c_int32), ("parent_slot", C.c_int32), ("resid_slot", C.c_int32),
+                ("dx", C.c_int32), ("dy", C.c_int32), ("rx", C.c_int32), ("ry", C.c_int32),
+                ("noise_r", C.c_int32), ("noise_l", C.c_int32), ("rs", C.c_float),
+                ("pixel_size", C.c_float), ("level", C.c_int32), ("tx", C.c_int32),
+                ("ty", C.c_int32), ("pad_", C.c_int32 * 2)]
+
+
+class NormScene(C.Structure):
+    _fields_ = [("tile_w", C.c_int32), ("grid", C.c_int32), ("elev_border", C.c_int32),
+                ("elev_filter", C.c_int32), ("parent_filter", C.c_int32), ("sphere", C.c_int32)]
+
+
+class NormReq(C.Structure):
+    _fields_ = [("out_slot", C.c_int32), ("elev_slot", C.c_int32), ("parent_slot", C.c_int32),
+                ("ptx", C.c_int32), ("pty", C.c_int32), ("level", C.c_int32),
+                ("deform", C.c_float * 4), ("corners", C.c_float * 12),
+                ("verticals", C.c_float * 12), ("norms", C.c_float * 4), ("w2t", C.c_float * 9),
+                ("p2t", C.c_float * 9), ("smooth", C.c_float), ("pad_", C.c_int32 * 3)]
+
+
+assert C.sizeof(ElevReq) == 64 and C.sizeof(NormReq) == 240 and C.sizeof(ElevScene) == 32
+
+ELEV_REQ_DTYPE = np.dtype([("out_slot", "i4"), ("parent_slot", "i4"), ("resid_slot", "i4"),
+                           ("dx", "i4"), ("dy", "i4"), ("rx", "i4"), ("ry", "i4"),
+                           ("noise_r", "i4"), ("noise_l", "i4"), ("rs", "f4"),
+                           ("pixel_size", "f4"), ("level", "i4"), ("tx", "i4"), ("ty", "i4"),
+                           ("pad_", "i4", (2,))])
+NORM_REQ_DTYPE = np.dtype([("out_slot", "i4"), ("elev_slot", "i4"), ("parent_slot", "i4"),
+                           ("ptx", "i4"), ("pty", "i4"), ("level", "i4"), ("deform", "f4", (4,)),
+                           ("corners", "f4", (12,)), ("verticals", "f4", (12,)),
+                           ("norms", "f4", (4,)), ("w2t", "f4", (9,)), ("p2t", "f4", (9,)),
+                           ("smooth", "f4"), ("pad_", "i4", (3,))])
+assert ELEV_REQ_DTYPE.itemsize == 64 and NORM_REQ_DTYPE.itemsize == 240
+
+_lib = None
+
+
+def build():
+    """Compile libproland_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", "-C", HERE])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PlError(PL_ERR_NO_DEVICE, "%s is missing: run `make -C %s` (there is no fallback path)"
+                          % (LIB_PATH, HERE))
+        L = C.CDLL(LIB_PATH)
+        L.pl_last_error.restype = C.c_char_p
+        L.pl_ctx_stream.restype = C.c_void_p
+        L.pl_ctx_launch_count.restype = C.c_uint64
+        L.pl_pool_tile_bytes.restype = C.c_size_t
+        L.pl_pool_slot_bytes.restype = C.c_size_t
+        L.pl_pool_device_ptr.restype = C.c_void_p
+        L.pl_cnoise2.restype = C.c_float
+        L.pl_cnoise2.argtypes = [C.c_float, C.c_float]
+        L.pl_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.pl_ctx_destroy.argtypes = [C.c_void_p]
+        L.pl_ctx_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.pl_ctx_stream.argtypes = [C.c_void_p]
+        L.pl_sync.argtypes = [C.c_void_p]
+        L.pl_ctx_launch_count.argtypes = [C.c_void_p]
+        L.pl_device_sm_count.argtypes = [C.c_void_p]
+        L.pl_pool_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pl_pool_destroy.argtypes = [C.c_void_p]
+        for f in (L.pl_pool_capacity, L.pl_pool_tile_w, L.pl_pool_tile_bytes, L.pl_pool_slot_bytes,
+                  L.pl_pool_device_ptr):
+            f.argtypes = [C.c_void_p]
+        L.pl_pool_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.pl_pool_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.pl_noise_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.pl_noise_select.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]
+        L.pl_noise_select.restype = None
+        L.pl_elev_make_req.argtypes = [C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.pl_elev_make_req.restype = None
+        L.pl_elevation_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p]
+        L.pl_elevation_batch_dev.argtypes = L.pl_elevation_batch.argtypes
+        L.pl_elev_stats_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pl_norm_make_req.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_void_p]
+        L.pl_norm_make_req.restype = None
+        L.pl_normal_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_void_p]
+        L.pl_normal_batch_dev.argtypes = L.pl_normal_batch.argtypes
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != PL_OK:
+        raise PlError(rc, lib().pl_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ----------------------------------------------------------------- host helpers
+
+def cnoise2(x, y):
+    return lib().pl_cnoise2(x, y)
+
+
+def noise_select(level, tx, ty, face):
+    r, l = C.c_int(), C.c_int()
+    lib().pl_noise_select(level, tx, ty, face, C.byref(r), C.byref(l))
+    return r.value, l.value
+
+
+def elev_make_reqs(tiles, *, tile_w=101, root_quad_size=100000.0, noise_amp=(), face=0,
+                   resid_tile_w=0, has_resid=None):
+    """tiles: iterable of (level, tx, ty) -> structured array of pl_elev_req (slots = -1)."""
+    tiles = list(tiles)
+    out = np.zeros(len(tiles), ELEV_REQ_DTYPE)
+    amp = np.asarray(noise_amp, np.float32)
+    L = lib()
+    for i, (level, tx, ty) in enumerate(tiles):
+        hr = 0 if has_resid is None else int(bool(has_resid[i]))
+        L.pl_elev_make_req(tile_w, C.c_float(root_quad_size), _ptr(amp), len(amp), face, level, tx,
+                           ty, resid_tile_w, hr, C.c_void_p(out.ctypes.data + 64 * i))
+    return out
+
+
+def norm_make_reqs(tiles, scene, *, root_quad_size=100000.0, components=2):
+    tiles = list(tiles)
+    out = np.zeros(len(tiles), NORM_REQ_DTYPE)
+    L = lib()
+    for i, (level, tx, ty) in enumerate(tiles):
+        L.pl_norm_make_req(C.byref(scene), C.c_double(root_quad_size), components, level, tx, ty,
+                           C.c_void_p(out.ctypes.data + 240 * i))
+    return out
+
+
+# ------------------------------------------------------------------- context
+
+class Pool:
+    def __init__(self, ctx, kind, tile_w, capacity):
+        self.ctx = ctx
+        self.kind = kind
+        h = C.c_void_p()
+        check(lib().pl_pool_create(ctx.h, kind, tile_w, capacity, C.byref(h)))
+        self.h = h
+        self.tile_w = tile_w
+        self.capacity = capacity
+        self.tile_bytes = lib().pl_pool_tile_bytes(h)
+        self.slot_bytes = lib().pl_pool_slot_bytes(h)
+
+    def close(self):
+        if self.h:
+            lib().pl_pool_destroy(self.h)
+            self.h = None
+
+    def _shape_dtype(self):
+        W = self.tile_w
+        return {POOL_ELEV: ((W, W, 3), np.float32), POOL_NORM2: ((W, W, 2), np.uint8),
+                POOL_NORM4: ((W, W, 4), np.uint8), POOL_RESID_F32: ((W, W), np.float32),
+                POOL_RESID_I16: ((W, W), np.int16)}[self.kind]
+
+    def download(self, slot):
+        shape, dt = self._shape_dtype()
+        out = np.empty(shape, dt)
+        check(lib().pl_pool_download(self.h, slot, _ptr(out), out.nbytes))
+        return out
+
+    def upload(self, slot, arr):
+        shape, dt = self._shape_dtype()
+        a = np.ascontiguousarray(arr, dt).reshape(shape)
+        check(lib().pl_pool_upload(self.h, slot, _ptr(a), a.nbytes))
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        check(lib().pl_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+        self._pools = []
+
+    def close(self):
+        for p in self._pools:
+            p.close()
+        self._pools = []
+        if self.h:
+            lib().pl_ctx_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def pool(self, kind, tile_w, capacity):
+        p = Pool(self, kind, tile_w, capacity)
+        self._pools.append(p)
+        return p
+
+    def set_stream(self, cuda_stream):
+        check(lib().pl_ctx_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    @property
+    def stream(self):
+        return lib().pl_ctx_stream(self.h)
+
+    def sync(self):
+        check(lib().pl_sync(self.h))
+
+    @property
+    def launches(self):
+        return lib().pl_ctx_launch_count(self.h)
+
+    @property
+    def sm_count(self):
+        return lib().pl_device_sm_count(self.h)
+
+    def noise_init(self, tile_w=101):
+        out = np.empty((6, tile_w, tile_w), np.float32)
+        check(lib().pl_noise_init(self.h, tile_w, _ptr(out)))
+        return out
+
+    def elevation_batch(self, scene, elev, reqs, resid=None):
+        reqs = np.ascontiguousarray(reqs, ELEV_REQ_DTYPE)
+        check(lib().pl_elevation_batch(self.h, C.byref(scene), elev.h, resid.h if resid else None,
+                                       len(reqs), _ptr(reqs)))
+
+    def elevation_batch_dev(self, scene, elev, n, dev_ptr, resid=None):
+        check(lib().pl_elevation_batch_dev(self.h, C.byref(scene), elev.h,
+                                           resid.h if resid else None, n, C.c_void_p(dev_ptr)))
+
+    def elev_stats(self, elev, slots):
+        slots = np.ascontiguousarray(slots, np.int32)
+        out = np.empty((len(slots), 2), np.float32)
+        check(lib().pl_elev_stats_download(self.h, elev.h, len(slots), _ptr(slots), _ptr(out)))
+        return out
+
+    def normal_batch(self, scene, norm, elev, reqs):
+        reqs = np.ascontiguousarray(reqs, NORM_REQ_DTYPE)
+        check(lib().pl_normal_batch(self.h, C.byref(scene), norm.h, elev.h, len(reqs), _ptr(reqs)))
+
+    def normal_batch_dev(self, scene, norm, elev, n, dev_ptr):
+        check(lib().pl_normal_batch_dev(self.h, C.byref(scene), norm.h, elev.h, n,
+                                        C.c_void_p(dev_ptr)))
+
+
+def elev_scene(tile_w=101, grid_size=24, flip=0, noise_mode=NOISE_SLOPE, no_clamp=0, want_stats=0,
+               resid_scale=1.0):
+    return ElevScene(tile_w, (tile_w - 5) // grid_size, flip, noise_mode, no_clamp, want_stats,
+                     resid_scale, 0)
+
+
+def norm_scene(tile_w=97, grid_size=24, elev_border=2, elev_filter=FILTER_LINEAR,
+               parent_filter=FILTER_LINEAR, sphere=0):
+    return NormScene(tile_w, (tile_w - 1) // grid_size, elev_border, elev_filter, parent_filter,
+                     sphere)
