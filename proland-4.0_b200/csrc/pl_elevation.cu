@@ -358,7 +358,7 @@ int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_
     const size_t smem = (size_t) a.box_w * a.box_h * 4 + (size_t) a.nk * a.nk * 4 + (size_t) a.W * 4;
     const int rk = !resid ? 0 : (resid->kind == PL_POOL_RESID_F32 ? 1 : 2);
     auto kern = rk == 0 ? elevation_kernel<0> : (rk == 1 ? elevation_kernel<1> : elevation_kernel<2>);
-    if (smem > 48 * 1024) PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    if (smem > 40 * 1024) PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     kern<<<n, kThreads, smem, ctx->stream>>>(elev->tm_parent, a);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;

@@ -259,7 +259,8 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
     const size_t smem = (size_t) (a.max_rows + 3) * a.epitch * 4 + (size_t) 3 * (a.max_rows + 2) * GW * 4 +
                         (size_t) ((GW + 3) & ~3) * 4 + (size_t) ((a.max_rows * a.W * a.channels + 15) & ~15);
     if (smem > 227 * 1024) return pl_set_error(PL_ERR_ARG, "normal tile_w %d needs %zu bytes of shared memory", a.W, smem);
-    if (smem > 48 * 1024)
+    /* static + dynamic must stay under the default 48 KB unless opted in */
+    if (smem > 40 * 1024)
         PL_CUDA(cudaFuncSetAttribute(normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     normal_kernel<<<n * a.nbands, kThreads, smem, ctx->stream>>>(a);
     PL_CUDA(cudaGetLastError());
