@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- elevation+normal tile pairs/sec on B200 (BASELINE.json's metric).
+
+Workload (config.workload): demo-fractalplanet -- the six cube faces of the
+fractal planet, every quadtree tile of levels 0..10 (8 388 606 elevation+normal
+pairs, sphere-deformed RG8 normals, slope/curvature-modulated noise).  One
+"step" produces the whole planet once.  The planet is cut into 96 subtrees (one
+per level-2 quad of each face); rank r owns subtrees r, r+N, ... and produces
+them breadth-first into a recycling device pool (no data-path collective; NCCL
+only gathers per-rank counters).  Total work is fixed as N grows -> "strong".
+
+  value : device-resident path -- pl_produce_range: the per-tile uniforms are
+          generated on the GPU, nothing but (level, Morton range) crosses PCIe.
+  e2e   : the per-tile plugin path -- per-tile uniforms built on the host like
+          ElevationProducer/NormalProducer::doCreateTile do, handed to
+          pl_elevation_batch / pl_normal_batch as HOST arrays (copied to the
+          device inside the timed region), per-tile (zmin,zmax) read back.
+
+  python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+  torchrun ... bench.py --gpus N ...          (one rank per GPU)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "proland-4.0_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PLANET_AMP = [-3250, -1590, -1125, -795, -561, -397, -140, -100, 15, 8, 5, 2.5, 1.5, 1, 0.5, 0.25,
+              0.1, 0.05]
+PLANET_SIZE = 12720000.0   # 2 * R, R = 6 360 000 m (fractalplanet.xml)
+ELEV_BYTES = 101 * 101 * 12 + 54 * 54 * 4        # elevation kernel: write + parent window
+ELEV_BYTES_L0 = 101 * 101 * 12
+NORM_BYTES = 99 * 99 * 4 + 97 * 97 * 2           # normal kernel: own zm read + RG8 write
+PAIR_BYTES = ELEV_BYTES + NORM_BYTES             # 192 098
+METRIC = "elevation+normal tile pairs/sec"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- the sweep
+
+class PlanetSweep:
+    """Breadth-first production of level-2 subtrees into a recycling pool."""
+
+    def __init__(self, pl, ctx, max_level, want_stats=1):
+        self.pl, self.ctx, self.max_level = pl, ctx, max_level
+        self.depths = max_level - 2
+        # slots: 21 face-resident (levels 0..2) + one region per depth below the unit root
+        self.off = [21]
+        for d in range(1, self.depths + 1):
+            self.off.append(self.off[-1] + 4 ** d)
+        self.capacity = self.off[-1]
+        self.elev = ctx.pool(pl.POOL_ELEV, 101, self.capacity)
+        self.norm = ctx.pool(pl.POOL_NORM2, 97, self.capacity)
+        ctx.noise_init(101)
+        self.scenes = {f: pl.sweep_scene(noise_amp=PLANET_AMP, face=f, root_quad_size=PLANET_SIZE,
+                                         sphere=1, elev_filter=pl.FILTER_LINEAR,
+                                         want_stats=want_stats) for f in range(1, 7)}
+        self.units = [(f, m2) for f in range(1, 7) for m2 in range(16)]
+
+    def pairs_of(self, units, count_roots):
+        per_unit = sum(4 ** d for d in range(1, self.depths + 1))
+        faces = len({f for f, _ in units})
+        return len(units) * per_unit + (21 * faces if count_roots else 0)
+
+    # the (level, morton0, n, out_slot0, parent_slot0, parent_morton0) batches of a unit list
+    def batches(self, units):
+        face_done = None
+        for f, m2 in units:
+            if f != face_done:
+                yield f, 0, 0, 1, 0, 0, 0
+                yield f, 1, 0, 4, 1, 0, 0
+                yield f, 2, 0, 16, 5, 1, 0
+                face_done = f
+            for d in range(1, self.depths + 1):
+                n = 4 ** d
+                m0 = m2 << (2 * d)
+                if d == 1:
+                    yield f, 2 + d, m0, n, self.off[0], 5 + m2, m2
+                else:
+                    yield f, 2 + d, m0, n, self.off[d - 1], self.off[d - 2], m0 >> 2
+
+    def run_device(self, units):
+        pr = self.ctx.produce_range
+        for f, level, m0, n, s0, p0, pm0 in self.batches(units):
+            pr(self.scenes[f], self.elev, self.norm, level, m0, n, s0, p0, pm0)
+
+    def run_host_requests(self, units, nthreads=0):
+        """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out."""
+        pl, ctx = self.pl, self.ctx
+        h2d = d2h = 0
+        for f, level, m0, n, s0, p0, pm0 in self.batches(units):
+            sc = self.scenes[f]
+            e, q = pl.make_requests_range(sc, level, m0, n, s0, p0, pm0, nthreads=nthreads)
+            ctx.elevation_batch(sc.elev, self.elev, e)
+            ctx.normal_batch(sc.norm, self.norm, self.elev, q)
+            h2d += e.nbytes + q.nbytes
+            if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile
+                st = ctx.elev_stats_range(self.elev, s0, n)
+                d2h += st.nbytes
+        return h2d, d2h
+
+
+# -------------------------------------------------------------- CPU baseline
+
+def cpu_sample(max_level, face=1, nthreads=0):
+    """The oracle (CPU restatement of the reference's GLSL path, OpenMP over the
+    tiles of a level) on one face of the same planet, levels 0..max_level."""
+    import orc
+    orc.build()
+    scene = orc.make_scene(W=101, gridMeshSize=24, rootQuadSize=PLANET_SIZE, face=face, flip=0,
+                           noise_mode=1, no_clamp=0, noiseAmp=PLANET_AMP, sphere=1, elev_filter=1)
+    t0 = time.perf_counter()
+    n, checksum, lo, hi = orc.produce_quadtree(scene, max_level, nthreads)
+    dt = time.perf_counter() - t0
+    return n, dt, checksum
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    level = 6            # 5461 pairs per step: a few seconds on the box's cores
+    for _ in range(args.warmup):
+        cpu_sample(min(level, 4))
+    t_total, n_total = 0.0, 0
+    for _ in range(args.steps):
+        n, dt, _ = cpu_sample(level)
+        t_total += dt
+        n_total += n
+    value = n_total / t_total
+    sample = "face 1 of the planet, levels 0..%d (%d pairs) per step" % (level, n_total // max(args.steps, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "demo-fractalplanet: 6 faces, levels 0..10, 8388606 pairs "
+                                   "(bounded CPU sample per step)", "tile_w": 101, "normal_w": 97},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------- main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--max-level", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import proland_b200 as pl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = pl.Context(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    ctx.set_stream(stream.cuda_stream)       # torch events see this stream
+    sweep = PlanetSweep(pl, ctx, args.max_level, want_stats=1)
+    my_units = sweep.units[rank::world]
+    total_pairs = sweep.pairs_of(sweep.units, True)            # counted once per step, whole job
+    launches0 = ctx.launches
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            sweep.run_device(my_units)
+        barrier()
+        ctx.timing_collect()
+        ctx.timing_enable(True)
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        launches_before = ctx.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(args.steps):
+            sweep.run_device(my_units)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        gpu_launches = ctx.launches - launches_before
+        clock_rec = clocks.stop() if rank == 0 else None
+        kt = ctx.timing_collect()
+        ctx.timing_enable(False)
+
+        # e2e: host-built requests through the per-tile C ABI, stats read back
+        e2e = None
+        if not args.no_e2e:
+            sweep.run_host_requests(my_units[:1])
+            barrier()
+            ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            ev2.record(stream)
+            h2d, d2h = sweep.run_host_requests(my_units)
+            ev3.record(stream)
+            barrier()
+            e2e_s = max(time.perf_counter() - t0, 1e-3 * ev2.elapsed_time(ev3))
+            e2e = (e2e_s, h2d, d2h)
+
+    t = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_s_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_kind = peaks()
+        secs = ms_max * 1e-3
+        value = total_pairs * args.steps / secs
+        # dominant kernel = the one with the larger share of the step
+        share = {k: v[0] for k, v in kt.items()}
+        dom = max(("elevation", "normal"), key=lambda k: share[k])
+        per_tile = {"elevation": ELEV_BYTES, "normal": NORM_BYTES}
+        roof = {}
+        for k in ("elevation", "normal"):
+            tot_ms, n_launch, n_tiles = kt[k]
+            gbs = per_tile[k] * n_tiles / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+            roof[k] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                       "frac": gbs / peak, "traffic": None, "launches": n_launch,
+                       "avg_launch_ms": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / ms_max,
+                       "bytes_per_tile": per_tile[k], "peak_kind": peak_kind}
+        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "demo-fractalplanet: 6 faces, levels 0..%d, %d pairs per step"
+                                       % (args.max_level, total_pairs),
+                           "tile_w": 101, "normal_w": 97, "partition": "96 level-2 subtrees, round-robin",
+                           "l2": "each step writes > 1 TB, far larger than L2", "pool_slots": sweep.capacity},
+                "hbm_gbs": value * PAIR_BYTES / 1e9, "hbm_frac": value * PAIR_BYTES / 1e9 / peak / world,
+                "roofline": dict(roof[dom], kernel=dom), "kernels": roof,
+                "gpu_launches": int(gpu_launches), "clocks": clock_rec}
+        if e2e:
+            line["e2e"] = {"value": total_pairs / e2e_s_max, "unit": "pairs/s",
+                           "h2d_bytes_per_step": int(e2e[1]) * world, "d2h_bytes_per_step": int(e2e[2]) * world,
+                           "path": "host-built per-tile requests -> pl_elevation_batch/pl_normal_batch, stats read back"}
+        if world == 1 and not args.no_cpu_baseline:
+            n, dt, _ = cpu_sample(7)
+            line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": os.cpu_count(),
+                                    "kind": "port",
+                                    "sample": "face 1 of the same planet, levels 0..7 (%d pairs), oracle "
+                                              "with OpenMP over the tiles of a level" % n}
+        print(json.dumps(line), flush=True)
+
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,14 @@ int pl_sync(pl_ctx *ctx);
 uint64_t pl_ctx_launch_count(const pl_ctx *ctx);
 int pl_device_sm_count(pl_ctx *ctx);
 
+/* Per-launch timing with CUDA events recorded on the launching stream (the
+ * reference's hook is Ork's monitorTask("CreateElevationTile")).
+ * pl_timing_collect synchronises, sums the elapsed time per kernel
+ * {0 elevation, 1 normal, 2 request generation, 3 residual decode} into the
+ * three 4-entry arrays and resets the record. */
+int pl_timing_enable(pl_ctx *ctx, int on);
+int pl_timing_collect(pl_ctx *ctx, double *ms, uint64_t *launches, uint64_t *tiles);
+
 /* ------------------------------------------------- tile pools (TileStorage) */
 
 /* Replaces GPUTileStorage (producer/GPUTileStorage.cpp:129-199) and, for
@@ -145,6 +153,9 @@ int pl_elevation_batch_dev(pl_ctx *ctx, const pl_elev_scene *scene, pl_pool *ele
                            pl_pool *resid, int n, const pl_elev_req *dev_reqs);
 /* per-slot (zmin,zmax) written by want_stats batches; out = 2*n floats */
 int pl_elev_stats_download(pl_ctx *ctx, pl_pool *elev, int n, const int32_t *slots, float *out);
+/* same for the contiguous slots [slot0, slot0+n) -- the readback TileSamplerZ does
+ * (core/sources/proland/terrain/TileSamplerZ.cpp:253-351), 8 bytes per tile */
+int pl_elev_stats_range(pl_ctx *ctx, pl_pool *elev, int slot0, int n, float *out);
 
 /* ----------------------------------------------------------------- normals */
 
@@ -183,6 +194,37 @@ int pl_normal_batch(pl_ctx *ctx, const pl_norm_scene *scene, pl_pool *norm, pl_p
                     int n, const pl_norm_req *reqs);
 int pl_normal_batch_dev(pl_ctx *ctx, const pl_norm_scene *scene, pl_pool *norm, pl_pool *elev,
                         int n, const pl_norm_req *dev_reqs);
+
+/* ------------------------------------------------ device-side batch driver */
+
+/* Everything a producer pair (elevationProducer + normalProducer resources)
+ * holds that does not depend on the tile. */
+typedef struct pl_sweep_scene {
+    pl_elev_scene elev;
+    pl_norm_scene norm;
+    float root_quad_size;   /* TileProducer::getRootQuadSize()                      */
+    int32_t face;           /* ElevationProducer.cpp:503-509                        */
+    int32_t n_amp;          /* noise="..." list (<= 32 levels)                      */
+    int32_t pad_;
+    float noise_amp[32];
+} pl_sweep_scene;
+
+/* Produce n tiles of one level, consecutive in Morton order from morton0 (the
+ * order TileSampler::getTiles visits children: x in the even bits), into slots
+ * out_slot0 .. out_slot0+n-1 of BOTH pools (norm may be NULL: elevation only).
+ * The parent of tile m is slot parent_slot0 + ((m >> 2) - parent_morton0) of
+ * the elevation pool.  The per-tile uniforms are generated on the device; no
+ * per-tile data crosses the PCIe bus.  Fractal scenes only (no residuals). */
+int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl_pool *norm,
+                     int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,
+                     uint64_t parent_morton0);
+/* The same requests built on the host with nthreads threads (<= 0: all): feeds
+ * pl_elevation_batch / pl_normal_batch, and checks the device generator. */
+int pl_make_requests_range(const pl_sweep_scene *scene, int level, uint64_t morton0, int n,
+                           int out_slot0, int parent_slot0, uint64_t parent_morton0,
+                           pl_elev_req *elev_reqs, pl_norm_req *norm_reqs, int nthreads);
+/* copy the requests the last pl_produce_range generated back to the host (tests) */
+int pl_debug_download_requests(pl_ctx *ctx, int n, pl_elev_req *elev_reqs, pl_norm_req *norm_reqs);
 
 /* --------------------------------------------------------------- residuals */
 

@@ -47,11 +47,13 @@ extern "C" int pl_ctx_create(int device, pl_ctx **out)
         return pl_set_error(PL_ERR_NO_DEVICE, "device %d is sm_%d%d; kernels are built for sm_100a only",
                             device, prop.major, prop.minor);
     pl_ctx *ctx = new pl_ctx();
-    memset(ctx, 0, sizeof(*ctx));
+    memset((void *) ctx, 0, sizeof(*ctx));
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     PL_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
+    ctx->timed = new std::vector<pl_ctx::TimedLaunch>();
+    ctx->event_pool = new std::vector<cudaEvent_t>();
     *out = ctx;
     return PL_OK;
 }
@@ -64,6 +66,14 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     if (ctx->noise_rot) cudaFree(ctx->noise_rot);
     if (ctx->req_dev) cudaFree(ctx->req_dev);
     if (ctx->req_pinned) cudaFreeHost(ctx->req_pinned);
+    if (ctx->perlin_perm) cudaFree(ctx->perlin_perm);
+    if (ctx->perlin_g2) cudaFree(ctx->perlin_g2);
+    if (ctx->gen_ereq) cudaFree(ctx->gen_ereq);
+    if (ctx->gen_nreq) cudaFree(ctx->gen_nreq);
+    for (auto &t : *ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto &e : *ctx->event_pool) cudaEventDestroy(e);
+    delete ctx->timed;
+    delete ctx->event_pool;
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -86,6 +96,65 @@ extern "C" int pl_sync(pl_ctx *ctx)
 
 extern "C" uint64_t pl_ctx_launch_count(const pl_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int pl_device_sm_count(pl_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+/* ------------------------------------------------------------------- timing */
+
+static cudaEvent_t take_event(pl_ctx *ctx)
+{
+    if (!ctx->event_pool->empty()) {
+        cudaEvent_t e = ctx->event_pool->back();
+        ctx->event_pool->pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+void pl_timing_begin(pl_ctx *ctx, int kernel, int tiles)
+{
+    if (!ctx->timing) return;
+    pl_ctx::TimedLaunch t;
+    t.a = take_event(ctx);
+    t.b = take_event(ctx);
+    t.kernel = kernel;
+    t.tiles = tiles;
+    cudaEventRecord(t.a, ctx->stream);
+    ctx->timed->push_back(t);
+}
+
+void pl_timing_end(pl_ctx *ctx)
+{
+    if (!ctx->timing) return;
+    cudaEventRecord(ctx->timed->back().b, ctx->stream);
+}
+
+extern "C" int pl_timing_enable(pl_ctx *ctx, int on)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    ctx->timing = on ? 1 : 0;
+    return PL_OK;
+}
+
+extern "C" int pl_timing_collect(pl_ctx *ctx, double *ms, uint64_t *launches, uint64_t *tiles)
+{
+    if (!ctx || !ms || !launches || !tiles) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < PL_K_COUNT; ++k) { ms[k] = 0.0; launches[k] = 0; tiles[k] = 0; }
+    for (auto &t : *ctx->timed) {
+        float dt = 0.0f;
+        if (cudaEventElapsedTime(&dt, t.a, t.b) == cudaSuccess) {
+            ms[t.kernel] += dt;
+            launches[t.kernel] += 1;
+            tiles[t.kernel] += (uint64_t) t.tiles;
+        }
+        ctx->event_pool->push_back(t.a);
+        ctx->event_pool->push_back(t.b);
+    }
+    ctx->timed->clear();
+    return PL_OK;
+}
 
 int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev)
 {
@@ -429,6 +498,17 @@ extern "C" int pl_elev_stats_download(pl_ctx *ctx, pl_pool *elev, int n, const i
         out[2 * i] = all[slots[i]].x;
         out[2 * i + 1] = all[slots[i]].y;
     }
+    return PL_OK;
+}
+
+extern "C" int pl_elev_stats_range(pl_ctx *ctx, pl_pool *elev, int slot0, int n, float *out)
+{
+    if (!ctx || !elev || !out || n < 0 || slot0 < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (elev->kind != PL_POOL_ELEV_F32x3) return pl_set_error(PL_ERR_ARG, "not an elevation pool");
+    if (slot0 + n > elev->capacity) return pl_set_error(PL_ERR_ARG, "slot range out of the pool");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    PL_CUDA(cudaMemcpyAsync(out, elev->stats + slot0, sizeof(float2) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
     return PL_OK;
 }
 

@@ -359,7 +359,9 @@ int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_
     const int rk = !resid ? 0 : (resid->kind == PL_POOL_RESID_F32 ? 1 : 2);
     auto kern = rk == 0 ? elevation_kernel<0> : (rk == 1 ? elevation_kernel<1> : elevation_kernel<2>);
     if (smem > 40 * 1024) PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    pl_timing_begin(ctx, PL_K_ELEVATION, n);
     kern<<<n, kThreads, smem, ctx->stream>>>(elev->tm_parent, a);
+    pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return PL_OK;

@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdarg.h>
+#include <vector>
 #include "proland_b200.h"
 
 /* ---- HBM layout of the pools (DESIGN.md "Data layout") ----------------------
@@ -46,6 +47,17 @@ struct pl_ctx {
     int noise_w;
     int noise_pitch;
     __half *noise_rot;
+    /* device-side request generation (pl_requests.cu) */
+    int *perlin_perm;
+    float *perlin_g2;
+    pl_elev_req *gen_ereq;
+    pl_norm_req *gen_nreq;
+    int gen_cap;
+    /* per-launch CUDA-event timing (pl_timing_*): events on the launching stream */
+    int timing;
+    struct TimedLaunch { cudaEvent_t a, b; int kernel; int tiles; };
+    std::vector<TimedLaunch> *timed;
+    std::vector<cudaEvent_t> *event_pool;
     /* request staging */
     void *req_dev;
     size_t req_dev_bytes;
@@ -62,6 +74,12 @@ int pl_set_error(int code, const char *fmt, ...);
                                     ? PL_ERR_NO_DEVICE : PL_ERR_CUDA,                       \
                                 "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
+
+/* kernel ids of pl_timing_collect */
+enum { PL_K_ELEVATION = 0, PL_K_NORMAL = 1, PL_K_GENREQ = 2, PL_K_RESIDUAL = 3, PL_K_COUNT = 4 };
+/* bracket a launch with events when timing is on: call begin before, end after */
+void pl_timing_begin(pl_ctx *ctx, int kernel, int tiles);
+void pl_timing_end(pl_ctx *ctx);
 
 /* stage n*bytes of host requests on the device (returns device pointer) */
 int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev);

@@ -262,7 +262,9 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
     /* static + dynamic must stay under the default 48 KB unless opted in */
     if (smem > 40 * 1024)
         PL_CUDA(cudaFuncSetAttribute(normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    pl_timing_begin(ctx, PL_K_NORMAL, n);
     normal_kernel<<<n * a.nbands, kThreads, smem, ctx->stream>>>(a);
+    pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return PL_OK;

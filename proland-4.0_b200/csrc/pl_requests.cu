@@ -1,0 +1,196 @@
+/*
+ * pl_requests.cu -- the device-side batch driver: requests for a whole Morton
+ * range of tiles are generated ON THE GPU (noise layer selection through cnoise,
+ * fp64 patch geometry), then the elevation and normal kernels run on them.
+ *
+ * This is what replaces the reference's per-tile host loop
+ * (TileProducer::createTile -> CreateTile::run -> doCreateTile, one GL draw per
+ * tile: producer/TileProducer.cpp:199-217, ElevationProducer.cpp:280-405): the
+ * host only says "level L, Morton range [m0, m0+n), slots from s0", 8 bytes of
+ * arguments per batch instead of ~300 bytes of uniforms per tile.
+ *
+ * The maths is pl_reqmath.cuh, the same source the host entry points compile,
+ * and is bit-identical to it (tests/test_gpu_parity.py::test_device_requests).
+ */
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "pl_reqmath.cuh"
+
+PerlinView pl_host_perlin();
+
+namespace {
+
+struct GenArgs {
+    PerlinView perlin;
+    pl_elev_req *ereq;
+    pl_norm_req *nreq;      /* may be NULL */
+    int tile_w, face, n_amp, sphere;
+    float root_quad_size;
+    float noise_amp[32];
+    int level, n;
+    unsigned long long morton0, parent_morton0;
+    int out_slot0, parent_slot0;
+};
+
+__host__ __device__ __forceinline__ void gen_one(const GenArgs &g, int i)
+{
+    const unsigned long long m = g.morton0 + (unsigned long long) i;
+    int tx, ty;
+    morton_decode(m, &tx, &ty);
+    pl_elev_req e;
+    elev_fill_req(g.perlin, g.tile_w, g.root_quad_size, g.noise_amp, g.n_amp, g.face, g.level, tx, ty, 0, 0, &e);
+    e.out_slot = g.out_slot0 + i;
+    e.parent_slot = g.level > 0 ? g.parent_slot0 + (int) ((m >> 2) - g.parent_morton0) : -1;
+    g.ereq[i] = e;
+    if (g.nreq) {
+        pl_norm_req q;
+        norm_fill_req(g.sphere, (double) g.root_quad_size, g.level, tx, ty, &q);
+        q.out_slot = g.out_slot0 + i;
+        q.elev_slot = g.out_slot0 + i;
+        g.nreq[i] = q;
+    }
+}
+
+__global__ void __launch_bounds__(128) gen_requests_kernel(const GenArgs g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < g.n) gen_one(g, i);
+}
+
+int ensure_perlin(pl_ctx *ctx)
+{
+    if (ctx->perlin_perm) return PL_OK;
+    const PerlinView h = pl_host_perlin();
+    PL_CUDA(cudaMalloc(&ctx->perlin_perm, sizeof(int) * kPerlinN));
+    PL_CUDA(cudaMalloc(&ctx->perlin_g2, sizeof(float) * 2 * kPerlinN));
+    PL_CUDA(cudaMemcpyAsync(ctx->perlin_perm, h.perm, sizeof(int) * kPerlinN, cudaMemcpyHostToDevice, ctx->stream));
+    PL_CUDA(cudaMemcpyAsync(ctx->perlin_g2, h.g2, sizeof(float) * 2 * kPerlinN, cudaMemcpyHostToDevice, ctx->stream));
+    return PL_OK;
+}
+
+int ensure_gen_buffers(pl_ctx *ctx, int n)
+{
+    if (n <= ctx->gen_cap) return PL_OK;
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gen_ereq) cudaFree(ctx->gen_ereq);
+    if (ctx->gen_nreq) cudaFree(ctx->gen_nreq);
+    ctx->gen_ereq = nullptr;
+    ctx->gen_nreq = nullptr;
+    ctx->gen_cap = 0;
+    const int cap = n + n / 4 + 256;
+    PL_CUDA(cudaMalloc(&ctx->gen_ereq, sizeof(pl_elev_req) * (size_t) cap));
+    PL_CUDA(cudaMalloc(&ctx->gen_nreq, sizeof(pl_norm_req) * (size_t) cap));
+    ctx->gen_cap = cap;
+    return PL_OK;
+}
+
+int check_range(const pl_sweep_scene *sc, pl_pool *elev, pl_pool *norm, int level, uint64_t morton0, int n,
+                int out_slot0, int parent_slot0, uint64_t parent_morton0)
+{
+    if (!sc || !elev) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (level < 0 || level > 24) return pl_set_error(PL_ERR_ARG, "level %d out of range", level);
+    const uint64_t count = 1ull << (2 * level);
+    if (n < 0 || morton0 + (uint64_t) n > count) return pl_set_error(PL_ERR_ARG, "Morton range exceeds level %d", level);
+    if (out_slot0 < 0 || out_slot0 + n > elev->capacity || (norm && out_slot0 + n > norm->capacity))
+        return pl_set_error(PL_ERR_POOL_FULL, "slots [%d,%d) exceed the pool capacity", out_slot0, out_slot0 + n);
+    if (level > 0 && n > 0) {
+        const uint64_t p_first = morton0 >> 2, p_last = (morton0 + n - 1) >> 2;
+        if (p_first < parent_morton0) return pl_set_error(PL_ERR_ARG, "parent range starts after the first parent");
+        const int64_t s_first = (int64_t) parent_slot0 + (int64_t) (p_first - parent_morton0);
+        const int64_t s_last = (int64_t) parent_slot0 + (int64_t) (p_last - parent_morton0);
+        if (s_first < 0 || s_last >= elev->capacity) return pl_set_error(PL_ERR_ARG, "parent slots out of range");
+        if (s_first < (int64_t) out_slot0 + n && s_last >= out_slot0)
+            return pl_set_error(PL_ERR_ARG, "parent slots overlap the output slots");
+    }
+    if (sc->n_amp < 0 || sc->n_amp > 32) return pl_set_error(PL_ERR_ARG, "n_amp out of range");
+    return PL_OK;
+}
+
+void fill_gen_args(GenArgs &g, const pl_sweep_scene *sc, int level, uint64_t morton0, int n, int out_slot0,
+                   int parent_slot0, uint64_t parent_morton0)
+{
+    g.tile_w = sc->elev.tile_w;
+    g.face = sc->face;
+    g.n_amp = sc->n_amp;
+    g.sphere = sc->norm.sphere;
+    g.root_quad_size = sc->root_quad_size;
+    memcpy(g.noise_amp, sc->noise_amp, sizeof(g.noise_amp));
+    g.level = level;
+    g.n = n;
+    g.morton0 = morton0;
+    g.parent_morton0 = parent_morton0;
+    g.out_slot0 = out_slot0;
+    g.parent_slot0 = parent_slot0;
+}
+
+}  // namespace
+
+extern "C" int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *elev, pl_pool *norm, int level,
+                                uint64_t morton0, int n, int out_slot0, int parent_slot0, uint64_t parent_morton0)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    int rc = check_range(sc, elev, norm, level, morton0, n, out_slot0, parent_slot0, parent_morton0);
+    if (rc) return rc;
+    if (n == 0) return PL_OK;
+    PL_CUDA(cudaSetDevice(ctx->device));
+    if ((rc = ensure_perlin(ctx)) != PL_OK) return rc;
+    if ((rc = ensure_gen_buffers(ctx, n)) != PL_OK) return rc;
+    GenArgs g;
+    g.perlin.perm = ctx->perlin_perm;
+    g.perlin.g2 = ctx->perlin_g2;
+    g.ereq = ctx->gen_ereq;
+    g.nreq = norm ? ctx->gen_nreq : nullptr;
+    fill_gen_args(g, sc, level, morton0, n, out_slot0, parent_slot0, parent_morton0);
+    pl_timing_begin(ctx, PL_K_GENREQ, n);
+    gen_requests_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    rc = pl_elevation_batch_dev(ctx, &sc->elev, elev, nullptr, n, ctx->gen_ereq);
+    if (rc) return rc;
+    if (norm) rc = pl_normal_batch_dev(ctx, &sc->norm, norm, elev, n, ctx->gen_nreq);
+    return rc;
+}
+
+/* the same requests built on the host (all hardware threads): the per-tile
+ * plugin path at batch granularity, and the checker of the device generator */
+extern "C" int pl_make_requests_range(const pl_sweep_scene *sc, int level, uint64_t morton0, int n, int out_slot0,
+                                      int parent_slot0, uint64_t parent_morton0, pl_elev_req *elev_reqs,
+                                      pl_norm_req *norm_reqs, int nthreads)
+{
+    if (!sc || !elev_reqs || n < 0 || level < 0 || level > 24) return pl_set_error(PL_ERR_ARG, "bad argument");
+    GenArgs g;
+    g.perlin = pl_host_perlin();
+    g.ereq = elev_reqs;
+    g.nreq = norm_reqs;
+    fill_gen_args(g, sc, level, morton0, n, out_slot0, parent_slot0, parent_morton0);
+    if (nthreads <= 0) nthreads = (int) std::thread::hardware_concurrency();
+    if (nthreads < 1) nthreads = 1;
+    if (n < 4096 || nthreads == 1) {
+        for (int i = 0; i < n; ++i) gen_one(g, i);
+        return PL_OK;
+    }
+    std::vector<std::thread> pool;
+    const int chunk = (n + nthreads - 1) / nthreads;
+    for (int t = 0; t < nthreads; ++t) {
+        const int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo >= hi) break;
+        pool.emplace_back([&g, lo, hi]() { for (int i = lo; i < hi; ++i) gen_one(g, i); });
+    }
+    for (auto &th : pool) th.join();
+    return PL_OK;
+}
+
+extern "C" int pl_debug_download_requests(pl_ctx *ctx, int n, pl_elev_req *elev_reqs, pl_norm_req *norm_reqs)
+{
+    if (!ctx || n < 0 || n > ctx->gen_cap) return pl_set_error(PL_ERR_ARG, "bad argument");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    if (elev_reqs)
+        PL_CUDA(cudaMemcpyAsync(elev_reqs, ctx->gen_ereq, sizeof(pl_elev_req) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (norm_reqs)
+        PL_CUDA(cudaMemcpyAsync(norm_reqs, ctx->gen_nreq, sizeof(pl_norm_req) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+    PL_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PL_OK;
+}

@@ -21,12 +21,14 @@ FILTER_NEAREST, FILTER_LINEAR = 0, 1
 # every symbol include/proland_b200.h declares (tests check the .so exports them all)
 EXPORTS = [
     "pl_last_error", "pl_abi_version", "pl_ctx_create", "pl_ctx_destroy", "pl_ctx_set_stream",
-    "pl_ctx_stream", "pl_sync", "pl_ctx_launch_count", "pl_device_sm_count", "pl_pool_create",
+    "pl_ctx_stream", "pl_sync", "pl_ctx_launch_count", "pl_device_sm_count", "pl_timing_enable",
+    "pl_timing_collect", "pl_pool_create",
     "pl_pool_destroy", "pl_pool_capacity", "pl_pool_tile_w", "pl_pool_tile_bytes",
     "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload",
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
-    "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_norm_make_req", "pl_normal_batch",
-    "pl_normal_batch_dev", "pl_residual_decode_batch",
+    "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_norm_make_req", "pl_normal_batch",
+    "pl_normal_batch_dev", "pl_produce_range", "pl_make_requests_range",
+    "pl_debug_download_requests", "pl_residual_decode_batch",
 ]
 
 
@@ -61,6 +63,12 @@ class NormReq(C.Structure):
                 ("deform", C.c_float * 4), ("corners", C.c_float * 12),
                 ("verticals", C.c_float * 12), ("norms", C.c_float * 4), ("w2t", C.c_float * 9),
                 ("p2t", C.c_float * 9), ("smooth", C.c_float), ("pad_", C.c_int32 * 3)]
+
+
+class SweepScene(C.Structure):
+    _fields_ = [("elev", ElevScene), ("norm", NormScene), ("root_quad_size", C.c_float),
+                ("face", C.c_int32), ("n_amp", C.c_int32), ("pad_", C.c_int32),
+                ("noise_amp", C.c_float * 32)]
 
 
 assert C.sizeof(ElevReq) == 64 and C.sizeof(NormReq) == 240 and C.sizeof(ElevScene) == 32
@@ -125,12 +133,20 @@ def lib():
                                          C.c_void_p]
         L.pl_elevation_batch_dev.argtypes = L.pl_elevation_batch.argtypes
         L.pl_elev_stats_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pl_elev_stats_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.pl_norm_make_req.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]
         L.pl_norm_make_req.restype = None
         L.pl_normal_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]
         L.pl_normal_batch_dev.argtypes = L.pl_normal_batch.argtypes
+        L.pl_produce_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]
+        L.pl_make_requests_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                             C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
+        L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
+        L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -178,6 +194,45 @@ def norm_make_reqs(tiles, scene, *, root_quad_size=100000.0, components=2):
         L.pl_norm_make_req(C.byref(scene), C.c_double(root_quad_size), components, level, tx, ty,
                            C.c_void_p(out.ctypes.data + 240 * i))
     return out
+
+
+def sweep_scene(*, noise_amp, face=0, root_quad_size=100000.0, tile_w=101, grid_size=24, flip=0,
+                noise_mode=NOISE_SLOPE, no_clamp=0, want_stats=0, sphere=0,
+                elev_filter=FILTER_LINEAR):
+    s = SweepScene()
+    s.elev = elev_scene(tile_w, grid_size, flip, noise_mode, no_clamp, want_stats)
+    s.norm = norm_scene(tile_w - 4, grid_size, 2, elev_filter, FILTER_LINEAR, sphere)
+    s.root_quad_size = root_quad_size
+    s.face = face
+    s.n_amp = len(noise_amp)
+    for i, a in enumerate(noise_amp):
+        s.noise_amp[i] = a
+    return s
+
+
+def make_requests_range(scene, level, morton0, n, out_slot0=0, parent_slot0=0, parent_morton0=0,
+                        nthreads=0, normals=True):
+    """Host-built requests of a Morton range (all hardware threads by default)."""
+    e = np.zeros(n, ELEV_REQ_DTYPE)
+    q = np.zeros(n, NORM_REQ_DTYPE) if normals else None
+    check(lib().pl_make_requests_range(C.byref(scene), level, morton0, n, out_slot0, parent_slot0,
+                                       parent_morton0, _ptr(e), _ptr(q) if normals else None, nthreads))
+    return e, q
+
+
+def morton_encode(tx, ty):
+    m = 0
+    for b in range(24):
+        m |= ((tx >> b) & 1) << (2 * b) | ((ty >> b) & 1) << (2 * b + 1)
+    return m
+
+
+def morton_decode(m):
+    tx = ty = 0
+    for b in range(24):
+        tx |= ((m >> (2 * b)) & 1) << b
+        ty |= ((m >> (2 * b + 1)) & 1) << b
+    return tx, ty
 
 
 # ------------------------------------------------------------------- context
@@ -282,6 +337,11 @@ class Context:
         check(lib().pl_elev_stats_download(self.h, elev.h, len(slots), _ptr(slots), _ptr(out)))
         return out
 
+    def elev_stats_range(self, elev, slot0, n):
+        out = np.empty((n, 2), np.float32)
+        check(lib().pl_elev_stats_range(self.h, elev.h, slot0, n, _ptr(out)))
+        return out
+
     def normal_batch(self, scene, norm, elev, reqs):
         reqs = np.ascontiguousarray(reqs, NORM_REQ_DTYPE)
         check(lib().pl_normal_batch(self.h, C.byref(scene), norm.h, elev.h, len(reqs), _ptr(reqs)))
@@ -289,6 +349,39 @@ class Context:
     def normal_batch_dev(self, scene, norm, elev, n, dev_ptr):
         check(lib().pl_normal_batch_dev(self.h, C.byref(scene), norm.h, elev.h, n,
                                         C.c_void_p(dev_ptr)))
+
+
+def _produce_range(self, scene, elev, norm, level, morton0, n, out_slot0, parent_slot0=0,
+                   parent_morton0=0):
+    check(lib().pl_produce_range(self.h, C.byref(scene), elev.h, norm.h if norm else None, level,
+                                 morton0, n, out_slot0, parent_slot0, parent_morton0))
+
+
+def _last_requests(self, n):
+    e = np.zeros(n, ELEV_REQ_DTYPE)
+    q = np.zeros(n, NORM_REQ_DTYPE)
+    check(lib().pl_debug_download_requests(self.h, n, _ptr(e), _ptr(q)))
+    return e, q
+
+
+def _timing_enable(self, on=True):
+    check(lib().pl_timing_enable(self.h, int(on)))
+
+
+def _timing_collect(self):
+    """-> {kernel name: (total ms, launches, tiles)} since the last collect (synchronises)."""
+    ms = np.zeros(4, np.float64)
+    cnt = np.zeros(4, np.uint64)
+    tiles = np.zeros(4, np.uint64)
+    check(lib().pl_timing_collect(self.h, _ptr(ms), _ptr(cnt), _ptr(tiles)))
+    names = ("elevation", "normal", "genreq", "residual")
+    return {n: (float(ms[i]), int(cnt[i]), int(tiles[i])) for i, n in enumerate(names)}
+
+
+Context.timing_enable = _timing_enable
+Context.timing_collect = _timing_collect
+Context.produce_range = _produce_range
+Context.last_requests = _last_requests
 
 
 def elev_scene(tile_w=101, grid_size=24, flip=0, noise_mode=NOISE_SLOPE, no_clamp=0, want_stats=0,

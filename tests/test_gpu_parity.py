@@ -49,3 +49,42 @@ def test_sphere_deep_chain(plb, ctx, oracle):
         return [(level, 397 >> (9 - level), 341 >> (9 - level))]
     _run(plb, ctx, oracle, 9, noise_amp=PLANET, face=3, root_quad_size=12720000.0, sphere=1,
          elev_filter=0, tiles_of=chain)
+
+
+@pytest.mark.parametrize("face,level", [(0, 5), (1, 6), (4, 6), (6, 7)])
+def test_device_requests_match_host(plb, ctx, face, level):
+    """pl_produce_range generates the per-tile uniforms on the device; they must be
+    byte-identical to the host's (integer decisions through cnoise, fp64 geometry)."""
+    sc = plb.sweep_scene(noise_amp=PLANET, face=face, root_quad_size=12720000.0, sphere=1)
+    n = min(4 ** level, 4096)
+    m0 = (4 ** level - n) // 4 * 4 if level > 5 else 0
+    elev = ctx.pool(plb.POOL_ELEV, 101, n + n // 4 + 8)
+    norm = ctx.pool(plb.POOL_NORM2, 97, n + n // 4 + 8)
+    ctx.noise_init(101)
+    p0 = n   # parents live after the outputs
+    ctx.produce_range(sc, elev, norm, level, m0, n, 0, p0, m0 >> 2)
+    de, dn = ctx.last_requests(n)
+    he, hn = plb.make_requests_range(sc, level, m0, n, 0, p0, m0 >> 2)
+    assert de.tobytes() == he.tobytes()
+    assert dn.tobytes() == hn.tobytes()
+
+
+def test_produce_range_equals_per_tile_path(plb, ctx, oracle):
+    """the device-driven Morton sweep and the per-tile request path give the same tiles."""
+    amp = PLANET
+    kw = dict(noise_amp=amp, face=2, root_quad_size=12720000.0, sphere=1)
+    sc = plb.sweep_scene(want_stats=1, **kw)
+    max_level = 4
+    total = sum(4 ** l for l in range(max_level + 1))
+    elev = ctx.pool(plb.POOL_ELEV, 101, total)
+    norm = ctx.pool(plb.POOL_NORM2, 97, total)
+    ctx.noise_init(101)
+    off = [sum(4 ** k for k in range(l)) for l in range(max_level + 1)]
+    for l in range(max_level + 1):
+        ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    ctx.sync()
+    ref = qt.oracle_quadtree(oracle, max_level, **kw)
+    for (l, tx, ty), (e, n, s) in ref.items():
+        slot = off[l] + plb.morton_encode(tx, ty)
+        assert np.array_equal(elev.download(slot), e), (l, tx, ty)
+        assert np.array_equal(norm.download(slot), n), (l, tx, ty)
