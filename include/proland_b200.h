@@ -223,6 +223,11 @@ int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl
 int pl_make_requests_range(const pl_sweep_scene *scene, int level, uint64_t morton0, int n,
                            int out_slot0, int parent_slot0, uint64_t parent_morton0,
                            pl_elev_req *elev_reqs, pl_norm_req *norm_reqs, int nthreads);
+/* test hooks: run the runtime-geometry kernels even for the shipped geometry;
+ * evaluate the branch-free div / rcp / sqrt next to the IEEE operators on the
+ * device: out = 6*n floats (div_rn, a/b, rcp_rn, 1/b, sqrt_rn(|a|), sqrtf(|a|)) */
+int pl_debug_force_generic(pl_ctx *ctx, int on);
+int pl_debug_fpexact(pl_ctx *ctx, int n, const float *a, const float *b, float *out);
 /* copy the requests the last pl_produce_range generated back to the host (tests) */
 int pl_debug_download_requests(pl_ctx *ctx, int n, pl_elev_req *elev_reqs, pl_norm_req *norm_reqs);
 

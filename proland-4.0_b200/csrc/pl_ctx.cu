@@ -129,6 +129,13 @@ void pl_timing_end(pl_ctx *ctx)
     cudaEventRecord(ctx->timed->back().b, ctx->stream);
 }
 
+extern "C" int pl_debug_force_generic(pl_ctx *ctx, int on)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    ctx->force_generic = on ? 1 : 0;
+    return PL_OK;
+}
+
 extern "C" int pl_timing_enable(pl_ctx *ctx, int on)
 {
     if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");

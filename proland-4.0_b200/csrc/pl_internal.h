@@ -53,6 +53,7 @@ struct pl_ctx {
     pl_elev_req *gen_ereq;
     pl_norm_req *gen_nreq;
     int gen_cap;
+    int force_generic;   /* tests: run the runtime-geometry kernels even for the shipped geometry */
     /* per-launch CUDA-event timing (pl_timing_*): events on the launching stream */
     int timing;
     struct TimedLaunch { cudaEvent_t a, b; int kernel; int tiles; };

@@ -28,7 +28,8 @@ EXPORTS = [
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_produce_range", "pl_make_requests_range",
-    "pl_debug_download_requests", "pl_residual_decode_batch",
+    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_fpexact",
+    "pl_residual_decode_batch",
 ]
 
 
@@ -145,6 +146,8 @@ def lib():
         L.pl_make_requests_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.pl_debug_force_generic.argtypes = [C.c_void_p, C.c_int]
+        L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
         L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -378,6 +381,20 @@ def _timing_collect(self):
     return {n: (float(ms[i]), int(cnt[i]), int(tiles[i])) for i, n in enumerate(names)}
 
 
+def _force_generic(self, on=True):
+    check(lib().pl_debug_force_generic(self.h, int(on)))
+
+
+def _fpexact(self, a, b):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    out = np.empty((6, len(a)), np.float32)
+    check(lib().pl_debug_fpexact(self.h, len(a), _ptr(a), _ptr(b), _ptr(out)))
+    return out
+
+
+Context.force_generic = _force_generic
+Context.fpexact = _fpexact
 Context.timing_enable = _timing_enable
 Context.timing_collect = _timing_collect
 Context.produce_range = _produce_range

@@ -24,6 +24,27 @@ def _run(plb, ctx, oracle, max_level, **kw):
     return n
 
 
+def test_fpexact_matches_ieee(plb, ctx):
+    """the branch-free division / reciprocal / sqrt of pl_fpexact.cuh are the IEEE results,
+    bit for bit, on the domain the tile path lives in (and at zero for sqrt / numerators)."""
+    rng = np.random.default_rng(7)
+    n = 1 << 22
+    mant = rng.random(n, np.float32) + np.float32(1.0)
+    a = (mant * np.exp2(rng.integers(-60, 60, n)).astype(np.float32)
+         * rng.choice(np.array([-1, 1], np.float32), n))
+    b = ((rng.random(n, np.float32) + np.float32(1.0)) * np.exp2(rng.integers(-30, 30, n)).astype(np.float32)
+         * rng.choice(np.array([-1, 1], np.float32), n))
+    a[:1000] = 0.0                                    # exact zeros: flat terrain
+    a[1000:2000] = np.float32(2.0) ** -100            # lower domain bound of sqrt
+    b[2000:3000] = np.float32(100000.0 / 96.0) / np.exp2(np.arange(1000) % 20).astype(np.float32)
+    out = ctx.fpexact(a, b)
+    for k, name in ((0, "div"), (2, "rcp"), (4, "sqrt")):
+        bad = np.flatnonzero(out[k].view(np.uint32) != out[k + 1].view(np.uint32))
+        # +0 / -0 compare equal as values
+        bad = bad[out[k][bad] != out[k + 1][bad]]
+        assert bad.size == 0, "%s: %d mismatches, first a=%r b=%r" % (name, bad.size, a[bad[0]], b[bad[0]])
+
+
 def test_fractalterrain_levels_0_4(plb, ctx, oracle):
     """config 1 (demo-fractalterrain): variant D, clamp, flat RG8 normals, LINEAR storage."""
     assert _run(plb, ctx, oracle, 4, noise_amp=FRACTAL) == 341
@@ -34,6 +55,12 @@ def test_shader_variants(plb, ctx, oracle, noise_mode, flip, no_clamp):
     """variants A (plain), B/D-noClamp, C (plain+flip), D+flip."""
     _run(plb, ctx, oracle, 3, noise_amp=FRACTAL[:2] + [30, 20], noise_mode=noise_mode, flip=flip,
          no_clamp=no_clamp)
+
+
+def test_generic_geometry_kernels(plb, ctx, oracle):
+    """the runtime-geometry kernels (used for tile sizes other than 101/97) on the same case"""
+    ctx.force_generic(True)
+    _run(plb, ctx, oracle, 3, noise_amp=FRACTAL[:2] + [30, 20], flip=1)
 
 
 @pytest.mark.parametrize("face", [1, 2, 5, 6])
