@@ -31,6 +31,7 @@
  * --fmad=false, fused operations spelled fmaf) -> bit-identical to the oracle.
  */
 #include "pl_internal.h"
+#include "pl_fpexact.cuh"
 
 namespace {
 
@@ -102,7 +103,10 @@ __device__ __forceinline__ unsigned int unorm8(float f)
     return (unsigned int) __float2int_rn(f * 255.0f);
 }
 
-__global__ void __launch_bounds__(kThreads) normal_kernel(const NormArgs a)
+/* ------------------------------------------------------------------------
+ * Generic kernel: runtime geometry (any tile width / border).
+ * ------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(kThreads) normal_kernel_generic(const NormArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t bar;
@@ -232,7 +236,159 @@ __global__ void __launch_bounds__(kThreads) normal_kernel(const NormArgs a)
     }
 }
 
+/* ------------------------------------------------------------------------
+ * Specialised kernel: compile-time geometry (TW normal tile width, border 2).
+ * Same arithmetic as the generic kernel; the kernel is issue-bound
+ * (profiles/), so what changes is the instruction count:
+ *   - index maths folds to immediates / multiply-shifts
+ *   - the four quotients alpha*L/dot(alpha,L) share ONE refined reciprocal
+ *     (pl_fpexact.cuh: 3 FFMA per IEEE quotient), normalisation is the
+ *     5-instruction IEEE sqrt + 3-instruction IEEE reciprocal, no branches
+ *   - positions live in shared memory as float4: 1 STS.128 per grid point and
+ *     4 LDS.128 per texel instead of 3 + 12 scalar accesses
+ *   - SPHERE / LINEAR are template parameters: no per-point tests
+ * ------------------------------------------------------------------------ */
+template <int TW>
+struct NGeo {
+    static constexpr int W = TW, B = 2;
+    static constexpr int EW = TW + 2 * B;
+    static constexpr int EPITCH = (EW + 3) & ~3;
+    static constexpr int EPLANE = EW * EPITCH;
+    static constexpr int GW = TW + 2;
+    static constexpr int NBANDS = TW / kBandRows;
+    static constexpr int MAX_ROWS = TW - (NBANDS - 1) * kBandRows;
+    static constexpr int ZROWS = MAX_ROWS + 3;
+    static constexpr int OUT_BYTES = (MAX_ROWS * TW * 2 + 15) & ~15;
+};
+
+template <int TW, bool SPHERE, bool LINEAR>
+__global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
+{
+    using GEO = NGeo<TW>;
+    constexpr int W = GEO::W, B = GEO::B, GW = GEO::GW, EPITCH = GEO::EPITCH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *zs = reinterpret_cast<float *>(smem_raw);                                   /* ZROWS x EPITCH */
+    uint8_t *outb = reinterpret_cast<uint8_t *>(zs + GEO::ZROWS * EPITCH);              /* band staging */
+    float4 *pos = reinterpret_cast<float4 *>(outb + GEO::OUT_BYTES);                   /* (MAX_ROWS+2) x GW */
+    float *ulut = reinterpret_cast<float *>(pos + (GEO::MAX_ROWS + 2) * GW);           /* GW */
+    __shared__ uint64_t bar;
+    __shared__ pl_norm_req rq;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x / GEO::NBANDS, band = blockIdx.x - tile * GEO::NBANDS;
+    const int y_begin = band * kBandRows;
+    const int rows = band == GEO::NBANDS - 1 ? W - y_begin : kBandRows;
+    const int grows = rows + 2;
+
+    {
+        const int *src = reinterpret_cast<const int *>(a.reqs + tile);
+        int *dst = reinterpret_cast<int *>(&rq);
+        if (tid < (int) (sizeof(pl_norm_req) / 4)) dst[tid] = __ldg(src + tid);
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    /* elevation rows y_begin .. y_begin+rows+2 (border 2: texel row Y+2 and, for LINEAR, Y+1) */
+    const int zr0 = y_begin;
+    const int zrows = min(y_begin + rows + B, GEO::EW - 1) - zr0 + 1;
+    if (tid == 0) {
+        const float *src = a.elev + (size_t) rq.elev_slot * 3 * GEO::EPLANE + 2 * GEO::EPLANE + zr0 * EPITCH;
+        const uint32_t bytes = (uint32_t) (zrows * EPITCH * sizeof(float));
+        mbar_expect_tx(&bar, bytes);
+        bulk_load(zs, src, bytes, &bar);
+    }
+    {
+        const float wm1 = (float) W - 1.0f;
+        const float rw = plfp::rcp_rn(wm1);
+        for (int q = tid; q < GW; q += kThreads) ulut[q] = plfp::div_rn((float) (q - 1), wm1, rw);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+
+    const float D = rq.deform[2], R = rq.deform[3];
+    const float x0f = rq.deform[0], y0f = rq.deform[1];
+    const float s = rq.smooth;
+
+    /* ---- world position of every grid point of the band ------------------- */
+    for (int q = tid; q < grows * GW; q += kThreads) {
+        const int gy = q / GW, gx = q - gy * GW;
+        /* grid point (X, Y) = (gx - 1, y_begin - 1 + gy): elevation texel (X + 2, Y + 2),
+         * staged row index (Y + 2) - zr0 = gy + 1 */
+        const float *zp = zs + (gy + 1) * EPITCH + (gx + 1);
+        float h;
+        if (!LINEAR) {
+            h = zp[0];
+        } else {
+            const float t00 = zp[-EPITCH - 1], t10 = zp[-EPITCH], t01 = zp[-1], t11 = zp[0];
+            h = fmaf(0.5625f, t11, fmaf(0.1875f, t01, fmaf(0.1875f, t10, 0.0625f * t00)));
+        }
+        const float u = ulut[gx], v = ulut[y_begin + gy];
+        float4 p;
+        if (!SPHERE) {
+            p.x = fmaf(D, u, x0f);
+            p.y = fmaf(D, v, y0f);
+            p.z = h;
+        } else {
+            const float U = 1.0f - u, V = 1.0f - v;
+            const float a0 = U * V, a1 = u * V, a2 = U * v, a3 = u * v;
+            const float l0 = a0 * rq.norms[0], l1 = a1 * rq.norms[1], l2 = a2 * rq.norms[2], l3 = a3 * rq.norms[3];
+            const float den = fmaf(a3, rq.norms[3], fmaf(a2, rq.norms[2], fmaf(a1, rq.norms[1], l0)));
+            const float rden = plfp::rcp_rn(den);
+            const float p0 = plfp::div_rn(l0, den, rden), p1 = plfp::div_rn(l1, den, rden);
+            const float p2 = plfp::div_rn(l2, den, rden), p3 = plfp::div_rn(l3, den, rden);
+            const float upx = dot4(rq.verticals + 0, p0, p1, p2, p3);
+            const float upy = dot4(rq.verticals + 4, p0, p1, p2, p3);
+            const float upz = dot4(rq.verticals + 8, p0, p1, p2, p3);
+            float hp = h;
+            if (s != 1.0f) {   /* tile-uniform: levels whose quad is larger than R/64 */
+                const float len = plfp::sqrt_rn(dot3(upx, upy, upz, upx, upy, upz));
+                const float kk = fmaf(1.0f, s, len * (1.0f - s));   /* mix(len, 1, s) */
+                hp = plfp::div_rn(fmaf(R, 1.0f - kk, h), kk, plfp::rcp_rn(kk));
+            }
+            p.x = fmaf(hp, upx, dot4(rq.corners + 0, p0, p1, p2, p3));
+            p.y = fmaf(hp, upy, dot4(rq.corners + 4, p0, p1, p2, p3));
+            p.z = fmaf(hp, upz, dot4(rq.corners + 8, p0, p1, p2, p3));
+        }
+        p.w = 0.0f;
+        pos[q] = p;
+    }
+    __syncthreads();
+
+    /* ---- normals of the band ----------------------------------------------- */
+    const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
+    const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
+    for (int q = tid; q < rows * W; q += kThreads) {
+        const int ry = q / W, x = q - ry * W;
+        const float4 *c = pos + (ry + 1) * GW + (x + 1);
+        const float4 pl = c[-1], pr = c[1], pd = c[-GW], pu = c[GW];
+        const float ax = pr.x - pl.x, ay = pr.y - pl.y, az = pr.z - pl.z;
+        const float cx = pu.x - pd.x, cy = pu.y - pd.y, cz = pu.z - pd.z;
+        float nx = fmaf(ay, cz, -(az * cy));
+        float ny = fmaf(az, cx, -(ax * cz));
+        float nz = fmaf(ax, cy, -(ay * cx));
+        const float inv = plfp::rcp_rn(plfp::sqrt_rn(dot3(nx, ny, nz, nx, ny, nz)));
+        nx *= inv; ny *= inv; nz *= inv;
+        const float tx = dot3(w00, w01, w02, nx, ny, nz);
+        const float ty = dot3(w10, w11, w12, nx, ny, nz);
+        /* unorm8: round(clamp(v, 0, 1) * 255), NaN -> 0 */
+        const int r8 = __float2int_rn(fminf(fmaxf(fmaf(tx, 0.5f, 0.5f), 0.0f), 1.0f) * 255.0f);
+        const int g8 = __float2int_rn(fminf(fmaxf(fmaf(ty, 0.5f, 0.5f), 0.0f), 1.0f) * 255.0f);
+        reinterpret_cast<unsigned short *>(outb)[q] = (unsigned short) (r8 | (g8 << 8));
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    if (tid == 0) {
+        uint8_t *dst = a.norm + (size_t) rq.out_slot * a.norm_slot_bytes + (size_t) y_begin * W * 2;
+        bulk_store(dst, outb, (uint32_t) ((rows * W * 2 + 15) & ~15));
+    }
+}
+
 }  // namespace
+
 
 int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, int n,
                      const pl_norm_req *dev_reqs)
@@ -258,13 +414,26 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
     const int GW = a.W + 2;
     const size_t smem = (size_t) (a.max_rows + 3) * a.epitch * 4 + (size_t) 3 * (a.max_rows + 2) * GW * 4 +
                         (size_t) ((GW + 3) & ~3) * 4 + (size_t) ((a.max_rows * a.W * a.channels + 15) & ~15);
-    if (smem > 227 * 1024) return pl_set_error(PL_ERR_ARG, "normal tile_w %d needs %zu bytes of shared memory", a.W, smem);
-    /* static + dynamic must stay under the default 48 KB unless opted in */
-    if (smem > 40 * 1024)
-        PL_CUDA(cudaFuncSetAttribute(normal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-    pl_timing_begin(ctx, PL_K_NORMAL, n);
-    normal_kernel<<<n * a.nbands, kThreads, smem, ctx->stream>>>(a);
-    pl_timing_end(ctx);
+    if (a.W == 97 && a.border == 2 && !ctx->force_generic) {
+        /* the geometry of every shipped archive: compile-time specialisation */
+        using GEO = NGeo<97>;
+        const size_t fsmem = (size_t) GEO::ZROWS * GEO::EPITCH * 4 + GEO::OUT_BYTES +
+                             (size_t) (GEO::MAX_ROWS + 2) * GEO::GW * 16 + (size_t) ((GEO::GW + 3) & ~3) * 4;
+        void (*kern)(NormArgs) = a.sphere ? (a.linear ? normal_kernel_fast<97, true, true> : normal_kernel_fast<97, true, false>)
+                                          : (a.linear ? normal_kernel_fast<97, false, true> : normal_kernel_fast<97, false, false>);
+        PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));
+        pl_timing_begin(ctx, PL_K_NORMAL, n);
+        kern<<<n * GEO::NBANDS, kThreads, fsmem, ctx->stream>>>(a);
+        pl_timing_end(ctx);
+    } else {
+        if (smem > 227 * 1024) return pl_set_error(PL_ERR_ARG, "normal tile_w %d needs %zu bytes of shared memory", a.W, smem);
+        /* static + dynamic must stay under the default 48 KB unless opted in */
+        if (smem > 40 * 1024)
+            PL_CUDA(cudaFuncSetAttribute(normal_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        pl_timing_begin(ctx, PL_K_NORMAL, n);
+        normal_kernel_generic<<<n * a.nbands, kThreads, smem, ctx->stream>>>(a);
+        pl_timing_end(ctx);
+    }
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
     return PL_OK;
