@@ -32,6 +32,7 @@
  */
 #include "pl_internal.h"
 #include "pl_fpexact.cuh"
+#include "pl_f2.cuh"
 
 namespace {
 
@@ -240,12 +241,15 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_generic(const NormArgs
  * Specialised kernel: compile-time geometry (TW normal tile width, border 2).
  * Same arithmetic as the generic kernel; the kernel is issue-bound
  * (profiles/), so what changes is the instruction count:
+ *   - every thread works on a PAIR of horizontally adjacent grid points /
+ *     texels and all fp32 maths is packed FFMA2/FMUL2/FADD2 (pl_f2.cuh):
+ *     half the issue slots for the same IEEE results
  *   - index maths folds to immediates / multiply-shifts
  *   - the four quotients alpha*L/dot(alpha,L) share ONE refined reciprocal
  *     (pl_fpexact.cuh: 3 FFMA per IEEE quotient), normalisation is the
  *     5-instruction IEEE sqrt + 3-instruction IEEE reciprocal, no branches
- *   - positions live in shared memory as float4: 1 STS.128 per grid point and
- *     4 LDS.128 per texel instead of 3 + 12 scalar accesses
+ *   - positions live in shared memory as three planes of row pitch GWP (even):
+ *     pair stores and the left/right pair loads are 8-byte accesses
  *   - SPHERE / LINEAR are template parameters: no per-point tests
  * ------------------------------------------------------------------------ */
 template <int TW>
@@ -254,23 +258,31 @@ struct NGeo {
     static constexpr int EW = TW + 2 * B;
     static constexpr int EPITCH = (EW + 3) & ~3;
     static constexpr int EPLANE = EW * EPITCH;
-    static constexpr int GW = TW + 2;
+    static constexpr int GW = TW + 2;                 /* grid points X = -1 .. W */
+    static constexpr int GWP = (GW + 1) & ~1;         /* padded to an even pitch */
+    static constexpr int GPAIRS = GWP / 2;            /* grid-point pairs per row */
+    static constexpr int XPAIRS = (TW + 1) / 2;       /* texel pairs per row */
     static constexpr int NBANDS = TW / kBandRows;
     static constexpr int MAX_ROWS = TW - (NBANDS - 1) * kBandRows;
     static constexpr int ZROWS = MAX_ROWS + 3;
     static constexpr int OUT_BYTES = (MAX_ROWS * TW * 2 + 15) & ~15;
+    static constexpr int POS_PLANE = (MAX_ROWS + 2) * GWP;
+    static constexpr size_t SMEM = (size_t) ZROWS * EPITCH * 4 + OUT_BYTES + (size_t) 3 * POS_PLANE * 4 + GWP * 4;
+    static_assert(EPITCH % 2 == 0 && EPITCH >= GWP + 2, "paired loads stay inside a staged row");
 };
 
 template <int TW, bool SPHERE, bool LINEAR>
 __global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
 {
+    using namespace plf2;
     using GEO = NGeo<TW>;
-    constexpr int W = GEO::W, B = GEO::B, GW = GEO::GW, EPITCH = GEO::EPITCH;
+    constexpr int W = GEO::W, B = GEO::B, GWP = GEO::GWP, EPITCH = GEO::EPITCH;
+    constexpr int GPAIRS = GEO::GPAIRS, XPAIRS = GEO::XPAIRS, PP = GEO::POS_PLANE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *zs = reinterpret_cast<float *>(smem_raw);                                   /* ZROWS x EPITCH */
     uint8_t *outb = reinterpret_cast<uint8_t *>(zs + GEO::ZROWS * EPITCH);              /* band staging */
-    float4 *pos = reinterpret_cast<float4 *>(outb + GEO::OUT_BYTES);                   /* (MAX_ROWS+2) x GW */
-    float *ulut = reinterpret_cast<float *>(pos + (GEO::MAX_ROWS + 2) * GW);           /* GW */
+    float *px = reinterpret_cast<float *>(outb + GEO::OUT_BYTES);                      /* 3 planes of (MAX_ROWS+2) x GWP */
+    float *ulut = px + 3 * PP;                                                         /* GWP */
     __shared__ uint64_t bar;
     __shared__ pl_norm_req rq;
 
@@ -300,83 +312,106 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
         mbar_expect_tx(&bar, bytes);
         bulk_load(zs, src, bytes, &bar);
     }
-    {
+    {   /* uv / (tileSDF.x - 1.0) for X = -1 .. W (+ pad entries) */
         const float wm1 = (float) W - 1.0f;
         const float rw = plfp::rcp_rn(wm1);
-        for (int q = tid; q < GW; q += kThreads) ulut[q] = plfp::div_rn((float) (q - 1), wm1, rw);
+        for (int q = tid; q < GWP; q += kThreads) ulut[q] = plfp::div_rn((float) (q - 1), wm1, rw);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
 
-    const float D = rq.deform[2], R = rq.deform[3];
-    const float x0f = rq.deform[0], y0f = rq.deform[1];
-    const float s = rq.smooth;
-
-    /* ---- world position of every grid point of the band ------------------- */
-    for (int q = tid; q < grows * GW; q += kThreads) {
-        const int gy = q / GW, gx = q - gy * GW;
-        /* grid point (X, Y) = (gx - 1, y_begin - 1 + gy): elevation texel (X + 2, Y + 2),
-         * staged row index (Y + 2) - zr0 = gy + 1 */
-        const float *zp = zs + (gy + 1) * EPITCH + (gx + 1);
-        float h;
-        if (!LINEAR) {
-            h = zp[0];
-        } else {
-            const float t00 = zp[-EPITCH - 1], t10 = zp[-EPITCH], t01 = zp[-1], t11 = zp[0];
-            h = fmaf(0.5625f, t11, fmaf(0.1875f, t01, fmaf(0.1875f, t10, 0.0625f * t00)));
-        }
-        const float u = ulut[gx], v = ulut[y_begin + gy];
-        float4 p;
-        if (!SPHERE) {
-            p.x = fmaf(D, u, x0f);
-            p.y = fmaf(D, v, y0f);
-            p.z = h;
-        } else {
-            const float U = 1.0f - u, V = 1.0f - v;
-            const float a0 = U * V, a1 = u * V, a2 = U * v, a3 = u * v;
-            const float l0 = a0 * rq.norms[0], l1 = a1 * rq.norms[1], l2 = a2 * rq.norms[2], l3 = a3 * rq.norms[3];
-            const float den = fmaf(a3, rq.norms[3], fmaf(a2, rq.norms[2], fmaf(a1, rq.norms[1], l0)));
-            const float rden = plfp::rcp_rn(den);
-            const float p0 = plfp::div_rn(l0, den, rden), p1 = plfp::div_rn(l1, den, rden);
-            const float p2 = plfp::div_rn(l2, den, rden), p3 = plfp::div_rn(l3, den, rden);
-            const float upx = dot4(rq.verticals + 0, p0, p1, p2, p3);
-            const float upy = dot4(rq.verticals + 4, p0, p1, p2, p3);
-            const float upz = dot4(rq.verticals + 8, p0, p1, p2, p3);
-            float hp = h;
-            if (s != 1.0f) {   /* tile-uniform: levels whose quad is larger than R/64 */
-                const float len = plfp::sqrt_rn(dot3(upx, upy, upz, upx, upy, upz));
-                const float kk = fmaf(1.0f, s, len * (1.0f - s));   /* mix(len, 1, s) */
-                hp = plfp::div_rn(fmaf(R, 1.0f - kk, h), kk, plfp::rcp_rn(kk));
+    /* ---- world position of every grid point of the band, two per thread ---- */
+    {
+        const float D = rq.deform[2], R = rq.deform[3];
+        const float x0f = rq.deform[0], y0f = rq.deform[1];
+        const float s = rq.smooth;
+        for (int q = tid; q < grows * GPAIRS; q += kThreads) {
+            const int gy = q / GPAIRS, gx = 2 * (q - gy * GPAIRS);
+            /* grid points (gx - 1, Y), (gx, Y), Y = y_begin - 1 + gy: elevation texels (gx + 1, Y + 2),
+             * (gx + 2, Y + 2); staged row (Y + 2) - zr0 = gy + 1 */
+            const float *zp = zs + (gy + 1) * EPITCH + gx;
+            F2 h;
+            if (!LINEAR) {
+                h = make_float2(zp[1], zp[2]);
+            } else {
+                const F2 t00 = *reinterpret_cast<const F2 *>(zp - EPITCH);         /* texels gx, gx+1 of the row below */
+                const F2 t10 = make_float2(t00.y, zp[-EPITCH + 2]);
+                const F2 t01 = *reinterpret_cast<const F2 *>(zp);
+                const F2 t11 = make_float2(t01.y, zp[2]);
+                h = fma2(bc(0.5625f), t11, fma2(bc(0.1875f), t01, fma2(bc(0.1875f), t10, mul2(bc(0.0625f), t00))));
             }
-            p.x = fmaf(hp, upx, dot4(rq.corners + 0, p0, p1, p2, p3));
-            p.y = fmaf(hp, upy, dot4(rq.corners + 4, p0, p1, p2, p3));
-            p.z = fmaf(hp, upz, dot4(rq.corners + 8, p0, p1, p2, p3));
+            const F2 u = *reinterpret_cast<const F2 *>(ulut + gx);
+            const float v = ulut[y_begin + gy];
+            F2 qx, qy, qz;
+            if (!SPHERE) {
+                qx = fma2(bc(D), u, bc(x0f));
+                qy = bc(fmaf(D, v, y0f));
+                qz = h;
+            } else {
+                const F2 U = sub2(bc(1.0f), u);
+                const float V = 1.0f - v;
+                const F2 a0 = mul2(U, bc(V)), a1 = mul2(u, bc(V)), a2 = mul2(U, bc(v)), a3 = mul2(u, bc(v));
+                const F2 l0 = mul2(a0, bc(rq.norms[0])), l1 = mul2(a1, bc(rq.norms[1]));
+                const F2 l2 = mul2(a2, bc(rq.norms[2])), l3 = mul2(a3, bc(rq.norms[3]));
+                const F2 den = fma2(a3, bc(rq.norms[3]), fma2(a2, bc(rq.norms[2]), fma2(a1, bc(rq.norms[1]), l0)));
+                const F2 rden = rcp_rn2(den);
+                const F2 p0 = div_rn2(l0, den, rden), p1 = div_rn2(l1, den, rden);
+                const F2 p2 = div_rn2(l2, den, rden), p3 = div_rn2(l3, den, rden);
+#define ROW4(M, r) fma2(bc(M[4 * (r) + 3]), p3, fma2(bc(M[4 * (r) + 2]), p2, fma2(bc(M[4 * (r) + 1]), p1, mul2(bc(M[4 * (r)]), p0))))
+                const F2 upx = ROW4(rq.verticals, 0), upy = ROW4(rq.verticals, 1), upz = ROW4(rq.verticals, 2);
+                F2 hp = h;
+                if (s != 1.0f) {   /* tile-uniform: levels whose quad is larger than R/64 */
+                    const F2 len = sqrt_rn2(plf2::dot3(upx, upy, upz, upx, upy, upz));
+                    const F2 kk = fma2(bc(1.0f), bc(s), mul2(len, bc(1.0f - s)));   /* mix(len, 1, s) */
+                    hp = div_rn2(fma2(bc(R), sub2(bc(1.0f), kk), h), kk, rcp_rn2(kk));
+                }
+                qx = fma2(hp, upx, ROW4(rq.corners, 0));
+                qy = fma2(hp, upy, ROW4(rq.corners, 1));
+                qz = fma2(hp, upz, ROW4(rq.corners, 2));
+#undef ROW4
+            }
+            float *o = px + gy * GWP + gx;
+            *reinterpret_cast<F2 *>(o) = qx;
+            *reinterpret_cast<F2 *>(o + PP) = qy;
+            *reinterpret_cast<F2 *>(o + 2 * PP) = qz;
         }
-        p.w = 0.0f;
-        pos[q] = p;
     }
     __syncthreads();
 
-    /* ---- normals of the band ----------------------------------------------- */
-    const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
-    const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
-    for (int q = tid; q < rows * W; q += kThreads) {
-        const int ry = q / W, x = q - ry * W;
-        const float4 *c = pos + (ry + 1) * GW + (x + 1);
-        const float4 pl = c[-1], pr = c[1], pd = c[-GW], pu = c[GW];
-        const float ax = pr.x - pl.x, ay = pr.y - pl.y, az = pr.z - pl.z;
-        const float cx = pu.x - pd.x, cy = pu.y - pd.y, cz = pu.z - pd.z;
-        float nx = fmaf(ay, cz, -(az * cy));
-        float ny = fmaf(az, cx, -(ax * cz));
-        float nz = fmaf(ax, cy, -(ay * cx));
-        const float inv = plfp::rcp_rn(plfp::sqrt_rn(dot3(nx, ny, nz, nx, ny, nz)));
-        nx *= inv; ny *= inv; nz *= inv;
-        const float tx = dot3(w00, w01, w02, nx, ny, nz);
-        const float ty = dot3(w10, w11, w12, nx, ny, nz);
-        /* unorm8: round(clamp(v, 0, 1) * 255), NaN -> 0 */
-        const int r8 = __float2int_rn(fminf(fmaxf(fmaf(tx, 0.5f, 0.5f), 0.0f), 1.0f) * 255.0f);
-        const int g8 = __float2int_rn(fminf(fmaxf(fmaf(ty, 0.5f, 0.5f), 0.0f), 1.0f) * 255.0f);
-        reinterpret_cast<unsigned short *>(outb)[q] = (unsigned short) (r8 | (g8 << 8));
+    /* ---- normals of the band, two texels (x, x+1) per thread ----------------- */
+    {
+        const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
+        const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
+        for (int q = tid; q < rows * XPAIRS; q += kThreads) {
+            const int ry = q / XPAIRS, x = 2 * (q - ry * XPAIRS);
+            /* texel (x, y) is grid point index (x + 1) of grid row ry + 1; its neighbours are
+             * x, x + 2 (left, right) and the rows above / below */
+            const float *c = px + (ry + 1) * GWP + x;
+            F2 d[3], e[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float *ck = c + k * PP;
+                const F2 pl = *reinterpret_cast<const F2 *>(ck);            /* grid x, x+1 */
+                const F2 pr = *reinterpret_cast<const F2 *>(ck + 2);        /* grid x+2, x+3 */
+                const F2 pd = make_float2(ck[1 - GWP], ck[2 - GWP]);
+                const F2 pu = make_float2(ck[1 + GWP], ck[2 + GWP]);
+                d[k] = sub2(pr, pl);
+                e[k] = sub2(pu, pd);
+            }
+            F2 nx = fma2(d[1], e[2], neg(mul2(d[2], e[1])));
+            F2 ny = fma2(d[2], e[0], neg(mul2(d[0], e[2])));
+            F2 nz = fma2(d[0], e[1], neg(mul2(d[1], e[0])));
+            const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
+            nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
+            const F2 tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
+            const F2 ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
+            /* unorm8: round(clamp(v, 0, 1) * 255), NaN -> 0 */
+            const F2 r = mul2(clamp2(fma2(tx, bc(0.5f), bc(0.5f)), 0.0f, 1.0f), bc(255.0f));
+            const F2 g = mul2(clamp2(fma2(ty, bc(0.5f), bc(0.5f)), 0.0f, 1.0f), bc(255.0f));
+            unsigned short *o = reinterpret_cast<unsigned short *>(outb) + ry * W + x;
+            o[0] = (unsigned short) (__float2int_rn(r.x) | (__float2int_rn(g.x) << 8));
+            if (x + 1 < W) o[1] = (unsigned short) (__float2int_rn(r.y) | (__float2int_rn(g.y) << 8));
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -417,8 +452,7 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
     if (a.W == 97 && a.border == 2 && !ctx->force_generic) {
         /* the geometry of every shipped archive: compile-time specialisation */
         using GEO = NGeo<97>;
-        const size_t fsmem = (size_t) GEO::ZROWS * GEO::EPITCH * 4 + GEO::OUT_BYTES +
-                             (size_t) (GEO::MAX_ROWS + 2) * GEO::GW * 16 + (size_t) ((GEO::GW + 3) & ~3) * 4;
+        const size_t fsmem = GEO::SMEM;
         void (*kern)(NormArgs) = a.sphere ? (a.linear ? normal_kernel_fast<97, true, true> : normal_kernel_fast<97, true, false>)
                                           : (a.linear ? normal_kernel_fast<97, false, true> : normal_kernel_fast<97, false, false>);
         PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));
