@@ -102,56 +102,33 @@ class ClockSampler:
 # ----------------------------------------------------------------- the sweep
 
 class PlanetSweep:
-    """Breadth-first production of level-2 subtrees into a recycling pool."""
+    """Breadth-first production of level-2 subtrees into a recycling pool (plan: sweep.py)."""
 
     def __init__(self, pl, ctx, max_level, want_stats=1):
-        self.pl, self.ctx, self.max_level = pl, ctx, max_level
-        self.depths = max_level - 2
-        # slots: 21 face-resident (levels 0..2) + one region per depth below the unit root
-        self.off = [21]
-        for d in range(1, self.depths + 1):
-            self.off.append(self.off[-1] + 4 ** d)
-        self.capacity = self.off[-1]
+        import sweep as plan
+        self.plan, self.pl, self.ctx, self.max_level = plan, pl, ctx, max_level
+        _, self.capacity = plan.region_offsets(max_level)
         self.elev = ctx.pool(pl.POOL_ELEV, 101, self.capacity)
         self.norm = ctx.pool(pl.POOL_NORM2, 97, self.capacity)
         ctx.noise_init(101)
         self.scenes = {f: pl.sweep_scene(noise_amp=PLANET_AMP, face=f, root_quad_size=PLANET_SIZE,
                                          sphere=1, elev_filter=pl.FILTER_LINEAR,
                                          want_stats=want_stats) for f in range(1, 7)}
-        self.units = [(f, m2) for f in range(1, 7) for m2 in range(16)]
+        self.units = plan.planet_units()
 
     def pairs_of(self, units, count_roots):
-        per_unit = sum(4 ** d for d in range(1, self.depths + 1))
-        faces = len({f for f, _ in units})
-        return len(units) * per_unit + (21 * faces if count_roots else 0)
-
-    # the (level, morton0, n, out_slot0, parent_slot0, parent_morton0) batches of a unit list
-    def batches(self, units):
-        face_done = None
-        for f, m2 in units:
-            if f != face_done:
-                yield f, 0, 0, 1, 0, 0, 0
-                yield f, 1, 0, 4, 1, 0, 0
-                yield f, 2, 0, 16, 5, 1, 0
-                face_done = f
-            for d in range(1, self.depths + 1):
-                n = 4 ** d
-                m0 = m2 << (2 * d)
-                if d == 1:
-                    yield f, 2 + d, m0, n, self.off[0], 5 + m2, m2
-                else:
-                    yield f, 2 + d, m0, n, self.off[d - 1], self.off[d - 2], m0 >> 2
+        return self.plan.pairs_in_units(units, self.max_level, count_roots)
 
     def run_device(self, units):
         pr = self.ctx.produce_range
-        for f, level, m0, n, s0, p0, pm0 in self.batches(units):
+        for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
             pr(self.scenes[f], self.elev, self.norm, level, m0, n, s0, p0, pm0)
 
     def run_host_requests(self, units, nthreads=0):
         """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out."""
         pl, ctx = self.pl, self.ctx
         h2d = d2h = 0
-        for f, level, m0, n, s0, p0, pm0 in self.batches(units):
+        for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
             sc = self.scenes[f]
             e, q = pl.make_requests_range(sc, level, m0, n, s0, p0, pm0, nthreads=nthreads)
             ctx.elevation_batch(sc.elev, self.elev, e)
@@ -245,7 +222,7 @@ def main():
     stream = torch.cuda.Stream(device=local_rank)
     ctx.set_stream(stream.cuda_stream)       # torch events see this stream
     sweep = PlanetSweep(pl, ctx, args.max_level, want_stats=1)
-    my_units = sweep.units[rank::world]
+    my_units = sweep.plan.units_of_rank(sweep.units, rank, world)
     total_pairs = sweep.pairs_of(sweep.units, True)            # counted once per step, whole job
     launches0 = ctx.launches
 

@@ -70,6 +70,7 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     if (ctx->perlin_g2) cudaFree(ctx->perlin_g2);
     if (ctx->gen_ereq) cudaFree(ctx->gen_ereq);
     if (ctx->gen_nreq) cudaFree(ctx->gen_nreq);
+    if (ctx->resid_scratch) cudaFree(ctx->resid_scratch);
     for (auto &t : *ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto &e : *ctx->event_pool) cudaEventDestroy(e);
     delete ctx->timed;

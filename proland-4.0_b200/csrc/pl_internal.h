@@ -59,6 +59,9 @@ struct pl_ctx {
     struct TimedLaunch { cudaEvent_t a, b; int kernel; int tiles; };
     std::vector<TimedLaunch> *timed;
     std::vector<cudaEvent_t> *event_pool;
+    /* residual decode scratch (dense inflated streams + status) */
+    void *resid_scratch;
+    size_t resid_scratch_bytes;
     /* request staging */
     void *req_dev;
     size_t req_dev_bytes;

@@ -1,0 +1,539 @@
+/*
+ * pl_residual.cu -- the ResidualProducer decode on the device: integer work,
+ * bit-exact by construction.
+ *
+ * Reference: ResidualProducer::readTile (terrain/sources/proland/dem/
+ * ResidualProducer.cpp:268-340) opens the tile's blob as an in-memory TIFF
+ * (TIFFClientOpen over util/mfs), reads its single DEFLATE strip with
+ * TIFFReadEncodedStrip (libtiff 3.x + zlib 1.x, third-party and absent from the
+ * reference tree) and converts little-endian int16 -> float * scale, adding the
+ * upsampled parent tile when composing the root levels.  File format:
+ * src/terrain/doc/overview.txt:147-216, writer preprocess/terrain/
+ * HeightMipmap.cpp:561-655.
+ *
+ * Here:
+ *   host   : the IFD of every blob is parsed (tags 256/257 size, 258/277 two
+ *            8-bit samples, 259 compression 1 / 8 / 32946, 273/279 the strip) and
+ *            the strips are copied to the device in one transfer
+ *   kernel1: inflate_kernel -- RFC 1950/1951 inflate, ONE WARP PER TILE.  Lane 0
+ *            walks the bit stream with a 64-bit bit buffer and table lookups (a
+ *            10-bit first-level table for literal/length codes and an 8-bit one
+ *            for distances, built per dynamic block in shared memory by all 32
+ *            lanes; longer codes fall back to the canonical count/symbol walk);
+ *            LZ77 matches are copied by all 32 lanes.  Output goes to a dense
+ *            scratch stream (back-references need the dense byte order).
+ *   kernel2: residual_store_kernel -- dense int16 -> the pool's pitched rows:
+ *            raw for an I16 pool, (float) z * scale (+ the tile in add_slot) for an
+ *            F32 pool, lower-left w x w corner of the slot exactly like the
+ *            reference's 197-stride CPU slot.
+ *
+ * Any conforming inflater yields the same bytes; parity is pinned on the
+ * reference's own fixture terrain4/DEM.dat (sha1 of every inflated tile,
+ * tests/golden/dem_dat.json).
+ */
+#include <cstring>
+#include <vector>
+
+#include "pl_internal.h"
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kLitBits = 10;     /* first-level table of the literal/length code */
+constexpr int kDistBits = 8;     /* first-level table of the distance code */
+
+enum {
+    INF_OK = 0,
+    INF_BAD_HEADER = 1,
+    INF_BAD_BLOCK = 2,
+    INF_BAD_CODE = 3,
+    INF_OVERRUN_IN = 4,
+    INF_OVERRUN_OUT = 5,
+    INF_BAD_DISTANCE = 6,
+    INF_SHORT = 7
+};
+
+struct WarpTables {
+    unsigned short lit_lut[1 << kLitBits];   /* (symbol << 4) | code length, 0 = not in the table */
+    unsigned short dist_lut[1 << kDistBits];
+    unsigned short lit_count[16], lit_sym[288];   /* canonical decode (codes longer than the table) */
+    unsigned short dist_count[16], dist_sym[32];
+    unsigned char lens[320];
+};
+
+struct BitReader {
+    const unsigned char *src;
+    unsigned int pos, end;
+    unsigned long long buf;
+    int cnt;
+    bool overrun;
+};
+
+__device__ __forceinline__ void br_init(BitReader &b, const unsigned char *src, unsigned int n)
+{
+    b.src = src; b.pos = 0; b.end = n; b.buf = 0; b.cnt = 0; b.overrun = false;
+}
+/* at least 32 valid bits afterwards (zero bits past the end; overrun noted when consumed) */
+__device__ __forceinline__ void br_fill(BitReader &b)
+{
+    while (b.cnt <= 56) {
+        const unsigned long long byte = b.pos < b.end ? (unsigned long long) __ldg(b.src + b.pos) : 0ull;
+        b.buf |= byte << b.cnt;
+        b.pos++;
+        b.cnt += 8;
+    }
+}
+__device__ __forceinline__ unsigned int br_peek(const BitReader &b, int n) { return (unsigned int) (b.buf & ((1ull << n) - 1)); }
+__device__ __forceinline__ void br_drop(BitReader &b, int n)
+{
+    b.buf >>= n;
+    b.cnt -= n;
+    /* bytes fetched so far minus whole bytes still buffered must not pass the end */
+    if ((long long) b.pos - (b.cnt >> 3) > (long long) b.end) b.overrun = true;
+}
+__device__ __forceinline__ unsigned int br_bits(BitReader &b, int n)
+{
+    if (b.cnt < n) br_fill(b);
+    const unsigned int v = br_peek(b, n);
+    br_drop(b, n);
+    return v;
+}
+
+__device__ __forceinline__ unsigned int bitrev(unsigned int v, int n) { return __brev(v) >> (32 - n); }
+
+/* Build count/symbol arrays and the first-level table of a canonical prefix code from
+ * lens[0..n) (all 32 lanes; lane 0 does the short serial parts).  Returns false for an
+ * over-subscribed code. */
+__device__ bool build_code(const unsigned char *lens, int n, unsigned short *count, unsigned short *sym,
+                           unsigned short *lut, int lut_bits, int lane)
+{
+    __shared__ unsigned short next_code_sh[kWarpsPerCta][16];
+    __shared__ unsigned short offs_sh[kWarpsPerCta][16];
+    unsigned short *next_code = next_code_sh[threadIdx.x >> 5];
+    unsigned short *offs = offs_sh[threadIdx.x >> 5];
+    bool ok = true;
+    if (lane == 0) {
+        for (int l = 0; l < 16; ++l) count[l] = 0;
+        for (int s = 0; s < n; ++s) count[lens[s]]++;
+        int left = 1;
+        for (int l = 1; l < 16; ++l) {
+            left <<= 1;
+            left -= count[l];
+            if (left < 0) ok = false;
+        }
+        unsigned int code = 0;
+        offs[1] = 0;
+        next_code[0] = 0;
+        for (int l = 1; l < 16; ++l) {
+            code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
+            next_code[l] = (unsigned short) code;
+            if (l < 15) offs[l + 1] = offs[l] + count[l];
+        }
+        /* symbols sorted by (length, value); next_code advanced in the same order */
+        for (int s = 0; s < n; ++s) {
+            const int l = lens[s];
+            if (l) sym[offs[l]++] = (unsigned short) s;
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    for (int k = lane; k < (1 << lut_bits); k += 32) lut[k] = 0;
+    __syncwarp();
+    if (!ok) return false;
+    /* canonical codes: symbol s of length l gets next_code[l] + (its rank among length-l symbols).
+     * The ranks follow from the sorted sym[] array: entries of length l start at start(l). */
+    if (lane == 0) {
+        unsigned int start = 0;
+        for (int l = 1; l < 16; ++l) { offs[l] = (unsigned short) start; start += count[l]; }
+    }
+    __syncwarp();
+    for (int l = 1; l <= lut_bits; ++l) {
+        const int c = count[l], base = offs[l];
+        for (int r = lane; r < c; r += 32) {
+            const unsigned int code = next_code[l] + r;
+            const unsigned int rev = bitrev(code, l);
+            const unsigned short e = (unsigned short) ((sym[base + r] << 4) | l);
+            for (unsigned int pad = rev; pad < (1u << lut_bits); pad += 1u << l) lut[pad] = e;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+/* canonical walk for codes longer than the first-level table (lane 0) */
+__device__ int slow_decode(BitReader &b, const unsigned short *count, const unsigned short *sym)
+{
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l < 16; ++l) {
+        code |= (int) br_bits(b, 1);
+        const int c = count[l];
+        if (code - c < first) return sym[index + (code - first)];
+        index += c;
+        first += c;
+        first <<= 1;
+        code <<= 1;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int decode_sym(BitReader &b, const unsigned short *lut, int lut_bits,
+                                          const unsigned short *count, const unsigned short *sym)
+{
+    if (b.cnt < 32) br_fill(b);
+    const unsigned short e = lut[br_peek(b, lut_bits)];
+    if (e) {
+        br_drop(b, e & 15);
+        return e >> 4;
+    }
+    return slow_decode(b, count, sym);
+}
+
+__constant__ unsigned short kLenBase[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
+__constant__ unsigned char kLenExtra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
+__constant__ unsigned short kDistBase[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577 };
+__constant__ unsigned char kDistExtra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
+__constant__ unsigned char kClOrder[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+
+struct InflateJob {
+    unsigned long long in_off;   /* strip start in the device blob buffer */
+    unsigned int in_len;
+    unsigned int out_len;        /* expected: w * w * 2 */
+    unsigned int compression;    /* 1 = stored strip, else zlib stream */
+};
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const InflateJob *jobs, const unsigned char *in,
+                                                                   unsigned char *out, size_t out_stride, int *status)
+{
+    __shared__ WarpTables tables[kWarpsPerCta];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int job = blockIdx.x * kWarpsPerCta + wid;
+    if (job >= n) return;
+    WarpTables &T = tables[wid];
+    const InflateJob J = jobs[job];
+    const unsigned char *src = in + J.in_off;
+    unsigned char *dst = out + (size_t) job * out_stride;
+    const unsigned int cap = J.out_len;
+    const unsigned int FULL = 0xffffffffu;
+
+    if (J.compression == 1) {   /* uncompressed strip */
+        for (unsigned int k = lane; k < min(J.in_len, cap); k += 32) dst[k] = __ldg(src + k);
+        if (lane == 0) status[job] = J.in_len == cap ? INF_OK : INF_SHORT;
+        return;
+    }
+
+    BitReader b;
+    br_init(b, src, J.in_len);
+    int err = INF_OK;
+    unsigned int pos = 0;
+    if (lane == 0) {   /* zlib header: CM = 8, no preset dictionary, header checksum */
+        const unsigned int cmf = br_bits(b, 8), flg = br_bits(b, 8);
+        if ((cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32) || ((cmf << 8) | flg) % 31 != 0) err = INF_BAD_HEADER;
+    }
+    err = __shfl_sync(FULL, err, 0);
+
+    int last = 0;
+    while (!err && !last) {
+        int type = 0;
+        if (lane == 0) {
+            last = (int) br_bits(b, 1);
+            type = (int) br_bits(b, 2);
+        }
+        last = __shfl_sync(FULL, last, 0);
+        type = __shfl_sync(FULL, type, 0);
+
+        if (type == 0) {   /* stored block */
+            unsigned int len = 0, src_pos = 0;
+            if (lane == 0) {
+                br_drop(b, b.cnt & 7);                 /* to the byte boundary */
+                len = br_bits(b, 16);
+                const unsigned int nlen = br_bits(b, 16);
+                if ((len ^ nlen) != 0xffffu) err = INF_BAD_BLOCK;
+                src_pos = b.pos - (unsigned int) (b.cnt >> 3);   /* next unread byte */
+                if (!err && src_pos + len > b.end) err = INF_OVERRUN_IN;
+                if (!err && pos + len > cap) err = INF_OVERRUN_OUT;
+            }
+            err = __shfl_sync(FULL, err, 0);
+            len = __shfl_sync(FULL, len, 0);
+            src_pos = __shfl_sync(FULL, src_pos, 0);
+            if (err) break;
+            for (unsigned int k = lane; k < len; k += 32) dst[pos + k] = __ldg(src + src_pos + k);
+            pos += len;
+            if (lane == 0) {   /* restart the bit reader after the stored bytes */
+                b.pos = src_pos + len;
+                b.buf = 0;
+                b.cnt = 0;
+            }
+            __syncwarp();
+            continue;
+        }
+        if (type == 3) { err = INF_BAD_BLOCK; break; }
+
+        int nlen = 288, ndist = 30;
+        if (type == 1) {   /* fixed code */
+            for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+            for (int s = lane; s < 32; s += 32) T.lens[288 + s] = 5;
+            ndist = 30;
+        } else {           /* dynamic code: read the code lengths (lane 0) */
+            if (lane == 0) {
+                nlen = (int) br_bits(b, 5) + 257;
+                ndist = (int) br_bits(b, 5) + 1;
+                const int ncode = (int) br_bits(b, 4) + 4;
+                if (nlen > 286 || ndist > 30) err = INF_BAD_BLOCK;
+                for (int k = 0; k < 19; ++k) T.lens[k] = 0;
+                for (int k = 0; k < ncode; ++k) T.lens[kClOrder[k]] = (unsigned char) br_bits(b, 3);
+            }
+            err = __shfl_sync(FULL, err, 0);
+            nlen = __shfl_sync(FULL, nlen, 0);
+            ndist = __shfl_sync(FULL, ndist, 0);
+            if (err) break;
+            __syncwarp();
+            /* the code-length code reuses the literal tables (7-bit codes fit the first-level table) */
+            if (!build_code(T.lens, 19, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane)) { err = INF_BAD_CODE; break; }
+            if (lane == 0) {
+                /* decode into a scratch area behind the 19 code-length lengths is unsafe (they are in
+                 * use through the tables only, which are already built), so lens[] is overwritten */
+                int idx = 0;
+                while (idx < nlen + ndist && !err) {
+                    const int s = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
+                    if (s < 0) { err = INF_BAD_CODE; break; }
+                    if (s < 16) {
+                        T.lens[idx++] = (unsigned char) s;
+                    } else {
+                        int prev = 0, rep;
+                        if (s == 16) {
+                            if (idx == 0) { err = INF_BAD_CODE; break; }
+                            prev = T.lens[idx - 1];
+                            rep = 3 + (int) br_bits(b, 2);
+                        } else if (s == 17) {
+                            rep = 3 + (int) br_bits(b, 3);
+                        } else {
+                            rep = 11 + (int) br_bits(b, 7);
+                        }
+                        if (idx + rep > nlen + ndist) { err = INF_BAD_CODE; break; }
+                        while (rep--) T.lens[idx++] = (unsigned char) prev;
+                    }
+                }
+                if (!err && T.lens[256] == 0) err = INF_BAD_CODE;   /* no end-of-block code */
+            }
+            err = __shfl_sync(FULL, err, 0);
+            if (err) break;
+            __syncwarp();
+        }
+        /* distance lengths follow the literal/length lengths in lens[]; build both codes */
+        __syncwarp();
+        {
+            /* the distance code first: building the literal tables must not overwrite lens[] before
+             * the distance lengths are consumed (they are separate arrays, order is free) */
+            const unsigned char *dl = T.lens + (type == 1 ? 288 : nlen);
+            const bool okd = build_code(dl, ndist, T.dist_count, T.dist_sym, T.dist_lut, kDistBits, lane);
+            const bool okl = build_code(T.lens, nlen, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane);
+            /* incomplete distance codes (a single distance code) are legal; over-subscription is not */
+            if (!okd || !okl) { err = INF_BAD_CODE; break; }
+        }
+
+        /* symbols of the block */
+        for (;;) {
+            int sym = 0;
+            unsigned int len = 0, dist = 0;
+            if (lane == 0) {
+                sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
+                if (sym < 0 || sym > 285) {
+                    err = INF_BAD_CODE;
+                } else if (sym < 256) {
+                    if (pos >= cap) err = INF_OVERRUN_OUT;
+                    else dst[pos] = (unsigned char) sym;
+                } else if (sym > 256) {
+                    const int li = sym - 257;
+                    len = kLenBase[li] + br_bits(b, kLenExtra[li]);
+                    const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
+                    if (ds < 0 || ds > 29) {
+                        err = INF_BAD_CODE;
+                    } else {
+                        dist = kDistBase[ds] + br_bits(b, kDistExtra[ds]);
+                        if (dist > pos) err = INF_BAD_DISTANCE;
+                        else if (pos + len > cap) err = INF_OVERRUN_OUT;
+                    }
+                }
+                if (b.overrun) err = INF_OVERRUN_IN;
+            }
+            err = __shfl_sync(FULL, err, 0);
+            sym = __shfl_sync(FULL, sym, 0);
+            if (err || sym == 256) break;
+            if (sym < 256) {
+                pos += 1;
+                continue;
+            }
+            len = __shfl_sync(FULL, len, 0);
+            dist = __shfl_sync(FULL, dist, 0);
+            __syncwarp();   /* lane 0's literal stores are visible to the copying lanes */
+            /* overlapping matches repeat their first `dist` bytes, all of which exist already */
+            if (dist >= len) {
+                for (unsigned int k = lane; k < len; k += 32) dst[pos + k] = dst[pos - dist + k];
+            } else {
+                for (unsigned int k = lane; k < len; k += 32) dst[pos + k] = dst[pos - dist + (k % dist)];
+            }
+            pos += len;
+            __syncwarp();
+        }
+    }
+    if (!err && pos != cap) err = INF_SHORT;
+    if (lane == 0) status[job] = err;
+}
+
+struct StoreJob {
+    int width;       /* w of this tile */
+    int out_slot;
+    int add_slot;    /* -1: none */
+};
+
+/* dense int16 (w x w) -> pitched pool rows; ResidualProducer.cpp:321-338 */
+template <bool F32>
+__global__ void __launch_bounds__(256) residual_store_kernel(const StoreJob *jobs, const unsigned char *dense, size_t dense_stride,
+                                                             unsigned char *pool, size_t slot_bytes, int pitch, float scale)
+{
+    const StoreJob J = jobs[blockIdx.x];
+    const short *src = reinterpret_cast<const short *>(dense + (size_t) blockIdx.x * dense_stride);
+    const int w = J.width;
+    for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
+        const int j = k / w, i = k - j * w;
+        const short z = src[k];
+        if (F32) {
+            float *dst = reinterpret_cast<float *>(pool + (size_t) J.out_slot * slot_bytes);
+            const float zs = (float) z * scale;
+            float v = zs;
+            if (J.add_slot >= 0) {
+                const float *add = reinterpret_cast<const float *>(pool + (size_t) J.add_slot * slot_bytes);
+                v = add[(size_t) j * pitch + i] + zs;
+            }
+            dst[(size_t) j * pitch + i] = v;
+        } else {
+            short *dst = reinterpret_cast<short *>(pool + (size_t) J.out_slot * slot_bytes);
+            dst[(size_t) j * pitch + i] = z;
+        }
+    }
+}
+
+inline unsigned int rd16(const uint8_t *p) { return (unsigned int) p[0] | ((unsigned int) p[1] << 8); }
+inline unsigned int rd32(const uint8_t *p) { return rd16(p) | (rd16(p + 2) << 16); }
+
+/* the first IFD of a little-endian baseline TIFF with one strip */
+int parse_tiff(const uint8_t *blob, uint32_t size, int want_w, InflateJob *job, uint64_t base)
+{
+    if (size < 8 || blob[0] != 'I' || blob[1] != 'I' || rd16(blob + 2) != 42) return -1;
+    const uint32_t ifd = rd32(blob + 4);
+    if ((uint64_t) ifd + 2 > size) return -2;
+    const int n = (int) rd16(blob + ifd);
+    if ((uint64_t) ifd + 2 + 12ull * n > size) return -3;
+    uint32_t w = 0, h = 0, comp = 1, soff = 0, slen = 0, spp = 1, bps = 8, predictor = 1;
+    for (int i = 0; i < n; ++i) {
+        const uint8_t *e = blob + ifd + 2 + 12 * i;
+        const unsigned int tag = rd16(e), type = rd16(e + 2), count = rd32(e + 4);
+        const uint32_t val = type == 3 ? rd16(e + 8) : rd32(e + 8);
+        switch (tag) {
+        case 256: w = val; break;
+        case 257: h = val; break;
+        case 258:   /* BitsPerSample: two shorts fit the value field; more than two are an offset */
+            bps = count <= 2 ? rd16(e + 8) : 0;
+            if (count == 2 && rd16(e + 10) != bps) bps = 0;
+            break;
+        case 259: comp = val; break;
+        case 273: soff = val; break;
+        case 277: spp = val; break;
+        case 279: slen = val; break;
+        case 317: predictor = val; break;
+        default: break;
+        }
+    }
+    if ((int) w != want_w || h != w) return -4;
+    if (spp * bps != 16 || predictor != 1) return -5;
+    if (comp != 1 && comp != 8 && comp != 32946) return -6;
+    if ((uint64_t) soff + slen > size) return -7;
+    job->in_off = base + soff;
+    job->in_len = slen;
+    job->out_len = w * w * 2;
+    job->compression = comp;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
+                                        const uint32_t *sizes, const int32_t *widths, const int32_t *out_slots,
+                                        const int32_t *add_slots, float scale)
+{
+    if (!ctx || !out || n < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (n == 0) return PL_OK;
+    if (!blobs || !offsets || !sizes || !widths || !out_slots) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (out->kind != PL_POOL_RESID_F32 && out->kind != PL_POOL_RESID_I16)
+        return pl_set_error(PL_ERR_ARG, "out is not a residual pool");
+    if (add_slots && out->kind != PL_POOL_RESID_F32) return pl_set_error(PL_ERR_ARG, "add_slots needs an F32 pool");
+    PL_CUDA(cudaSetDevice(ctx->device));
+
+    /* pack the blobs back to back (8-byte aligned) and parse their IFDs */
+    std::vector<InflateJob> jobs(n);
+    std::vector<StoreJob> sjobs(n);
+    std::vector<uint64_t> packed_off(n);
+    uint64_t total = 0;
+    int max_w = 0;
+    for (int j = 0; j < n; ++j) {
+        if (widths[j] < 1 || widths[j] > out->tile_w) return pl_set_error(PL_ERR_ARG, "tile %d: width %d exceeds the pool tile", j, widths[j]);
+        if (out_slots[j] < 0 || out_slots[j] >= out->capacity || (add_slots && add_slots[j] >= out->capacity))
+            return pl_set_error(PL_ERR_ARG, "tile %d: slot out of range", j);
+        packed_off[j] = total;
+        total += ((uint64_t) sizes[j] + 7) & ~7ull;
+        const int rc = parse_tiff(blobs + offsets[j], sizes[j], widths[j], &jobs[j], packed_off[j]);
+        if (rc) return pl_set_error(PL_ERR_CORRUPT, "tile %d: not a single-strip 16-bit TIFF blob (code %d)", j, rc);
+        sjobs[j].width = widths[j];
+        sjobs[j].out_slot = out_slots[j];
+        sjobs[j].add_slot = add_slots ? add_slots[j] : -1;
+        if (widths[j] > max_w) max_w = widths[j];
+    }
+    const size_t dense_stride = ((size_t) max_w * max_w * 2 + 15) & ~(size_t) 15;
+    const size_t bytes_in = (size_t) total + 16;
+
+    /* staging: pinned host buffer -> device, one async copy */
+    void *dev = nullptr;
+    {
+        const size_t job_off = (bytes_in + 15) & ~(size_t) 15;
+        std::vector<uint8_t> stage(job_off + sizeof(InflateJob) * n + sizeof(StoreJob) * n, 0);
+        for (int j = 0; j < n; ++j) memcpy(stage.data() + packed_off[j], blobs + offsets[j], sizes[j]);
+        memcpy(stage.data() + job_off, jobs.data(), sizeof(InflateJob) * n);
+        memcpy(stage.data() + job_off + sizeof(InflateJob) * n, sjobs.data(), sizeof(StoreJob) * n);
+        int rc = pl_stage_requests(ctx, stage.data(), stage.size(), &dev);
+        if (rc) return rc;
+        /* scratch for the dense streams + status */
+        const size_t scratch = dense_stride * n + sizeof(int) * n;
+        if (scratch > ctx->resid_scratch_bytes) {
+            PL_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctx->resid_scratch) cudaFree(ctx->resid_scratch);
+            ctx->resid_scratch = nullptr;
+            ctx->resid_scratch_bytes = 0;
+            PL_CUDA(cudaMalloc(&ctx->resid_scratch, scratch + scratch / 4));
+            ctx->resid_scratch_bytes = scratch + scratch / 4;
+        }
+        const unsigned char *d_in = static_cast<const unsigned char *>(dev);
+        const InflateJob *d_jobs = reinterpret_cast<const InflateJob *>(d_in + job_off);
+        const StoreJob *d_sjobs = reinterpret_cast<const StoreJob *>(d_in + job_off + sizeof(InflateJob) * n);
+        unsigned char *d_dense = static_cast<unsigned char *>(ctx->resid_scratch);
+        int *d_status = reinterpret_cast<int *>(d_dense + dense_stride * n);
+
+        pl_timing_begin(ctx, PL_K_RESIDUAL, n);
+        inflate_kernel<<<(n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, ctx->stream>>>(n, d_jobs, d_in, d_dense,
+                                                                                                dense_stride, d_status);
+        PL_CUDA(cudaGetLastError());
+        if (out->kind == PL_POOL_RESID_F32)
+            residual_store_kernel<true><<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes, out->pitch, scale);
+        else
+            residual_store_kernel<false><<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes, out->pitch, scale);
+        PL_CUDA(cudaGetLastError());
+        pl_timing_end(ctx);
+        ctx->launches += 2;
+
+        std::vector<int> status(n);
+        PL_CUDA(cudaMemcpyAsync(status.data(), d_status, sizeof(int) * n, cudaMemcpyDeviceToHost, ctx->stream));
+        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < n; ++j)
+            if (status[j] != INF_OK)
+                return pl_set_error(PL_ERR_CORRUPT, "tile %d: DEFLATE stream is corrupt (inflate code %d)", j, status[j]);
+    }
+    return PL_OK;
+}

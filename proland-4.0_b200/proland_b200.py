@@ -148,6 +148,8 @@ def lib():
         L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pl_debug_force_generic.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
         L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -393,6 +395,21 @@ def _fpexact(self, a, b):
     return out
 
 
+def _residual_decode(self, pool, blobs, widths, out_slots, add_slots=None, scale=1.0):
+    """blobs: list of bytes (one TIFF blob per tile)."""
+    n = len(blobs)
+    buf = np.frombuffer(b"".join(blobs), np.uint8)
+    sizes = np.array([len(b) for b in blobs], np.uint32)
+    offs = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
+    widths = np.ascontiguousarray(widths, np.int32)
+    out_slots = np.ascontiguousarray(out_slots, np.int32)
+    add = np.ascontiguousarray(add_slots, np.int32) if add_slots is not None else None
+    check(lib().pl_residual_decode_batch(self.h, pool.h, n, _ptr(buf), _ptr(offs), _ptr(sizes), _ptr(widths),
+                                         _ptr(out_slots), _ptr(add) if add is not None else None,
+                                         C.c_float(scale)))
+
+
+Context.residual_decode = _residual_decode
 Context.force_generic = _force_generic
 Context.fpexact = _fpexact
 Context.timing_enable = _timing_enable

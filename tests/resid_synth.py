@@ -1,0 +1,107 @@
+"""Synthetic residual containers in the exact format ResidualProducer reads
+(src/terrain/doc/overview.txt:147-216; writer preprocess/terrain/HeightMipmap.cpp:561-655):
+
+  header  : 6 int32 (minLevel, maxLevel, tileSize, rootLevel, rootTx, rootTy) + float32 scale
+  offsets : ntiles x (begin, end) uint32, relative to the end of the offset table
+  blobs   : one little-endian TIFF per tile: 1 strip, 2 x 8-bit samples (= LE int16),
+            MINISBLACK, compression 32946 (DEFLATE), strip at byte 8, IFD after the strip
+
+TEST INFRASTRUCTURE (also used by bench-style residual workloads): real DEM1..6.dat are
+download-only (README.TXT:50-57), so config 3 runs on files made here.
+"""
+import struct
+import zlib
+
+import numpy as np
+
+
+def tiff_blob(tile, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, compression=32946):
+    """tile: (w, w) int16 -> TIFF bytes"""
+    tile = np.ascontiguousarray(tile, "<i2")
+    w = tile.shape[0]
+    raw = tile.tobytes()
+    if compression == 1:
+        strip = raw
+    else:
+        co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        strip = co.compress(raw) + co.flush()
+    ifd_off = 8 + len(strip)
+    if ifd_off % 2:
+        strip += b"\0"
+        ifd_off += 1
+    tags = [(256, 4, 1, w), (257, 4, 1, w), (258, 3, 2, 8 | (8 << 16)), (259, 3, 1, compression),
+            (262, 3, 1, 1), (273, 4, 1, 8), (274, 3, 1, 4), (277, 3, 1, 2), (279, 4, 1, len(strip)),
+            (284, 3, 1, 1)]
+    out = b"II*\0" + struct.pack("<I", ifd_off) + strip + struct.pack("<H", len(tags))
+    for tag, typ, cnt, val in tags:
+        out += struct.pack("<HHII", tag, typ, cnt, val)
+    return out + struct.pack("<I", 0)
+
+
+def tile_width(min_level, tile_size, l):
+    return (tile_size >> (min_level - l) if l < min_level else tile_size) + 5
+
+
+def n_tiles(min_level, max_level):
+    return min_level + ((1 << (max(max_level - min_level, 0) * 2 + 2)) - 1) // 3
+
+
+def tile_id(min_level, l, tx, ty):
+    if l < min_level:
+        return l
+    d = l - min_level
+    return min_level + tx + ty * (1 << d) + ((1 << (2 * d)) - 1) // 3
+
+
+def fractal_tile(rng, w, amp):
+    """smooth-ish int16 residuals: a few octaves of bilinear noise, amplitude ~amp"""
+    z = np.zeros((w, w), np.float64)
+    step, a = max(w // 2, 1), float(amp)
+    while step >= 1 and a >= 0.5:
+        n = w // step + 2
+        coarse = rng.normal(0, a, (n, n))
+        yy, xx = np.mgrid[0:w, 0:w] / step
+        x0, y0 = xx.astype(int), yy.astype(int)
+        fx, fy = xx - x0, yy - y0
+        z += ((1 - fx) * (1 - fy) * coarse[y0, x0] + fx * (1 - fy) * coarse[y0, x0 + 1]
+              + (1 - fx) * fy * coarse[y0 + 1, x0] + fx * fy * coarse[y0 + 1, x0 + 1])
+        step //= 2
+        a *= 0.55
+    return np.clip(np.rint(z), -32768, 32767).astype(np.int16)
+
+
+def container(min_level=3, max_level=5, tile_size=192, root=(0, 0, 0), scale=1.0, seed=20240612,
+              amps=(359, 43, 15, 3.9, 1.0, 0.5, 0.25, 0.12), zero_fraction=0.15, level=6):
+    """-> (file bytes, {tile id: int16 array})"""
+    rng = np.random.default_rng(seed)
+    nt = n_tiles(min_level, max_level)
+    tiles, blobs = {}, {}
+    zero_blob = None
+    for l in range(0, max_level + 1):
+        cnt = 1 if l < min_level else 1 << (l - min_level)
+        w = tile_width(min_level, tile_size, l)
+        for ty in range(cnt):
+            for tx in range(cnt):
+                tid = tile_id(min_level, l, tx, ty)
+                if l >= min_level and rng.random() < zero_fraction:
+                    t = np.zeros((w, w), np.int16)          # constant tiles share one blob
+                    if zero_blob is None:
+                        zero_blob = tiff_blob(t, level)
+                    blobs[tid] = zero_blob
+                else:
+                    t = fractal_tile(rng, w, amps[min(l, len(amps) - 1)])
+                    blobs[tid] = tiff_blob(t, level)
+                tiles[tid] = t
+    body = b""
+    offsets = []
+    pos_of = {}
+    for tid in range(nt):
+        b = blobs[tid]
+        if id(b) in pos_of:                                   # de-duplicated (HeightMipmap.cpp:601-611)
+            offsets += list(pos_of[id(b)])
+            continue
+        pos_of[id(b)] = (len(body), len(body) + len(b))
+        offsets += [len(body), len(body) + len(b)]
+        body += b
+    head = struct.pack("<6if", min_level, max_level, tile_size, root[0], root[1], root[2], scale)
+    return head + struct.pack("<%dI" % len(offsets), *offsets) + body, tiles

@@ -115,3 +115,136 @@ def test_produce_range_equals_per_tile_path(plb, ctx, oracle):
         slot = off[l] + plb.morton_encode(tx, ty)
         assert np.array_equal(elev.download(slot), e), (l, tx, ty)
         assert np.array_equal(norm.download(slot), n), (l, tx, ty)
+
+
+# ----------------------------------------------------------------- residuals
+
+import base64
+import hashlib
+import json
+import os
+import zlib
+
+import resid_synth as rs
+
+DEM = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dem_dat.json")))
+
+
+def test_residual_decode_reference_fixture(plb, ctx):
+    """the reference's own fixture (terrain4/DEM.dat): inflated int16 tiles, sha1 by sha1"""
+    ids = sorted(int(t) for t in DEM["blobs"])
+    blobs = [base64.b64decode(DEM["blobs"][str(t)]) for t in ids]
+    widths = [DEM["tile_width"][t] for t in ids]
+    pool = ctx.pool(plb.POOL_RESID_I16, 197, len(ids))
+    ctx.residual_decode(pool, blobs, widths, list(range(len(ids))))
+    for s, (t, w) in enumerate(zip(ids, widths)):
+        got = pool.download(s)[:w, :w]
+        assert hashlib.sha1(np.ascontiguousarray(got, "<i2").tobytes()).hexdigest() == DEM["tile_sha1"][t], t
+    # float pool: (float) z * scale, lower-left corner of the 197-stride slot, rest untouched
+    fpool = ctx.pool(plb.POOL_RESID_F32, 197, len(ids) + 1)
+    ctx.residual_decode(fpool, blobs, widths, list(range(len(ids))), scale=2.5)
+    for s, w in enumerate(widths):
+        f = fpool.download(s)
+        np.testing.assert_array_equal(f[:w, :w], pool.download(s)[:w, :w].astype(np.float32) * np.float32(2.5))
+        assert np.all(f[w:, :] == 0) and np.all(f[:, w:] == 0)
+
+
+@pytest.mark.parametrize("level,strategy", [(0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY),
+                                            (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_FILTERED),
+                                            (6, zlib.Z_FIXED), (6, zlib.Z_RLE), (6, zlib.Z_HUFFMAN_ONLY)])
+def test_residual_decode_deflate_variants(plb, ctx, level, strategy):
+    """stored, fixed-Huffman and dynamic-Huffman blocks; long matches (constant tiles), incompressible noise"""
+    rng = np.random.default_rng(level * 10 + strategy)
+    tiles = [rs.fractal_tile(rng, 197, 300), np.zeros((197, 197), np.int16),
+             rng.integers(-32768, 32767, (197, 197)).astype(np.int16), rs.fractal_tile(rng, 53, 40),
+             np.full((29, 29), -7, np.int16), (np.arange(197 * 197).reshape(197, 197) % 251 - 100).astype(np.int16)]
+    blobs = [rs.tiff_blob(t, level, strategy) for t in tiles]
+    blobs.append(rs.tiff_blob(tiles[0], compression=1))       # uncompressed strip
+    tiles.append(tiles[0])
+    pool = ctx.pool(plb.POOL_RESID_I16, 197, len(tiles))
+    ctx.residual_decode(pool, blobs, [t.shape[0] for t in tiles], list(range(len(tiles))))
+    for s, t in enumerate(tiles):
+        np.testing.assert_array_equal(pool.download(s)[:t.shape[0], :t.shape[0]], t)
+
+
+def test_residual_decode_root_composition_and_errors(plb, ctx):
+    rng = np.random.default_rng(11)
+    a, b = rs.fractal_tile(rng, 101, 50), rs.fractal_tile(rng, 101, 10)
+    pool = ctx.pool(plb.POOL_RESID_F32, 197, 3)
+    base = rng.normal(0, 100, (197, 197)).astype(np.float32)
+    pool.upload(1, base)
+    # result = tile[add_slot] + int16 * scale (ResidualProducer.cpp:333-336), in place allowed
+    ctx.residual_decode(pool, [rs.tiff_blob(a), rs.tiff_blob(b)], [101, 101], [0, 1], add_slots=[-1, 1], scale=0.5)
+    np.testing.assert_array_equal(pool.download(0)[:101, :101], a.astype(np.float32) * np.float32(0.5))
+    np.testing.assert_array_equal(pool.download(1)[:101, :101], base[:101, :101] + b.astype(np.float32) * np.float32(0.5))
+    np.testing.assert_array_equal(pool.download(1)[101:, :], base[101:, :])
+    good = rs.tiff_blob(a)
+    bad = bytearray(good)
+    bad[40] ^= 0x5A                                            # corrupt the DEFLATE stream
+    with pytest.raises(plb.PlError) as e:
+        ctx.residual_decode(pool, [bytes(bad)], [101], [2])
+    assert e.value.code == plb.PL_ERR_CORRUPT
+    with pytest.raises(plb.PlError) as e:
+        ctx.residual_decode(pool, [good[:30]], [101], [2])     # truncated: not a TIFF
+    assert e.value.code == plb.PL_ERR_CORRUPT
+    with pytest.raises(plb.PlError) as e:
+        ctx.residual_decode(pool, [good], [53], [2])           # width mismatch
+    assert e.value.code == plb.PL_ERR_CORRUPT
+
+
+@pytest.mark.parametrize("kind", ["f32", "i16"])
+def test_elevation_with_residuals(plb, ctx, oracle, kind):
+    """config 3 shape: 197-wide residual tiles (mod 2), flip, NEAREST storage, sphere normals;
+    residual float tiles from the oracle's ResidualProducer restatement (delta = 0) uploaded to
+    the F32 pool, or the raw int16 tiles consumed directly from an I16 pool"""
+    data, tiles = rs.container(min_level=0, max_level=2, tile_size=192, scale=0.5, zero_fraction=0.2)
+    res = oracle.Resid(data, delta=0)
+    amp = [0, 0, 5, 2.5, 1]
+    W = 101
+    kw = dict(noise_amp=amp, face=2, root_quad_size=12720000.0, sphere=1, flip=1, elev_filter=0)
+    scene = oracle.make_scene(W=W, rootQuadSize=kw["root_quad_size"], face=2, flip=1, noiseAmp=amp, sphere=1,
+                              elev_filter=0, resid=res)
+    noise = oracle.dem_noise(W)
+    max_level = 3
+    ntile = sum(4 ** l for l in range(max_level + 1))
+    elev = ctx.pool(plb.POOL_ELEV, W, ntile)
+    norm = ctx.pool(plb.POOL_NORM2, W - 4, ntile)
+    rpool = ctx.pool(plb.POOL_RESID_F32 if kind == "f32" else plb.POOL_RESID_I16, 197, 32)
+    ctx.noise_init(W)
+    es = plb.elev_scene(W, 24, 1, 1, 0, 1, resid_scale=0.5)
+    ns = plb.norm_scene(W - 4, 24, 2, 0, 1, 1)
+    # residual tiles: one per (level, tx/2, ty/2) that the file has
+    rslot = {}
+    for l in range(max_level + 1):
+        for ty in range(max(1, (1 << l) // 2)):
+            for tx in range(max(1, (1 << l) // 2)):
+                if res.has_tile(l, tx, ty):
+                    s = len(rslot)
+                    rslot[(l, tx, ty)] = s
+                    if kind == "f32":
+                        rpool.upload(s, res.create_tile(l, tx, ty))
+                    else:
+                        rpool.upload(s, tiles[rs.tile_id(0, l, tx, ty)])
+    slot_of, ref = {}, {}
+    for l in range(max_level + 1):
+        tl = qt.level_tiles(l)
+        has = [res.has_tile(l, tx // 2, ty // 2) for (_, tx, ty) in tl]
+        reqs = plb.elev_make_reqs(tl, tile_w=W, root_quad_size=kw["root_quad_size"], noise_amp=amp, face=2,
+                                  resid_tile_w=197, has_resid=has)
+        nreqs = plb.norm_make_reqs(tl, ns, root_quad_size=kw["root_quad_size"])
+        for i, t in enumerate(tl):
+            slot_of[t] = len(slot_of)
+            reqs["out_slot"][i] = nreqs["out_slot"][i] = nreqs["elev_slot"][i] = slot_of[t]
+            if l:
+                reqs["parent_slot"][i] = slot_of[(l - 1, t[1] // 2, t[2] // 2)]
+            if has[i]:
+                reqs["resid_slot"][i] = rslot[(l, t[1] // 2, t[2] // 2)]
+            parent = ref[(l - 1, t[1] // 2, t[2] // 2)][0] if l else None
+            rt = res.create_tile(l, t[1] // 2, t[2] // 2) if has[i] else None
+            ref[t] = oracle.produce_pair(scene, noise, l, t[1], t[2], parent, rt)
+        ctx.elevation_batch(es, elev, reqs, resid=rpool)
+        ctx.normal_batch(ns, norm, elev, nreqs)
+    assert any(res.has_tile(3, x, y) for x in range(4) for y in range(4)) is False   # maxLevel 2: level 3 is noise only
+    for t, (e, n) in ref.items():
+        assert np.array_equal(elev.download(slot_of[t]), e), t
+        assert np.array_equal(norm.download(slot_of[t]), n), t
