@@ -53,9 +53,9 @@ def test_dem_noise_kats(oracle):
     np.testing.assert_allclose(n32[0, 5, 5:9], [0.88749158, 0.00105512, 0.15307450, -0.10569286], rtol=2e-6, atol=0)
     np.testing.assert_allclose(n16[0, 5, 5:9], [0.88769531, 0.00105476, 0.15307617, -0.10571289], rtol=5e-6, atol=0)
     np.testing.assert_array_equal(n16, n32.astype(np.float16).astype(np.float32))   # RNE like numpy
-    # first border values: seed 7654321 -> 0.05766881 * 2 - 1, seed 5647381 -> 0.30257297 * 2 - 1
-    np.testing.assert_allclose(n32[0, 2, 5], 0.05766881 * 2 - 1, rtol=2e-6)    # layer 0: all borders seed A
-    np.testing.assert_allclose(n32[5, 2, 5], 0.30257297 * 2 - 1, rtol=2e-6)    # layer 5: all borders seed B
+    # first border values: seed 7654321 -> 0.05766881, seed 5647381 -> 0.30257297
+    np.testing.assert_allclose(n32[0, 2, 5], 0.05766881, rtol=2e-6)    # layer 0: all borders seed A
+    np.testing.assert_allclose(n32[5, 2, 5], 0.30257297, rtol=2e-6)    # layer 5: all borders seed B
     # corners stay zero, values in [-1, 1)
     assert np.all(n32[:, :5, :5] == 0) and np.all(n32[:, -5:, -5:] == 0)
     assert n32.min() >= -1 and n32.max() < 1
