@@ -36,7 +36,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 224;
 constexpr int kBandRows = 24;
 
 struct NormArgs {
@@ -259,30 +259,43 @@ struct NGeo {
     static constexpr int EPITCH = (EW + 3) & ~3;
     static constexpr int EPLANE = EW * EPITCH;
     static constexpr int GW = TW + 2;                 /* grid points X = -1 .. W */
-    static constexpr int GWP = (GW + 1) & ~1;         /* padded to an even pitch */
-    static constexpr int GPAIRS = GWP / 2;            /* grid-point pairs per row */
-    static constexpr int XPAIRS = (TW + 1) / 2;       /* texel pairs per row */
+    static constexpr int GWP = ((GW + 1) & ~1) + 4;   /* row pitch of a position plane: even, room for the row shift and the pad pairs */
+    static constexpr int GPAIRS = (GW + 2) / 2;       /* grid-point pairs per row (covers an odd start) */
+    static constexpr int XPAIRS = (TW + 2) / 2;       /* texel pairs per row (covers an odd start) */
     static constexpr int NBANDS = TW / kBandRows;
     static constexpr int MAX_ROWS = TW - (NBANDS - 1) * kBandRows;
+    static constexpr int MAX_BROWS = (MAX_ROWS + 1) / 2;   /* 2-row texel blocks per band */
     static constexpr int ZROWS = MAX_ROWS + 3;
     static constexpr int OUT_BYTES = (MAX_ROWS * TW * 2 + 15) & ~15;
-    static constexpr int POS_PLANE = (MAX_ROWS + 2) * GWP;
-    static constexpr size_t SMEM = (size_t) ZROWS * EPITCH * 4 + OUT_BYTES + (size_t) 3 * POS_PLANE * 4 + GWP * 4;
-    static_assert(EPITCH % 2 == 0 && EPITCH >= GWP + 2, "paired loads stay inside a staged row");
+    static constexpr int POS_ROWS = 2 * MAX_BROWS + 2;     /* grid rows a band touches (incl. the dummy row of an odd band) */
+    static constexpr int POS_PLANE = POS_ROWS * GWP;
+    static constexpr size_t SMEM = (size_t) ZROWS * EPITCH * 4 + OUT_BYTES + (size_t) 3 * POS_PLANE * 4 + (GW + 3) * 4;
+    static_assert(EPITCH % 2 == 0 && EPITCH >= GW + 3, "paired loads stay inside a staged row");
+    static_assert(kBandRows % 4 == 0, "the row-shift pattern restarts with every band");
 };
+
+/* Shared-memory layout of the position planes.  A thread of the normal phase owns a 2x2 block of
+ * texels: it needs 4 consecutive grid points of the block's two rows and the 2 middle ones of the
+ * rows below / above.  Grid row g is stored shifted right by shift(g) = ((g + 3) >> 1) & 1 elements and
+ * texel blocks of block row k start at x = (k & 1) - 1 (mod 2): with that every one of those accesses is
+ * an ALIGNED 8-byte pair (shared-memory wavefronts are the limiter of this kernel, profiles/):
+ *   block row k even (x even): rows 2k+1, 2k+2 shift 0 -> pairs at x, x+2; rows 2k, 2k+3 shift 1 -> pair at x+1+1
+ *   block row k odd  (x odd) : rows 2k+1, 2k+2 shift 1 -> pairs at x+1, x+3; rows 2k, 2k+3 shift 0 -> pair at x+1
+ */
+__device__ __forceinline__ int row_shift(int g) { return ((g + 3) >> 1) & 1; }
 
 template <int TW, bool SPHERE, bool LINEAR>
 __global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
 {
     using namespace plf2;
     using GEO = NGeo<TW>;
-    constexpr int W = GEO::W, B = GEO::B, GWP = GEO::GWP, EPITCH = GEO::EPITCH;
+    constexpr int W = GEO::W, B = GEO::B, GW = GEO::GW, GWP = GEO::GWP, EPITCH = GEO::EPITCH;
     constexpr int GPAIRS = GEO::GPAIRS, XPAIRS = GEO::XPAIRS, PP = GEO::POS_PLANE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *zs = reinterpret_cast<float *>(smem_raw);                                   /* ZROWS x EPITCH */
     uint8_t *outb = reinterpret_cast<uint8_t *>(zs + GEO::ZROWS * EPITCH);              /* band staging */
-    float *px = reinterpret_cast<float *>(outb + GEO::OUT_BYTES);                      /* 3 planes of (MAX_ROWS+2) x GWP */
-    float *ulut = px + 3 * PP;                                                         /* GWP */
+    float *px = reinterpret_cast<float *>(outb + GEO::OUT_BYTES);                      /* 3 planes of POS_ROWS x GWP */
+    float *ulut = px + 3 * PP;                                                         /* u of X = -2 .. W (index X + 2) */
     __shared__ uint64_t bar;
     __shared__ pl_norm_req rq;
 
@@ -312,11 +325,14 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
         mbar_expect_tx(&bar, bytes);
         bulk_load(zs, src, bytes, &bar);
     }
-    {   /* uv / (tileSDF.x - 1.0) for X = -1 .. W (+ pad entries) */
+    {   /* uv / (tileSDF.x - 1.0) for X = -2 .. W (X = -2 is the pad of an odd-start pair) */
         const float wm1 = (float) W - 1.0f;
         const float rw = plfp::rcp_rn(wm1);
-        for (int q = tid; q < GWP; q += kThreads) ulut[q] = plfp::div_rn((float) (q - 1), wm1, rw);
+        for (int q = tid; q < GW + 3; q += kThreads) ulut[q] = plfp::div_rn((float) (q - 2), wm1, rw);
     }
+    /* an odd band's last texel block reads one grid row that does not exist: keep it finite */
+    if (rows & 1)
+        for (int q = tid; q < 3 * GWP; q += kThreads) px[(q / GWP) * PP + grows * GWP + q % GWP] = 0.0f;
     __syncthreads();
     mbar_wait(&bar, 0);
 
@@ -326,22 +342,26 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
         const float x0f = rq.deform[0], y0f = rq.deform[1];
         const float s = rq.smooth;
         for (int q = tid; q < grows * GPAIRS; q += kThreads) {
-            const int gy = q / GPAIRS, gx = 2 * (q - gy * GPAIRS);
-            /* grid points (gx - 1, Y), (gx, Y), Y = y_begin - 1 + gy: elevation texels (gx + 1, Y + 2),
-             * (gx + 2, Y + 2); staged row (Y + 2) - zr0 = gy + 1 */
-            const float *zp = zs + (gy + 1) * EPITCH + gx;
+            const int gy = q / GPAIRS;
+            const int sh = row_shift(gy);
+            const int gx = 2 * (q - gy * GPAIRS) - sh;       /* first grid column of the pair: -1, 1, .. or 0, 2, .. */
+            /* grid points gx, gx+1 (X = gx - 1, gx): elevation texels (gx + 1, Y + 2), (gx + 2, Y + 2),
+             * Y = y_begin - 1 + gy; staged row (Y + 2) - zr0 = gy + 1.  Column -1 / GW of a shifted or
+             * last pair is a pad: it reads inside the staged row and is never used. */
+            const float *row1 = zs + (gy + 1) * EPITCH, *row0 = row1 - EPITCH;
+            const int c0 = max(gx, 0), c1 = gx + 1, c2 = gx + 2;
             F2 h;
             if (!LINEAR) {
-                h = make_float2(zp[1], zp[2]);
+                h = make_float2(row1[c1], row1[c2]);
             } else {
-                const F2 t00 = *reinterpret_cast<const F2 *>(zp - EPITCH);         /* texels gx, gx+1 of the row below */
-                const F2 t10 = make_float2(t00.y, zp[-EPITCH + 2]);
-                const F2 t01 = *reinterpret_cast<const F2 *>(zp);
-                const F2 t11 = make_float2(t01.y, zp[2]);
+                const F2 t00 = make_float2(row0[c0], row0[c1]);
+                const F2 t10 = make_float2(t00.y, row0[c2]);
+                const F2 t01 = make_float2(row1[c0], row1[c1]);
+                const F2 t11 = make_float2(t01.y, row1[c2]);
                 h = fma2(bc(0.5625f), t11, fma2(bc(0.1875f), t01, fma2(bc(0.1875f), t10, mul2(bc(0.0625f), t00))));
             }
-            const F2 u = *reinterpret_cast<const F2 *>(ulut + gx);
-            const float v = ulut[y_begin + gy];
+            const F2 u = make_float2(ulut[gx + 1], ulut[gx + 2]);      /* X = gx - 1, gx */
+            const float v = ulut[y_begin + gy + 1];                    /* Y = y_begin - 1 + gy */
             F2 qx, qy, qz;
             if (!SPHERE) {
                 qx = fma2(bc(D), u, bc(x0f));
@@ -370,47 +390,64 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_fast(const NormArgs a)
                 qz = fma2(hp, upz, ROW4(rq.corners, 2));
 #undef ROW4
             }
-            float *o = px + gy * GWP + gx;
-            *reinterpret_cast<F2 *>(o) = qx;
-            *reinterpret_cast<F2 *>(o + PP) = qy;
-            *reinterpret_cast<F2 *>(o + 2 * PP) = qz;
+            /* stored at column gx + shift + 2 (the +2 keeps the odd-start pad at a non-negative, even slot) */
+            float *o3 = px + gy * GWP + gx + sh + 2;
+            *reinterpret_cast<F2 *>(o3) = qx;
+            *reinterpret_cast<F2 *>(o3 + PP) = qy;
+            *reinterpret_cast<F2 *>(o3 + 2 * PP) = qz;
         }
     }
     __syncthreads();
 
-    /* ---- normals of the band, two texels (x, x+1) per thread ----------------- */
+    /* ---- normals of the band: a 2 x 2 block of texels per thread ------------- */
     {
         const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
         const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
-        for (int q = tid; q < rows * XPAIRS; q += kThreads) {
-            const int ry = q / XPAIRS, x = 2 * (q - ry * XPAIRS);
-            /* texel (x, y) is grid point index (x + 1) of grid row ry + 1; its neighbours are
-             * x, x + 2 (left, right) and the rows above / below */
-            const float *c = px + (ry + 1) * GWP + x;
-            F2 d[3], e[3];
+        const int brows = (rows + 1) >> 1;
+        for (int q = tid; q < brows * XPAIRS; q += kThreads) {
+            const int k = q / XPAIRS;
+            const int odd = k & 1;
+            const int x = 2 * (q - k * XPAIRS) - odd;        /* -1, 1, 3, .. on odd block rows, 0, 2, .. on even ones */
+            const int ry = 2 * k;
+            /* texel (x, ry) is grid column x + 1 of grid row ry + 1.  Centre rows g1 = ry+1, g2 = ry+2 have
+             * shift `odd`; outer rows g0 = ry, g3 = ry+3 have shift 1 - odd.  Stored column = grid column + shift + 2. */
+            const float *c1 = px + (ry + 1) * GWP + x + odd + 2;          /* grid column x of row g1 (aligned) */
+            const float *c0 = px + ry * GWP + (x + 1) + (1 - odd) + 2;    /* grid column x+1 of row g0 (aligned) */
+            F2 d1[3], e1[3], d2[3], e2[3];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float *ck = c + k * PP;
-                const F2 pl = *reinterpret_cast<const F2 *>(ck);            /* grid x, x+1 */
-                const F2 pr = *reinterpret_cast<const F2 *>(ck + 2);        /* grid x+2, x+3 */
-                const F2 pd = make_float2(ck[1 - GWP], ck[2 - GWP]);
-                const F2 pu = make_float2(ck[1 + GWP], ck[2 + GWP]);
-                d[k] = sub2(pr, pl);
-                e[k] = sub2(pu, pd);
+            for (int cpt = 0; cpt < 3; ++cpt) {
+                const F2 l1 = *reinterpret_cast<const F2 *>(c1 + cpt * PP);                 /* g1: x, x+1 */
+                const F2 r1 = *reinterpret_cast<const F2 *>(c1 + cpt * PP + 2);             /* g1: x+2, x+3 */
+                const F2 l2 = *reinterpret_cast<const F2 *>(c1 + cpt * PP + GWP);           /* g2: x, x+1 */
+                const F2 r2 = *reinterpret_cast<const F2 *>(c1 + cpt * PP + GWP + 2);       /* g2: x+2, x+3 */
+                const F2 m0 = *reinterpret_cast<const F2 *>(c0 + cpt * PP);                 /* g0: x+1, x+2 */
+                const F2 m3 = *reinterpret_cast<const F2 *>(c0 + cpt * PP + 3 * GWP);       /* g3: x+1, x+2 */
+                const F2 m1 = make_float2(l1.y, r1.x), m2 = make_float2(l2.y, r2.x);        /* g1, g2: x+1, x+2 */
+                d1[cpt] = sub2(r1, l1);   /* texel row ry:   right - left */
+                d2[cpt] = sub2(r2, l2);   /* texel row ry+1 */
+                e1[cpt] = sub2(m2, m0);   /* texel row ry:   up - down */
+                e2[cpt] = sub2(m3, m1);   /* texel row ry+1 */
             }
-            F2 nx = fma2(d[1], e[2], neg(mul2(d[2], e[1])));
-            F2 ny = fma2(d[2], e[0], neg(mul2(d[0], e[2])));
-            F2 nz = fma2(d[0], e[1], neg(mul2(d[1], e[0])));
-            const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
-            nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
-            const F2 tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
-            const F2 ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
-            /* unorm8: round(clamp(v, 0, 1) * 255), NaN -> 0 */
-            const F2 r = mul2(clamp2(fma2(tx, bc(0.5f), bc(0.5f)), 0.0f, 1.0f), bc(255.0f));
-            const F2 g = mul2(clamp2(fma2(ty, bc(0.5f), bc(0.5f)), 0.0f, 1.0f), bc(255.0f));
-            unsigned short *o = reinterpret_cast<unsigned short *>(outb) + ry * W + x;
-            o[0] = (unsigned short) (__float2int_rn(r.x) | (__float2int_rn(g.x) << 8));
-            if (x + 1 < W) o[1] = (unsigned short) (__float2int_rn(r.y) | (__float2int_rn(g.y) << 8));
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const F2 *d = half ? d2 : d1, *e = half ? e2 : e1;
+                F2 nx = fma2(d[1], e[2], neg(mul2(d[2], e[1])));
+                F2 ny = fma2(d[2], e[0], neg(mul2(d[0], e[2])));
+                F2 nz = fma2(d[0], e[1], neg(mul2(d[1], e[0])));
+                const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
+                nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
+                const F2 tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
+                const F2 ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
+                /* unorm8: round(clamp(v, 0, 1) * 255), NaN -> 0 */
+                const F2 r = mul2(clamp2(fma2(tx, bc(0.5f), bc(0.5f)), 0.0f, 1.0f), bc(255.0f));
+                const F2 g = mul2(clamp2(fma2(ty, bc(0.5f), bc(0.5f)), 0.0f, 1.0f), bc(255.0f));
+                const int yy = ry + half;
+                if (yy < rows) {
+                    unsigned short *o = reinterpret_cast<unsigned short *>(outb) + yy * W + x;
+                    if (x >= 0) o[0] = (unsigned short) (__float2int_rn(r.x) | (__float2int_rn(g.x) << 8));
+                    if (x + 1 < W) o[1] = (unsigned short) (__float2int_rn(r.y) | (__float2int_rn(g.y) << 8));
+                }
+            }
         }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
