@@ -244,6 +244,17 @@ int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *bl
                              const int32_t *widths, const int32_t *out_slots,
                              const int32_t *add_slots, float scale);
 
+/* A slot argument of the residual entry points may be PL_SLOT_SCRATCH: the hidden extra slot every
+ * F32 residual pool carries (the `tmp` array of ResidualProducer::doCreateTile,
+ * ResidualProducer.cpp:219). */
+#define PL_SLOT_SCRATCH (-2)
+
+/* ResidualProducer::upsample (ResidualProducer.cpp:342-384): dst = the (tile_size + 5)^2 tile of root
+ * level `level` (tile_size = getTileSize(level)) upsampled from the quadrant (tx%2, ty%2) of the parent
+ * tile in src, in the reference's CPU evaluation order.  Both slots are in the same F32 pool. */
+int pl_residual_upsample(pl_ctx *ctx, pl_pool *pool, int src_slot, int dst_slot, int tile_size,
+                         int tx, int ty);
+
 #ifdef __cplusplus
 }
 #endif

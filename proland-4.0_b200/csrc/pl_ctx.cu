@@ -259,16 +259,19 @@ extern "C" int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, p
         p->slot_bytes = (size_t) pl_round_up(tile_w * p->pitch * 2, 128);
         break;
     }
-    cudaError_t e = cudaMalloc(&p->base, p->slot_bytes * capacity);
+    /* F32 residual pools carry one hidden scratch slot (index capacity, PL_SLOT_SCRATCH): the
+     * temporary of the root-level composition, ResidualProducer.cpp:218-228 */
+    const size_t nslots = (size_t) capacity + (kind == PL_POOL_RESID_F32 ? 1 : 0);
+    cudaError_t e = cudaMalloc(&p->base, p->slot_bytes * nslots);
     if (e != cudaSuccess) {
-        const size_t want = p->slot_bytes * capacity;
+        const size_t want = p->slot_bytes * nslots;
         delete p;
         cudaGetLastError();
         return pl_set_error(PL_ERR_POOL_FULL, "cudaMalloc of %zu bytes for %d slots failed: %s", want, capacity,
                             cudaGetErrorString(e));
     }
     /* pad columns / bytes are part of whole-sector writes later; start from zero */
-    PL_CUDA(cudaMemsetAsync(p->base, 0, p->slot_bytes * capacity, ctx->stream));
+    PL_CUDA(cudaMemsetAsync(p->base, 0, p->slot_bytes * nslots, ctx->stream));
 
     if (kind == PL_POOL_ELEV_F32x3) {
         PL_CUDA(cudaMalloc(&p->stats, sizeof(float2) * capacity));

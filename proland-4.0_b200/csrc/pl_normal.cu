@@ -48,7 +48,9 @@ struct NormArgs {
     int border;
     int linear;              /* elevation storage filter */
     int sphere;
-    int channels;            /* 2 (RG8) */
+    int channels;            /* 2 (RG8) or 4 (RGBA8: fine + coarse normal) */
+    int grid;                /* tileSDF.y */
+    int parent_linear;       /* normal storage filter (parent coarse normal fetch) */
     int nbands, max_rows;    /* bands per tile, rows of the largest band */
     long long norm_slot_bytes;
 };
@@ -102,6 +104,26 @@ __device__ __forceinline__ unsigned int unorm8(float f)
     if (!(f > 0.0f)) return 0u;
     if (f >= 1.0f) return 255u;
     return (unsigned int) __float2int_rn(f * 255.0f);
+}
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+/* .xy of the parent's RGBA8 normal tile at texel coordinate (cx, cy) (already offset by +0.25,
+ * NormalProducer.cpp:201-205) through the normal storage's filter; unorm8 -> float is c / 255
+ * (OpenGL 3.3 spec 2.1.5), CLAMP_TO_EDGE */
+__device__ __forceinline__ float2 fetch_parent_xy(const uchar4 *parent, int W, bool linear, float cx, float cy)
+{
+    auto PN = [&](int i, int j) {
+        const uchar4 t = __ldg(parent + min(max(j, 0), W - 1) * W + min(max(i, 0), W - 1));
+        return make_float2((float) t.x / 255.0f, (float) t.y / 255.0f);
+    };
+    if (!linear) return PN((int) floorf(cx), (int) floorf(cy));
+    const float fx = cx - 0.5f, fy = cy - 0.5f;
+    const int i0 = (int) floorf(fx), j0 = (int) floorf(fy);
+    const float fa = fx - (float) i0, fb = fy - (float) j0;
+    const float2 t00 = PN(i0, j0), t10 = PN(i0 + 1, j0), t01 = PN(i0, j0 + 1), t11 = PN(i0 + 1, j0 + 1);
+    const float w11 = fa * fb, w01 = (1.0f - fa) * fb, w10 = fa * (1.0f - fb), w00 = (1.0f - fa) * (1.0f - fb);
+    return make_float2(fmaf(w11, t11.x, fmaf(w01, t01.x, fmaf(w10, t10.x, w00 * t00.x))),
+                       fmaf(w11, t11.y, fmaf(w01, t01.y, fmaf(w10, t10.y, w00 * t00.y))));
 }
 
 /* ------------------------------------------------------------------------
@@ -223,7 +245,32 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_generic(const NormArgs
         const float tx = dot3(rq.w2t[0], rq.w2t[1], rq.w2t[2], nx, ny, nz);
         const float ty = dot3(rq.w2t[3], rq.w2t[4], rq.w2t[5], nx, ny, nz);
         const unsigned int r8 = unorm8(fmaf(tx, 0.5f, 0.5f)), g8 = unorm8(fmaf(ty, 0.5f, 0.5f));
-        reinterpret_cast<uchar2 *>(outb)[k] = make_uchar2((unsigned char) r8, (unsigned char) g8);
+        if (C == 2) {
+            reinterpret_cast<uchar2 *>(outb)[k] = make_uchar2((unsigned char) r8, (unsigned char) g8);
+        } else {
+            /* RGBA8 (tileSDF.z = 1): .zw = the parent's coarse normal, normalShader.glsl:100-114 */
+            float ncx = tx, ncy = ty;
+            if (rq.parent_slot >= 0) {
+                const uchar4 *parent = reinterpret_cast<const uchar4 *>(a.norm + (size_t) rq.parent_slot * a.norm_slot_bytes);
+                const int g = a.grid, y = y_begin + ry;
+                const float offx = (float) rq.ptx * ((float) W / 2.0f) + 0.25f, offy = (float) rq.pty * ((float) W / 2.0f) + 0.25f;
+                const float2 nc0 = fetch_parent_xy(parent, W, a.parent_linear != 0, (float) (g * floordiv(x + g, 2 * g)) + offx,
+                                                   (float) (g * floordiv(y, 2 * g)) + offy);
+                const float2 nc1 = fetch_parent_xy(parent, W, a.parent_linear != 0, (float) (g * floordiv(x, 2 * g)) + offx,
+                                                   (float) (g * floordiv(y + g, 2 * g)) + offy);
+                ncx = fmaf((nc0.x + nc1.x) * 0.5f, 2.0f, -1.0f);
+                ncy = fmaf((nc0.y + nc1.y) * 0.5f, 2.0f, -1.0f);
+                if (sphere) {
+                    const float ncz = sqrtf(1.0f - fmaf(ncy, ncy, ncx * ncx));
+                    const float qx = dot3(rq.p2t[0], rq.p2t[1], rq.p2t[2], ncx, ncy, ncz);
+                    const float qy = dot3(rq.p2t[3], rq.p2t[4], rq.p2t[5], ncx, ncy, ncz);
+                    ncx = qx;
+                    ncy = qy;
+                }
+            }
+            const unsigned int b8 = unorm8(fmaf(ncx, 0.5f, 0.5f)), a8 = unorm8(fmaf(ncy, 0.5f, 0.5f));
+            reinterpret_cast<uchar4 *>(outb)[k] = make_uchar4((unsigned char) r8, (unsigned char) g8, (unsigned char) b8, (unsigned char) a8);
+        }
     }
     /* generic-proxy writes -> visible to the bulk (async proxy) store */
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -466,8 +513,8 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
                      const pl_norm_req *dev_reqs)
 {
     PL_CUDA(cudaSetDevice(ctx->device));
-    if (norm->kind != PL_POOL_NORM_UN8x2)
-        return pl_set_error(PL_ERR_ARG, "only RG8 normal pools are implemented (every shipped archive uses RG8)");
+    if (norm->kind != PL_POOL_NORM_UN8x2 && norm->kind != PL_POOL_NORM_UN8x4)
+        return pl_set_error(PL_ERR_ARG, "normal pool must be RG8 or RGBA8");
     NormArgs a;
     a.elev = reinterpret_cast<const float *>(elev->base);
     a.norm = norm->base;
@@ -479,14 +526,16 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
     a.border = sc->elev_border;
     a.linear = sc->elev_filter == PL_FILTER_LINEAR;
     a.sphere = sc->sphere;
-    a.channels = 2;
+    a.channels = norm->kind == PL_POOL_NORM_UN8x4 ? 4 : 2;
+    a.grid = sc->grid;
+    a.parent_linear = sc->parent_filter == PL_FILTER_LINEAR;
     a.nbands = a.W / kBandRows > 0 ? a.W / kBandRows : 1;
     a.max_rows = a.W - (a.nbands - 1) * kBandRows;
     a.norm_slot_bytes = (long long) norm->slot_bytes;
     const int GW = a.W + 2;
     const size_t smem = (size_t) (a.max_rows + 3) * a.epitch * 4 + (size_t) 3 * (a.max_rows + 2) * GW * 4 +
                         (size_t) ((GW + 3) & ~3) * 4 + (size_t) ((a.max_rows * a.W * a.channels + 15) & ~15);
-    if (a.W == 97 && a.border == 2 && !ctx->force_generic) {
+    if (a.W == 97 && a.border == 2 && a.channels == 2 && !ctx->force_generic) {
         /* the geometry of every shipped archive: compile-time specialisation */
         using GEO = NGeo<97>;
         const size_t fsmem = GEO::SMEM;

@@ -412,6 +412,46 @@ __global__ void __launch_bounds__(256) residual_store_kernel(const StoreJob *job
     }
 }
 
+/* ResidualProducer::upsample (ResidualProducer.cpp:342-384): the (ts + 5)^2 tile of the next root
+ * level from the quadrant (tx%2, ty%2) of its parent, in the CPU evaluation order of the reference
+ * (NOT the GLSL mdot order): ((z1 + z2) * 9 - (z0 + z3)) / 16 on the axes, and for odd/odd texels the
+ * running sum z += (f * g) * parent over dj = -1..2 (outer), di = -1..2 (inner).  Compiled with
+ * --fmad=false: every product and sum rounds on its own, like the x86-64 SSE build of the reference. */
+__global__ void __launch_bounds__(256) residual_upsample_kernel(const float *parent, float *result, int pitch, int ts, int px, int py)
+{
+    const int w = ts + 5;
+    for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < w * w; k += blockDim.x * gridDim.x) {
+        const int j = k / w, i = k - j * w;
+        const int cx = i / 2 + px, cy = j / 2 + py;
+#define P(a, b) parent[(a) + (b) * pitch]
+        float z;
+        if (j % 2 == 0) {
+            if (i % 2 == 0) {
+                z = P(cx, cy);
+            } else {
+                const float z0 = P(cx - 1, cy), z1 = P(cx, cy), z2 = P(cx + 1, cy), z3 = P(cx + 2, cy);
+                z = ((z1 + z2) * 9.0f - (z0 + z3)) / 16.0f;
+            }
+        } else {
+            if (i % 2 == 0) {
+                const float z0 = P(cx, cy - 1), z1 = P(cx, cy), z2 = P(cx, cy + 1), z3 = P(cx, cy + 2);
+                z = ((z1 + z2) * 9.0f - (z0 + z3)) / 16.0f;
+            } else {
+                z = 0.0f;
+                for (int dj = -1; dj <= 2; ++dj) {
+                    const float f = (dj == -1 || dj == 2) ? -1 / 16.0f : 9 / 16.0f;
+                    for (int di = -1; di <= 2; ++di) {
+                        const float g = (di == -1 || di == 2) ? -1 / 16.0f : 9 / 16.0f;
+                        z = z + (f * g) * P(cx + di, cy + dj);
+                    }
+                }
+            }
+        }
+#undef P
+        result[i + j * pitch] = z;
+    }
+}
+
 inline unsigned int rd16(const uint8_t *p) { return (unsigned int) p[0] | ((unsigned int) p[1] << 8); }
 inline unsigned int rd32(const uint8_t *p) { return rd16(p) | (rd16(p + 2) << 16); }
 
@@ -476,15 +516,17 @@ extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const 
     int max_w = 0;
     for (int j = 0; j < n; ++j) {
         if (widths[j] < 1 || widths[j] > out->tile_w) return pl_set_error(PL_ERR_ARG, "tile %d: width %d exceeds the pool tile", j, widths[j]);
-        if (out_slots[j] < 0 || out_slots[j] >= out->capacity || (add_slots && add_slots[j] >= out->capacity))
+        const int os = out_slots[j] == PL_SLOT_SCRATCH ? out->capacity : out_slots[j];
+        const int as = !add_slots ? -1 : (add_slots[j] == PL_SLOT_SCRATCH ? out->capacity : add_slots[j]);
+        if (os < 0 || os > out->capacity || as > out->capacity || (os == out->capacity && out->kind != PL_POOL_RESID_F32))
             return pl_set_error(PL_ERR_ARG, "tile %d: slot out of range", j);
         packed_off[j] = total;
         total += ((uint64_t) sizes[j] + 7) & ~7ull;
         const int rc = parse_tiff(blobs + offsets[j], sizes[j], widths[j], &jobs[j], packed_off[j]);
         if (rc) return pl_set_error(PL_ERR_CORRUPT, "tile %d: not a single-strip 16-bit TIFF blob (code %d)", j, rc);
         sjobs[j].width = widths[j];
-        sjobs[j].out_slot = out_slots[j];
-        sjobs[j].add_slot = add_slots ? add_slots[j] : -1;
+        sjobs[j].out_slot = os;
+        sjobs[j].add_slot = as < 0 ? -1 : as;
         if (widths[j] > max_w) max_w = widths[j];
     }
     const size_t dense_stride = ((size_t) max_w * max_w * 2 + 15) & ~(size_t) 15;
@@ -535,5 +577,29 @@ extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const 
             if (status[j] != INF_OK)
                 return pl_set_error(PL_ERR_CORRUPT, "tile %d: DEFLATE stream is corrupt (inflate code %d)", j, status[j]);
     }
+    return PL_OK;
+}
+
+extern "C" int pl_residual_upsample(pl_ctx *ctx, pl_pool *pool, int src_slot, int dst_slot, int tile_size, int tx, int ty)
+{
+    if (!ctx || !pool) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (pool->kind != PL_POOL_RESID_F32) return pl_set_error(PL_ERR_ARG, "pl_residual_upsample needs an F32 residual pool");
+    const int src = src_slot == PL_SLOT_SCRATCH ? pool->capacity : src_slot;
+    const int dst = dst_slot == PL_SLOT_SCRATCH ? pool->capacity : dst_slot;
+    if (src < 0 || src > pool->capacity || dst < 0 || dst > pool->capacity || src == dst)
+        return pl_set_error(PL_ERR_ARG, "pl_residual_upsample: slots %d -> %d", src_slot, dst_slot);
+    /* parent reads span [px - 1, (ts + 4) / 2 + px + 2]: inside the parent tile for ts <= tile_w - 5 */
+    if (tile_size < 2 || tile_size % 2 != 0 || tile_size + 5 > pool->tile_w || tx < 0 || ty < 0)
+        return pl_set_error(PL_ERR_ARG, "pl_residual_upsample: tile size %d does not fit a %d pool", tile_size, pool->tile_w);
+    PL_CUDA(cudaSetDevice(ctx->device));
+    const int px = 1 + (tx % 2) * tile_size / 2, py = 1 + (ty % 2) * tile_size / 2;
+    const float *parent = reinterpret_cast<const float *>(pool->base + (size_t) src * pool->slot_bytes);
+    float *result = reinterpret_cast<float *>(pool->base + (size_t) dst * pool->slot_bytes);
+    const int w = tile_size + 5;
+    pl_timing_begin(ctx, PL_K_RESIDUAL, 1);
+    residual_upsample_kernel<<<(w * w + 255) / 256, 256, 0, ctx->stream>>>(parent, result, pool->pitch, tile_size, px, py);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
     return PL_OK;
 }

@@ -1,0 +1,80 @@
+/*
+ * proland_host.h -- flat C view of the C++ host layer (namespace proland:
+ * TileStorage / TileCache / TileProducer / Elevation-, Normal-, ResidualProducer /
+ * ResourceManager / BatchScheduler), used by the Python tests, bench.py and tools
+ * through ctypes.  Handles are opaque pointers to the C++ objects.  Functions
+ * returning int give 0 on success, -1 on error (text in plh_last_error());
+ * functions returning a handle give NULL on error.
+ */
+#ifndef PROLAND_HOST_H
+#define PROLAND_HOST_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char *plh_last_error(void);
+
+/* resources of an XML archive (ResourceManager) */
+void *plh_open(const char *xml, const char *data_dir, int device);
+void plh_close(void *mgr);
+void plh_shutdown(void);
+void *plh_producer(void *mgr, const char *name);
+void *plh_cache(void *mgr, const char *name);
+void *plh_scheduler(void *mgr, const char *name);
+void *plh_producer_cache(void *prod);
+void *plh_cache_scheduler(void *cache);
+
+/* TileProducer */
+void plh_set_root_quad_size(void *prod, float size);
+int plh_producer_info(void *prod, int out[6]);   /* id, border, gpu, tile size, #referenced producers, root quad size */
+const char *plh_producer_type(void *prod);
+const char *plh_producer_task_type(void *prod);
+int plh_has_tile(void *prod, int level, int tx, int ty);
+int plh_has_children(void *prod, int level, int tx, int ty);
+void *plh_get_tile(void *prod, int level, int tx, int ty, unsigned int deadline);
+void *plh_find_tile(void *prod, int level, int tx, int ty, int include_cache, int done);
+int plh_put_tile(void *prod, void *tile);
+int plh_prefetch_tile(void *prod, int level, int tx, int ty);
+void plh_invalidate_tiles(void *prod);
+void plh_invalidate_tile(void *prod, int level, int tx, int ty);
+int plh_producer_counts(void *prod, unsigned long long out[2]);   /* tiles made, batches launched */
+
+/* TileCache::Tile */
+int plh_tile_done(void *tile);
+int plh_tile_slot(void *tile);
+int plh_tile_download(void *tile, void *buf, size_t bytes);
+int plh_tile_minmax(void *prod, void *tile, float out[2]);
+
+/* Scheduler::run over the tasks of n tiles */
+int plh_run(void *scheduler, void **tiles, int n);
+int plh_cache_stats(void *cache, int out[6]);   /* used, unused, capacity, free slots, queries, misses */
+int plh_scheduler_stats(void *scheduler, unsigned long long out[4]);   /* frame, waves, tasks, queued prefetches */
+
+/* ResidualProducer file arithmetic */
+int plh_residual_info(void *prod, int out[3]);   /* minLevel, maxLevel, deltaLevel */
+int plh_residual_tile_id(void *prod, int level, int tx, int ty);
+int plh_residual_tile_size(void *prod, int level);
+
+unsigned long long plh_device_launches(int device);
+int plh_device_sync(int device);
+void plh_debug_log(int on, int echo);
+unsigned long plh_debug_log_lines(void);
+void plh_quiet_errors(int quiet);
+int plh_upsample_variant(const char *prog, int out[2]);
+
+/* CPU-only scene with a recording producer (cache / task / scheduler logic without a device) */
+void *plh_test_scene(int capacity, int tile_size, int max_level, int prefetch_rate, int prefetch_queue);
+void plh_test_scene_close(void *scene);
+void *plh_test_producer(void *scene);
+void *plh_test_cache(void *scene);
+void *plh_test_scheduler(void *scene);
+int plh_test_calls(void *scene, int *out, int max_calls);
+int plh_test_begin_end(void *scene, int out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

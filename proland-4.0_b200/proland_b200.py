@@ -29,7 +29,7 @@ EXPORTS = [
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_fpexact",
-    "pl_residual_decode_batch",
+    "pl_residual_decode_batch", "pl_residual_upsample",
 ]
 
 
@@ -150,6 +150,7 @@ def lib():
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+        L.pl_residual_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
         L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -409,7 +410,13 @@ def _residual_decode(self, pool, blobs, widths, out_slots, add_slots=None, scale
                                          C.c_float(scale)))
 
 
+def _residual_upsample(self, pool, src_slot, dst_slot, tile_size, tx=0, ty=0):
+    check(lib().pl_residual_upsample(self.h, pool.h, src_slot, dst_slot, tile_size, tx, ty))
+
+
+SLOT_SCRATCH = -2
 Context.residual_decode = _residual_decode
+Context.residual_upsample = _residual_upsample
 Context.force_generic = _force_generic
 Context.fpexact = _fpexact
 Context.timing_enable = _timing_enable

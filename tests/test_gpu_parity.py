@@ -248,3 +248,68 @@ def test_elevation_with_residuals(plb, ctx, oracle, kind):
     for t, (e, n) in ref.items():
         assert np.array_equal(elev.download(slot_of[t]), e), t
         assert np.array_equal(norm.download(slot_of[t]), n), t
+
+
+@pytest.mark.parametrize("sphere,parent_filter", [(0, 1), (1, 1), (1, 0)])
+def test_rgba8_normals_with_parent_coarse_normal(plb, ctx, oracle, sphere, parent_filter):
+    """4-channel normal storages (tileSDF.z = 1, normalShader.glsl:100-119): .zw = the parent
+    tile's normal at the coarse mesh vertices, rotated by parentToTangentFrame on a sphere."""
+    W, rq = 101, 12720000.0 if sphere else 100000.0
+    amp = PLANET if sphere else FRACTAL
+    tiles = [t for l in range(3) for t in qt.level_tiles(l)]
+    slot = {t: i for i, t in enumerate(tiles)}
+    elev = ctx.pool(plb.POOL_ELEV, W, len(tiles))
+    norm = ctx.pool(plb.POOL_NORM4, W - 4, len(tiles))
+    ctx.noise_init(W)
+    es = plb.elev_scene(W, 24, 0, 1, 0, 0)
+    ns = plb.norm_scene(W - 4, 24, 2, 1, parent_filter, sphere)
+    for level in range(3):
+        lt = qt.level_tiles(level)
+        reqs = plb.elev_make_reqs(lt, tile_w=W, root_quad_size=rq, noise_amp=amp, face=3 if sphere else 0)
+        nreqs = plb.norm_make_reqs(lt, ns, root_quad_size=rq, components=4)
+        for i, t in enumerate(lt):
+            reqs["out_slot"][i] = nreqs["out_slot"][i] = nreqs["elev_slot"][i] = slot[t]
+            if level > 0:
+                reqs["parent_slot"][i] = nreqs["parent_slot"][i] = slot[(level - 1, t[1] // 2, t[2] // 2)]
+        ctx.elevation_batch(es, elev, reqs)
+        ctx.normal_batch(ns, norm, elev, nreqs)
+    ctx.sync()
+    ref = {}
+    for t in tiles:
+        level, tx, ty = t
+        e = elev.download(slot[t])
+        p = oracle.normal_uniforms(level, tx, ty, components=4, parent_filter=parent_filter, rootQuadSize=rq, sphere=sphere)
+        parent = None
+        if level > 0:   # what the GL sampler returns for the parent's RGBA8 texels: c / 255
+            parent = ref[(level - 1, tx // 2, ty // 2)].astype(np.float32) / np.float32(255.0)
+        ref[t] = oracle.pack_unorm8(oracle.normal_tile(p, e, parent), 4)
+        got = norm.download(slot[t])
+        assert np.array_equal(got, ref[t]), "tile %r: %d bytes differ" % (t, np.count_nonzero(got != ref[t]))
+    # the coarse channels really differ from the fine ones below the root
+    deep = ref[(2, 1, 2)]
+    assert np.count_nonzero(deep[..., 2:] != deep[..., :2]) > 1000
+
+
+@pytest.mark.parametrize("delta", [1, 2, 3])
+def test_residual_root_composition_delta(plb, ctx, oracle, delta):
+    """ResidualProducer.cpp:218-228 + upsample (:342-384): with delta > 0 the root tile is the stored
+    level-0 tile upsampled `delta` times, each time adding the stored residual of that level
+    (earth-srtm.xml: delta="2"; DEM.dat geometry: minLevel 3, tileSize 192 -> 29, 53, 101, 197)"""
+    data, _ = rs.container(min_level=3, max_level=4, tile_size=192, scale=0.25, seed=77 + delta)
+    res = oracle.Resid(data, delta=delta)
+    want = res.create_tile(0, 0, 0)                      # stored level `delta`, composed
+    pool = ctx.pool(plb.POOL_RESID_F32, 197, 2)
+    pool.upload(0, np.full((197, 197), 7.0, np.float32))   # stale content must not leak in
+    ctx.residual_decode(pool, [res.blob(0)], [res.tile_size(0) + 5], [0], scale=0.25)
+    for i in range(1, delta + 1):
+        ts = res.tile_size(i)
+        ctx.residual_upsample(pool, 0, plb.SLOT_SCRATCH, ts)
+        ctx.residual_decode(pool, [res.blob(res.tile_id(i, 0, 0))], [ts + 5], [0], add_slots=[plb.SLOT_SCRATCH], scale=0.25)
+    w = res.tile_size(delta) + 5
+    got = pool.download(0)
+    assert np.array_equal(got[:w, :w], want[:w, :w])
+    assert np.abs(want[:w, :w]).max() > 10
+    with pytest.raises(plb.PlError):
+        ctx.residual_upsample(pool, 0, 0, 96)            # in place is not defined
+    with pytest.raises(plb.PlError):
+        ctx.residual_upsample(pool, 0, 1, 194)           # does not fit the pool
