@@ -58,7 +58,7 @@ protected:
         if (level > 0) {
             TileCache::Tile *t = getTile(level - 1, tx / 2, ty / 2, deadline);
             if (t == NULL) {
-                throw std::runtime_error("Insufficient tile cache size");
+                cacheFull("RecordingProducer");
             }
             result->addTask(t->task);
             result->addDependency(task, t->task);

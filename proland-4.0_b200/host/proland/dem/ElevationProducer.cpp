@@ -95,17 +95,23 @@ ptr<Task> ElevationProducer::startCreateTile(int level, int tx, int ty, unsigned
                                              ptr<TaskGraph> owner)
 {
     ptr<TaskGraph> result = owner == NULL ? createTaskGraph(task) : owner;
+    TileCache::Tile *parentTile = NULL;
     if (level > 0) {
-        TileCache::Tile *t = getTile(level - 1, tx / 2, ty / 2, deadline);
-        assert(t != NULL);
-        result->addTask(t->task);
-        result->addDependency(task, t->task);
+        parentTile = getTile(level - 1, tx / 2, ty / 2, deadline);
+        if (parentTile == NULL) {
+            cacheFull("ElevationProducer");
+        }
+        result->addTask(parentTile->task);
+        result->addDependency(task, parentTile->task);
     }
     if (residualTiles != NULL) {
         const int mod = residualMod();
         if (residualTiles->hasTile(level, tx / mod, ty / mod)) {
             TileCache::Tile *t = residualTiles->getTile(level, tx / mod, ty / mod, deadline);
-            assert(t != NULL);
+            if (t == NULL) {
+                if (parentTile != NULL) putTile(parentTile);
+                cacheFull("ResidualProducer");
+            }
             result->addTask(t->task);
             result->addDependency(task, t->task);
         }

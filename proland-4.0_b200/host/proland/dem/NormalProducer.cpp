@@ -79,14 +79,26 @@ ptr<Task> NormalProducer::startCreateTile(int level, int tx, int ty, unsigned in
                                           ptr<TaskGraph> owner)
 {
     ptr<TaskGraph> result = owner == NULL ? createTaskGraph(task) : owner;
+    TileCache::Tile *parentTile = NULL;
     if (level > 0) {
-        TileCache::Tile *t = getTile(level - 1, tx / 2, ty / 2, deadline);
-        assert(t != NULL);
-        result->addTask(t->task);
-        result->addDependency(task, t->task);
+        parentTile = getTile(level - 1, tx / 2, ty / 2, deadline);
+        if (parentTile == NULL) {
+            cacheFull("NormalProducer");
+        }
+        result->addTask(parentTile->task);
+        result->addDependency(task, parentTile->task);
     }
-    TileCache::Tile *t = elevationTiles->getTile(level, tx, ty, deadline);
-    assert(t != NULL);
+    TileCache::Tile *t = NULL;
+    try {
+        t = elevationTiles->getTile(level, tx, ty, deadline);
+    } catch (...) {
+        if (parentTile != NULL) putTile(parentTile);
+        throw;
+    }
+    if (t == NULL) {
+        if (parentTile != NULL) putTile(parentTile);
+        cacheFull("ElevationProducer");
+    }
     result->addTask(t->task);
     result->addDependency(task, t->task);
     return result;

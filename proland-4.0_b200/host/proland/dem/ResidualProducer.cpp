@@ -101,7 +101,7 @@ void ResidualProducer::init(ptr<TileCache> cache, const char *name, int deltaLev
             throw std::invalid_argument("ResidualProducer: the storage tile size must be the file's tile size + 5");
         }
     }
-    assert(this->deltaLevel <= minLevel);
+    assert(fileData == NULL || this->deltaLevel <= minLevel);
 }
 
 ResidualProducer::~ResidualProducer()

@@ -141,7 +141,13 @@ ptr<Task> TileCache::makeTask(int producerId, const Tile::TId &id, int level, in
         task = d->second;
         deletedTiles.erase(d);
     }
-    return producers[producerId]->createTile(level, tx, ty, data, deadline, task);
+    try {
+        return producers[producerId]->createTile(level, tx, ty, data, deadline, task);
+    } catch (...) {
+        /* the tile's inputs could not be acquired: the slot goes back, the error to the caller */
+        storage->deleteSlot(data);
+        throw;
+    }
 }
 
 void TileCache::rerun(ptr<Task> task, Task::reason r, unsigned int deadline)
@@ -183,7 +189,15 @@ TileCache::Tile *TileCache::getTile(int producerId, int level, int tx, int ty, u
             usedTiles.insert(std::make_pair(id, t));
             if (reused) {
                 /* the data is gone but the task survived: it must run again (TileCache.cpp:224-233) */
-                rerun(t->task, Task::DATA_NEEDED, deadline);
+                try {
+                    rerun(t->task, Task::DATA_NEEDED, deadline);
+                } catch (...) {
+                    /* restarting the task could not re-acquire its inputs (cache full): the tile stays in
+                     * the cache, unused, its task not done; the error goes to the caller */
+                    usedTiles.erase(id);
+                    unusedTiles[id] = unusedTilesOrder.insert(unusedTilesOrder.end(), t);
+                    throw;
+                }
             }
         }
         if (Logger::DEBUG_LOGGER != NULL) {

@@ -17,6 +17,7 @@
 #include <list>
 #include <map>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -29,6 +30,13 @@ namespace proland
 {
 
 class TileProducer;
+
+/* getTile found no free slot and no unused tile to evict while acquiring the inputs of a tile */
+class CacheFullError : public std::runtime_error
+{
+public:
+    CacheFullError(const std::string &what) : std::runtime_error(what) {}
+};
 
 PROLAND_API class TileCache : public Object
 {
@@ -111,6 +119,13 @@ private:
     void createTileTaskDeleted(int producerId, int level, int tx, int ty);
 
     friend class TileProducer;
+
+/* getTile found no free slot and no unused tile to evict while acquiring the inputs of a tile */
+class CacheFullError : public std::runtime_error
+{
+public:
+    CacheFullError(const std::string &what) : std::runtime_error(what) {}
+};
     friend class CreateTile;
 };
 

@@ -72,7 +72,7 @@ public:
         if (parent != NULL) {
             parent->clearDependencies();
         }
-        owner->startCreateTile(level, tx, ty, getDeadline(), this, parent);
+        owner->startCreateTile(level, tx, ty, getDeadline(), this, parent);   /* may throw: nothing acquired then */
         if (parent != NULL) {
             /* tasks nobody needs any more (inputs of a previous incarnation) leave the graph */
             TaskGraph::TaskIterator i = parent->getLastTasks();
@@ -390,7 +390,13 @@ ptr<Task> TileProducer::createTile(int level, int tx, int ty, TileStorage::Slot 
         return old;
     }
     ptr<CreateTile> t = new CreateTile(this, level, tx, ty, data, deadline);
-    ptr<Task> r = startCreateTile(level, tx, ty, deadline, t, NULL);
+    ptr<Task> r;
+    try {
+        r = startCreateTile(level, tx, ty, deadline, t, NULL);
+    } catch (...) {
+        t->initialized = false;   /* startCreateTile released what it had acquired */
+        throw;
+    }
     std::lock_guard<std::mutex> lock(mutex);
     tasks.push_back(t.get());
     if (r.get() != t.get()) {
@@ -409,6 +415,15 @@ ptr<TaskGraph> TileProducer::createTaskGraph(ptr<Task> task)
     r->root = t.get();
     t->parent = r.get();
     return r;
+}
+
+void TileProducer::cacheFull(const char *producerType)
+{
+    const std::string msg = std::string("Insufficient tile cache size (") + producerType + ")";
+    if (Logger::ERROR_LOGGER != NULL) {
+        Logger::ERROR_LOGGER->log("CACHE", msg);
+    }
+    throw CacheFullError(msg);
 }
 
 void TileProducer::removeCreateTile(Task *t)

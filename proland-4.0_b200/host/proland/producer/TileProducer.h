@@ -73,6 +73,11 @@ protected:
 
     void removeCreateTile(Task *t);
     ptr<TaskGraph> createTaskGraph(ptr<Task> task);
+    /* A tile this one is made from could not be acquired: TileCache::getTile returned NULL.  The
+     * reference asserts here and logs "Insufficient tile cache size" in TileSampler
+     * (terrain/TileSampler.cpp:441-444); here the message is logged and CacheFullError thrown.
+     * startCreateTile must have released what it had acquired before calling this. */
+    static void cacheFull(const char *producerType);
 
     friend class CreateTile;
     friend class CreateTileTaskGraph;

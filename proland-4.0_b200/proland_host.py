@@ -250,8 +250,11 @@ class Scene:
     def __enter__(self):
         return self
 
-    def __exit__(self, *a):
-        self.close()
+    def __exit__(self, exc_type, *a):
+        # closing a scene whose tiles are still in use is an assertion failure (TileCache.cpp:113-117);
+        # when the block is left by an exception the scene is leaked so that the exception is what is seen
+        if exc_type is None:
+            self.close()
 
     def producer(self, name, channels=2):
         h = lib().plh_producer(self.h, name.encode())

@@ -56,8 +56,10 @@ def check_against(ref, normals, elevations, tiles):
 
 
 def test_fractalterrain_archive_levels_0_3(ph, oracle):
-    """config 1 through the plugin surface; one kernel launch per producer per quadtree level"""
-    ref = qt.oracle_quadtree(oracle, 3, noise_amp=FRACTAL)
+    """config 1 through the plugin surface; one kernel launch per producer per quadtree level.
+    As in the reference's fractalterrain.xml the producer is called groundElevations1, and a name
+    ending in 1..6 selects that cube face's noise lattice (ElevationProducer.cpp:503-509): face 1."""
+    ref = qt.oracle_quadtree(oracle, 3, noise_amp=FRACTAL, face=1)
     with ph.Scene(terrain_archive()) as scene:
         normals, elevations = scene.producer("groundNormals1"), scene.producer("groundElevations1")
         assert (elevations.type, elevations.task_type) == ("ElevationProducer", "CreateElevationTile")
@@ -116,7 +118,7 @@ def test_shader_variant_flip_and_gridsize_attributes(ph, oracle):
 
 def test_small_cache_evicts_recomputes_and_invalidates(ph, oracle):
     """TileCache under pressure: 24 slots for a 85-tile quadtree walked quad by quad"""
-    ref = qt.oracle_quadtree(oracle, 3, noise_amp=FRACTAL)
+    ref = qt.oracle_quadtree(oracle, 3, noise_amp=FRACTAL, face=1)
     with ph.Scene(terrain_archive(n_tiles=24)) as scene:
         normals, elevations = scene.producer("groundNormals1"), scene.producer("groundElevations1")
         normals.set_root_quad_size(100000.0)
@@ -141,6 +143,9 @@ def test_small_cache_evicts_recomputes_and_invalidates(ph, oracle):
                 for tx in range(8):
                     held.append(normals.get_tile(3, tx, ty))
         ph.lib().plh_quiet_errors(0)
+        # what was acquired is usable: tasks that hold input tiles must run (or die) before the scene closes
+        sched.run(held)
+        check_against(ref, normals, elevations, held)
         for t in held:
             normals.put_tile(t)
         # invalidating the elevations re-runs them and the normals that depend on them
@@ -156,7 +161,7 @@ def test_small_cache_evicts_recomputes_and_invalidates(ph, oracle):
 
 
 def test_prefetch_produces_tiles_ahead(ph, oracle):
-    ref = qt.oracle_quadtree(oracle, 2, noise_amp=FRACTAL)
+    ref = qt.oracle_quadtree(oracle, 2, noise_amp=FRACTAL, face=1)
     with ph.Scene(terrain_archive(prefetch='prefetchRate="2" prefetchQueue="64"')) as scene:
         normals = scene.producer("groundNormals1")
         normals.set_root_quad_size(100000.0)

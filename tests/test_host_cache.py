@@ -238,3 +238,19 @@ def test_archive_errors(ph):
     with pytest.raises(ph.HostError, match="duplicate resource name"):
         ph.Scene(ARCHIVE.replace('name="groundNormals1" cache', 'name="groundElevations1" cache'))
     ph.lib().plh_quiet_errors(0)
+
+
+def test_cache_full_while_acquiring_inputs_leaves_the_cache_consistent(ph):
+    """the reference asserts when an input tile cannot be acquired; here CacheFullError, and every slot
+    and user count taken on the way is given back"""
+    ph.lib().plh_quiet_errors(1)
+    s = ph.TestScene(capacity=2)
+    with pytest.raises(ph.HostError, match="Insufficient tile cache size"):
+        s.producer.get_tile(3, 1, 1)                 # needs 4 slots
+    assert s.cache.stats()["used"] == 0 and s.cache.stats()["unused"] == 0 and s.cache.stats()["free"] == 2
+    t = s.producer.get_tile(1, 1, 1)                 # 2 slots: fits
+    s.scheduler.run([t])
+    assert [c[:3] for c in s.calls()] == [(0, 0, 0), (1, 1, 1)]
+    s.producer.put_tile(t)
+    s.close()
+    ph.lib().plh_quiet_errors(0)
