@@ -17,6 +17,8 @@
 #include "proland/producer/TileCache.h"
 #include "proland/producer/TileProducer.h"
 #include "proland/resource/ResourceManager.h"
+#include "proland/terrain/TerrainQuad.h"
+#include "proland/terrain/TileSampler.h"
 
 using namespace proland;
 
@@ -361,6 +363,96 @@ int plh_upsample_variant(const char *prog, int out[2])
     return ok ? 0 : -1;
 }
 
+/* ---------------------------------------------------------------- terrain quadtree + samplers */
+
+void *plh_terrain_create(float size, float zmin, float zmax, float split_factor, int max_level)
+{
+    PLH_TRY
+    TerrainNode *n = new TerrainNode(size, zmin, zmax, split_factor, max_level);
+    n->acquire();
+    return n;
+    PLH_CATCH(NULL)
+}
+
+void plh_terrain_destroy(void *node) { if (node) static_cast<TerrainNode *>(node)->release(); }
+
+float plh_split_distance(float split_factor, float viewport_width, float fov_radians)
+{
+    return TerrainNode::splitDistance(split_factor, viewport_width, fov_radians);
+}
+
+int plh_terrain_update(void *node, double x, double y, double z, float split_dist, float dist_factor)
+{
+    PLH_TRY
+    TerrainNode *n = static_cast<TerrainNode *>(node);
+    n->update(x, y, z, split_dist, dist_factor);
+    return n->root->getSize();
+    PLH_CATCH(-1)
+}
+
+static void list_quads(TerrainQuad *q, int *out, int max_quads, int *n)
+{
+    if (*n < max_quads) {
+        out[4 * *n] = q->level;
+        out[4 * *n + 1] = q->tx;
+        out[4 * *n + 2] = q->ty;
+        out[4 * *n + 3] = q->isLeaf() ? 1 : 0;
+    }
+    ++*n;
+    if (!q->isLeaf()) {
+        for (int i = 0; i < 4; ++i) list_quads(q->children[i].get(), out, max_quads, n);
+    }
+}
+
+/* the quadtree in pre-order (children 0..3) as (level, tx, ty, leaf) quadruples; returns the quad count */
+int plh_terrain_quads(void *node, int *out, int max_quads)
+{
+    int n = 0;
+    list_quads(static_cast<TerrainNode *>(node)->root.get(), out, max_quads, &n);
+    return n;
+}
+
+void *plh_sampler_create(const char *name, void *prod, int async, int store_parent)
+{
+    PLH_TRY
+    TileSampler *s = new TileSampler(name, static_cast<TileProducer *>(prod));
+    s->setStoreParent(store_parent != 0);
+    s->setAsynchronous(async != 0);
+    s->acquire();
+    return s;
+    PLH_CATCH(NULL)
+}
+
+void plh_sampler_destroy(void *sampler)
+{
+    if (sampler) {
+        static_cast<TileSampler *>(sampler)->release();
+        static_cast<Object *>(static_cast<TileSampler *>(sampler))->release();
+    }
+}
+
+int plh_sampler_tile_count(void *sampler) { return static_cast<TileSampler *>(sampler)->getTileCount(); }
+
+/* One frame: every sampler updates against the terrain's quadtree (putTiles / getTiles / prefetch), the
+ * tasks they return form one graph, the scheduler runs it.  Returns the number of tasks the graph held. */
+int plh_frame_update(void *scheduler, void *node, void **samplers, int n)
+{
+    PLH_TRY
+    ptr<TaskGraph> frame = new TaskGraph();
+    int tasks = 0;
+    for (int i = 0; i < n; ++i) {
+        ptr<TaskGraph> g = static_cast<TileSampler *>(samplers[i])->update(static_cast<TerrainNode *>(node)->root);
+        TaskGraph::TaskIterator it = g->getAllTasks();
+        while (it.hasNext()) {
+            frame->addTask(it.next());
+            ++tasks;
+        }
+    }
+    static_cast<BatchScheduler *>(scheduler)->run(frame);
+    return tasks;
+    PLH_CATCH(-1)
+}
+
 /* ---------------------------------------------------------------- CPU-only test double */
 
 void *plh_test_scene(int capacity, int tile_size, int max_level, int prefetch_rate, int prefetch_queue)
@@ -377,6 +469,7 @@ void *plh_test_scene(int capacity, int tile_size, int max_level, int prefetch_ra
 void plh_test_scene_close(void *scene)
 {
     TestScene *s = static_cast<TestScene *>(scene);
+    s->scheduler->clear();
     s->producer = NULL;
     s->cache = NULL;
     s->scheduler = NULL;

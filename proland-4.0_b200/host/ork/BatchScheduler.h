@@ -37,6 +37,8 @@ public:
     virtual void schedule(ptr<Task> task);
     virtual void reschedule(ptr<Task> task, Task::reason r, unsigned int deadline);
     virtual void run(ptr<Task> task);
+    /* forget the queued prefetch tasks (before the caches they belong to go away) */
+    void clear() { prefetch.clear(); }
 
     /* the date given to the tasks of the current / last run (Ork: the frame number) */
     unsigned int getFrame() const { return frame; }

@@ -67,14 +67,29 @@ void TileCache::init(ptr<TileStorage> storage, std::string name, ptr<Scheduler> 
 
 TileCache::~TileCache()
 {
-    /* users release their tiles before they drop the cache (TileCache.cpp:113-117) */
-    assert(usedTiles.size() == 0);
-    unusedTiles.clear();
-    for (Order::iterator i = unusedTilesOrder.begin(); i != unusedTilesOrder.end(); ++i) {
-        storage->deleteSlot((*i)->data);
-        delete *i;
+    /* Unused tiles go first, newest first: a tile whose task never ran still pins the tiles it is made
+     * from, and deleting it (and with it its task) releases them into the unused list. */
+    while (!unusedTilesOrder.empty()) {
+        Tile *t = unusedTilesOrder.back();
+        unusedTilesOrder.pop_back();
+        unusedTiles.erase(t->getTId());
+        storage->deleteSlot(t->data);
+        delete t;
     }
-    unusedTilesOrder.clear();
+    /* users release their tiles before they drop the cache: the reference asserts usedTiles is empty
+     * here (TileCache.cpp:113-117).  Tiles pinned by tasks that something else keeps alive end up here
+     * too; they are reported and freed with the cache. */
+    if (!usedTiles.empty()) {
+        if (Logger::WARNING_LOGGER != NULL) {
+            Logger::WARNING_LOGGER->logf("CACHE", "%s: %d tiles still in use when the cache is deleted", name.c_str(),
+                                         (int) usedTiles.size());
+        }
+        for (std::map<Tile::TId, Tile *>::iterator i = usedTiles.begin(); i != usedTiles.end(); ++i) {
+            storage->deleteSlot(i->second->data);
+            delete i->second;
+        }
+        usedTiles.clear();
+    }
     deletedTiles.clear();
 }
 

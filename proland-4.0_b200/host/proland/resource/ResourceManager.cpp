@@ -136,6 +136,13 @@ ResourceManager::~ResourceManager()
 
 void ResourceManager::close()
 {
+    /* queued prefetch tasks pin tiles: drop them first */
+    for (std::map<std::string, ptr<Object> >::iterator i = resources.begin(); i != resources.end(); ++i) {
+        BatchScheduler *s = dynamic_cast<BatchScheduler *>(i->second.get());
+        if (s != NULL) {
+            s->clear();
+        }
+    }
     /* users before what they use */
     while (!order.empty()) {
         resources.erase(order.back());

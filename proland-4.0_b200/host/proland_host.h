@@ -65,6 +65,17 @@ unsigned long plh_debug_log_lines(void);
 void plh_quiet_errors(int quiet);
 int plh_upsample_variant(const char *prog, int out[2]);
 
+/* TerrainNode / TerrainQuad (view-dependent quadtree) and TileSampler (which tiles the quads need) */
+void *plh_terrain_create(float size, float zmin, float zmax, float split_factor, int max_level);
+void plh_terrain_destroy(void *node);
+float plh_split_distance(float split_factor, float viewport_width, float fov_radians);
+int plh_terrain_update(void *node, double x, double y, double z, float split_dist, float dist_factor);
+int plh_terrain_quads(void *node, int *out, int max_quads);   /* pre-order (level, tx, ty, leaf) */
+void *plh_sampler_create(const char *name, void *prod, int async, int store_parent);
+void plh_sampler_destroy(void *sampler);
+int plh_sampler_tile_count(void *sampler);
+int plh_frame_update(void *scheduler, void *node, void **samplers, int n);
+
 /* CPU-only scene with a recording producer (cache / task / scheduler logic without a device) */
 void *plh_test_scene(int capacity, int tile_size, int max_level, int prefetch_rate, int prefetch_queue);
 void plh_test_scene_close(void *scene);

@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libproland_b200.so")
+LIB_PATH = os.environ.get("PL_LIB", os.path.join(HERE, "libproland_b200.so"))
 
 PL_OK, PL_ERR_ARG, PL_ERR_POOL_FULL, PL_ERR_CUDA, PL_ERR_CORRUPT, PL_ERR_NO_DEVICE, PL_ERR_IO = range(7)
 POOL_ELEV, POOL_NORM2, POOL_NORM4, POOL_RESID_F32, POOL_RESID_I16 = range(5)

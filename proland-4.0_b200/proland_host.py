@@ -29,7 +29,8 @@ EXPORTS = [
     "plh_residual_info", "plh_residual_tile_id", "plh_residual_tile_size", "plh_device_launches", "plh_device_sync",
     "plh_debug_log", "plh_debug_log_lines", "plh_quiet_errors", "plh_upsample_variant", "plh_test_scene",
     "plh_test_scene_close", "plh_test_producer", "plh_test_cache", "plh_test_scheduler", "plh_test_calls",
-    "plh_test_begin_end",
+    "plh_test_begin_end", "plh_terrain_create", "plh_terrain_destroy", "plh_split_distance", "plh_terrain_update",
+    "plh_terrain_quads", "plh_sampler_create", "plh_sampler_destroy", "plh_sampler_tile_count", "plh_frame_update",
 ]
 
 
@@ -51,7 +52,7 @@ def lib():
         L.plh_last_error.restype = C.c_char_p
         for name in ("plh_open", "plh_producer", "plh_cache", "plh_scheduler", "plh_producer_cache", "plh_cache_scheduler",
                      "plh_get_tile", "plh_find_tile", "plh_test_scene", "plh_test_producer", "plh_test_cache",
-                     "plh_test_scheduler"):
+                     "plh_test_scheduler", "plh_terrain_create", "plh_sampler_create"):
             getattr(L, name).restype = vp
         L.plh_producer_type.restype = C.c_char_p
         L.plh_producer_task_type.restype = C.c_char_p
@@ -84,6 +85,16 @@ def lib():
         L.plh_quiet_errors.argtypes = [i]
         L.plh_upsample_variant.argtypes = [C.c_char_p, vp]
         L.plh_test_scene.argtypes = [i, i, i, i, i]
+        L.plh_terrain_create.argtypes = [C.c_float, C.c_float, C.c_float, C.c_float, i]
+        L.plh_terrain_destroy.argtypes = [vp]
+        L.plh_split_distance.argtypes = [C.c_float, C.c_float, C.c_float]
+        L.plh_split_distance.restype = C.c_float
+        L.plh_terrain_update.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float]
+        L.plh_terrain_quads.argtypes = [vp, vp, i]
+        L.plh_sampler_create.argtypes = [C.c_char_p, vp, i, i]
+        L.plh_sampler_destroy.argtypes = [vp]
+        L.plh_sampler_tile_count.argtypes = [vp]
+        L.plh_frame_update.argtypes = [vp, vp, vp, i]
         L.plh_test_calls.argtypes = [vp, vp, i]
         _lib = L
     return _lib
@@ -304,6 +315,60 @@ class TestScene:
         if self.h:
             lib().plh_test_scene_close(self.h)
             self.h = None
+
+
+class Terrain:
+    """TerrainNode: the view-dependent quadtree over the root quad [-size, size]^2."""
+
+    def __init__(self, size, zmin=0.0, zmax=5000.0, split_factor=2.0, max_level=16):
+        self.h = lib().plh_terrain_create(size, zmin, zmax, split_factor, max_level)
+        self.split_factor = split_factor
+
+    def update(self, x, y, z, split_dist=None, dist_factor=1.0, viewport_width=1024.0, fov=1.3962634):
+        if split_dist is None:
+            split_dist = lib().plh_split_distance(self.split_factor, viewport_width, fov)
+        n = lib().plh_terrain_update(self.h, x, y, z, split_dist, dist_factor)
+        if n < 0:
+            raise HostError(_err())
+        return n
+
+    def quads(self):
+        n = lib().plh_terrain_quads(self.h, None, 0)
+        out = (C.c_int * (4 * n))()
+        lib().plh_terrain_quads(self.h, out, n)
+        return [tuple(out[4 * k:4 * k + 4]) for k in range(n)]
+
+    def close(self):
+        if self.h:
+            lib().plh_terrain_destroy(self.h)
+            self.h = None
+
+
+class Sampler:
+    """TileSampler: holds the tiles of one producer that the terrain's quads need."""
+
+    def __init__(self, name, producer, asynchronous=False, store_parent=True):
+        self.h = lib().plh_sampler_create(name.encode(), producer.h, int(asynchronous), int(store_parent))
+        if not self.h:
+            raise HostError(_err())
+
+    @property
+    def tile_count(self):
+        return lib().plh_sampler_tile_count(self.h)
+
+    def close(self):
+        if self.h:
+            lib().plh_sampler_destroy(self.h)
+            self.h = None
+
+
+def frame_update(scheduler, terrain, samplers):
+    """One frame of every sampler against the terrain + Scheduler::run; returns the task count."""
+    arr = (C.c_void_p * len(samplers))(*[s.h for s in samplers])
+    n = lib().plh_frame_update(scheduler.h, terrain.h, arr, len(samplers))
+    if n < 0:
+        raise HostError(_err())
+    return n
 
 
 def upsample_variant(prog):
