@@ -74,3 +74,72 @@ def morton_decode(m):
         tx |= ((m >> (2 * b)) & 1) << b
         ty |= ((m >> (2 * b + 1)) & 1) << b
     return tx, ty
+
+
+# ------------------------------------------------------------------ config 4: subtree sweep
+
+class SubtreeSweep:
+    """BASELINE config 4: every descendant, down to `depth` levels, of ONE tile (root_level, tx, ty)
+    -- 4**depth leaf tiles plus a third as many ancestors -- partitioned by subtree.
+
+    Slots: [0, root_level] the ancestor chain of the sweep root (levels 0 .. root_level, replicated on
+    every rank), then the top tree (depths 1 .. k below the root, replicated: (4**(k+1) - 4) / 3 tiles),
+    then one recycled region per depth k+1 .. depth for the unit being produced.  The 4**k units (the
+    root's descendants at depth k) are dealt round-robin to the ranks; a unit is a contiguous Morton
+    range at every level, so each of its levels is ONE pl_produce_range call.
+    """
+
+    def __init__(self, root_level, tx, ty, depth, unit_depth=7):
+        assert 0 <= tx < (1 << root_level) and 0 <= ty < (1 << root_level)
+        self.root_level, self.tx, self.ty, self.depth = root_level, tx, ty, depth
+        self.k = max(depth - unit_depth, 0)           # units are the root's descendants at depth k
+        self.root_morton = morton_encode(tx, ty)
+        self.chain_slots = root_level + 1
+        self.top_off = [self.chain_slots]              # slot offset of top-tree depth j = 1 .. k
+        for j in range(1, self.k + 1):
+            self.top_off.append(self.top_off[-1] + 4 ** j)
+        self.unit_off = [self.top_off[-1]]             # slot offset of unit depth e = 1 .. depth - k
+        for e in range(1, depth - self.k + 1):
+            self.unit_off.append(self.unit_off[-1] + 4 ** e)
+        self.capacity = self.unit_off[-1]
+        self.top_off, self.unit_off = self.top_off[:-1], self.unit_off[:-1]
+
+    def units(self):
+        return list(range(4 ** self.k))
+
+    def units_of_rank(self, rank, world):
+        return self.units()[rank::world]
+
+    def tiles_in_unit(self):
+        return sum(4 ** e for e in range(1, self.depth - self.k + 1))
+
+    def replicated_tiles(self):
+        return self.chain_slots + sum(4 ** j for j in range(1, self.k + 1))
+
+    def total_tiles(self):
+        """every tile of the sweep once: chain + subtree"""
+        return self.root_level + sum(4 ** j for j in range(self.depth + 1))
+
+    def leaf_region(self):
+        """(slot0, n) of the unit's deepest level"""
+        return self.unit_off[-1] if self.unit_off else self.chain_slots - 1, 4 ** (self.depth - self.k)
+
+    def prologue(self):
+        """batches every rank produces first: the chain and the top tree.
+        yields (level, morton0, n, out_slot0, parent_slot0, parent_morton0)"""
+        for l in range(self.root_level + 1):
+            m = self.root_morton >> (2 * (self.root_level - l))
+            yield l, m, 1, l, max(l - 1, 0), m >> 2
+        for j in range(1, self.k + 1):
+            m0 = self.root_morton << (2 * j)
+            parent_slot0 = self.root_level if j == 1 else self.top_off[j - 2]
+            yield self.root_level + j, m0, 4 ** j, self.top_off[j - 1], parent_slot0, m0 >> 2
+
+    def unit_batches(self, unit):
+        """the levels of one unit, breadth first"""
+        um = (self.root_morton << (2 * self.k)) | unit           # the unit root's Morton index at depth k
+        unit_root_slot = self.root_level if self.k == 0 else self.top_off[self.k - 1] + unit
+        for e in range(1, self.depth - self.k + 1):
+            m0 = um << (2 * e)
+            parent_slot0 = unit_root_slot if e == 1 else self.unit_off[e - 2]
+            yield self.root_level + self.k + e, m0, 4 ** e, self.unit_off[e - 1], parent_slot0, m0 >> 2

@@ -1,0 +1,114 @@
+"""Config 4 (full-subtree batch sweep at level 14) on the GPU: sampled leaf tiles against the oracle's
+15-level parent chains, and invariance of the result under the subtree partition (1 / 2 / 4 ranks)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import resid_synth as rs
+
+pytestmark = pytest.mark.gpu
+
+FRACTAL = [-140, -100, -15, -8, 5, 2.5, 1.5, 1, 0.5, 0.25, 0.1, 0.05]
+
+
+def oracle_chain(oracle, scene, noise, level, tx, ty, resid_of=None):
+    parent = None
+    for l in range(level + 1):
+        x, y = tx >> (level - l), ty >> (level - l)
+        rt = resid_of(l, x, y) if resid_of else None
+        e, n = oracle.produce_pair(scene, noise, l, x, y, parent, rt)
+        parent = e
+    return e, n
+
+
+def test_subtree_sweep_d6_leaves_match_the_oracle(plb, ctx, oracle):
+    import subtree_sweep as ss
+    import sweep
+    d = 6
+    plan = sweep.SubtreeSweep(14 - d, (1 << 8) // 3, (1 << 8) // 5, d, unit_depth=4)
+    first = plan.root_morton << (2 * d)
+    want = [first, first + 1, first + 4 ** d // 2 + 77, first + 4 ** d - 1]
+    keep = {"want": want}
+    n, fp, plan = ss.run_sweep(plb, ctx, d, unit_depth=4, keep=keep)
+    assert n == plan.total_tiles() == 8 + sum(4 ** j for j in range(d + 1))
+    scene = oracle.make_scene(W=101, rootQuadSize=100000.0, face=0, noiseAmp=FRACTAL, sphere=0, elev_filter=1)
+    noise = oracle.dem_noise(101)
+    for m in want:
+        tx, ty = plb.morton_decode(m)
+        e, nrm = oracle_chain(oracle, scene, noise, 14, tx, ty)
+        assert np.array_equal(keep[m][0], e), (tx, ty)
+        assert np.array_equal(keep[m][1], nrm), (tx, ty)
+    assert fp["lo"] >= 0.0 and fp["hi"] >= fp["lo"]      # zm = max(zf, 0): this subtree may be all sea
+
+
+@pytest.mark.parametrize("d,unit_depth", [(7, 5), (8, 6)])
+def test_subtree_sweep_is_invariant_under_the_partition(plb, ctx, d, unit_depth):
+    """the union over the ranks of a 2- / 4-rank partition equals the 1-rank sweep: same tile count, same
+    fingerprint of the per-tile statistics (sum, min, max, xor of the raw bits)"""
+    import subtree_sweep as ss
+    n1, fp1, plan = ss.run_sweep(plb, ctx, d, unit_depth=unit_depth)
+    for world in (2, 4):
+        parts = [ss.run_sweep(plb, ctx, d, rank=r, world=world, unit_depth=unit_depth) for r in range(world)]
+        total = sum(p[0] for p in parts) - (world - 1) * plan.replicated_tiles()
+        assert total == n1 == plan.total_tiles()
+        assert np.bitwise_xor.reduce([p[1]["xor"] for p in parts]) == fp1["xor"]
+        assert min(p[1]["lo"] for p in parts) == fp1["lo"] and max(p[1]["hi"] for p in parts) == fp1["hi"]
+        assert abs(sum(p[1]["sum"] for p in parts) - fp1["sum"]) <= 1e-9 * abs(fp1["sum"])
+    # a different unit size changes the batch shapes, not the tiles
+    n2, fp2, _ = ss.run_sweep(plb, ctx, d, unit_depth=unit_depth - 2)
+    assert n2 == n1 and fp2["xor"] == fp1["xor"] and fp2["lo"] == fp1["lo"] and fp2["hi"] == fp1["hi"]
+
+
+def test_subtree_sweep_with_residual_params_d4(plb, ctx, oracle):
+    """config 4 repeated with config-3 parameters: int16 residual tiles (a small synthetic set, reused
+    by tile index) added at every swept level, flip, NEAREST storage; host-built requests"""
+    import sweep
+    d, W = 4, 101
+    plan = sweep.SubtreeSweep(14 - d, 300, 700, d, unit_depth=4)
+    amp = [0] * 11 + [5, 2.5, 1, 0.5, 0.25]
+    rng = np.random.default_rng(9)
+    rtiles = [rs.fractal_tile(rng, 197, 3.0) for _ in range(8)]
+    rpool = ctx.pool(plb.POOL_RESID_I16, 197, len(rtiles))
+    for s, t in enumerate(rtiles):
+        rpool.upload(s, t)
+    resid_slot = lambda level, tx, ty: (level * 7 + (tx // 2) * 3 + (ty // 2)) % len(rtiles)
+    elev = ctx.pool(plb.POOL_ELEV, W, plan.capacity)
+    norm = ctx.pool(plb.POOL_NORM2, W - 4, plan.capacity)
+    ctx.noise_init(W)
+    sc = plb.sweep_scene(noise_amp=amp, face=0, root_quad_size=100000.0, sphere=0, flip=1, elev_filter=plb.FILTER_NEAREST,
+                         want_stats=0)
+    sc.elev.resid_scale = 0.25
+    batches = list(plan.prologue()) + [b for u in plan.units() for b in plan.unit_batches(u)]
+    for level, m0, n, s0, p0, pm0 in batches:
+        e, q = plb.make_requests_range(sc, level, m0, n, s0, p0, pm0)
+        if level >= 10:                                       # the swept levels carry residuals
+            for i in range(n):
+                tx, ty = plb.morton_decode(m0 + i)
+                e["resid_slot"][i] = resid_slot(level, tx, ty)
+                e["rx"][i], e["ry"][i] = (tx % 2) * 96, (ty % 2) * 96
+        ctx.elevation_batch(sc.elev, elev, e, resid=rpool)
+        ctx.normal_batch(sc.norm, norm, elev, q)
+    # the oracle takes the residual tile width (197: mod 2 windows) from an opened residual file
+    geometry, _ = rs.container(min_level=0, max_level=0, tile_size=192)
+    scene = oracle.make_scene(W=W, rootQuadSize=100000.0, face=0, flip=1, noiseAmp=amp, sphere=0, elev_filter=0,
+                              resid=oracle.Resid(geometry))
+    noise = oracle.dem_noise(W)
+
+    def resid_of(level, tx, ty):
+        if level < 10:
+            return None
+        return rtiles[resid_slot(level, tx, ty)].astype(np.float32) * np.float32(0.25)
+
+    slot0, nleaf = plan.leaf_region()
+    first = plan.root_morton << (2 * d)
+    for m in (first, first + 37, first + nleaf - 1):
+        tx, ty = plb.morton_decode(m)
+        e, nrm = oracle_chain(oracle, scene, noise, 14, tx, ty, resid_of)
+        s = slot0 + (m - first)
+        assert np.array_equal(elev.download(s), e), (tx, ty)
+        assert np.array_equal(norm.download(s), nrm), (tx, ty)
