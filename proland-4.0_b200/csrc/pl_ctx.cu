@@ -431,7 +431,7 @@ extern "C" int pl_noise_init(pl_ctx *ctx, int tile_w, float *host_out)
                     case 2: sx = W - 1 - x; sy = W - 1 - y; break;
                     default: sx = W - 1 - y; sy = x; break;
                     }
-                    rot[((size_t) (r * 6 + l) * W + y) * pitch + x] = h6[(size_t) l * W * W + sx + (size_t) sy * W];
+                    rot[((size_t) (r * 6 + l) * W + y) * pitch + pl_noise_col(x)] = h6[(size_t) l * W * W + sx + (size_t) sy * W];
                 }
     if (ctx->noise_rot) {
         PL_CUDA(cudaStreamSynchronize(ctx->stream));

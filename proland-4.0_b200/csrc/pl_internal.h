@@ -99,4 +99,13 @@ void pl_host_dem_noise(int W, float *out6);      /* fp32, before the R16F roundi
 
 static inline int pl_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+/* Column of texel x inside a row of the pre-rotated noise planes.  Each group of four texels is
+ * stored as (x0, x0+2, x0+1, x0+3): the elevation kernel works on the two horizontally adjacent
+ * 2x2 quads of a group with packed fp32x2 maths, lane 0 = first quad, lane 1 = second, so one
+ * 8-byte load yields the half2 (even texel of both quads), then the half2 (odd texel of both). */
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+static inline int pl_noise_col(int x) { return (x & ~3) | ((x & 1) << 1) | ((x >> 1) & 1); }
+
 #endif
