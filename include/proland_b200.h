@@ -59,8 +59,10 @@ int pl_device_sm_count(pl_ctx *ctx);
 /* Per-launch timing with CUDA events recorded on the launching stream (the
  * reference's hook is Ork's monitorTask("CreateElevationTile")).
  * pl_timing_collect synchronises, sums the elapsed time per kernel
- * {0 elevation, 1 normal, 2 request generation, 3 residual decode} into the
- * three 4-entry arrays and resets the record. */
+ * {0 elevation, 1 normal, 2 request generation, 3 residual decode, 4 fused
+ * elevation+normal} into the three PL_TIMING_KERNELS-entry arrays and resets
+ * the record. */
+#define PL_TIMING_KERNELS 5
 int pl_timing_enable(pl_ctx *ctx, int on);
 int pl_timing_collect(pl_ctx *ctx, double *ms, uint64_t *launches, uint64_t *tiles);
 
@@ -227,6 +229,9 @@ int pl_make_requests_range(const pl_sweep_scene *scene, int level, uint64_t mort
  * evaluate the branch-free div / rcp / sqrt next to the IEEE operators on the
  * device: out = 6*n floats (div_rn, a/b, rcp_rn, 1/b, sqrt_rn(|a|), sqrtf(|a|)) */
 int pl_debug_force_generic(pl_ctx *ctx, int on);
+/* tests / profiling: make pl_produce_range and pl_pair_batch[_dev] launch the elevation and the normal
+ * pass as two kernels instead of the fused one (same results, bit for bit) */
+int pl_debug_no_fuse(pl_ctx *ctx, int on);
 int pl_debug_fpexact(pl_ctx *ctx, int n, const float *a, const float *b, float *out);
 /* copy the requests the last pl_produce_range generated back to the host (tests) */
 int pl_debug_download_requests(pl_ctx *ctx, int n, pl_elev_req *elev_reqs, pl_norm_req *norm_reqs);

@@ -137,6 +137,13 @@ extern "C" int pl_debug_force_generic(pl_ctx *ctx, int on)
     return PL_OK;
 }
 
+extern "C" int pl_debug_no_fuse(pl_ctx *ctx, int on)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    ctx->no_fuse = on ? 1 : 0;
+    return PL_OK;
+}
+
 extern "C" int pl_timing_enable(pl_ctx *ctx, int on)
 {
     if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");

@@ -27,78 +27,13 @@
  * the result is bit-identical to the CPU oracle.  Zero-weight taps of the GLSL
  * constant matrices are dropped (value-identical for finite inputs).
  */
-#include "pl_internal.h"
-#include "pl_fpexact.cuh"
-#include "pl_f2.cuh"
+#include "pl_elevation_tile.cuh"
 
 namespace {
 
+using namespace plelev;
+
 constexpr int kThreads = 192;
-
-struct ElevArgs {
-    float *elev;
-    const void *resid;
-    const __half *noise;
-    const pl_elev_req *reqs;
-    float2 *stats;
-    int W, pitch, plane;
-    int grid, flip, noise_mode, no_clamp, want_stats;
-    int box_w, box_h, nk;
-    int noise_pitch, noise_plane;
-    int resid_pitch;
-    long long resid_slot_elems;
-    float resid_scale;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t) tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-
-__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
-__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
-
-/* dot(cz[c], w) with all four weights non-zero: canonical left-to-right chain */
-__device__ __forceinline__ float chain4(float a0, float a1, float a2, float a3, float w0, float w1, float w2, float w3)
-{
-    return fmaf(a3, w3, fmaf(a2, w2, fmaf(a1, w1, a0 * w0)));
-}
-
-/* noise amplitude factor of variants B / D: upsampleShader.glsl:166-170 */
-__device__ __forceinline__ float noise_amp(float nvx, float nvy, float curv_num, float nvz, float pixel)
-{
-    const float slope = sqrtf(fmaf(nvy, nvy, nvx * nvx)) / nvz;
-    const float curvature = curv_num / pixel;
-    return fmaxf(clampf(4.0f * curvature, 0.0f, 1.5f), clampf(fmaf(2.0f, slope, -0.5f), 0.1f, 4.0f));
-}
-
-/* NOISE: 0 = none (rs == 0), 1 = plain |rs|*n, 2 = rs < 0 (zf -= rs*n), 3 = slope/curvature modulated */
-enum { NZ_NONE = 0, NZ_PLAIN = 1, NZ_NEG = 2, NZ_SLOPE = 3 };
-/* RESID: 0 = none, 1 = float pool, 2 = int16 pool */
 
 /* ------------------------------------------------------------------------
  * Generic kernel: any odd tile width, any grid divisor (runtime geometry).
@@ -332,402 +267,30 @@ __global__ void __launch_bounds__(kThreads) elevation_kernel_generic(const __gri
 }
 
 /* ------------------------------------------------------------------------
- * Specialised kernel: compile-time geometry (TW = tile width, TG = grid
- * divisor, TG even).  Same arithmetic as the generic kernel, far fewer
- * instructions around it (the kernel is issue-bound, profiles/):
- *   - all index maths folds to immediates; the item -> (row pair, quad) split
- *     is a multiply-shift
- *   - the tile-uniform switches (noise variant) are hoisted out of the loop:
- *     one loop instance per variant
- *   - divisions by the tile's pixel size cost 3 FFMA each (pl_fpexact.cuh: the
- *     reciprocal is refined once per thread), sqrt is the 5-instruction IEEE
- *     fast path, no range-check branches
- *   - with TG even the two texels of a quad in x (and in y) share their coarse
- *     lattice indices: zc needs 2 lattice reads per quad, not 8; only texel
- *     (x0, y0) can satisfy the diagonal-flip test
- *   - rows 0..TW-2 are processed as TW/2 full row pairs without bounds checks,
- *     row TW-1 by a short tail; the pad columns of a row (x >= TW) are
- *     "don't care": they are computed like texels (all reads stay inside the
- *     staged window / padded planes) and stored, so sectors are written whole,
- *     and nobody ever reads them (TMA zero-fills x >= TW, downloads skip them)
+ * Specialised kernel: compile-time geometry, one CTA per tile; the per-tile
+ * device code lives in pl_elevation_tile.cuh (shared with pl_pair.cu).
  * ------------------------------------------------------------------------ */
-template <int TW, int TG>
-struct Geo {
-    static constexpr int W = TW, G = TG;
-    static constexpr int PITCH = (TW + 3) & ~3;
-    static constexpr int PLANE = TW * PITCH;
-    static constexpr int BOX_H = (TW - 5) / 2 + 6;
-    static constexpr int BOX_W = (BOX_H + 3) & ~3;
-    static constexpr int NK = (TW - 3 + TG) / (2 * TG) + 2;
-    static constexpr int QW = PITCH / 2;          /* quads per row pair (incl. pad quads) */
-    static constexpr int QH = (TW - 1) / 2;       /* full row pairs */
-    static_assert(TW % 2 == 1 && TG % 2 == 0, "odd tile width, even grid divisor");
-};
-
-struct QuadCtx {
-    const float *winA;         /* staged parent zf window */
-    const float *winB;         /* the same window one texel to the right: winB[k] = winA[k + 1] */
-    const float *lat;          /* parent zm lattice */
-    const int *lutx, *luty;    /* per quad column / row pair: lattice indices + flip bit */
-    float *out;                /* zf plane of the output slot */
-    const __half *nplane;      /* rotated noise plane (columns permuted: pl_noise_col) */
-    const void *resid;         /* residual tile origin (slot base + window origin) or NULL */
-    int noise_pitch, resid_pitch;
-    float rs, ars, pixel, nvz, rcp_pixel, rcp_nvz, resid_scale;
-    float zm_floor;            /* 0, or -inf under NO_CLAMP */
-    bool has_parent, has_resid, flip, want_stats;
-};
-
-/* max(clamp(a, 0, 1.5), clamp(b, 0.1, 4)) = max3(min(a, 1.5), min(b, 4), 0.1) for finite a, b: the lower
- * clamp of a is absorbed by b's (>= 0.1) and clamp(b, 0.1, 4) = max(min(b, 4), 0.1); one FMNMX3 */
-__device__ __forceinline__ float amp_clamp(float a, float b)
-{
-    return fmaxf(fmaxf(fminf(a, 1.5f), fminf(b, 4.0f)), 0.1f);
-}
-/* noise amplitude factor of two texels: upsampleShader.glsl:166-170 */
-__device__ __forceinline__ plf2::F2 amp_of2(const QuadCtx &k, plf2::F2 sx, plf2::F2 sy, plf2::F2 cv)
-{
-    using namespace plf2;
-    const F2 slope = div_rn2(sqrt_rn2(fma2(sy, sy, mul2(sx, sx))), bc(k.nvz), bc(k.rcp_nvz));
-    const F2 curvature = div_rn2(cv, bc(k.pixel), bc(k.rcp_pixel));
-    const F2 a = mul2(bc(4.0f), curvature), b = fma2(bc(2.0f), slope, bc(-0.5f));
-    return make_float2(amp_clamp(a.x, b.x), amp_clamp(a.y, b.y));
-}
-
-/* Two horizontally adjacent 2x2 quads (texel columns 4*ip .. 4*ip+3, rows 2*j, 2*j+1) per call; every
- * fp32 operation of the canonical order is issued ONCE for both quads as a packed fp32x2 instruction:
- * lane .x = quad A (columns 4ip, 4ip+1), lane .y = quad B (columns 4ip+2, 4ip+3).
- * TAIL: only the first row of the quads exists (row TW-1). */
-template <class GEO, int NZ, int RESID, bool TAIL>
-__device__ __forceinline__ void do_quad2(const QuadCtx &k, const int ip, const int j, float &lo, float &hi)
-{
-    using namespace plf2;
-    constexpr int BW = GEO::BOX_W, PITCH = GEO::PITCH, PLANE = GEO::PLANE;
-    const int i = 2 * ip, x0 = 4 * ip, y0 = 2 * j;
-
-    /* residual texels (residualOSH.w * texel): r<x><y><quad> */
-    float r00A = 0.0f, r10A = 0.0f, r00B = 0.0f, r10B = 0.0f, r01A = 0.0f, r11A = 0.0f, r01B = 0.0f, r11B = 0.0f;
-    if (RESID != 0 && k.has_resid) {
-        const int off = y0 * k.resid_pitch + x0;
-        if (RESID == 1) {
-            const float *rp = static_cast<const float *>(k.resid) + off;
-            const float4 t0 = __ldg(reinterpret_cast<const float4 *>(rp));
-            r00A = t0.x; r10A = t0.y; r00B = t0.z; r10B = t0.w;
-            if (!TAIL) {
-                const float4 t1 = __ldg(reinterpret_cast<const float4 *>(rp + k.resid_pitch));
-                r01A = t1.x; r11A = t1.y; r01B = t1.z; r11B = t1.w;
-            }
-        } else {
-            const short *rp = static_cast<const short *>(k.resid) + off;
-            const short4 t0 = __ldg(reinterpret_cast<const short4 *>(rp));
-            r00A = (float) t0.x * k.resid_scale; r10A = (float) t0.y * k.resid_scale;
-            r00B = (float) t0.z * k.resid_scale; r10B = (float) t0.w * k.resid_scale;
-            if (!TAIL) {
-                const short4 t1 = __ldg(reinterpret_cast<const short4 *>(rp + k.resid_pitch));
-                r01A = (float) t1.x * k.resid_scale; r11A = (float) t1.y * k.resid_scale;
-                r01B = (float) t1.z * k.resid_scale; r11B = (float) t1.w * k.resid_scale;
-            }
-        }
-    }
-
-    /* noise texels (already rotated); one 8-byte load = (even texel of A, of B), (odd texel of A, of B) */
-    F2 n00 = bc(0.0f), n10 = bc(0.0f), n01 = bc(0.0f), n11 = bc(0.0f);
-    if (NZ != NZ_NONE) {
-        const __half *np = k.nplane + y0 * k.noise_pitch + x0;
-        const uint2 t0 = __ldg(reinterpret_cast<const uint2 *>(np));
-        n00 = __half22float2(*reinterpret_cast<const __half2 *>(&t0.x));
-        n10 = __half22float2(*reinterpret_cast<const __half2 *>(&t0.y));
-        if (!TAIL) {
-            const uint2 t1 = __ldg(reinterpret_cast<const uint2 *>(np + k.noise_pitch));
-            n01 = __half22float2(*reinterpret_cast<const __half2 *>(&t1.x));
-            n11 = __half22float2(*reinterpret_cast<const __half2 *>(&t1.y));
-        }
-    }
-
-    /* cz[c][r] = parent.zf[bx + r, by + c] -> z<c><r> = (quad A, quad B): quad B's taps are quad A's one
-     * window column further right, so even r are aligned pairs of winA, odd r aligned pairs of winB */
-    const float *wa = k.winA + j * BW + i, *wb = k.winB + j * BW + i;
-#define LDP(p) (*reinterpret_cast<const F2 *>(p))
-    const F2 z00 = LDP(wa), z01 = LDP(wb), z02 = LDP(wa + 2), z03 = LDP(wb + 2);
-    const F2 z10 = LDP(wa + BW), z11 = LDP(wb + BW), z12 = LDP(wa + BW + 2), z13 = LDP(wb + BW + 2);
-    const F2 z20 = LDP(wa + 2 * BW), z21 = LDP(wb + 2 * BW), z22 = LDP(wa + 2 * BW + 2), z23 = LDP(wb + 2 * BW + 2);
-    F2 z30 = bc(0.0f), z31 = bc(0.0f), z32 = bc(0.0f), z33 = bc(0.0f);
-    if (!TAIL) { z30 = LDP(wa + 3 * BW); z31 = LDP(wb + 3 * BW); z32 = LDP(wa + 3 * BW + 2); z33 = LDP(wb + 3 * BW + 2); }
-#undef LDP
-
-    /* noise term scale per texel: T<x><y> */
-    F2 t00 = bc(0.0f), t10 = bc(0.0f), t01 = bc(0.0f), t11 = bc(0.0f);
-    if (NZ == NZ_PLAIN) {
-        t00 = t10 = t01 = t11 = bc(k.ars);
-    } else if (NZ == NZ_NEG) {
-        t00 = t10 = t01 = t11 = bc(-k.rs);
-    } else if (NZ == NZ_SLOPE) {
-        {   /* parity 0: slopex/slopey/curvature matrices [0] */
-            const F2 sx = sub2(z10, z12);
-            const F2 sy = sub2(z01, z21);
-            const F2 cv = sub2(add2(neg(z01), sub2(fma2(z11, bc(4.0f), neg(z10)), z12)), z21);
-            t00 = mul2(amp_of2(k, sx, sy, cv), bc(k.rs));
-        }
-        {   /* parity 1: [1] */
-            const F2 sx = plf2::chain4(z10, z11, z12, z13, 0.5f, 0.5f, -0.5f, -0.5f);
-            const F2 lowr = fma2(z22, bc(-0.5f), mul2(z21, bc(-0.5f)));
-            const F2 sy = add2(fma2(z02, bc(0.5f), mul2(z01, bc(0.5f))), lowr);
-            const F2 cv = add2(add2(fma2(z02, bc(-0.5f), mul2(z01, bc(-0.5f))), plf2::chain4(z10, z11, z12, z13, -0.5f, 1.5f, 1.5f, -0.5f)), lowr);
-            t10 = mul2(amp_of2(k, sx, sy, cv), bc(k.rs));
-        }
-        if (!TAIL) {
-            {   /* parity 2: [2]; every bare product below has a power-of-two weight (exact) */
-                const F2 sx = add2(fma2(z12, bc(-0.5f), mul2(z10, bc(0.5f))), fma2(z22, bc(-0.5f), mul2(z20, bc(0.5f))));
-                const F2 sy = add2(add2(add2(mul2(z01, bc(0.5f)), mul2(z11, bc(0.5f))), mul2(z21, bc(-0.5f))), mul2(z31, bc(-0.5f)));
-                const F2 cv = add2(add2(add2(mul2(z01, bc(-0.5f)), fma2(z12, bc(-0.5f), fma2(z11, bc(1.5f), mul2(z10, bc(-0.5f))))),
-                                        fma2(z22, bc(-0.5f), fma2(z21, bc(1.5f), mul2(z20, bc(-0.5f))))), mul2(z31, bc(-0.5f)));
-                t01 = mul2(amp_of2(k, sx, sy, cv), bc(k.rs));
-            }
-            {   /* parity 3: [3] */
-                const F2 sx = add2(plf2::chain4(z10, z11, z12, z13, 0.25f, 0.25f, -0.25f, -0.25f),
-                                   plf2::chain4(z20, z21, z22, z23, 0.25f, 0.25f, -0.25f, -0.25f));
-                const F2 lowr = fma2(z32, bc(-0.25f), mul2(z31, bc(-0.25f)));
-                const F2 sy = add2(add2(add2(fma2(z02, bc(0.25f), mul2(z01, bc(0.25f))), fma2(z12, bc(0.25f), mul2(z11, bc(0.25f)))),
-                                        fma2(z22, bc(-0.25f), mul2(z21, bc(-0.25f)))), lowr);
-                const F2 cv = add2(add2(add2(fma2(z02, bc(-0.25f), mul2(z01, bc(-0.25f))), plf2::chain4(z10, z11, z12, z13, -0.25f, 0.5f, 0.5f, -0.25f)),
-                                        plf2::chain4(z20, z21, z22, z23, -0.25f, 0.5f, 0.5f, -0.25f)), lowr);
-                t11 = mul2(amp_of2(k, sx, sy, cv), bc(k.rs));
-            }
-        }
-    }
-
-    /* upsampleMatrix[0..3]; at level 0 the window is all zeros and the term adds 0 */
-    const float W1 = -1.0f / 16.0f, W9 = 9.0f / 16.0f;
-    const float V1 = 1.0f / 256.0f, V9 = -9.0f / 256.0f, V81 = 81.0f / 256.0f;
-    const F2 u00 = z11;
-    const F2 u10 = plf2::chain4(z10, z11, z12, z13, W1, W9, W9, W1);
-    F2 u01 = bc(0.0f), u11 = bc(0.0f);
-    if (!TAIL) {
-        /* ((z01*W1 + z11*W9) + z21*W9) + z31*W1: products by W1 are exact, so they may ride in an fma;
-         * the product z21*W9 must round on its own and ptxas would contract a packed multiply into the
-         * packed add that follows (pl_f2.cuh) -> that one step is scalar */
-        const F2 x = fma2(z01, bc(W1), mul2(z11, bc(W9)));
-        const float qx = __fmul_rn(z21.x, W9), qy = __fmul_rn(z21.y, W9);
-        u01 = fma2(z31, bc(W1), make_float2(__fadd_rn(x.x, qx), __fadd_rn(x.y, qy)));
-        u11 = add2(add2(add2(plf2::chain4(z00, z01, z02, z03, V1, V9, V9, V1), plf2::chain4(z10, z11, z12, z13, V9, V81, V81, V9)),
-                        plf2::chain4(z20, z21, z22, z23, V9, V81, V81, V9)), plf2::chain4(z30, z31, z32, z33, V1, V9, V9, V1));
-    }
-
-    /* zf = residual + scale * noise, then + upsample.  The last step is scalar so that its results can
-     * land directly in store order (A.x0, A.x0+1, B.x0+2, B.x0+3): one 16-byte store per row and plane */
-    float f00A, f10A, f00B, f10B, f01A = 0.0f, f11A = 0.0f, f01B = 0.0f, f11B = 0.0f;
-    if (NZ == NZ_NONE) {
-        f00A = r00A; f10A = r10A; f00B = r00B; f10B = r10B;
-        f01A = r01A; f11A = r11A; f01B = r01B; f11B = r11B;
-    } else {
-        f00A = fmaf(t00.x, n00.x, r00A); f00B = fmaf(t00.y, n00.y, r00B);
-        f10A = fmaf(t10.x, n10.x, r10A); f10B = fmaf(t10.y, n10.y, r10B);
-        if (!TAIL) {
-            f01A = fmaf(t01.x, n01.x, r01A); f01B = fmaf(t01.y, n01.y, r01B);
-            f11A = fmaf(t11.x, n11.x, r11A); f11B = fmaf(t11.y, n11.y, r11B);
-        }
-    }
-    /* level 0: zc = zf before the (zero) upsample term: keep those for the zc plane */
-    const float4 g0 = make_float4(f00A, f10A, f00B, f10B), g1 = make_float4(f01A, f11A, f01B, f11B);
-    f00A = f00A + u00.x; f00B = f00B + u00.y; f10A = f10A + u10.x; f10B = f10B + u10.y;
-    if (!TAIL) { f01A = f01A + u01.x; f01B = f01B + u01.y; f11A = f11A + u11.x; f11B = f11B + u11.y; }
-
-    /* zm = max(zf, 0), or zf itself under NO_CLAMP (floor = -inf) */
-    const float m00A = fmaxf(f00A, k.zm_floor), m10A = fmaxf(f10A, k.zm_floor), m00B = fmaxf(f00B, k.zm_floor), m10B = fmaxf(f10B, k.zm_floor);
-    float m01A = 0.0f, m11A = 0.0f, m01B = 0.0f, m11B = 0.0f;
-    if (!TAIL) { m01A = fmaxf(f01A, k.zm_floor); m11A = fmaxf(f11A, k.zm_floor); m01B = fmaxf(f01B, k.zm_floor); m11B = fmaxf(f11B, k.zm_floor); }
-
-    float *o0 = k.out + y0 * PITCH + x0;
-    *reinterpret_cast<float4 *>(o0) = make_float4(f00A, f10A, f00B, f10B);
-    *reinterpret_cast<float4 *>(o0 + 2 * PLANE) = make_float4(m00A, m10A, m00B, m10B);
-    if (!TAIL) {
-        *reinterpret_cast<float4 *>(o0 + PITCH) = make_float4(f01A, f11A, f01B, f11B);
-        *reinterpret_cast<float4 *>(o0 + 2 * PLANE + PITCH) = make_float4(m01A, m11A, m01B, m11B);
-    }
-
-    if (k.has_parent) {
-        /* TG even: both texels of a quad in x (in y) round to the same lattice column (row);
-         * zc1 = zm[round_x, floor_y], zc3 = zm[floor_x, round_y] */
-        const int2 lx = *reinterpret_cast<const int2 *>(k.lutx + i);
-        const int ly = k.luty[j];
-        const int kfy = ly & 0x7fff, kry = (ly >> 16) & 0x7fff;      /* premultiplied by NK */
-        const int krxA = lx.x & 0x7fff, kfxA = (lx.x >> 16) & 0x7fff;
-        const int krxB = lx.y & 0x7fff, kfxB = (lx.y >> 16) & 0x7fff;
-        const float zc1A = k.lat[krxA + kfy], zc3A = k.lat[kfxA + kry];
-        const float zc1B = k.lat[krxB + kfy], zc3B = k.lat[kfxB + kry];
-        const float zcA = (zc1A + zc3A) * 0.5f, zcB = (zc1B + zc3B) * 0.5f;
-        if (!TAIL) *reinterpret_cast<float4 *>(o0 + PLANE + PITCH) = make_float4(zcA, zcA, zcB, zcB);
-        float c00A = zcA, c00B = zcB;
-        if (k.flip && (ly & 0x8000)) {   /* only texel (x0, y0) of a quad can sit on a flipped diagonal */
-            if (lx.x & 0x8000) {
-                const float zc0 = k.lat[kfxA + kfy], zc2 = k.lat[krxA + kry];
-                c00A = (zc3A + zc1A >= zc0 + zc2 ? zc1A + zc3A : zc0 + zc2) * 0.5f;
-            }
-            if (lx.y & 0x8000) {
-                const float zc0 = k.lat[kfxB + kfy], zc2 = k.lat[krxB + kry];
-                c00B = (zc3B + zc1B >= zc0 + zc2 ? zc1B + zc3B : zc0 + zc2) * 0.5f;
-            }
-        }
-        *reinterpret_cast<float4 *>(o0 + PLANE) = make_float4(c00A, zcA, c00B, zcB);
-    } else {
-        *reinterpret_cast<float4 *>(o0 + PLANE) = g0;
-        if (!TAIL) *reinterpret_cast<float4 *>(o0 + PLANE + PITCH) = g1;
-    }
-
-    if (k.want_stats && !TAIL) {   /* TileSamplerZ.cpp:60-64: texels [2, W-3]^2 of zm; row W-1 is outside */
-        const bool pA = x0 >= 2 && x0 + 1 <= GEO::W - 3;             /* both columns of quad A */
-        const bool pBe = x0 + 2 <= GEO::W - 3, pBo = x0 + 3 <= GEO::W - 3;
-        const bool py0 = j >= 1, py1 = j >= 1 && y0 + 1 <= GEO::W - 3;   /* y0 <= W-3 always holds here */
-        /* quad B's odd column is outside only in the last real quad pair: fold it onto the even column */
-        const float b0 = pBo ? m10B : m00B, b1 = pBo ? m11B : m01B;
-        if (pA && py0) { lo = fminf(fminf(lo, m00A), m10A); hi = fmaxf(fmaxf(hi, m00A), m10A); }
-        if (pA && py1) { lo = fminf(fminf(lo, m01A), m11A); hi = fmaxf(fmaxf(hi, m01A), m11A); }
-        if (pBe && py0) { lo = fminf(fminf(lo, m00B), b0); hi = fmaxf(fmaxf(hi, m00B), b0); }
-        if (pBe && py1) { lo = fminf(fminf(lo, m01B), b1); hi = fmaxf(fmaxf(hi, m01B), b1); }
-    }
-}
-
-template <class GEO, int NZ, int RESID>
-__device__ __forceinline__ void tile_loop(const QuadCtx &k, const int tid, float &lo, float &hi)
-{
-    constexpr int QP = GEO::QW / 2, QH = GEO::QH;   /* quad pairs per row pair, full row pairs */
-    constexpr int DJ = kThreads / QP, DI = kThreads - DJ * QP;   /* one stride of kThreads items in (row pair, quad pair) */
-    int j = tid / QP, ip = tid - j * QP;
-    while (j < QH) {
-        do_quad2<GEO, NZ, RESID, false>(k, ip, j, lo, hi);
-        ip += DI; j += DJ;
-        if (ip >= QP) { ip -= QP; j += 1; }
-    }
-    if (tid < QP) do_quad2<GEO, NZ, RESID, true>(k, tid, QH, lo, hi);
-}
-
 template <int TW, int TG, int RESID>
 __global__ void __launch_bounds__(kThreads) elevation_kernel_fast(const __grid_constant__ CUtensorMap tm, const ElevArgs a)
 {
-    using GEO = Geo<TW, TG>;
-    constexpr int W = GEO::W, G = GEO::G, NK = GEO::NK, QW = GEO::QW;
-    static_assert(QW % 2 == 0 && GEO::BOX_W % 4 == 0 && GEO::BOX_W >= QW + 4, "quad pairs read aligned float pairs inside a window row");
-    __shared__ __align__(128) float winA[GEO::BOX_H * GEO::BOX_W];
-    __shared__ __align__(128) float winB[GEO::BOX_H * GEO::BOX_W];
-    __shared__ float lat[NK * NK];
-    __shared__ __align__(8) int lutx[QW];
-    __shared__ int luty[QW];
+    __shared__ __align__(128) float smem[ElevSmem<TW, TG>::FLOATS];
     __shared__ uint64_t bar;
-    __shared__ float red_lo[kThreads / 32], red_hi[kThreads / 32];
-
     const int tid = threadIdx.x;
     const pl_elev_req rq = a.reqs[blockIdx.x];
-    const bool has_parent = rq.parent_slot >= 0;
-
     if (tid == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (has_parent) {
-            mbar_expect_tx(&bar, (uint32_t) (GEO::BOX_W * GEO::BOX_H * sizeof(float)));
-            tma_load_3d(winA, &tm, &bar, rq.dx, rq.dy, rq.parent_slot * 3);
-        }
-    }
-    /* lattice indices of quad column / row pair q (texel 2q): round and floor variants */
-    if (tid < QW) {
-        const int ij = 2 * tid - 2;
-        const int kr = floordiv(ij + G, 2 * G) + 1, kf = floordiv(ij, 2 * G) + 1;
-        int m = ij % (2 * G);
-        if (m < 0) m += 2 * G;
-        const int fl = (m == G) ? 0x8000 : 0;
-        lutx[tid] = kr | fl | (kf << 16);
-        luty[tid] = (kf * NK) | fl | ((kr * NK) << 16);
-    }
-    if (has_parent) {
-        const float *pzm = a.elev + (size_t) rq.parent_slot * 3 * GEO::PLANE + 2 * GEO::PLANE;
-        for (int q = tid; q < NK * NK; q += kThreads) {
-            const int kx = q % NK - 1, ky = q / NK - 1;
-            const int px = min(max(2 + G * kx + rq.dx, 0), W - 1);   /* CLAMP_TO_EDGE */
-            const int py = min(max(2 + G * ky + rq.dy, 0), W - 1);
-            lat[q] = __ldg(pzm + py * GEO::PITCH + px);
-        }
-    } else {
-        for (int q = tid; q < GEO::BOX_W * GEO::BOX_H; q += kThreads) { winA[q] = 0.0f; winB[q] = 0.0f; }
-        for (int q = tid; q < NK * NK; q += kThreads) lat[q] = 0.0f;
     }
     __syncthreads();
-    if (has_parent) {
-        mbar_wait(&bar, 0);
-        /* the window a second time, one texel to the right: packed loads of odd window columns become
-         * aligned pairs of the copy.  (A second TMA load at dx + 1 is not possible: without swizzle the
-         * inner coordinate of a tiled fp32 copy must start on a 16-byte boundary -- measured on B200.) */
-        constexpr int G4 = GEO::BOX_W / 4;
-        for (int q = tid; q < GEO::BOX_H * G4; q += kThreads) {
-            const int g = q % G4;
-            const float4 v = *reinterpret_cast<const float4 *>(winA + 4 * q);
-            const float nxt = g + 1 < G4 ? winA[4 * q + 4] : 0.0f;
-            *reinterpret_cast<float4 *>(winB + 4 * q) = make_float4(v.y, v.z, v.w, nxt);
-        }
-        __syncthreads();
-    }
-
-    QuadCtx k;
-    k.winA = winA;
-    k.winB = winB;
-    k.lat = lat;
-    k.lutx = lutx;
-    k.luty = luty;
-    k.out = a.elev + (size_t) rq.out_slot * 3 * GEO::PLANE;
-    k.nplane = a.noise + (size_t) (rq.noise_r * 6 + rq.noise_l) * a.noise_plane;
-    k.noise_pitch = a.noise_pitch;
-    k.resid_pitch = a.resid_pitch;
-    k.has_resid = RESID != 0 && rq.resid_slot >= 0;
-    k.resid = nullptr;
-    if (k.has_resid) {
-        const size_t off = (size_t) rq.resid_slot * a.resid_slot_elems + (size_t) rq.ry * a.resid_pitch + rq.rx;
-        k.resid = RESID == 1 ? static_cast<const void *>(static_cast<const float *>(a.resid) + off)
-                             : static_cast<const void *>(static_cast<const short *>(a.resid) + off);
-    }
-    k.rs = rq.rs;
-    k.ars = fabsf(rq.rs);
-    k.pixel = rq.pixel_size;
-    k.nvz = 2.0f * rq.pixel_size;
-    k.rcp_pixel = plfp::rcp_rn(k.pixel);
-    k.rcp_nvz = plfp::rcp_rn(k.nvz);
-    k.resid_scale = a.resid_scale;
-    k.has_parent = has_parent;
-    k.flip = a.flip != 0;
-    k.zm_floor = a.no_clamp ? -INFINITY : 0.0f;
-    k.want_stats = a.want_stats != 0;
-
-    float lo = INFINITY, hi = -INFINITY;
-    /* tile-uniform noise variant; rs == 0 adds exactly 0 in every variant */
-    const int nz = rq.rs == 0.0f ? NZ_NONE : (a.noise_mode == PL_NOISE_PLAIN ? NZ_PLAIN : (rq.rs < 0.0f ? NZ_NEG : NZ_SLOPE));
-    switch (nz) {
-    case NZ_NONE: tile_loop<GEO, NZ_NONE, RESID>(k, tid, lo, hi); break;
-    case NZ_PLAIN: tile_loop<GEO, NZ_PLAIN, RESID>(k, tid, lo, hi); break;
-    case NZ_NEG: tile_loop<GEO, NZ_NEG, RESID>(k, tid, lo, hi); break;
-    default: tile_loop<GEO, NZ_SLOPE, RESID>(k, tid, lo, hi); break;
-    }
-
-    if (k.want_stats) {
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, s));
-            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
-        }
-        if ((tid & 31) == 0) { red_lo[tid >> 5] = lo; red_hi[tid >> 5] = hi; }
-        __syncthreads();
-        if (tid == 0) {
-#pragma unroll
-            for (int q = 1; q < kThreads / 32; ++q) { lo = fminf(lo, red_lo[q]); hi = fmaxf(hi, red_hi[q]); }
-            a.stats[rq.out_slot] = make_float2(lo, hi);
-        }
-    }
+    elevation_tile<TW, TG, RESID, kThreads, false>(&tm, a, rq, smem, &bar, 0, nullptr, tid);
 }
 
 }  // namespace
 
 
-int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n,
-                        const pl_elev_req *dev_reqs)
+int pl_elev_fill_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, const pl_elev_req *dev_reqs,
+                      plelev::ElevArgs &a)
 {
-    PL_CUDA(cudaSetDevice(ctx->device));
-    ElevArgs a;
     a.elev = reinterpret_cast<float *>(elev->base);
     a.resid = resid ? resid->base : nullptr;
     a.noise = ctx->noise_rot;
@@ -751,6 +314,16 @@ int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_
     a.resid_pitch = resid ? resid->pitch : 0;
     a.resid_slot_elems = resid ? (long long) (resid->slot_bytes / (resid->kind == PL_POOL_RESID_F32 ? 4 : 2)) : 0;
     a.resid_scale = sc->resid_scale;
+    return PL_OK;
+}
+
+int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n,
+                        const pl_elev_req *dev_reqs)
+{
+    PL_CUDA(cudaSetDevice(ctx->device));
+    ElevArgs a;
+    int rc = pl_elev_fill_args(ctx, sc, elev, resid, dev_reqs, a);
+    if (rc) return rc;
 
     const size_t smem = (size_t) a.box_w * a.box_h * 4 + (size_t) a.nk * a.nk * 4 + (size_t) a.W * 4;
     const int rk = !resid ? 0 : (resid->kind == PL_POOL_RESID_F32 ? 1 : 2);

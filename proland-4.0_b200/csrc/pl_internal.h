@@ -54,6 +54,7 @@ struct pl_ctx {
     pl_norm_req *gen_nreq;
     int gen_cap;
     int force_generic;   /* tests: run the runtime-geometry kernels even for the shipped geometry */
+    int no_fuse;         /* tests / profiling: pl_produce_range launches the two passes separately */
     /* per-launch CUDA-event timing (pl_timing_*): events on the launching stream */
     int timing;
     struct TimedLaunch { cudaEvent_t a, b; int kernel; int tiles; };
@@ -80,7 +81,7 @@ int pl_set_error(int code, const char *fmt, ...);
     } while (0)
 
 /* kernel ids of pl_timing_collect */
-enum { PL_K_ELEVATION = 0, PL_K_NORMAL = 1, PL_K_GENREQ = 2, PL_K_RESIDUAL = 3, PL_K_COUNT = 4 };
+enum { PL_K_ELEVATION = 0, PL_K_NORMAL = 1, PL_K_GENREQ = 2, PL_K_RESIDUAL = 3, PL_K_PAIR = 4, PL_K_COUNT = PL_TIMING_KERNELS };
 /* bracket a launch with events when timing is on: call begin before, end after */
 void pl_timing_begin(pl_ctx *ctx, int kernel, int tiles);
 void pl_timing_end(pl_ctx *ctx);
@@ -93,6 +94,12 @@ int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_
                         int n, const pl_elev_req *dev_reqs);
 int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev,
                      int n, const pl_norm_req *dev_reqs);
+
+/* fused elevation + normal pass (pl_pair.cu): one CTA per tile pair */
+bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, const pl_pool *elev,
+                       const pl_pool *norm);
+int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
+                   pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs);
 
 /* host maths shared with the request builders (pl_hostmath.cpp) */
 void pl_host_dem_noise(int W, float *out6);      /* fp32, before the R16F rounding */

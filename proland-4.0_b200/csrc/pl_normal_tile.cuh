@@ -1,0 +1,347 @@
+/*
+ * pl_normal_tile.cuh -- device code of the NormalProducer pass for ONE tile of the shipped geometry
+ * (compile-time tile width, border 2, RG8), shared by the normal kernel (pl_normal.cu) and the fused
+ * elevation+normal kernel (pl_pair.cu).
+ *
+ * Reference: normalShader.glsl:60-125 after NormalProducer::doCreateTile (NormalProducer.cpp:164-289)
+ * has set the uniforms.  Arithmetic: canonical order of oracle/orc_fp.h.
+ */
+#ifndef PL_NORMAL_TILE_CUH
+#define PL_NORMAL_TILE_CUH
+
+#include "pl_internal.h"
+#include "pl_fpexact.cuh"
+#include "pl_f2.cuh"
+
+namespace plnorm {
+
+
+struct NormArgs {
+    const float *elev;       /* elevation pool base */
+    uint8_t *norm;           /* normal pool base */
+    const pl_norm_req *reqs;
+    int W;                   /* normal tile width */
+    int EW, epitch, eplane;  /* elevation tile width, row pitch, plane elems */
+    int border;
+    int linear;              /* elevation storage filter */
+    int sphere;
+    int channels;            /* 2 (RG8) or 4 (RGBA8: fine + coarse normal) */
+    int grid;                /* tileSDF.y */
+    int parent_linear;       /* normal storage filter (parent coarse normal fetch) */
+    int nbands, max_rows;    /* bands per tile, rows of the largest band */
+    long long norm_slot_bytes;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+__device__ __forceinline__ float dot3(float a0, float a1, float a2, float b0, float b1, float b2)
+{
+    return fmaf(a2, b2, fmaf(a1, b1, a0 * b0));
+}
+__device__ __forceinline__ float dot4(const float *m, float v0, float v1, float v2, float v3)
+{
+    return fmaf(m[3], v3, fmaf(m[2], v2, fmaf(m[1], v1, m[0] * v0)));
+}
+/* OpenGL 3.3 spec 2.1.5: float -> unorm8, round to nearest */
+__device__ __forceinline__ unsigned int unorm8(float f)
+{
+    if (!(f > 0.0f)) return 0u;
+    if (f >= 1.0f) return 255u;
+    return (unsigned int) __float2int_rn(f * 255.0f);
+}
+__device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+
+/* .xy of the parent's RGBA8 normal tile at texel coordinate (cx, cy) (already offset by +0.25,
+ * NormalProducer.cpp:201-205) through the normal storage's filter; unorm8 -> float is c / 255
+ * (OpenGL 3.3 spec 2.1.5), CLAMP_TO_EDGE */
+__device__ __forceinline__ float2 fetch_parent_xy(const uchar4 *parent, int W, bool linear, float cx, float cy)
+{
+    auto PN = [&](int i, int j) {
+        const uchar4 t = __ldg(parent + min(max(j, 0), W - 1) * W + min(max(i, 0), W - 1));
+        return make_float2((float) t.x / 255.0f, (float) t.y / 255.0f);
+    };
+    if (!linear) return PN((int) floorf(cx), (int) floorf(cy));
+    const float fx = cx - 0.5f, fy = cy - 0.5f;
+    const int i0 = (int) floorf(fx), j0 = (int) floorf(fy);
+    const float fa = fx - (float) i0, fb = fy - (float) j0;
+    const float2 t00 = PN(i0, j0), t10 = PN(i0 + 1, j0), t01 = PN(i0, j0 + 1), t11 = PN(i0 + 1, j0 + 1);
+    const float w11 = fa * fb, w01 = (1.0f - fa) * fb, w10 = fa * (1.0f - fb), w00 = (1.0f - fa) * (1.0f - fb);
+    return make_float2(fmaf(w11, t11.x, fmaf(w01, t01.x, fmaf(w10, t10.x, w00 * t00.x))),
+                       fmaf(w11, t11.y, fmaf(w01, t01.y, fmaf(w10, t10.y, w00 * t00.y))));
+}
+
+/* ------------------------------------------------------------------------
+ * Specialised kernel: compile-time geometry (TW normal tile width, border 2).
+ * Same arithmetic as the generic kernel; the pass is issue-bound (profiles/),
+ * so everything here is about the instruction count per texel:
+ *   - ONE CTA PER TILE: the whole zm plane of the tile arrives by one bulk copy
+ *     (its rows are contiguous in the pitched plane); the CTA then walks the tile
+ *     in bands of kTileBand rows, so the per-CTA set-up (request, uv table,
+ *     barrier) is paid once per tile, and the two grid rows a band shares with
+ *     the next one are carried over instead of recomputed
+ *   - every thread works on a PAIR of horizontally adjacent grid points and on
+ *     a 2x2 block of texels; all fp32 maths is packed FFMA2/FMUL2/FADD2
+ *     (pl_f2.cuh): half the issue slots for the same IEEE results
+ *   - index maths folds to immediates / multiply-shifts
+ *   - the four quotients alpha*L/dot(alpha,L) share ONE refined reciprocal
+ *     (pl_fpexact.cuh: 3 FFMA per IEEE quotient), normalisation is the
+ *     5-instruction IEEE sqrt + 3-instruction IEEE reciprocal, no branches
+ *   - positions live in shared memory as three planes of row pitch GWP (even),
+ *     rows shifted so that every access of the normal phase is an aligned pair
+ *   - the RG8 texels go from registers straight to HBM (2-byte stores; the L2
+ *     merges the two halves of every sector before it is written back)
+ *   - SPHERE / LINEAR are template parameters: no per-point tests
+ * ------------------------------------------------------------------------ */
+constexpr int kTileBand = 20;     /* texel rows per band: 20 x 50 point pairs and 10 x 49 texel blocks fill 256 threads 4x and 2x */
+
+template <int TW>
+struct NGeo {
+    static constexpr int W = TW, B = 2;
+    static constexpr int EW = TW + 2 * B;
+    static constexpr int EPITCH = (EW + 3) & ~3;
+    static constexpr int EPLANE = EW * EPITCH;
+    static constexpr int GW = TW + 2;                 /* grid points X = -1 .. W */
+    static constexpr int GWP = ((GW + 1) & ~1) + 4;   /* row pitch of a position plane: even, room for the row shift and the pad pairs */
+    static constexpr int GPAIRS = (GW + 2) / 2;       /* grid-point pairs per row (covers an odd start) */
+    static constexpr int XPAIRS = (TW + 2) / 2;       /* texel pairs per row (covers an odd start) */
+    static constexpr int NBANDS = (TW + kTileBand - 1) / kTileBand;
+    static constexpr int LAST_ROWS = TW - (NBANDS - 1) * kTileBand;
+    static constexpr int POS_ROWS = kTileBand + 2;    /* grid rows a band touches */
+    static constexpr int POS_PLANE = POS_ROWS * GWP;
+    static constexpr int ULUT = (GW + 4) & ~1;        /* u of X = -2 .. W+1, twice (second copy one entry further) */
+    static constexpr size_t SMEM = 16 + (size_t) EPLANE * 4 + (size_t) 3 * POS_PLANE * 4 + (size_t) 2 * ULUT * 4;   /* 16: guard floats in front of the zm plane */
+    static_assert(EPITCH % 2 == 0 && EPITCH >= GW + 3, "paired loads stay inside a staged row");
+    static_assert(kTileBand % 4 == 0, "the row-shift pattern restarts with every band");
+    static_assert((LAST_ROWS + 1) / 2 * 2 + 2 <= POS_ROWS, "the last band's blocks stay inside the position rows");
+    static_assert((2 * GWP * 3) % 4 == 0 && GWP % 4 == 0, "the carried rows move as float4");
+};
+
+/* Shared-memory layout of the position planes.  A thread of the normal phase owns a 2x2 block of
+ * texels: it needs 4 consecutive grid points of the block's two rows and the 2 middle ones of the
+ * rows below / above.  Grid row g is stored shifted right by shift(g) = ((g + 3) >> 1) & 1 elements and
+ * texel blocks of block row k start at x = (k & 1) - 1 (mod 2): with that every one of those accesses is
+ * an ALIGNED 8-byte pair (shared-memory wavefronts are a limiter of this kernel, profiles/):
+ *   block row k even (x even): rows 2k+1, 2k+2 shift 0 -> pairs at x, x+2; rows 2k, 2k+3 shift 1 -> pair at x+1+1
+ *   block row k odd  (x odd) : rows 2k+1, 2k+2 shift 1 -> pairs at x+1, x+3; rows 2k, 2k+3 shift 0 -> pair at x+1
+ * Bands start on multiples of 4 rows, so the shift of a row depends only on its row inside the band. */
+__device__ __forceinline__ int row_shift(int g) { return ((g + 3) >> 1) & 1; }
+
+/* Normals of one tile.  zs: the tile's zm plane (EW rows of pitch EPITCH) in shared memory; pos: 3
+ * position planes of POS_ROWS x GWP; ulut: the two uv tables; out: the tile's RG8 texels in HBM.
+ * All threads of the CTA call this; it contains __syncthreads(). */
+template <int TW, bool SPHERE, bool LINEAR, int NT>
+__device__ __forceinline__ void normal_tile(const float *zs, float *pos, const float *ulut, const pl_norm_req &rq,
+                                            unsigned short *out, const int tid)
+{
+    using namespace plf2;
+    using GEO = NGeo<TW>;
+    constexpr int W = GEO::W, GWP = GEO::GWP, EPITCH = GEO::EPITCH, UL = GEO::ULUT;
+    constexpr int GPAIRS = GEO::GPAIRS, XPAIRS = GEO::XPAIRS, PP = GEO::POS_PLANE;
+
+    const float D = rq.deform[2], R = rq.deform[3];
+    const float x0f = rq.deform[0], y0f = rq.deform[1];
+    const float s = rq.smooth;
+    const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
+    const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
+
+    /* position phase: thread = (pair column, row lane) */
+    constexpr int PR = NT / GPAIRS;                    /* grid rows per pass */
+    const int rl0 = tid / GPAIRS, pc2 = 2 * (tid - rl0 * GPAIRS);
+    const bool pc_ok = rl0 < PR;
+    const float *uA = ulut + pc2, *uB = ulut + UL + pc2;
+    /* normal phase: thread = (block column, block row lane) */
+    constexpr int KR = NT / XPAIRS;                    /* block rows per pass */
+    const int kl0 = tid / XPAIRS, xc2 = 2 * (tid - kl0 * XPAIRS);
+    const bool xc_ok = kl0 < KR;
+
+#pragma unroll 1
+    for (int band = 0; band < GEO::NBANDS; ++band) {
+        const int y_begin = band * kTileBand;
+        const int rows = band == GEO::NBANDS - 1 ? GEO::LAST_ROWS : kTileBand;
+        /* grid rows of the band: local r = 0 .. rows+1 (grid row g = y_begin + r is Y = g - 1);
+         * rows 0, 1 of every band but the first were computed by the band before */
+        const int r_lo = band == 0 ? 0 : 2;
+        if (band != 0) {
+            __syncthreads();   /* the band before has read its positions */
+            constexpr int N4 = 2 * GWP / 4;
+            if (tid < 3 * N4) {
+                const int pl = tid / N4, c = tid - pl * N4;
+                float4 *dst = reinterpret_cast<float4 *>(pos + pl * PP) + c;
+                *dst = *reinterpret_cast<const float4 *>(pos + pl * PP + kTileBand * GWP + 4 * c);
+            }
+            __syncthreads();   /* rows kTileBand, kTileBand+1 are about to be rewritten */
+        }
+        /* ---- world position of the new grid points of the band, two per thread ----
+         * thread = (pair column pc, row lane rl0): its columns never change, rows advance by PR per pass,
+         * so every address below is the previous one plus a constant */
+        {
+            const int r_hi = rows + 2;
+            int r = r_lo + rl0;
+            const float *zrow = zs + (y_begin + r + 1) * EPITCH + pc2;   /* row Y + 2 of the tile, column pc2 */
+            const float *vp = ulut + y_begin + r + 1;                    /* Y = y_begin + r - 1 */
+            float *o3 = pos + r * GWP + pc2 + 2;
+            if (pc_ok)
+            for (; r < r_hi; r += PR, zrow += PR * EPITCH, vp += PR, o3 += PR * GWP) {
+                const int sh = row_shift(r);
+                /* grid points gx, gx+1 with gx = pc2 - sh (X = gx - 1, gx): elevation texels (gx + 1, Y + 2),
+                 * (gx + 2, Y + 2).  Column -1 / GW of a shifted or last pair is a pad: it reads inside the
+                 * staged plane (or the guard floats in front of it) and is never used. */
+                const float *row1 = zrow - sh, *row0 = row1 - EPITCH;
+                F2 h;
+                if (!LINEAR) {
+                    h = make_float2(row1[1], row1[2]);
+                } else {
+                    const F2 t00 = make_float2(row0[0], row0[1]);
+                    const F2 t10 = make_float2(t00.y, row0[2]);
+                    const F2 t01 = make_float2(row1[0], row1[1]);
+                    const F2 t11 = make_float2(t01.y, row1[2]);
+                    h = fma2(bc(0.5625f), t11, fma2(bc(0.1875f), t01, fma2(bc(0.1875f), t10, mul2(bc(0.0625f), t00))));
+                }
+                /* u of X = gx - 1, gx: table index X + 2; the pair is aligned in the first copy when gx is odd,
+                 * in the second (one entry further) when it is even */
+                const F2 u = *reinterpret_cast<const F2 *>(sh ? uA : uB);
+                const float v = *vp;
+                F2 qx, qy, qz;
+                if (!SPHERE) {
+                    qx = fma2(bc(D), u, bc(x0f));
+                    qy = bc(fmaf(D, v, y0f));
+                    qz = h;
+                } else {
+                    const F2 U = sub2(bc(1.0f), u);
+                    const float V = 1.0f - v;
+                    const F2 a0 = mul2(U, bc(V)), a1 = mul2(u, bc(V)), a2 = mul2(U, bc(v)), a3 = mul2(u, bc(v));
+                    const F2 l0 = mul2(a0, bc(rq.norms[0])), l1 = mul2(a1, bc(rq.norms[1]));
+                    const F2 l2 = mul2(a2, bc(rq.norms[2])), l3 = mul2(a3, bc(rq.norms[3]));
+                    const F2 den = fma2(a3, bc(rq.norms[3]), fma2(a2, bc(rq.norms[2]), fma2(a1, bc(rq.norms[1]), l0)));
+                    const F2 rden = rcp_rn2(den);
+                    const F2 p0 = div_rn2(l0, den, rden), p1 = div_rn2(l1, den, rden);
+                    const F2 p2q = div_rn2(l2, den, rden), p3 = div_rn2(l3, den, rden);
+#define ROW4(M, r_) fma2(bc(M[4 * (r_) + 3]), p3, fma2(bc(M[4 * (r_) + 2]), p2q, fma2(bc(M[4 * (r_) + 1]), p1, mul2(bc(M[4 * (r_)]), p0))))
+                    const F2 upx = ROW4(rq.verticals, 0), upy = ROW4(rq.verticals, 1), upz = ROW4(rq.verticals, 2);
+                    F2 hp = h;
+                    if (s != 1.0f) {   /* tile-uniform: levels whose quad is larger than R/64 */
+                        const F2 len = sqrt_rn2(plf2::dot3(upx, upy, upz, upx, upy, upz));
+                        const F2 kk = fma2(bc(1.0f), bc(s), mul2(len, bc(1.0f - s)));   /* mix(len, 1, s) */
+                        hp = div_rn2(fma2(bc(R), sub2(bc(1.0f), kk), h), kk, rcp_rn2(kk));
+                    }
+                    qx = fma2(hp, upx, ROW4(rq.corners, 0));
+                    qy = fma2(hp, upy, ROW4(rq.corners, 1));
+                    qz = fma2(hp, upz, ROW4(rq.corners, 2));
+#undef ROW4
+                }
+                /* stored at column gx + shift + 2 (the +2 keeps the odd-start pad at a non-negative, even slot) */
+                *reinterpret_cast<F2 *>(o3) = qx;
+                *reinterpret_cast<F2 *>(o3 + PP) = qy;
+                *reinterpret_cast<F2 *>(o3 + 2 * PP) = qz;
+            }
+        }
+        __syncthreads();
+
+        /* ---- normals of the band: a 2 x 2 block of texels per thread ------------- */
+        /* thread = (block column xc, block row lane kl0): columns fixed, block rows advance by KR per pass */
+        const int nbr = (rows + 1) >> 1;
+        int k = kl0;
+        const float *c1 = pos + (2 * k + 1) * GWP + xc2 + 2;       /* grid column x of row g1 (aligned pair) */
+        unsigned short *ob = out + (y_begin + 2 * k) * W + xc2;
+        if (xc_ok)
+        for (; k < nbr; k += KR, c1 += 2 * KR * GWP, ob += 2 * KR * W) {
+            const int odd = k & 1;
+            const int x = xc2 - odd;                         /* -1, 1, 3, .. on odd block rows, 0, 2, .. on even ones */
+            const int ry = 2 * k;
+            /* texel (x, ry) is grid column x + 1 of grid row ry + 1.  Centre rows g1 = ry+1, g2 = ry+2 have
+             * shift `odd`; outer rows g0 = ry, g3 = ry+3 have shift 1 - odd.  Stored column = grid column + shift + 2,
+             * so row g1 starts at x + odd + 2 = xc2 + 2 and row g0 (grid column x + 1) at xc2 + 4 - 2 odd. */
+            const float *c0 = c1 - GWP + 2 - 2 * odd;
+            F2 d1[3], e1[3], d2[3], e2[3];
+#pragma unroll
+            for (int cpt = 0; cpt < 3; ++cpt) {
+                const F2 l1 = *reinterpret_cast<const F2 *>(c1 + cpt * PP);                 /* g1: x, x+1 */
+                const F2 r1 = *reinterpret_cast<const F2 *>(c1 + cpt * PP + 2);             /* g1: x+2, x+3 */
+                const F2 l2 = *reinterpret_cast<const F2 *>(c1 + cpt * PP + GWP);           /* g2: x, x+1 */
+                const F2 r2 = *reinterpret_cast<const F2 *>(c1 + cpt * PP + GWP + 2);       /* g2: x+2, x+3 */
+                const F2 m0 = *reinterpret_cast<const F2 *>(c0 + cpt * PP);                 /* g0: x+1, x+2 */
+                const F2 m3 = *reinterpret_cast<const F2 *>(c0 + cpt * PP + 3 * GWP);       /* g3: x+1, x+2 */
+                const F2 m1 = make_float2(l1.y, r1.x), m2 = make_float2(l2.y, r2.x);        /* g1, g2: x+1, x+2 */
+                d1[cpt] = sub2(r1, l1);   /* texel row ry:   right - left */
+                d2[cpt] = sub2(r2, l2);   /* texel row ry+1 */
+                e1[cpt] = sub2(m2, m0);   /* texel row ry:   up - down */
+                e2[cpt] = sub2(m3, m1);   /* texel row ry+1 */
+            }
+            unsigned int rg[2][2];   /* [row][texel]: r | g << 8 */
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const F2 *d = half ? d2 : d1, *e = half ? e2 : e1;
+                F2 nx = fma2(d[1], e[2], neg(mul2(d[2], e[1])));
+                F2 ny = fma2(d[2], e[0], neg(mul2(d[0], e[2])));
+                F2 nz = fma2(d[0], e[1], neg(mul2(d[1], e[0])));
+                const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
+                nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
+                const F2 tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
+                const F2 ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
+                /* unorm8: round(clamp(v * 0.5 + 0.5, 0, 1) * 255), NaN -> 0 */
+                const F2 r = mul2(make_float2(__saturatef(fmaf(tx.x, 0.5f, 0.5f)), __saturatef(fmaf(tx.y, 0.5f, 0.5f))), bc(255.0f));
+                const F2 g = mul2(make_float2(__saturatef(fmaf(ty.x, 0.5f, 0.5f)), __saturatef(fmaf(ty.y, 0.5f, 0.5f))), bc(255.0f));
+                rg[half][0] = (unsigned int) __float2int_rn(r.x) + ((unsigned int) __float2int_rn(g.x) << 8);
+                rg[half][1] = (unsigned int) __float2int_rn(r.y) + ((unsigned int) __float2int_rn(g.y) << 8);
+            }
+            unsigned short *o = ob - odd;
+            const bool px0 = x >= 0, px1 = x + 1 < W, py1 = ry + 1 < rows;
+            if (px0) o[0] = (unsigned short) rg[0][0];
+            if (px1) o[1] = (unsigned short) rg[0][1];
+            if (px0 && py1) o[W] = (unsigned short) rg[1][0];
+            if (px1 && py1) o[W + 1] = (unsigned short) rg[1][1];
+        }
+    }
+}
+
+/* uv / (tileSDF.x - 1.0) for X = -2 .. (X = -2 and W+1 are pads of odd-start pairs), twice: the second
+ * copy starts one entry further, so that a pair starting at an odd index is an aligned pair there */
+template <int TW, int NT>
+__device__ __forceinline__ void normal_uv_tables(float *ulut, const int tid)
+{
+    using GEO = NGeo<TW>;
+    const float wm1 = (float) GEO::W - 1.0f;
+    const float rw = plfp::rcp_rn(wm1);
+    for (int q = tid; q < GEO::ULUT; q += NT) {
+        const float uq = plfp::div_rn((float) (q - 2), wm1, rw);
+        ulut[q] = uq;
+        if (q >= 1) ulut[GEO::ULUT + q - 1] = uq;
+    }
+    if (tid == 0) ulut[2 * GEO::ULUT - 1] = 0.0f;
+}
+
+}  // namespace plnorm
+#endif

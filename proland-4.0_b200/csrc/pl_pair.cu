@@ -1,0 +1,123 @@
+/*
+ * pl_pair.cu -- the fused elevation + normal pass for sm_100a: one CTA produces the elevation tile
+ * (zf, zc, zm planes) AND the RG8 normal tile derived from it.
+ *
+ * The reference runs two GL passes per tile pair: ElevationProducer::doCreateTile draws upsampleShader
+ * (ElevationProducer.cpp:280-405, upsampleShader.glsl:140-203), then NormalProducer::doCreateTile
+ * draws normalShader on the finished elevation tile (NormalProducer.cpp:164-289,
+ * normalShader.glsl:60-125).  The two separate kernels (pl_elevation.cu, pl_normal.cu) mirror that; on
+ * B200 they leave each other's resource idle: the elevation pass is bound by the HBM write of the three
+ * planes and keeps the fp32 pipe about 60 % busy, the normal pass is bound by the fp32 pipe (the
+ * spherical world position of every grid point) and uses about 15 % of the HBM bandwidth.  Fused,
+ *   - the zm plane the normal pass needs never comes back from HBM: the elevation phase leaves a copy
+ *     in shared memory (39 KB of the 58 KB the normal pass would read and write)
+ *   - CTAs resident on one SM are in different phases, so the fp32 pipe works on normals while other
+ *     CTAs wait for their elevation stores, and one launch replaces two
+ * The per-tile device code is the same as the separate kernels' (pl_elevation_tile.cuh,
+ * pl_normal_tile.cuh): results are bit-identical.
+ *
+ * Shared memory of a CTA: [guard 96 B | zm plane 42 016 B | elevation windows + tables, reused as the
+ * position planes of the normal phase 27 456 B | uv tables 816 B] = 70.3 KB -> 3 CTAs per SM.
+ */
+#include "pl_elevation_tile.cuh"
+#include "pl_normal_tile.cuh"
+
+int pl_elev_fill_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, const pl_elev_req *dev_reqs,
+                      plelev::ElevArgs &a);
+int pl_norm_fill_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, const pl_norm_req *dev_reqs,
+                      plnorm::NormArgs &a);
+
+namespace {
+
+constexpr int kPairThreads = 256;
+
+template <int TW, int TG>
+struct PairSmem {
+    using EG = plelev::Geo<TW, TG>;
+    using NG = plnorm::NGeo<TW - 4>;
+    static constexpr int GUARD = 24;                                           /* floats in front of the zm plane (>= 4; makes ZM a multiple of 128 bytes) */
+    static constexpr int ZM = GUARD + EG::PLANE;                               /* floats: guard + zm plane */
+    static constexpr int ELEV = plelev::ElevSmem<TW, TG>::FLOATS;
+    static constexpr int POS = 3 * NG::POS_PLANE;
+    static constexpr int WORK = ((ELEV > POS ? ELEV : POS) + 3) & ~3;           /* elevation scratch, then positions */
+    static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT) * 4;
+    static_assert(EG::PITCH == NG::EPITCH && EG::PLANE == NG::EPLANE, "both passes agree on the plane layout");
+    static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
+};
+
+template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR>
+__global__ void __launch_bounds__(kPairThreads, 3)
+tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
+{
+    using SM = PairSmem<TW, TG>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *zs = reinterpret_cast<float *>(smem_raw) + SM::GUARD;   /* zm plane behind the guard floats */
+    float *work = zs + plelev::Geo<TW, TG>::PLANE;
+    float *ulut = work + SM::WORK;
+    __shared__ uint64_t bar;
+    __shared__ pl_norm_req nrq;
+
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const pl_elev_req erq = ea.reqs[tile];
+    {
+        const int *src = reinterpret_cast<const int *>(na.reqs + tile);
+        int *dst = reinterpret_cast<int *>(&nrq);
+        if (tid < (int) (sizeof(pl_norm_req) / 4)) dst[tid] = __ldg(src + tid);
+    }
+    if (tid == 0) {
+        plelev::mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    plnorm::normal_uv_tables<TW - 4, kPairThreads>(ulut, tid);
+    __syncthreads();
+
+    /* elevation: planes to HBM, zm also to shared memory */
+    plelev::elevation_tile<TW, TG, RESID, kPairThreads, true>(&tm, ea, erq, work, &bar, 0, zs, tid);
+    __syncthreads();   /* zm plane complete; the elevation scratch is free */
+
+    /* normals from the shared zm plane */
+    unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
+    plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads>(zs, work, ulut, nrq, out, tid);
+}
+
+template <int RESID>
+int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const plnorm::NormArgs &na, int n)
+{
+    using SM = PairSmem<101, 4>;
+    void (*kern)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
+        na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true> : tile_pair_kernel<101, 4, RESID, true, false>)
+                  : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true> : tile_pair_kernel<101, 4, RESID, false, false>);
+    PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SM::BYTES));
+    pl_timing_begin(ctx, PL_K_PAIR, n);
+    kern<<<n, kPairThreads, SM::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return PL_OK;
+}
+
+}  // namespace
+
+/* true when the fused kernel serves this geometry (the one of every shipped archive) */
+bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, const pl_pool *elev,
+                       const pl_pool *norm)
+{
+    return !ctx->force_generic && !ctx->no_fuse && elev->tile_w == 101 && esc->grid == 4 && norm->tile_w == 97 &&
+           nsc->elev_border == 2 && norm->kind == PL_POOL_NORM_UN8x2;
+}
+
+/* n tile pairs: normal request i must describe the normal tile of elevation request i
+ * (nreq[i].elev_slot == ereq[i].out_slot) */
+int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
+                   pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs)
+{
+    PL_CUDA(cudaSetDevice(ctx->device));
+    plelev::ElevArgs ea;
+    plnorm::NormArgs na;
+    int rc = pl_elev_fill_args(ctx, esc, elev, resid, dev_ereqs, ea);
+    if (rc) return rc;
+    if ((rc = pl_norm_fill_args(ctx, nsc, norm, elev, dev_nreqs, na)) != PL_OK) return rc;
+    const int rk = !resid ? 0 : (resid->kind == PL_POOL_RESID_F32 ? 1 : 2);
+    return rk == 0 ? launch_pair<0>(ctx, elev, ea, na, n) : (rk == 1 ? launch_pair<1>(ctx, elev, ea, na, n) : launch_pair<2>(ctx, elev, ea, na, n));
+}

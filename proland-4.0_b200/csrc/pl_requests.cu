@@ -148,6 +148,9 @@ extern "C" int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *
     pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    /* request i of both arrays describes tile i: the fused kernel applies */
+    if (norm && pl_pair_supported(ctx, &sc->elev, &sc->norm, elev, norm))
+        return pl_launch_pair(ctx, &sc->elev, &sc->norm, elev, norm, nullptr, n, ctx->gen_ereq, ctx->gen_nreq);
     rc = pl_elevation_batch_dev(ctx, &sc->elev, elev, nullptr, n, ctx->gen_ereq);
     if (rc) return rc;
     if (norm) rc = pl_normal_batch_dev(ctx, &sc->norm, norm, elev, n, ctx->gen_nreq);

@@ -28,7 +28,7 @@ EXPORTS = [
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_produce_range", "pl_make_requests_range",
-    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_fpexact",
+    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample",
 ]
 
@@ -147,6 +147,7 @@ def lib():
                                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
         L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pl_debug_force_generic.argtypes = [C.c_void_p, C.c_int]
+        L.pl_debug_no_fuse.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
@@ -376,16 +377,21 @@ def _timing_enable(self, on=True):
 
 def _timing_collect(self):
     """-> {kernel name: (total ms, launches, tiles)} since the last collect (synchronises)."""
-    ms = np.zeros(4, np.float64)
-    cnt = np.zeros(4, np.uint64)
-    tiles = np.zeros(4, np.uint64)
+    ms = np.zeros(5, np.float64)
+    cnt = np.zeros(5, np.uint64)
+    tiles = np.zeros(5, np.uint64)
     check(lib().pl_timing_collect(self.h, _ptr(ms), _ptr(cnt), _ptr(tiles)))
-    names = ("elevation", "normal", "genreq", "residual")
+    names = ("elevation", "normal", "genreq", "residual", "pair")
     return {n: (float(ms[i]), int(cnt[i]), int(tiles[i])) for i, n in enumerate(names)}
 
 
 def _force_generic(self, on=True):
     check(lib().pl_debug_force_generic(self.h, int(on)))
+
+
+def _no_fuse(self, on=True):
+    """pl_produce_range launches the elevation and normal passes separately (same results)."""
+    check(lib().pl_debug_no_fuse(self.h, int(on)))
 
 
 def _fpexact(self, a, b):
@@ -418,6 +424,7 @@ SLOT_SCRATCH = -2
 Context.residual_decode = _residual_decode
 Context.residual_upsample = _residual_upsample
 Context.force_generic = _force_generic
+Context.no_fuse = _no_fuse
 Context.fpexact = _fpexact
 Context.timing_enable = _timing_enable
 Context.timing_collect = _timing_collect

@@ -117,6 +117,43 @@ def test_produce_range_equals_per_tile_path(plb, ctx, oracle):
         assert np.array_equal(norm.download(slot), n), (l, tx, ty)
 
 
+@pytest.mark.parametrize("sphere,elev_filter", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_fused_pair_kernel_equals_the_two_passes(plb, ctx, oracle, sphere, elev_filter):
+    """pl_produce_range runs the fused elevation+normal kernel (pl_pair.cu); with pl_debug_no_fuse it
+    launches the two passes separately.  Same tiles, same statistics, bit for bit -- and both equal
+    the oracle (levels 0..4 of one face: negative, and at level 8+ amplitudes positive noise)."""
+    amp = [-3250, -1590, 15, 8, 5]          # levels 2.. take the slope/curvature path
+    kw = dict(noise_amp=amp, face=3 if sphere else 0, root_quad_size=12720000.0 if sphere else 100000.0,
+              sphere=sphere, elev_filter=elev_filter)
+    sc = plb.sweep_scene(want_stats=1, **kw)
+    max_level = 4
+    total = sum(4 ** l for l in range(max_level + 1))
+    off = [sum(4 ** k for k in range(l)) for l in range(max_level + 1)]
+    ctx.noise_init(101)
+    out = []
+    for fuse in (True, False):
+        ctx.no_fuse(not fuse)
+        elev = ctx.pool(plb.POOL_ELEV, 101, total)
+        norm = ctx.pool(plb.POOL_NORM2, 97, total)
+        n0 = ctx.launches
+        for l in range(max_level + 1):
+            ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+        ctx.sync()
+        assert ctx.launches - n0 == (2 if fuse else 3) * (max_level + 1)
+        out.append((elev, norm))
+    ref = qt.oracle_quadtree(oracle, max_level, **kw)
+    (fe, fn), (se, sn) = out
+    for (l, tx, ty), (e, n, s) in ref.items():
+        slot = off[l] + plb.morton_encode(tx, ty)
+        a, b = fe.download(slot), se.download(slot)
+        assert a.tobytes() == b.tobytes(), (l, tx, ty)
+        assert np.array_equal(a, e), (l, tx, ty)
+        a, b = fn.download(slot), sn.download(slot)
+        assert a.tobytes() == b.tobytes(), (l, tx, ty)
+        assert np.array_equal(a, n), (l, tx, ty)
+    assert ctx.elev_stats_range(fe, 0, total).tobytes() == ctx.elev_stats_range(se, 0, total).tobytes()
+
+
 # ----------------------------------------------------------------- residuals
 
 import base64
