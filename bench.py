@@ -13,8 +13,8 @@ only gathers per-rank counters).  Total work is fixed as N grows -> "strong".
           generated on the GPU, nothing but (level, Morton range) crosses PCIe.
   e2e   : the per-tile plugin path -- per-tile uniforms built on the host like
           ElevationProducer/NormalProducer::doCreateTile do, handed to
-          pl_elevation_batch / pl_normal_batch as HOST arrays (copied to the
-          device inside the timed region), per-tile (zmin,zmax) read back.
+          pl_pair_batch as HOST arrays (copied to the device inside the timed
+          region), per-tile (zmin,zmax) read back.
 
   python bench.py [--gpus N --steps K --warmup W] [--impl reference]
   torchrun ... bench.py --gpus N ...          (one rank per GPU)
@@ -41,6 +41,9 @@ ELEV_BYTES_L0 = 101 * 101 * 12
 NORM_BYTES = 99 * 99 * 4 + 97 * 97 * 2           # normal kernel: own zm read + RG8 write
 PAIR_BYTES = ELEV_BYTES + NORM_BYTES             # 192 098
 METRIC = "elevation+normal tile pairs/sec"
+# dram__bytes_read.sum + dram__bytes_write.sum per tile of one `ncu --set full` capture (profiles/README.md):
+# 16384 level-8 tiles in one launch
+TRAFFIC = {"pair": 155752, "elevation": 136520, "normal": 59565}
 
 
 def peaks():
@@ -125,18 +128,40 @@ class PlanetSweep:
             pr(self.scenes[f], self.elev, self.norm, level, m0, n, s0, p0, pm0)
 
     def run_host_requests(self, units, nthreads=0):
-        """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out."""
+        """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out.  The uniforms of batch
+        k+1 are built (all host threads, in C) while batch k is submitted and its statistics are read
+        back -- the reference overlaps the same way: CreateTile tasks run on the scheduler's threads
+        while the previous frame's read-backs drain (TileSamplerZ + ReadbackManager)."""
+        from concurrent.futures import ThreadPoolExecutor
         pl, ctx = self.pl, self.ctx
+        if not hasattr(self, "_req_bufs"):
+            nmax = 4 ** max(self.max_level - 2, 1)
+            self._req_bufs = [(np.zeros(nmax, pl.ELEV_REQ_DTYPE), np.zeros(nmax, pl.NORM_REQ_DTYPE))
+                              for _ in range(2)]
+            self._pool = ThreadPoolExecutor(1)
         h2d = d2h = 0
-        for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
+        todo = list(self.plan.batches(units, self.max_level))
+
+        def build(i):
+            f, level, m0, n, s0, p0, pm0 = todo[i]
+            return pl.make_requests_range(self.scenes[f], level, m0, n, s0, p0, pm0, nthreads=nthreads,
+                                          out=self._req_bufs[i & 1])
+        nxt = self._pool.submit(build, 0) if todo else None
+        pending = None
+        for i, (f, level, m0, n, s0, p0, pm0) in enumerate(todo):
             sc = self.scenes[f]
-            e, q = pl.make_requests_range(sc, level, m0, n, s0, p0, pm0, nthreads=nthreads)
-            ctx.elevation_batch(sc.elev, self.elev, e)
-            ctx.normal_batch(sc.norm, self.norm, self.elev, q)
+            e, q = nxt.result()
+            ctx.pair_batch(sc.elev, sc.norm, self.elev, self.norm, e, q)   # copies e, q before it returns
+            if i + 1 < len(todo):
+                nxt = self._pool.submit(build, i + 1)
             h2d += e.nbytes + q.nbytes
-            if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile
-                st = ctx.elev_stats_range(self.elev, s0, n)
-                d2h += st.nbytes
+            if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile, collected one
+                tk = ctx.elev_stats_readback_begin(self.elev, s0, n)     # batch later, like ReadbackManager
+                if pending is not None:
+                    d2h += ctx.elev_stats_readback_end(pending).nbytes
+                pending = tk
+        if pending is not None:
+            d2h += ctx.elev_stats_readback_end(pending).nbytes
         return h2d, d2h
 
 
@@ -272,18 +297,20 @@ def main():
         peak, peak_kind = peaks()
         secs = ms_max * 1e-3
         value = total_pairs * args.steps / secs
-        # dominant kernel = the one with the larger share of the step
-        share = {k: v[0] for k, v in kt.items()}
-        dom = max(("elevation", "normal"), key=lambda k: share[k])
-        per_tile = {"elevation": ELEV_BYTES, "normal": NORM_BYTES}
+        # dominant kernel = the one with the largest share of the step (the fused elevation+normal
+        # kernel on this path; the separate passes appear when fusion is off)
+        per_tile = {"pair": PAIR_BYTES, "elevation": ELEV_BYTES, "normal": NORM_BYTES}
         roof = {}
-        for k in ("elevation", "normal"):
+        for k in per_tile:
             tot_ms, n_launch, n_tiles = kt[k]
+            if n_launch == 0:
+                continue
             gbs = per_tile[k] * n_tiles / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
             roof[k] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                       "frac": gbs / peak, "traffic": None, "launches": n_launch,
+                       "frac": gbs / peak, "traffic": TRAFFIC.get(k), "launches": n_launch,
                        "avg_launch_ms": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / ms_max,
                        "bytes_per_tile": per_tile[k], "peak_kind": peak_kind}
+        dom = max(roof, key=lambda k: roof[k]["share_of_step"])
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -298,7 +325,7 @@ def main():
         if e2e:
             line["e2e"] = {"value": total_pairs / e2e_s_max, "unit": "pairs/s",
                            "h2d_bytes_per_step": int(e2e[1]) * world, "d2h_bytes_per_step": int(e2e[2]) * world,
-                           "path": "host-built per-tile requests -> pl_elevation_batch/pl_normal_batch, stats read back"}
+                           "path": "host-built per-tile requests -> pl_pair_batch (HOST arrays), stats read back"}
         if world == 1 and not args.no_cpu_baseline:
             n, dt, _ = cpu_sample(7)
             line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": os.cpu_count(),

@@ -158,6 +158,12 @@ int pl_elev_stats_download(pl_ctx *ctx, pl_pool *elev, int n, const int32_t *slo
 /* same for the contiguous slots [slot0, slot0+n) -- the readback TileSamplerZ does
  * (core/sources/proland/terrain/TileSamplerZ.cpp:253-351), 8 bytes per tile */
 int pl_elev_stats_range(pl_ctx *ctx, pl_pool *elev, int slot0, int n, float *out);
+/* The same read-back, asynchronous: _begin enqueues the copy behind the work already on the stream and
+ * returns a ticket, _end waits for that copy only and delivers n (zmin, zmax) pairs.  This is how the
+ * reference consumes the values: TileSamplerZ reads them back through ReadbackManager a few frames late
+ * (TileSamplerZ.cpp:253-351).  At most 4 read-backs can be in flight. */
+int pl_elev_stats_readback_begin(pl_ctx *ctx, pl_pool *elev, int slot0, int n, int *ticket);
+int pl_elev_stats_readback_end(pl_ctx *ctx, int ticket, float *out);
 
 /* ----------------------------------------------------------------- normals */
 
@@ -201,6 +207,20 @@ int pl_normal_batch_dev(pl_ctx *ctx, const pl_norm_scene *scene, pl_pool *norm, 
 
 /* Everything a producer pair (elevationProducer + normalProducer resources)
  * holds that does not depend on the tile. */
+/* ------------------------------------------------- tile pairs (both passes) */
+
+/* An elevation tile and the normal tile derived from it, produced by ONE kernel (pl_pair.cu): what the
+ * reference runs as CreateElevationTile followed by CreateNormalTile on the same (level, tx, ty)
+ * (TileProducer.cpp:199-217 -> ElevationProducer.cpp:280-405, NormalProducer.cpp:164-289).  Request i of
+ * both arrays describes tile i: nreqs[i].elev_slot == ereqs[i].out_slot.  Results are bit-identical to
+ * pl_elevation_batch followed by pl_normal_batch; geometries the fused kernel does not cover (tile
+ * sizes other than 101/97, RGBA8 normals) run as those two passes. */
+int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *escene, const pl_norm_scene *nscene, pl_pool *elev,
+                  pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *ereqs, const pl_norm_req *nreqs);
+int pl_pair_batch_dev(pl_ctx *ctx, const pl_elev_scene *escene, const pl_norm_scene *nscene, pl_pool *elev,
+                      pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *dev_ereqs,
+                      const pl_norm_req *dev_nreqs);
+
 typedef struct pl_sweep_scene {
     pl_elev_scene elev;
     pl_norm_scene norm;

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "pl_internal.h"
@@ -64,8 +66,15 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->noise_rot) cudaFree(ctx->noise_rot);
-    if (ctx->req_dev) cudaFree(ctx->req_dev);
-    if (ctx->req_pinned) cudaFreeHost(ctx->req_pinned);
+    for (auto &rb : ctx->readback) {
+        if (rb.pinned) cudaFreeHost(rb.pinned);
+        if (rb.done) cudaEventDestroy(rb.done);
+    }
+    for (auto &st : ctx->stage) {
+        if (st.dev) cudaFree(st.dev);
+        if (st.pinned) cudaFreeHost(st.pinned);
+        if (st.copied) cudaEventDestroy(st.copied);
+    }
     if (ctx->perlin_perm) cudaFree(ctx->perlin_perm);
     if (ctx->perlin_g2) cudaFree(ctx->perlin_g2);
     if (ctx->gen_ereq) cudaFree(ctx->gen_ereq);
@@ -171,28 +180,81 @@ extern "C" int pl_timing_collect(pl_ctx *ctx, double *ms, uint64_t *launches, ui
     return PL_OK;
 }
 
-int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev)
+namespace {
+
+struct StageTicket { pl_ctx::StageSlot *st; size_t aoff, bytes; };
+
+/* a free staging slot large enough for both arrays; returns where to write them on the host */
+int stage_acquire(pl_ctx *ctx, size_t abytes, size_t bbytes, StageTicket *tk, void **apinned, void **bpinned)
 {
     PL_CUDA(cudaSetDevice(ctx->device));
-    if (bytes > ctx->req_dev_bytes) {
-        /* the previous batch may still be reading the old buffer */
+    const size_t aoff = (abytes + 255) & ~(size_t) 255;
+    const size_t bytes = aoff + bbytes;
+    pl_ctx::StageSlot &st = ctx->stage[ctx->stage_next];
+    ctx->stage_next = (ctx->stage_next + 1) % pl_ctx::kStageSlots;
+    if (!st.copied) PL_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
+    if (bytes > st.cap) {
+        /* kernels of earlier batches may still be reading the old device buffer */
         PL_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->req_dev) cudaFree(ctx->req_dev);
-        if (ctx->req_pinned) cudaFreeHost(ctx->req_pinned);
-        ctx->req_dev = nullptr;
-        ctx->req_pinned = nullptr;
-        size_t cap = bytes + bytes / 2 + 4096;
-        PL_CUDA(cudaMalloc(&ctx->req_dev, cap));
-        PL_CUDA(cudaMallocHost(&ctx->req_pinned, cap));
-        ctx->req_dev_bytes = ctx->req_pinned_bytes = cap;
+        if (st.dev) cudaFree(st.dev);
+        if (st.pinned) cudaFreeHost(st.pinned);
+        st.dev = st.pinned = nullptr;
+        st.cap = 0;
+        const size_t cap = bytes + bytes / 2 + 4096;
+        PL_CUDA(cudaMalloc(&st.dev, cap));
+        PL_CUDA(cudaMallocHost(&st.pinned, cap));
+        st.cap = cap;
     } else {
-        /* the pinned staging buffer is reused: wait until the last copy left it */
-        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+        /* the pinned half is reused: wait until the copy that last read it has finished */
+        PL_CUDA(cudaEventSynchronize(st.copied));
     }
-    memcpy(ctx->req_pinned, host, bytes);
-    PL_CUDA(cudaMemcpyAsync(ctx->req_dev, ctx->req_pinned, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    *dev = ctx->req_dev;
+    tk->st = &st;
+    tk->aoff = aoff;
+    tk->bytes = bytes;
+    *apinned = st.pinned;
+    if (bpinned) *bpinned = static_cast<char *>(st.pinned) + aoff;
     return PL_OK;
+}
+
+/* enqueue the copy of a filled slot; returns the device addresses of the two arrays */
+int stage_commit(pl_ctx *ctx, const StageTicket &tk, void **adev, void **bdev)
+{
+    PL_CUDA(cudaMemcpyAsync(tk.st->dev, tk.st->pinned, tk.bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PL_CUDA(cudaEventRecord(tk.st->copied, ctx->stream));
+    *adev = tk.st->dev;
+    if (bdev) *bdev = static_cast<char *>(tk.st->dev) + tk.aoff;
+    return PL_OK;
+}
+
+/* f(lo, hi) over [0, n) on up to 16 host threads (the calling thread takes the first chunk) */
+template <class F>
+void parallel_chunks(int n, int min_chunk, F f)
+{
+    int nt = (int) std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+    if (nt > n / min_chunk) nt = n / min_chunk;
+    if (nt <= 1) { f(0, n); return; }
+    const int chunk = (n + nt - 1) / nt;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) {
+        const int lo = t * chunk, hi = lo + chunk < n ? lo + chunk : n;
+        if (lo < hi) pool.emplace_back([=]() { f(lo, hi); });
+    }
+    f(0, chunk < n ? chunk : n);
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+int pl_stage_requests2(pl_ctx *ctx, const void *a, size_t abytes, const void *b, size_t bbytes, void **adev, void **bdev)
+{
+    StageTicket tk;
+    void *pa = nullptr, *pb = nullptr;
+    int rc = stage_acquire(ctx, abytes, b ? bbytes : 0, &tk, &pa, &pb);
+    if (rc) return rc;
+    memcpy(pa, a, abytes);
+    if (b) memcpy(pb, b, bbytes);
+    return stage_commit(ctx, tk, adev, bdev);
 }
 
 /* -------------------------------------------------------------------- pools */
@@ -482,13 +544,8 @@ extern "C" int pl_elevation_batch_dev(pl_ctx *ctx, const pl_elev_scene *sc, pl_p
     return pl_launch_elevation(ctx, sc, elev, resid, n, dev_reqs);
 }
 
-extern "C" int pl_elevation_batch(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n,
-                                  const pl_elev_req *reqs)
+static int check_elev_reqs(const pl_pool *elev, const pl_pool *resid, int n, const pl_elev_req *reqs)
 {
-    int rc = check_elev_args(ctx, sc, elev, resid, n);
-    if (rc) return rc;
-    if (n == 0) return PL_OK;
-    if (!reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
     const int rcap = resid ? resid->capacity : 0;
     for (int i = 0; i < n; ++i) {
         const pl_elev_req &q = reqs[i];
@@ -497,6 +554,17 @@ extern "C" int pl_elevation_batch(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool 
             q.parent_slot == q.out_slot)
             return pl_set_error(PL_ERR_ARG, "request %d: slot / noise index out of range", i);
     }
+    return PL_OK;
+}
+
+extern "C" int pl_elevation_batch(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid, int n,
+                                  const pl_elev_req *reqs)
+{
+    int rc = check_elev_args(ctx, sc, elev, resid, n);
+    if (rc) return rc;
+    if (n == 0) return PL_OK;
+    if (!reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    if ((rc = check_elev_reqs(elev, resid, n, reqs)) != PL_OK) return rc;
     void *dev = nullptr;
     rc = pl_stage_requests(ctx, reqs, sizeof(pl_elev_req) * (size_t) n, &dev);
     if (rc) return rc;
@@ -530,6 +598,49 @@ extern "C" int pl_elev_stats_range(pl_ctx *ctx, pl_pool *elev, int slot0, int n,
     return PL_OK;
 }
 
+/* Asynchronous read-back of per-tile (zmin, zmax): the copy is enqueued behind the kernels already on
+ * the stream, the caller collects it later -- the reference reads tile z ranges back through PBOs a few
+ * frames late (TileSamplerZ.cpp:253-351, ReadbackManager). */
+extern "C" int pl_elev_stats_readback_begin(pl_ctx *ctx, pl_pool *elev, int slot0, int n, int *ticket)
+{
+    if (!ctx || !elev || !ticket || n < 0 || slot0 < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (elev->kind != PL_POOL_ELEV_F32x3) return pl_set_error(PL_ERR_ARG, "not an elevation pool");
+    if (slot0 + n > elev->capacity) return pl_set_error(PL_ERR_ARG, "slot range out of the pool");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    int k = -1;
+    for (int i = 0; i < pl_ctx::kReadbacks; ++i)
+        if (!ctx->readback[i].busy) { k = i; break; }
+    if (k < 0) return pl_set_error(PL_ERR_ARG, "all %d read-backs are in flight: collect one first", (int) pl_ctx::kReadbacks);
+    pl_ctx::Readback &rb = ctx->readback[k];
+    if (!rb.done) PL_CUDA(cudaEventCreateWithFlags(&rb.done, cudaEventDisableTiming));
+    const size_t bytes = sizeof(float2) * (size_t) n;
+    if (bytes > rb.cap) {
+        if (rb.pinned) cudaFreeHost(rb.pinned);
+        rb.pinned = nullptr;
+        rb.cap = 0;
+        PL_CUDA(cudaMallocHost(&rb.pinned, bytes + bytes / 2 + 4096));
+        rb.cap = bytes + bytes / 2 + 4096;
+    }
+    if (n) PL_CUDA(cudaMemcpyAsync(rb.pinned, elev->stats + slot0, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PL_CUDA(cudaEventRecord(rb.done, ctx->stream));
+    rb.n = n;
+    rb.busy = 1;
+    *ticket = k;
+    return PL_OK;
+}
+
+extern "C" int pl_elev_stats_readback_end(pl_ctx *ctx, int ticket, float *out)
+{
+    if (!ctx || !out || ticket < 0 || ticket >= pl_ctx::kReadbacks || !ctx->readback[ticket].busy)
+        return pl_set_error(PL_ERR_ARG, "bad read-back ticket");
+    pl_ctx::Readback &rb = ctx->readback[ticket];
+    PL_CUDA(cudaSetDevice(ctx->device));
+    PL_CUDA(cudaEventSynchronize(rb.done));
+    memcpy(out, rb.pinned, sizeof(float2) * (size_t) rb.n);
+    rb.busy = 0;
+    return PL_OK;
+}
+
 static int check_norm_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, int n)
 {
     if (!ctx || !sc || !norm || !elev) return pl_set_error(PL_ERR_ARG, "NULL argument");
@@ -554,6 +665,17 @@ extern "C" int pl_normal_batch_dev(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool
     return pl_launch_normal(ctx, sc, norm, elev, n, dev_reqs);
 }
 
+static int check_norm_reqs(const pl_pool *norm, const pl_pool *elev, int n, const pl_norm_req *reqs)
+{
+    for (int i = 0; i < n; ++i) {
+        const pl_norm_req &q = reqs[i];
+        if (q.out_slot < 0 || q.out_slot >= norm->capacity || q.elev_slot < 0 || q.elev_slot >= elev->capacity ||
+            q.parent_slot >= norm->capacity || (q.parent_slot >= 0 && q.parent_slot == q.out_slot))
+            return pl_set_error(PL_ERR_ARG, "request %d: slot out of range", i);
+    }
+    return PL_OK;
+}
+
 extern "C" int pl_normal_batch(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev, int n,
                                const pl_norm_req *reqs)
 {
@@ -561,14 +683,83 @@ extern "C" int pl_normal_batch(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *no
     if (rc) return rc;
     if (n == 0) return PL_OK;
     if (!reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
-    for (int i = 0; i < n; ++i) {
-        const pl_norm_req &q = reqs[i];
-        if (q.out_slot < 0 || q.out_slot >= norm->capacity || q.elev_slot < 0 || q.elev_slot >= elev->capacity ||
-            q.parent_slot >= norm->capacity || (q.parent_slot >= 0 && q.parent_slot == q.out_slot))
-            return pl_set_error(PL_ERR_ARG, "request %d: slot out of range", i);
-    }
+    if ((rc = check_norm_reqs(norm, elev, n, reqs)) != PL_OK) return rc;
     void *dev = nullptr;
     rc = pl_stage_requests(ctx, reqs, sizeof(pl_norm_req) * (size_t) n, &dev);
     if (rc) return rc;
     return pl_launch_normal(ctx, sc, norm, elev, n, (const pl_norm_req *) dev);
+}
+
+/* ------------------------------------------------------------ tile pairs */
+
+
+extern "C" int pl_pair_batch_dev(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev,
+                                 pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *dev_ereqs,
+                                 const pl_norm_req *dev_nreqs)
+{
+    int rc = check_elev_args(ctx, esc, elev, resid, n);
+    if (rc) return rc;
+    if ((rc = check_norm_args(ctx, nsc, norm, elev, n)) != PL_OK) return rc;
+    if (n == 0) return PL_OK;
+    if (!dev_ereqs || !dev_nreqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    if (pl_pair_supported(ctx, esc, nsc, elev, norm))
+        return pl_launch_pair(ctx, esc, nsc, elev, norm, resid, n, dev_ereqs, dev_nreqs);
+    /* other geometries / RGBA8 normals: the two passes, one after the other */
+    if ((rc = pl_launch_elevation(ctx, esc, elev, resid, n, dev_ereqs)) != PL_OK) return rc;
+    return pl_launch_normal(ctx, nsc, norm, elev, n, dev_nreqs);
+}
+
+extern "C" int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev,
+                             pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *ereqs, const pl_norm_req *nreqs)
+{
+    int rc = check_elev_args(ctx, esc, elev, resid, n);
+    if (rc) return rc;
+    if ((rc = check_norm_args(ctx, nsc, norm, elev, n)) != PL_OK) return rc;
+    if (n == 0) return PL_OK;
+    if (!ereqs || !nreqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    /* validate the requests and copy them into the pinned staging slot in one pass, on all host
+     * threads for large batches (a planet level is 65 536 requests = 20 MB) */
+    StageTicket tk;
+    void *pe = nullptr, *pn = nullptr;
+    rc = stage_acquire(ctx, sizeof(pl_elev_req) * (size_t) n, sizeof(pl_norm_req) * (size_t) n, &tk, &pe, &pn);
+    if (rc) return rc;
+    std::atomic<int> bad(n);
+    const int rcap = resid ? resid->capacity : 0;
+    parallel_chunks(n, 4096, [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) {
+            const pl_elev_req &e = ereqs[i];
+            const pl_norm_req &q = nreqs[i];
+            int kind = 0;
+            if (e.out_slot < 0 || e.out_slot >= elev->capacity || e.parent_slot >= elev->capacity || e.resid_slot >= rcap ||
+                e.noise_r < 0 || e.noise_r > 3 || e.noise_l < 0 || e.noise_l > 5 || e.parent_slot == e.out_slot)
+                kind = 1;
+            else if (q.out_slot < 0 || q.out_slot >= norm->capacity || q.elev_slot < 0 || q.elev_slot >= elev->capacity ||
+                     q.parent_slot >= norm->capacity || (q.parent_slot >= 0 && q.parent_slot == q.out_slot))
+                kind = 2;
+            else if (q.elev_slot != e.out_slot)
+                kind = 3;
+            if (kind) {
+                int cur = bad.load();
+                while (i < cur && !bad.compare_exchange_weak(cur, i)) {}
+                return;
+            }
+        }
+        memcpy(static_cast<pl_elev_req *>(pe) + lo, ereqs + lo, sizeof(pl_elev_req) * (size_t) (hi - lo));
+        memcpy(static_cast<pl_norm_req *>(pn) + lo, nreqs + lo, sizeof(pl_norm_req) * (size_t) (hi - lo));
+    });
+    if (bad.load() < n) {
+        const int i = bad.load();
+        /* re-derive the kind for the first bad request (threads may have raced on bad_kind) */
+        const pl_elev_req &e = ereqs[i];
+        const bool ebad = e.out_slot < 0 || e.out_slot >= elev->capacity || e.parent_slot >= elev->capacity || e.resid_slot >= rcap ||
+                          e.noise_r < 0 || e.noise_r > 3 || e.noise_l < 0 || e.noise_l > 5 || e.parent_slot == e.out_slot;
+        if (ebad) return pl_set_error(PL_ERR_ARG, "request %d: slot / noise index out of range", i);
+        if (nreqs[i].elev_slot != e.out_slot && nreqs[i].elev_slot >= 0 && nreqs[i].elev_slot < elev->capacity &&
+            nreqs[i].out_slot >= 0 && nreqs[i].out_slot < norm->capacity)
+            return pl_set_error(PL_ERR_ARG, "request %d: the normal request does not read the elevation tile of the same index", i);
+        return pl_set_error(PL_ERR_ARG, "request %d: slot out of range", i);
+    }
+    void *de = nullptr, *dn = nullptr;
+    if ((rc = stage_commit(ctx, tk, &de, &dn)) != PL_OK) return rc;
+    return pl_pair_batch_dev(ctx, esc, nsc, elev, norm, resid, n, (const pl_elev_req *) de, (const pl_norm_req *) dn);
 }

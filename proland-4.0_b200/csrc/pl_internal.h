@@ -64,10 +64,16 @@ struct pl_ctx {
     void *resid_scratch;
     size_t resid_scratch_bytes;
     /* request staging */
-    void *req_dev;
-    size_t req_dev_bytes;
-    void *req_pinned;
-    size_t req_pinned_bytes;
+    /* a ring of staging slots: the pinned half of a slot is reused once its copy has left it (event),
+     * the device half is protected by stream order */
+    struct StageSlot { void *dev; void *pinned; size_t cap; cudaEvent_t copied; };
+    enum { kStageSlots = 3 };
+    StageSlot stage[kStageSlots];
+    int stage_next;
+    /* asynchronous statistics read-backs (pl_elev_stats_readback_*) */
+    struct Readback { void *pinned; size_t cap; cudaEvent_t done; int n; int busy; };
+    enum { kReadbacks = 4 };
+    Readback readback[kReadbacks];
 };
 
 int pl_set_error(int code, const char *fmt, ...);
@@ -86,8 +92,13 @@ enum { PL_K_ELEVATION = 0, PL_K_NORMAL = 1, PL_K_GENREQ = 2, PL_K_RESIDUAL = 3, 
 void pl_timing_begin(pl_ctx *ctx, int kernel, int tiles);
 void pl_timing_end(pl_ctx *ctx);
 
-/* stage n*bytes of host requests on the device (returns device pointer) */
-int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev);
+/* stage host requests on the device (returns device pointers; b may be NULL).  Both arrays travel in one
+ * copy; nothing here waits for the GPU unless all staging slots are still in flight */
+int pl_stage_requests2(pl_ctx *ctx, const void *a, size_t abytes, const void *b, size_t bbytes, void **adev, void **bdev);
+static inline int pl_stage_requests(pl_ctx *ctx, const void *host, size_t bytes, void **dev)
+{
+    return pl_stage_requests2(ctx, host, bytes, nullptr, 0, dev, nullptr);
+}
 
 /* kernel launchers (defined next to their kernels) */
 int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_pool *resid,

@@ -26,8 +26,9 @@ EXPORTS = [
     "pl_pool_destroy", "pl_pool_capacity", "pl_pool_tile_w", "pl_pool_tile_bytes",
     "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload",
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
-    "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_norm_make_req", "pl_normal_batch",
-    "pl_normal_batch_dev", "pl_produce_range", "pl_make_requests_range",
+    "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
+    "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
+    "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample",
 ]
@@ -135,12 +136,17 @@ def lib():
         L.pl_elevation_batch_dev.argtypes = L.pl_elevation_batch.argtypes
         L.pl_elev_stats_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pl_elev_stats_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pl_elev_stats_readback_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.pl_elev_stats_readback_end.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pl_norm_make_req.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int,
                                        C.c_void_p]
         L.pl_norm_make_req.restype = None
         L.pl_normal_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p]
         L.pl_normal_batch_dev.argtypes = L.pl_normal_batch.argtypes
+        L.pl_pair_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_void_p]
+        L.pl_pair_batch_dev.argtypes = L.pl_pair_batch.argtypes
         L.pl_produce_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]
         L.pl_make_requests_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
@@ -218,10 +224,14 @@ def sweep_scene(*, noise_amp, face=0, root_quad_size=100000.0, tile_w=101, grid_
 
 
 def make_requests_range(scene, level, morton0, n, out_slot0=0, parent_slot0=0, parent_morton0=0,
-                        nthreads=0, normals=True):
-    """Host-built requests of a Morton range (all hardware threads by default)."""
-    e = np.zeros(n, ELEV_REQ_DTYPE)
-    q = np.zeros(n, NORM_REQ_DTYPE) if normals else None
+                        nthreads=0, normals=True, out=None):
+    """Host-built requests of a Morton range (all hardware threads by default).  out = (e, q):
+    preallocated request arrays of at least n entries to fill instead of allocating new ones."""
+    if out is not None:
+        e, q = out[0][:n], (out[1][:n] if normals else None)
+    else:
+        e = np.zeros(n, ELEV_REQ_DTYPE)
+        q = np.zeros(n, NORM_REQ_DTYPE) if normals else None
     check(lib().pl_make_requests_range(C.byref(scene), level, morton0, n, out_slot0, parent_slot0,
                                        parent_morton0, _ptr(e), _ptr(q) if normals else None, nthreads))
     return e, q
@@ -349,9 +359,28 @@ class Context:
         check(lib().pl_elev_stats_range(self.h, elev.h, slot0, n, _ptr(out)))
         return out
 
+    def elev_stats_readback_begin(self, elev, slot0, n):
+        """enqueue the read-back of n (zmin, zmax) pairs; -> ticket for elev_stats_readback_end"""
+        t = C.c_int()
+        check(lib().pl_elev_stats_readback_begin(self.h, elev.h, slot0, n, C.byref(t)))
+        return (t.value, n)
+
+    def elev_stats_readback_end(self, ticket):
+        out = np.empty((ticket[1], 2), np.float32)
+        check(lib().pl_elev_stats_readback_end(self.h, ticket[0], _ptr(out)))
+        return out
+
     def normal_batch(self, scene, norm, elev, reqs):
         reqs = np.ascontiguousarray(reqs, NORM_REQ_DTYPE)
         check(lib().pl_normal_batch(self.h, C.byref(scene), norm.h, elev.h, len(reqs), _ptr(reqs)))
+
+    def pair_batch(self, escene, nscene, elev, norm, ereqs, nreqs, resid=None):
+        """elevation + normal tile pairs from HOST request arrays, one fused kernel (pl_pair_batch)."""
+        ereqs = np.ascontiguousarray(ereqs, ELEV_REQ_DTYPE)
+        nreqs = np.ascontiguousarray(nreqs, NORM_REQ_DTYPE)
+        assert len(ereqs) == len(nreqs)
+        check(lib().pl_pair_batch(self.h, C.byref(escene), C.byref(nscene), elev.h, norm.h,
+                                  resid.h if resid else None, len(ereqs), _ptr(ereqs), _ptr(nreqs)))
 
     def normal_batch_dev(self, scene, norm, elev, n, dev_ptr):
         check(lib().pl_normal_batch_dev(self.h, C.byref(scene), norm.h, elev.h, n,

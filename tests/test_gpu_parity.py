@@ -154,6 +154,63 @@ def test_fused_pair_kernel_equals_the_two_passes(plb, ctx, oracle, sphere, elev_
     assert ctx.elev_stats_range(fe, 0, total).tobytes() == ctx.elev_stats_range(se, 0, total).tobytes()
 
 
+def test_pair_batch_host_requests(plb, ctx, oracle):
+    """pl_pair_batch: host-built request arrays for both passes, one fused launch per level; equals the
+    oracle; a normal request that does not read the elevation tile of the same index is an argument
+    error (nothing is launched)."""
+    kw = dict(noise_amp=PLANET, face=5, root_quad_size=12720000.0, sphere=1)
+    sc = plb.sweep_scene(want_stats=1, **kw)
+    max_level = 3
+    total = sum(4 ** l for l in range(max_level + 1))
+    off = [sum(4 ** k for k in range(l)) for l in range(max_level + 1)]
+    elev = ctx.pool(plb.POOL_ELEV, 101, total)
+    norm = ctx.pool(plb.POOL_NORM2, 97, total)
+    ctx.noise_init(101)
+    n0 = ctx.launches
+    for l in range(max_level + 1):
+        e, q = plb.make_requests_range(sc, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+        ctx.pair_batch(sc.elev, sc.norm, elev, norm, e, q)
+    ctx.sync()
+    assert ctx.launches - n0 == max_level + 1
+    ref = qt.oracle_quadtree(oracle, max_level, **kw)
+    for (l, tx, ty), (e, n, s) in ref.items():
+        slot = off[l] + plb.morton_encode(tx, ty)
+        assert np.array_equal(elev.download(slot), e), (l, tx, ty)
+        assert np.array_equal(norm.download(slot), n), (l, tx, ty)
+    e, q = plb.make_requests_range(sc, 1, 0, 4, off[1], 0, 0)
+    q["elev_slot"][2] = off[1]          # reads another tile's elevation
+    with pytest.raises(plb.PlError) as err:
+        ctx.pair_batch(sc.elev, sc.norm, elev, norm, e, q)
+    assert err.value.code == plb.PL_ERR_ARG
+    assert ctx.launches - n0 == max_level + 1
+
+
+def test_async_stats_readback(plb, ctx):
+    """pl_elev_stats_readback_begin/_end deliver the values pl_elev_stats_range does, also when more
+    work was enqueued (and the slots rewritten) between begin and end; at most 4 are in flight."""
+    sc = plb.sweep_scene(want_stats=1, noise_amp=FRACTAL)
+    elev = ctx.pool(plb.POOL_ELEV, 101, 21)
+    norm = ctx.pool(plb.POOL_NORM2, 97, 21)
+    ctx.noise_init(101)
+    off = [0, 1, 5]
+    for l in range(3):
+        ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    want = ctx.elev_stats_range(elev, 5, 16)
+    tk = ctx.elev_stats_readback_begin(elev, 5, 16)
+    sc2 = plb.sweep_scene(want_stats=1, noise_amp=[x * 2 for x in FRACTAL])
+    ctx.produce_range(sc2, elev, norm, 2, 0, 16, 5, 1, 0)          # rewrites slots 5..20 behind the read-back
+    got = ctx.elev_stats_readback_end(tk)
+    assert got.tobytes() == want.tobytes()
+    assert ctx.elev_stats_range(elev, 5, 16).tobytes() != want.tobytes()
+    tks = [ctx.elev_stats_readback_begin(elev, 0, 1) for _ in range(4)]
+    with pytest.raises(plb.PlError):
+        ctx.elev_stats_readback_begin(elev, 0, 1)
+    for t in tks:
+        ctx.elev_stats_readback_end(t)
+    with pytest.raises(plb.PlError):
+        ctx.elev_stats_readback_end(tks[0])
+
+
 # ----------------------------------------------------------------- residuals
 
 import base64
