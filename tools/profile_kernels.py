@@ -20,6 +20,8 @@ with pl.Context(0) as ctx:
     elev = ctx.pool(pl.POOL_ELEV, 101, off[8] + 16384)
     norm = ctx.pool(pl.POOL_NORM2, 97, off[8] + 16384)
     ctx.noise_init(101)
+    if os.environ.get("PL_NO_FUSE"):
+        ctx.no_fuse(True)      # time the elevation and the normal kernel separately
     for l in range(8):
         ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
     ctx.timing_enable(True)
