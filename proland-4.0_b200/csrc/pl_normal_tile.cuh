@@ -177,14 +177,27 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
     const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
     const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
 
+    /* Thread -> (column, row lane) of both phases.  A warp's lanes must not straddle two rows inside a
+     * half-warp: the two rows' 8-byte accesses would then share banks (2.5 instead of 2 wavefronts per
+     * LDS.64 / STS.64: measured, and shared-memory wavefronts are as scarce as fp32 issue here).  So the
+     * first 48 columns (three half-warps) of every row lane go to threads 0 .. 48*LANES-1, and the one
+     * or two columns that are left to the threads after them. */
+    constexpr int CMAIN = 48;
+    constexpr int PR = (NT / GPAIRS) < (NT / CMAIN) ? (NT / GPAIRS) : (NT / CMAIN);   /* grid rows per pass */
+    constexpr int KR = (NT / XPAIRS) < (NT / CMAIN) ? (NT / XPAIRS) : (NT / CMAIN);   /* block rows per pass */
+    static_assert(GPAIRS >= CMAIN && XPAIRS >= CMAIN && PR * GPAIRS <= NT && KR * XPAIRS <= NT, "thread mapping");
     /* position phase: thread = (pair column, row lane) */
-    constexpr int PR = NT / GPAIRS;                    /* grid rows per pass */
-    const int rl0 = tid / GPAIRS, pc2 = 2 * (tid - rl0 * GPAIRS);
+    int rl0, pc;
+    if (tid < CMAIN * PR) { rl0 = tid / CMAIN; pc = tid - rl0 * CMAIN; }
+    else { const int e = tid - CMAIN * PR; rl0 = e / (GPAIRS - CMAIN); pc = CMAIN + e - rl0 * (GPAIRS - CMAIN); }
+    const int pc2 = 2 * pc;
     const bool pc_ok = rl0 < PR;
     const float *uA = ulut + pc2, *uB = ulut + UL + pc2;
     /* normal phase: thread = (block column, block row lane) */
-    constexpr int KR = NT / XPAIRS;                    /* block rows per pass */
-    const int kl0 = tid / XPAIRS, xc2 = 2 * (tid - kl0 * XPAIRS);
+    int kl0, xc;
+    if (tid < CMAIN * KR) { kl0 = tid / CMAIN; xc = tid - kl0 * CMAIN; }
+    else { const int e = tid - CMAIN * KR; kl0 = e / (XPAIRS - CMAIN); xc = CMAIN + e - kl0 * (XPAIRS - CMAIN); }
+    const int xc2 = 2 * xc;
     const bool xc_ok = kl0 < KR;
 
 #pragma unroll 1
