@@ -128,40 +128,41 @@ class PlanetSweep:
             pr(self.scenes[f], self.elev, self.norm, level, m0, n, s0, p0, pm0)
 
     def run_host_requests(self, units, nthreads=0):
-        """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out.  The uniforms of batch
-        k+1 are built (all host threads, in C) while batch k is submitted and its statistics are read
-        back -- the reference overlaps the same way: CreateTile tasks run on the scheduler's threads
-        while the previous frame's read-backs drain (TileSamplerZ + ReadbackManager)."""
-        from concurrent.futures import ThreadPoolExecutor
+        """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out.  Per batch: build the
+        uniforms (all host threads, in C), hand both arrays to pl_pair_batch (validates, stages, uploads
+        on the copy stream, launches), enqueue the statistics read-back and collect the one enqueued three
+        read-backs earlier -- the reference's TileSamplerZ collects its read-backs a few frames late in
+        the same way (ReadbackManager).  Nothing here waits for the GPU except that collection."""
         pl, ctx = self.pl, self.ctx
         if not hasattr(self, "_req_bufs"):
             nmax = 4 ** max(self.max_level - 2, 1)
-            self._req_bufs = [(np.zeros(nmax, pl.ELEV_REQ_DTYPE), np.zeros(nmax, pl.NORM_REQ_DTYPE))
-                              for _ in range(2)]
-            self._pool = ThreadPoolExecutor(1)
+            self._req_bufs = (np.zeros(nmax, pl.ELEV_REQ_DTYPE), np.zeros(nmax, pl.NORM_REQ_DTYPE))
         h2d = d2h = 0
-        todo = list(self.plan.batches(units, self.max_level))
-
-        def build(i):
-            f, level, m0, n, s0, p0, pm0 = todo[i]
-            return pl.make_requests_range(self.scenes[f], level, m0, n, s0, p0, pm0, nthreads=nthreads,
-                                          out=self._req_bufs[i & 1])
-        nxt = self._pool.submit(build, 0) if todo else None
-        pending = None
-        for i, (f, level, m0, n, s0, p0, pm0) in enumerate(todo):
+        pending = []
+        prof = [0.0] * 4 if os.environ.get("PL_E2E_PROFILE") else None
+        for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
             sc = self.scenes[f]
-            e, q = nxt.result()
+            t0 = time.perf_counter()
+            e, q = pl.make_requests_range(sc, level, m0, n, s0, p0, pm0, nthreads=nthreads, out=self._req_bufs)
+            t1 = time.perf_counter()
             ctx.pair_batch(sc.elev, sc.norm, self.elev, self.norm, e, q)   # copies e, q before it returns
-            if i + 1 < len(todo):
-                nxt = self._pool.submit(build, i + 1)
+            t2 = time.perf_counter()
             h2d += e.nbytes + q.nbytes
-            if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile, collected one
-                tk = ctx.elev_stats_readback_begin(self.elev, s0, n)     # batch later, like ReadbackManager
-                if pending is not None:
-                    d2h += ctx.elev_stats_readback_end(pending).nbytes
-                pending = tk
-        if pending is not None:
-            d2h += ctx.elev_stats_readback_end(pending).nbytes
+            t3 = t2
+            if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile, collected three
+                if len(pending) == 3:                                    # read-backs later (ReadbackManager
+                    d2h += ctx.elev_stats_readback_end(pending.pop(0)).nbytes   # keeps several in flight)
+                t3 = time.perf_counter()
+                pending.append(ctx.elev_stats_readback_begin(self.elev, s0, n))
+            if prof is not None:
+                t4 = time.perf_counter()
+                for j, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
+                    prof[j] += dt
+        for tk in pending:
+            d2h += ctx.elev_stats_readback_end(tk).nbytes
+        if prof is not None:
+            print("e2e host profile (s): build requests %.3f, pair_batch %.3f, readback wait %.3f, "
+                  "readback begin %.3f" % tuple(prof), file=sys.stderr)
         return h2d, d2h
 
 

@@ -65,16 +65,26 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->noise_rot) cudaFree(ctx->noise_rot);
     for (auto &rb : ctx->readback) {
         if (rb.pinned) cudaFreeHost(rb.pinned);
         if (rb.done) cudaEventDestroy(rb.done);
     }
-    for (auto &st : ctx->stage) {
-        if (st.dev) cudaFree(st.dev);
-        if (st.pinned) cudaFreeHost(st.pinned);
-        if (st.copied) cudaEventDestroy(st.copied);
+    if (ctx->stage_fifo) {
+        for (auto &e : *ctx->stage_fifo) {
+            cudaEventDestroy(e.copied);
+            cudaEventDestroy(e.consumed);
+        }
+        delete ctx->stage_fifo;
     }
+    if (ctx->stage_events) {
+        for (auto &e : *ctx->stage_events) cudaEventDestroy(e);
+        delete ctx->stage_events;
+    }
+    if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+    if (ctx->stage_pinned) cudaFreeHost(ctx->stage_pinned);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->perlin_perm) cudaFree(ctx->perlin_perm);
     if (ctx->perlin_g2) cudaFree(ctx->perlin_g2);
     if (ctx->gen_ereq) cudaFree(ctx->gen_ereq);
@@ -182,47 +192,114 @@ extern "C" int pl_timing_collect(pl_ctx *ctx, double *ms, uint64_t *launches, ui
 
 namespace {
 
-struct StageTicket { pl_ctx::StageSlot *st; size_t aoff, bytes; };
+struct StageTicket { size_t off, aoff, bytes; };
 
-/* a free staging slot large enough for both arrays; returns where to write them on the host */
-int stage_acquire(pl_ctx *ctx, size_t abytes, size_t bbytes, StageTicket *tk, void **apinned, void **bpinned)
+cudaEvent_t stage_event(pl_ctx *ctx)
 {
-    PL_CUDA(cudaSetDevice(ctx->device));
-    const size_t aoff = (abytes + 255) & ~(size_t) 255;
-    const size_t bytes = aoff + bbytes;
-    pl_ctx::StageSlot &st = ctx->stage[ctx->stage_next];
-    ctx->stage_next = (ctx->stage_next + 1) % pl_ctx::kStageSlots;
-    if (!st.copied) PL_CUDA(cudaEventCreateWithFlags(&st.copied, cudaEventDisableTiming));
-    if (bytes > st.cap) {
-        /* kernels of earlier batches may still be reading the old device buffer */
-        PL_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (st.dev) cudaFree(st.dev);
-        if (st.pinned) cudaFreeHost(st.pinned);
-        st.dev = st.pinned = nullptr;
-        st.cap = 0;
-        const size_t cap = bytes + bytes / 2 + 4096;
-        PL_CUDA(cudaMalloc(&st.dev, cap));
-        PL_CUDA(cudaMallocHost(&st.pinned, cap));
-        st.cap = cap;
-    } else {
-        /* the pinned half is reused: wait until the copy that last read it has finished */
-        PL_CUDA(cudaEventSynchronize(st.copied));
+    if (!ctx->stage_events) ctx->stage_events = new std::vector<cudaEvent_t>();
+    if (!ctx->stage_events->empty()) {
+        cudaEvent_t e = ctx->stage_events->back();
+        ctx->stage_events->pop_back();
+        return e;
     }
-    tk->st = &st;
-    tk->aoff = aoff;
-    tk->bytes = bytes;
-    *apinned = st.pinned;
-    if (bpinned) *bpinned = static_cast<char *>(st.pinned) + aoff;
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+
+/* the oldest entry leaves the ring: its pinned bytes are free when its upload is done, its device bytes
+ * when its consumer kernel is done (later uploads are ordered behind that kernel) */
+int stage_retire_front(pl_ctx *ctx)
+{
+    pl_ctx::StageEntry &e = ctx->stage_fifo->front();
+    if (!e.consumed_rec) {   /* the newest entry: its consumer has been launched by now (see stage_acquire) */
+        PL_CUDA(cudaEventRecord(e.consumed, ctx->stream));
+        e.consumed_rec = 1;
+    }
+    PL_CUDA(cudaEventSynchronize(e.copied));
+    PL_CUDA(cudaStreamWaitEvent(ctx->copy_stream, e.consumed, 0));
+    ctx->stage_events->push_back(e.copied);
+    ctx->stage_events->push_back(e.consumed);
+    ctx->stage_fifo->pop_front();
     return PL_OK;
 }
 
-/* enqueue the copy of a filled slot; returns the device addresses of the two arrays */
+/* room for both arrays in the staging ring; returns where to write them on the host */
+int stage_acquire(pl_ctx *ctx, size_t abytes, size_t bbytes, StageTicket *tk, void **apinned, void **bpinned)
+{
+    PL_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) PL_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->stage_fifo) ctx->stage_fifo = new std::deque<pl_ctx::StageEntry>();
+    /* the kernel that consumes the previous commit has been launched by now (callers launch right after
+     * the commit): everything on the stream up to here reads that entry's device bytes */
+    if (!ctx->stage_fifo->empty() && !ctx->stage_fifo->back().consumed_rec) {
+        PL_CUDA(cudaEventRecord(ctx->stage_fifo->back().consumed, ctx->stream));
+        ctx->stage_fifo->back().consumed_rec = 1;
+    }
+    const size_t aoff = (abytes + 255) & ~(size_t) 255;
+    const size_t bytes = (aoff + bbytes + 255) & ~(size_t) 255;
+    if (bytes * 3 > ctx->stage_size) {
+        /* grow: four of the largest batch seen, at least 32 MB.  Everything in flight must drain first */
+        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+        PL_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+        while (!ctx->stage_fifo->empty()) {
+            ctx->stage_events->push_back(ctx->stage_fifo->front().copied);
+            ctx->stage_events->push_back(ctx->stage_fifo->front().consumed);
+            ctx->stage_fifo->pop_front();
+        }
+        if (ctx->stage_dev) cudaFree(ctx->stage_dev);
+        if (ctx->stage_pinned) cudaFreeHost(ctx->stage_pinned);
+        ctx->stage_dev = ctx->stage_pinned = nullptr;
+        ctx->stage_size = ctx->stage_w = 0;
+        size_t size = bytes * 4;
+        if (size < ((size_t) 32 << 20)) size = (size_t) 32 << 20;
+        PL_CUDA(cudaMalloc(&ctx->stage_dev, size));
+        PL_CUDA(cudaMallocHost(&ctx->stage_pinned, size));
+        ctx->stage_size = size;
+    }
+    /* first fit at the write offset, wrapping once; retire the oldest entries that are in the way */
+    size_t off;
+    for (;;) {
+        std::deque<pl_ctx::StageEntry> &q = *ctx->stage_fifo;
+        if (q.empty()) { ctx->stage_w = 0; off = 0; break; }
+        const size_t f = q.front().off, w = ctx->stage_w;
+        if (f < w || (f == w && false)) {                 /* occupied [f, w): free [w, size) and [0, f) */
+            if (w + bytes <= ctx->stage_size) { off = w; break; }
+            if (bytes <= f) { off = 0; break; }
+        } else {                                          /* occupied [f, size) + [0, w): free [w, f) */
+            if (w + bytes <= f) { off = w; break; }
+        }
+        int rc = stage_retire_front(ctx);
+        if (rc) return rc;
+    }
+    tk->off = off;
+    tk->aoff = aoff;
+    tk->bytes = bytes;
+    *apinned = static_cast<char *>(ctx->stage_pinned) + off;
+    if (bpinned) *bpinned = static_cast<char *>(ctx->stage_pinned) + off + aoff;
+    return PL_OK;
+}
+
+/* enqueue the upload of a filled range on the copy stream -- beside the kernels of earlier batches --
+ * and make the kernel stream wait for it; returns the device addresses of the two arrays */
 int stage_commit(pl_ctx *ctx, const StageTicket &tk, void **adev, void **bdev)
 {
-    PL_CUDA(cudaMemcpyAsync(tk.st->dev, tk.st->pinned, tk.bytes, cudaMemcpyHostToDevice, ctx->stream));
-    PL_CUDA(cudaEventRecord(tk.st->copied, ctx->stream));
-    *adev = tk.st->dev;
-    if (bdev) *bdev = static_cast<char *>(tk.st->dev) + tk.aoff;
+    pl_ctx::StageEntry e;
+    e.off = tk.off;
+    e.bytes = tk.bytes;
+    e.copied = stage_event(ctx);
+    e.consumed = stage_event(ctx);
+    e.consumed_rec = 0;
+    if (!e.copied || !e.consumed) return pl_set_error(PL_ERR_CUDA, "cudaEventCreate failed");
+    char *d = static_cast<char *>(ctx->stage_dev) + tk.off;
+    PL_CUDA(cudaMemcpyAsync(d, static_cast<char *>(ctx->stage_pinned) + tk.off, tk.bytes, cudaMemcpyHostToDevice,
+                            ctx->copy_stream));
+    PL_CUDA(cudaEventRecord(e.copied, ctx->copy_stream));
+    PL_CUDA(cudaStreamWaitEvent(ctx->stream, e.copied, 0));
+    ctx->stage_fifo->push_back(e);
+    ctx->stage_w = tk.off + tk.bytes;
+    *adev = d;
+    if (bdev) *bdev = d + tk.aoff;
     return PL_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdarg.h>
+#include <deque>
 #include <vector>
 #include "proland_b200.h"
 
@@ -64,12 +65,16 @@ struct pl_ctx {
     void *resid_scratch;
     size_t resid_scratch_bytes;
     /* request staging */
-    /* a ring of staging slots: the pinned half of a slot is reused once its copy has left it (event),
-     * the device half is protected by stream order */
-    struct StageSlot { void *dev; void *pinned; size_t cap; cudaEvent_t copied; };
-    enum { kStageSlots = 3 };
-    StageSlot stage[kStageSlots];
-    int stage_next;
+    /* Request staging: ONE pinned ring + ONE device ring of the same size, sub-allocated in FIFO order.
+     * An entry's pinned bytes are reused once its upload has finished (event, host wait), its device
+     * bytes once the kernel that consumed it has finished (event, the copy stream waits).  The host can
+     * run a whole root-to-leaf chain of batches ahead of the GPU. */
+    struct StageEntry { size_t off, bytes; cudaEvent_t copied, consumed; int consumed_rec; };
+    void *stage_dev, *stage_pinned;
+    size_t stage_size, stage_w;
+    std::deque<StageEntry> *stage_fifo;
+    std::vector<cudaEvent_t> *stage_events;   /* recycled (timing disabled: not interchangeable with event_pool) */
+    cudaStream_t copy_stream;    /* request uploads run here, beside the kernels of earlier batches */
     /* asynchronous statistics read-backs (pl_elev_stats_readback_*) */
     struct Readback { void *pinned; size_t cap; cudaEvent_t done; int n; int busy; };
     enum { kReadbacks = 4 };
