@@ -1,15 +1,18 @@
 /*
  * pl_f2.cuh -- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, new on sm_100):
  * one instruction issues the same IEEE operation on two independent values.
- * Both kernels are issue-bound (profiles/), so every hot loop works on PAIRS of
- * texels and spells its maths with these helpers; each half rounds exactly as
- * the scalar operation would, so results stay bit-identical to the oracle.
+ * Every hot loop works on PAIRS of texels and spells its maths with these
+ * helpers; each half rounds exactly as the scalar operation would, so results
+ * stay bit-identical to the oracle.  A packed instruction halves the issue
+ * slots, not the register-operand traffic: with three register-pair operands
+ * it issues every 3 cycles, with an immediate every 2 (DESIGN.md 3.5,
+ * tools/microbench/rf_operands.cu).
  *
  * ptxas caveat (12.9, checked in SASS): a FMUL2 feeding a FADD2 is contracted
  * into FFMA2 even under --fmad=false and despite the .rn modifiers, so code in
  * the canonical order must never spell "RN(a*b) + c" with these helpers unless
  * the product is exact (a power-of-two weight).  Every such place uses the
- * scalar __fmul_rn/__fadd_rn instead (pl_elevation.cu: upsampleMatrix[2]); an
+ * scalar __fmul_rn/__fadd_rn instead (pl_elevation_tile.cuh: upsampleMatrix[2]); an
  * fma chain whose first term is a product (acc = a0*b0; acc = fma(a1,b1,acc))
  * is safe: no instruction computes two products.  The parity tests compare
  * whole tiles bit for bit and would catch any contraction that changed a value.
