@@ -178,7 +178,24 @@ def cpu_sample(max_level, face=1, nthreads=0):
     t0 = time.perf_counter()
     n, checksum, lo, hi = orc.produce_quadtree(scene, max_level, nthreads)
     dt = time.perf_counter() - t0
-    return n, dt, checksum
+    return n, dt, (checksum, lo, hi)
+
+
+def gpu_fingerprint(pl, ctx, max_level, face=1):
+    """The same tiles as cpu_sample on the GPU (fused kernel, resident pool): the sum over all tiles of
+    (zmin + zmax) and the global extremes of the per-tile statistics -- the oracle's checksum of checksums."""
+    off = [sum(4 ** k for k in range(l)) for l in range(max_level + 2)]
+    elev = ctx.pool(pl.POOL_ELEV, 101, off[max_level + 1])
+    norm = ctx.pool(pl.POOL_NORM2, 97, off[max_level + 1])
+    sc = pl.sweep_scene(noise_amp=PLANET_AMP, face=face, root_quad_size=PLANET_SIZE, sphere=1,
+                        elev_filter=pl.FILTER_LINEAR, want_stats=1)
+    for l in range(max_level + 1):
+        ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    st = ctx.elev_stats_range(elev, 0, off[max_level + 1]).astype(np.float64)
+    out = float(st.sum()), float(st[:, 0].min()), float(st[:, 1].max())
+    norm.close()
+    elev.close()
+    return out
 
 
 def run_reference(args, rank):
@@ -328,11 +345,18 @@ def main():
                            "h2d_bytes_per_step": int(e2e[1]) * world, "d2h_bytes_per_step": int(e2e[2]) * world,
                            "path": "host-built per-tile requests -> pl_pair_batch (HOST arrays), stats read back"}
         if world == 1 and not args.no_cpu_baseline:
-            n, dt, _ = cpu_sample(7)
+            n, dt, (csum, clo, chi) = cpu_sample(7)
             line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": os.cpu_count(),
                                     "kind": "port",
                                     "sample": "face 1 of the same planet, levels 0..7 (%d pairs), oracle "
                                               "with OpenMP over the tiles of a level" % n}
+            # the oracle run doubles as the checker: same tiles on the GPU, same checksum of checksums
+            gsum, glo, ghi = gpu_fingerprint(pl, ctx, 7)
+            line["parity"] = {"tiles": n, "vs": "oracle (cpu_baseline sample)",
+                              "what": "sum over tiles of per-tile (zmin + zmax) of zm, and the global extremes",
+                              "checksum_rel_err": abs(gsum - csum) / max(abs(csum), 1e-30),
+                              "zmin_equal": glo == clo, "zmax_equal": ghi == chi,
+                              "height_range_m": [clo, chi]}
         print(json.dumps(line), flush=True)
 
     ctx.close()

@@ -286,9 +286,11 @@ def test_residual_decode_root_composition_and_errors(plb, ctx):
     assert e.value.code == plb.PL_ERR_CORRUPT
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("kind", ["f32", "i16"])
-def test_elevation_with_residuals(plb, ctx, oracle, kind):
-    """config 3 shape: 197-wide residual tiles (mod 2), flip, NEAREST storage, sphere normals;
+def test_elevation_with_residuals(plb, ctx, oracle, kind, fused):
+    """(fused: both passes through pl_pair_batch, the fused kernel's residual variants)
+    config 3 shape: 197-wide residual tiles (mod 2), flip, NEAREST storage, sphere normals;
     residual float tiles from the oracle's ResidualProducer restatement (delta = 0) uploaded to
     the F32 pool, or the raw int16 tiles consumed directly from an I16 pool"""
     data, tiles = rs.container(min_level=0, max_level=2, tile_size=192, scale=0.5, zero_fraction=0.2)
@@ -336,8 +338,11 @@ def test_elevation_with_residuals(plb, ctx, oracle, kind):
             parent = ref[(l - 1, t[1] // 2, t[2] // 2)][0] if l else None
             rt = res.create_tile(l, t[1] // 2, t[2] // 2) if has[i] else None
             ref[t] = oracle.produce_pair(scene, noise, l, t[1], t[2], parent, rt)
-        ctx.elevation_batch(es, elev, reqs, resid=rpool)
-        ctx.normal_batch(ns, norm, elev, nreqs)
+        if fused:
+            ctx.pair_batch(es, ns, elev, norm, reqs, nreqs, resid=rpool)
+        else:
+            ctx.elevation_batch(es, elev, reqs, resid=rpool)
+            ctx.normal_batch(ns, norm, elev, nreqs)
     assert any(res.has_tile(3, x, y) for x in range(4) for y in range(4)) is False   # maxLevel 2: level 3 is noise only
     for t, (e, n) in ref.items():
         assert np.array_equal(elev.download(slot_of[t]), e), t
