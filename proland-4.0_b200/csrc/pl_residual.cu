@@ -16,12 +16,14 @@
  *            8-bit samples, 259 compression 1 / 8 / 32946, 273/279 the strip) and
  *            the strips are copied to the device in one transfer
  *   kernel1: inflate_kernel -- RFC 1950/1951 inflate, ONE WARP PER TILE.  Lane 0
- *            walks the bit stream with a 64-bit bit buffer and table lookups (a
- *            10-bit first-level table for literal/length codes and an 8-bit one
- *            for distances, built per dynamic block in shared memory by all 32
- *            lanes; longer codes fall back to the canonical count/symbol walk);
- *            LZ77 matches are copied by all 32 lanes.  Output goes to a dense
- *            scratch stream (back-references need the dense byte order).
+ *            walks the bit stream with a 64-bit bit buffer fed by prefetched
+ *            aligned words and table lookups (a 10-bit first-level table for
+ *            literal/length codes and an 8-bit one for distances, built per
+ *            dynamic block in shared memory by all 32 lanes; longer codes fall
+ *            back to the canonical count/symbol walk).  Literals and LZ77 matches
+ *            land in a 4 KB ring of recent output in shared memory; the warp
+ *            flushes finished kilobytes to a dense scratch stream in HBM and
+ *            serves the rare match that reaches behind the ring from there.
  *   kernel2: residual_store_kernel -- dense int16 -> the pool's pitched rows:
  *            raw for an I16 pool, (float) z * scale (+ the tile in add_slot) for an
  *            F32 pool, lower-left w x w corner of the slot exactly like the
@@ -38,7 +40,9 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 4;
+constexpr int kRing = 4096;      /* bytes of recent output per warp in shared memory (a power of two) */
+constexpr int kFlush = 1024;     /* ... of which finished units of this size go to HBM */
 constexpr int kLitBits = 10;     /* first-level table of the literal/length code */
 constexpr int kDistBits = 8;     /* first-level table of the distance code */
 
@@ -61,26 +65,58 @@ struct WarpTables {
     unsigned char lens[320];
 };
 
+/* The bit reader of lane 0.  Input comes in ALIGNED 32-bit words, one word prefetched ahead of the bit
+ * buffer so that the load latency overlaps the decoding of the 32 bits before it (byte loads on the
+ * critical path were a third of the old kernel's time).  Bytes past the end of the strip read as zero;
+ * consuming one of them sets `overrun`. */
 struct BitReader {
-    const unsigned char *src;
-    unsigned int pos, end;
+    const unsigned char *src;    /* strip start */
+    unsigned int end;            /* strip length in bytes */
+    int org;                     /* strip offset of byte 0 of word 0 (src + org is 4-byte aligned; may be < 0) */
+    unsigned int k;              /* index of the prefetched word `nxt` */
+    unsigned int merged;         /* strip offset just past the bytes already merged into buf */
+    unsigned int nxt;
     unsigned long long buf;
     int cnt;
     bool overrun;
 };
 
+/* word k of the stream: strip bytes [org + 4k, org + 4k + 4), zero beyond the end */
+__device__ __forceinline__ unsigned int br_word(const BitReader &b, unsigned int k)
+{
+    const int lo = b.org + 4 * (int) k;
+    if (lo >= (int) b.end) return 0u;
+    unsigned int w = __ldg(reinterpret_cast<const unsigned int *>(b.src + lo));
+    const int valid = (int) b.end - lo;          /* bytes of this word inside the strip (>= 1) */
+    if (valid < 4) w &= (1u << (8 * valid)) - 1u;
+    return w;
+}
+/* start reading at strip offset t */
+__device__ __forceinline__ void br_seek(BitReader &b, unsigned int t)
+{
+    const unsigned int a = (unsigned int) (reinterpret_cast<unsigned long long>(b.src + t) & 3ull);
+    b.org = (int) t - (int) a;
+    const unsigned int w0 = br_word(b, 0);
+    b.buf = (unsigned long long) (w0 >> (8 * a));
+    b.cnt = 32 - 8 * (int) a;
+    b.merged = (unsigned int) (b.org + 4);
+    b.k = 1;
+    b.nxt = br_word(b, 1);
+}
 __device__ __forceinline__ void br_init(BitReader &b, const unsigned char *src, unsigned int n)
 {
-    b.src = src; b.pos = 0; b.end = n; b.buf = 0; b.cnt = 0; b.overrun = false;
+    b.src = src; b.end = n; b.overrun = false;
+    br_seek(b, 0);
 }
-/* at least 32 valid bits afterwards (zero bits past the end; overrun noted when consumed) */
+/* at least 33 valid bits afterwards (zero bits past the end; overrun noted when consumed) */
 __device__ __forceinline__ void br_fill(BitReader &b)
 {
-    while (b.cnt <= 56) {
-        const unsigned long long byte = b.pos < b.end ? (unsigned long long) __ldg(b.src + b.pos) : 0ull;
-        b.buf |= byte << b.cnt;
-        b.pos++;
-        b.cnt += 8;
+    if (b.cnt <= 32) {
+        b.buf |= (unsigned long long) b.nxt << b.cnt;
+        b.cnt += 32;
+        b.merged += 4;
+        b.k += 1;
+        b.nxt = br_word(b, b.k);
     }
 }
 __device__ __forceinline__ unsigned int br_peek(const BitReader &b, int n) { return (unsigned int) (b.buf & ((1ull << n) - 1)); }
@@ -88,8 +124,9 @@ __device__ __forceinline__ void br_drop(BitReader &b, int n)
 {
     b.buf >>= n;
     b.cnt -= n;
-    /* bytes fetched so far minus whole bytes still buffered must not pass the end */
-    if ((long long) b.pos - (b.cnt >> 3) > (long long) b.end) b.overrun = true;
+    /* bytes merged so far minus whole bytes still buffered must not pass the end; only possible once
+     * padding words have been merged (one compare on the hot path) */
+    if (b.merged > b.end && b.merged - (unsigned int) (b.cnt >> 3) > b.end) b.overrun = true;
 }
 __device__ __forceinline__ unsigned int br_bits(BitReader &b, int n)
 {
@@ -98,6 +135,8 @@ __device__ __forceinline__ unsigned int br_bits(BitReader &b, int n)
     br_drop(b, n);
     return v;
 }
+/* strip offset of the next unread byte (call at a byte boundary) */
+__device__ __forceinline__ unsigned int br_byte_pos(const BitReader &b) { return b.merged - (unsigned int) (b.cnt >> 3); }
 
 __device__ __forceinline__ unsigned int bitrev(unsigned int v, int n) { return __brev(v) >> (32 - n); }
 
@@ -200,19 +239,39 @@ struct InflateJob {
     unsigned int compression;    /* 1 = stored strip, else zlib stream */
 };
 
+/* Events lane 0 hands to the warp */
+enum { EV_NONE = 0, EV_EOB = 1, EV_FLUSH = 2, EV_FAR = 3, EV_ERR = 4 };
+
+/* ring[flushed .. flushed + n) -> dst (n, flushed multiples of 16; both sides 16-byte aligned) */
+__device__ __forceinline__ void flush_ring(const unsigned char *ring, unsigned char *dst, unsigned int flushed, unsigned int n, int lane)
+{
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(ring + (flushed & (kRing - 1)));
+    uint4 *dst4 = reinterpret_cast<uint4 *>(dst + flushed);
+    for (unsigned int q = lane; q < n / 16; q += 32) dst4[q] = src4[q];
+}
+
+/* One warp per tile.  Lane 0 decodes on its own -- literals and near matches (distance < kRing) go
+ * straight into a ring of the last kRing output bytes in shared memory -- and wakes the other lanes only
+ * for what a warp does better: building the code tables of a block, flushing kFlush finished bytes to the
+ * dense stream in HBM with 16-byte stores, and the rare match that reaches behind the ring (its source
+ * has been flushed by then and is read back from HBM).  The old kernel kept the output in HBM and paid an
+ * L2 round trip for every match and two warp shuffles for every symbol. */
 __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const InflateJob *jobs, const unsigned char *in,
                                                                    unsigned char *out, size_t out_stride, int *status)
 {
     __shared__ WarpTables tables[kWarpsPerCta];
+    __shared__ __align__(16) unsigned char rings[kWarpsPerCta][kRing];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int job = blockIdx.x * kWarpsPerCta + wid;
     if (job >= n) return;
     WarpTables &T = tables[wid];
+    unsigned char *ring = rings[wid];
     const InflateJob J = jobs[job];
     const unsigned char *src = in + J.in_off;
     unsigned char *dst = out + (size_t) job * out_stride;
     const unsigned int cap = J.out_len;
     const unsigned int FULL = 0xffffffffu;
+    constexpr unsigned int M = kRing - 1;
 
     if (J.compression == 1) {   /* uncompressed strip */
         for (unsigned int k = lane; k < min(J.in_len, cap); k += 32) dst[k] = __ldg(src + k);
@@ -221,9 +280,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
     }
 
     BitReader b;
-    br_init(b, src, J.in_len);
+    if (lane == 0) br_init(b, src, J.in_len);
     int err = INF_OK;
-    unsigned int pos = 0;
+    unsigned int pos = 0, flushed = 0;     /* bytes produced / bytes already in HBM (a multiple of kFlush) */
     if (lane == 0) {   /* zlib header: CM = 8, no preset dictionary, header checksum */
         const unsigned int cmf = br_bits(b, 8), flg = br_bits(b, 8);
         if ((cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32) || ((cmf << 8) | flg) % 31 != 0) err = INF_BAD_HEADER;
@@ -247,7 +306,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
                 len = br_bits(b, 16);
                 const unsigned int nlen = br_bits(b, 16);
                 if ((len ^ nlen) != 0xffffu) err = INF_BAD_BLOCK;
-                src_pos = b.pos - (unsigned int) (b.cnt >> 3);   /* next unread byte */
+                src_pos = br_byte_pos(b);              /* next unread byte */
                 if (!err && src_pos + len > b.end) err = INF_OVERRUN_IN;
                 if (!err && pos + len > cap) err = INF_OVERRUN_OUT;
             }
@@ -255,14 +314,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
             len = __shfl_sync(FULL, len, 0);
             src_pos = __shfl_sync(FULL, src_pos, 0);
             if (err) break;
-            for (unsigned int k = lane; k < len; k += 32) dst[pos + k] = __ldg(src + src_pos + k);
-            pos += len;
-            if (lane == 0) {   /* restart the bit reader after the stored bytes */
-                b.pos = src_pos + len;
-                b.buf = 0;
-                b.cnt = 0;
+            /* through the ring, a flush unit at a time (later matches may refer to these bytes) */
+            unsigned int done = 0;
+            while (done < len) {
+                const unsigned int piece = min(len - done, (unsigned int) kFlush - (pos - flushed));
+                for (unsigned int k = lane; k < piece; k += 32) ring[(pos + k) & M] = __ldg(src + src_pos + done + k);
+                pos += piece;
+                done += piece;
+                __syncwarp();
+                if (pos - flushed >= kFlush) {
+                    flush_ring(ring, dst, flushed, kFlush, lane);
+                    flushed += kFlush;
+                    __syncwarp();
+                }
             }
-            __syncwarp();
+            if (lane == 0) br_seek(b, src_pos + len);   /* restart the bit reader after the stored bytes */
             continue;
         }
         if (type == 3) { err = INF_BAD_BLOCK; break; }
@@ -289,8 +355,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
             /* the code-length code reuses the literal tables (7-bit codes fit the first-level table) */
             if (!build_code(T.lens, 19, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane)) { err = INF_BAD_CODE; break; }
             if (lane == 0) {
-                /* decode into a scratch area behind the 19 code-length lengths is unsafe (they are in
-                 * use through the tables only, which are already built), so lens[] is overwritten */
+                /* the 19 code-length lengths are in use through the tables only, which are already
+                 * built, so lens[] is overwritten */
                 int idx = 0;
                 while (idx < nlen + ndist && !err) {
                     const int s = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
@@ -321,8 +387,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
         /* distance lengths follow the literal/length lengths in lens[]; build both codes */
         __syncwarp();
         {
-            /* the distance code first: building the literal tables must not overwrite lens[] before
-             * the distance lengths are consumed (they are separate arrays, order is free) */
             const unsigned char *dl = T.lens + (type == 1 ? 288 : nlen);
             const bool okd = build_code(dl, ndist, T.dist_count, T.dist_sym, T.dist_lut, kDistBits, lane);
             const bool okl = build_code(T.lens, nlen, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane);
@@ -330,52 +394,67 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
             if (!okd || !okl) { err = INF_BAD_CODE; break; }
         }
 
-        /* symbols of the block */
+        /* symbols of the block: lane 0 runs until it needs the warp */
         for (;;) {
-            int sym = 0;
+            int ev = EV_NONE;
             unsigned int len = 0, dist = 0;
             if (lane == 0) {
-                sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
-                if (sym < 0 || sym > 285) {
-                    err = INF_BAD_CODE;
-                } else if (sym < 256) {
-                    if (pos >= cap) err = INF_OVERRUN_OUT;
-                    else dst[pos] = (unsigned char) sym;
-                } else if (sym > 256) {
-                    const int li = sym - 257;
-                    len = kLenBase[li] + br_bits(b, kLenExtra[li]);
-                    const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
-                    if (ds < 0 || ds > 29) {
-                        err = INF_BAD_CODE;
+                for (;;) {
+                    const int sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
+                    if (sym < 256) {
+                        if (sym < 0) { err = INF_BAD_CODE; ev = EV_ERR; break; }
+                        if (pos >= cap) { err = INF_OVERRUN_OUT; ev = EV_ERR; break; }
+                        ring[pos & M] = (unsigned char) sym;
+                        pos += 1;
+                    } else if (sym == 256) {
+                        ev = EV_EOB;
+                        break;
                     } else {
+                        if (sym > 285) { err = INF_BAD_CODE; ev = EV_ERR; break; }
+                        const int li = sym - 257;
+                        len = kLenBase[li] + br_bits(b, kLenExtra[li]);
+                        const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
+                        if (ds < 0 || ds > 29) { err = INF_BAD_CODE; ev = EV_ERR; break; }
                         dist = kDistBase[ds] + br_bits(b, kDistExtra[ds]);
-                        if (dist > pos) err = INF_BAD_DISTANCE;
-                        else if (pos + len > cap) err = INF_OVERRUN_OUT;
+                        if (dist > pos) { err = INF_BAD_DISTANCE; ev = EV_ERR; break; }
+                        if (pos + len > cap) { err = INF_OVERRUN_OUT; ev = EV_ERR; break; }
+                        if (dist >= (unsigned int) kRing) { ev = EV_FAR; break; }
+                        /* near match: byte by byte inside the ring (overlapping matches repeat naturally) */
+                        for (unsigned int k = 0; k < len; ++k) ring[(pos + k) & M] = ring[(pos + k - dist) & M];
+                        pos += len;
                     }
+                    if (b.overrun) { err = INF_OVERRUN_IN; ev = EV_ERR; break; }
+                    if (pos - flushed >= (unsigned int) kFlush) { ev = EV_FLUSH; break; }
                 }
-                if (b.overrun) err = INF_OVERRUN_IN;
+                if (!err && b.overrun) { err = INF_OVERRUN_IN; ev = EV_ERR; }
             }
-            err = __shfl_sync(FULL, err, 0);
-            sym = __shfl_sync(FULL, sym, 0);
-            if (err || sym == 256) break;
-            if (sym < 256) {
-                pos += 1;
-                continue;
+            ev = __shfl_sync(FULL, ev, 0);
+            pos = __shfl_sync(FULL, pos, 0);
+            if (ev == EV_ERR) { err = __shfl_sync(FULL, err, 0); break; }
+            __syncwarp();   /* lane 0's ring stores are visible to the other lanes */
+            if (ev == EV_FAR) {
+                len = __shfl_sync(FULL, len, 0);
+                dist = __shfl_sync(FULL, dist, 0);
+                /* the source lies at least kRing - 258 bytes behind pos: flushed long ago (dist > len) */
+                for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = dst[pos - dist + k];
+                pos += len;
+                __syncwarp();
             }
-            len = __shfl_sync(FULL, len, 0);
-            dist = __shfl_sync(FULL, dist, 0);
-            __syncwarp();   /* lane 0's literal stores are visible to the copying lanes */
-            /* overlapping matches repeat their first `dist` bytes, all of which exist already */
-            if (dist >= len) {
-                for (unsigned int k = lane; k < len; k += 32) dst[pos + k] = dst[pos - dist + k];
-            } else {
-                for (unsigned int k = lane; k < len; k += 32) dst[pos + k] = dst[pos - dist + (k % dist)];
+            while (pos - flushed >= (unsigned int) kFlush) {
+                flush_ring(ring, dst, flushed, kFlush, lane);
+                flushed += kFlush;
             }
-            pos += len;
-            __syncwarp();
+            __syncwarp();   /* the flushed bytes are visible to later far matches of any lane */
+            if (ev == EV_EOB) break;
         }
     }
+    err = __shfl_sync(FULL, err, 0);
     if (!err && pos != cap) err = INF_SHORT;
+    if (!err) {   /* the tail: whole 16-byte words, then bytes */
+        const unsigned int rest = pos - flushed, r16 = rest & ~15u;
+        flush_ring(ring, dst, flushed, r16, lane);
+        for (unsigned int k = r16 + lane; k < rest; k += 32) dst[flushed + k] = ring[(flushed + k) & M];
+    }
     if (lane == 0) status[job] = err;
 }
 
