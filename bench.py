@@ -246,6 +246,9 @@ def main():
         run_reference(args, rank)
         return
 
+    # one rank per GPU on one box: the ranks share the host cores
+    host_threads = max(1, (os.cpu_count() or 1) // max(world, 1))
+    os.environ.setdefault("PL_HOST_THREADS", str(host_threads))
     import torch
     import torch.distributed as dist
     import proland_b200 as pl
@@ -295,12 +298,12 @@ def main():
         # e2e: host-built requests through the per-tile C ABI, stats read back
         e2e = None
         if not args.no_e2e:
-            sweep.run_host_requests(my_units[:1])
+            sweep.run_host_requests(my_units[:1], nthreads=host_threads)
             barrier()
             ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             ev2.record(stream)
-            h2d, d2h = sweep.run_host_requests(my_units)
+            h2d, d2h = sweep.run_host_requests(my_units, nthreads=host_threads)
             ev3.record(stream)
             barrier()
             e2e_s = max(time.perf_counter() - t0, 1e-3 * ev2.elapsed_time(ev3))

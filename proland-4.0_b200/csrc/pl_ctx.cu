@@ -213,7 +213,7 @@ int stage_retire_front(pl_ctx *ctx)
 {
     pl_ctx::StageEntry &e = ctx->stage_fifo->front();
     if (!e.consumed_rec) {   /* the newest entry: its consumer has been launched by now (see stage_acquire) */
-        PL_CUDA(cudaEventRecord(e.consumed, ctx->stream));
+        PL_CUDA(cudaEventRecord(e.consumed, e.stream));
         e.consumed_rec = 1;
     }
     PL_CUDA(cudaEventSynchronize(e.copied));
@@ -233,7 +233,7 @@ int stage_acquire(pl_ctx *ctx, size_t abytes, size_t bbytes, StageTicket *tk, vo
     /* the kernel that consumes the previous commit has been launched by now (callers launch right after
      * the commit): everything on the stream up to here reads that entry's device bytes */
     if (!ctx->stage_fifo->empty() && !ctx->stage_fifo->back().consumed_rec) {
-        PL_CUDA(cudaEventRecord(ctx->stage_fifo->back().consumed, ctx->stream));
+        PL_CUDA(cudaEventRecord(ctx->stage_fifo->back().consumed, ctx->stage_fifo->back().stream));   /* the stream it was committed for */
         ctx->stage_fifo->back().consumed_rec = 1;
     }
     const size_t aoff = (abytes + 255) & ~(size_t) 255;
@@ -290,6 +290,7 @@ int stage_commit(pl_ctx *ctx, const StageTicket &tk, void **adev, void **bdev)
     e.copied = stage_event(ctx);
     e.consumed = stage_event(ctx);
     e.consumed_rec = 0;
+    e.stream = ctx->stream;
     if (!e.copied || !e.consumed) return pl_set_error(PL_ERR_CUDA, "cudaEventCreate failed");
     char *d = static_cast<char *>(ctx->stage_dev) + tk.off;
     PL_CUDA(cudaMemcpyAsync(d, static_cast<char *>(ctx->stage_pinned) + tk.off, tk.bytes, cudaMemcpyHostToDevice,
@@ -309,6 +310,9 @@ void parallel_chunks(int n, int min_chunk, F f)
 {
     int nt = (int) std::thread::hardware_concurrency();
     nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+    /* several ranks share one box: PL_HOST_THREADS caps the threads of one process */
+    static const int cap = []() { const char *e = getenv("PL_HOST_THREADS"); return e ? atoi(e) : 0; }();
+    if (cap > 0 && nt > cap) nt = cap;
     if (nt > n / min_chunk) nt = n / min_chunk;
     if (nt <= 1) { f(0, n); return; }
     const int chunk = (n + nt - 1) / nt;

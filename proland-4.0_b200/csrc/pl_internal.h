@@ -69,7 +69,7 @@ struct pl_ctx {
      * An entry's pinned bytes are reused once its upload has finished (event, host wait), its device
      * bytes once the kernel that consumed it has finished (event, the copy stream waits).  The host can
      * run a whole root-to-leaf chain of batches ahead of the GPU. */
-    struct StageEntry { size_t off, bytes; cudaEvent_t copied, consumed; int consumed_rec; };
+    struct StageEntry { size_t off, bytes; cudaEvent_t copied, consumed; int consumed_rec; cudaStream_t stream; };
     void *stage_dev, *stage_pinned;
     size_t stage_size, stage_w;
     std::deque<StageEntry> *stage_fifo;
