@@ -42,20 +42,28 @@ def run_sweep(pl, ctx, d, rank=0, world=1, unit_depth=7, root=None, scene_kw=Non
         produced += n
     slot0, nleaf = plan.leaf_region()
     fp_sum, fp_lo, fp_hi, fp_xor = 0.0, np.inf, -np.inf, np.uint32(0)
-    for unit in plan.units_of_rank(rank, world):
-        for level, m0, n, s0, p0, pm0 in plan.unit_batches(unit):
-            ctx.produce_range(sc, elev, norm, level, m0, n, s0, p0, pm0)
-            produced += n
-        st = ctx.elev_stats_range(elev, slot0, nleaf)           # TileSamplerZ's readback, 8 bytes per tile
+    def fold(st):
+        nonlocal fp_sum, fp_lo, fp_hi, fp_xor
         fp_sum += float(st.astype(np.float64).sum())
         fp_lo, fp_hi = min(fp_lo, float(st[:, 0].min())), max(fp_hi, float(st[:, 1].max()))
         fp_xor ^= np.bitwise_xor.reduce(st.view(np.uint32).ravel())
+
+    pending = []      # TileSamplerZ's readback, 8 bytes per leaf tile: enqueued behind the unit's kernels,
+    for unit in plan.units_of_rank(rank, world):          # collected two units later (ReadbackManager)
+        for level, m0, n, s0, p0, pm0 in plan.unit_batches(unit):
+            ctx.produce_range(sc, elev, norm, level, m0, n, s0, p0, pm0)
+            produced += n
+        if len(pending) == 2:
+            fold(ctx.elev_stats_readback_end(pending.pop(0)))
+        pending.append(ctx.elev_stats_readback_begin(elev, slot0, nleaf))
         if keep is not None:
             leaf_m0 = ((plan.root_morton << (2 * plan.k)) | unit) << (2 * (d - plan.k))
             for m in keep["want"]:
                 if leaf_m0 <= m < leaf_m0 + nleaf:
                     s = slot0 + (m - leaf_m0)
                     keep[m] = (elev.download(s), norm.download(s))
+    for tk in pending:
+        fold(ctx.elev_stats_readback_end(tk))
     ctx.sync()
     elev.close()
     norm.close()
