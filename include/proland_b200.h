@@ -252,6 +252,9 @@ int pl_debug_force_generic(pl_ctx *ctx, int on);
 /* tests / profiling: make pl_produce_range and pl_pair_batch[_dev] launch the elevation and the normal
  * pass as two kernels instead of the fused one (same results, bit for bit) */
 int pl_debug_no_fuse(pl_ctx *ctx, int on);
+/* tests: the smallest request staging ring to allocate (default 32 MB); a small ring makes the FIFO
+ * wrap around and grow within a few batches */
+int pl_debug_stage_ring(pl_ctx *ctx, size_t min_bytes);
 int pl_debug_fpexact(pl_ctx *ctx, int n, const float *a, const float *b, float *out);
 /* copy the requests the last pl_produce_range generated back to the host (tests) */
 int pl_debug_download_requests(pl_ctx *ctx, int n, pl_elev_req *elev_reqs, pl_norm_req *norm_reqs);

@@ -156,6 +156,13 @@ extern "C" int pl_debug_force_generic(pl_ctx *ctx, int on)
     return PL_OK;
 }
 
+extern "C" int pl_debug_stage_ring(pl_ctx *ctx, size_t min_bytes)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    ctx->stage_min = min_bytes;
+    return PL_OK;
+}
+
 extern "C" int pl_debug_no_fuse(pl_ctx *ctx, int on)
 {
     if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
@@ -252,7 +259,8 @@ int stage_acquire(pl_ctx *ctx, size_t abytes, size_t bbytes, StageTicket *tk, vo
         ctx->stage_dev = ctx->stage_pinned = nullptr;
         ctx->stage_size = ctx->stage_w = 0;
         size_t size = bytes * 4;
-        if (size < ((size_t) 32 << 20)) size = (size_t) 32 << 20;
+        const size_t floor_size = ctx->stage_min ? ctx->stage_min : ((size_t) 32 << 20);
+        if (size < floor_size) size = floor_size;
         PL_CUDA(cudaMalloc(&ctx->stage_dev, size));
         PL_CUDA(cudaMallocHost(&ctx->stage_pinned, size));
         ctx->stage_size = size;

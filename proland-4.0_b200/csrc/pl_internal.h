@@ -72,6 +72,7 @@ struct pl_ctx {
     struct StageEntry { size_t off, bytes; cudaEvent_t copied, consumed; int consumed_rec; cudaStream_t stream; };
     void *stage_dev, *stage_pinned;
     size_t stage_size, stage_w;
+    size_t stage_min;            /* smallest ring to allocate (0: 32 MB); tests shrink it to force wrap-around */
     std::deque<StageEntry> *stage_fifo;
     std::vector<cudaEvent_t> *stage_events;   /* recycled (timing disabled: not interchangeable with event_pool) */
     cudaStream_t copy_stream;    /* request uploads run here, beside the kernels of earlier batches */

@@ -29,7 +29,7 @@ EXPORTS = [
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
-    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_fpexact",
+    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample",
 ]
 
@@ -154,6 +154,7 @@ def lib():
         L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pl_debug_force_generic.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_no_fuse.argtypes = [C.c_void_p, C.c_int]
+        L.pl_debug_stage_ring.argtypes = [C.c_void_p, C.c_size_t]
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
@@ -454,6 +455,7 @@ Context.residual_decode = _residual_decode
 Context.residual_upsample = _residual_upsample
 Context.force_generic = _force_generic
 Context.no_fuse = _no_fuse
+Context.stage_ring = lambda self, min_bytes: check(lib().pl_debug_stage_ring(self.h, min_bytes))
 Context.fpexact = _fpexact
 Context.timing_enable = _timing_enable
 Context.timing_collect = _timing_collect

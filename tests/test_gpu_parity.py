@@ -211,6 +211,44 @@ def test_async_stats_readback(plb, ctx):
         ctx.elev_stats_readback_end(tks[0])
 
 
+def test_request_staging_ring_wraps_and_grows(plb, ctx, oracle):
+    """host request arrays travel through a FIFO staging ring (pinned + device halves, uploads on a copy
+    stream).  With a 256 KB ring the level-4 batches (78 KB) wrap it every third batch while earlier
+    uploads and kernels are still in flight, and the level-5 batch (311 KB) makes it grow; the tiles
+    must come out as if every batch had been staged on its own."""
+    ctx.stage_ring(256 << 10)
+    kw = dict(noise_amp=PLANET, face=4, root_quad_size=12720000.0, sphere=1)
+    sc = plb.sweep_scene(want_stats=1, **kw)
+    max_level = 5
+    total = sum(4 ** l for l in range(max_level + 1))
+    off = [sum(4 ** k for k in range(l)) for l in range(max_level + 1)]
+    elev = ctx.pool(plb.POOL_ELEV, 101, total)
+    norm = ctx.pool(plb.POOL_NORM2, 97, total)
+    ctx.noise_init(101)
+    reqs = [plb.make_requests_range(sc, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0) for l in range(max_level + 1)]
+    for rep in range(12):                       # levels 0..4 over and over: 60 batches, ~1.2 MB through 256 KB
+        for l in range(5):
+            ctx.pair_batch(sc.elev, sc.norm, elev, norm, *reqs[l])
+    ctx.pair_batch(sc.elev, sc.norm, elev, norm, *reqs[5])        # grows the ring with batches in flight
+    for l in range(5):
+        ctx.elevation_batch(sc.elev, elev, reqs[l][0])            # the single-array users share the ring
+        ctx.normal_batch(sc.norm, norm, elev, reqs[l][1])
+    ctx.sync()
+    ref = qt.oracle_quadtree(oracle, 4, **kw)
+    for (l, tx, ty), (e, n, s) in ref.items():
+        slot = off[l] + plb.morton_encode(tx, ty)
+        assert np.array_equal(elev.download(slot), e), (l, tx, ty)
+        assert np.array_equal(norm.download(slot), n), (l, tx, ty)
+    # level 5 against the device-generated path
+    elev2 = ctx.pool(plb.POOL_ELEV, 101, total)
+    norm2 = ctx.pool(plb.POOL_NORM2, 97, total)
+    for l in range(max_level + 1):
+        ctx.produce_range(sc, elev2, norm2, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    for slot in range(off[5], total, 37):
+        assert elev.download(slot).tobytes() == elev2.download(slot).tobytes(), slot
+        assert norm.download(slot).tobytes() == norm2.download(slot).tobytes(), slot
+
+
 # ----------------------------------------------------------------- residuals
 
 import base64
