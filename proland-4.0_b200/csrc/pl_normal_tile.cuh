@@ -200,6 +200,24 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
     const int xc2 = 2 * xc;
     const bool xc_ok = kl0 < KR;
 
+    /* Flat terrain: p = (x0 + D u, y0 + D v, h), so the x difference of two horizontal neighbours depends
+     * on the column only, the y difference of two vertical neighbours on the row only, and the other
+     * cross terms are exact zeros.  Only h needs a plane; the two difference tables live in the third
+     * plane (unused then): dxa[k] = x(X = k - 1) - x(X = k - 3) (texel k - 2), dxb[k] = dxa[k + 1] for
+     * aligned pairs at odd texels, dyt likewise with y0.  Same fp32 operations as the general formula. */
+    float *dxa = pos + 2 * PP, *dxb = dxa + GWP, *dyt = dxb + GWP;
+    if (!SPHERE) {
+        for (int k = tid; k < W + 4; k += NT) {
+            const bool in = k >= 1 && k + 1 < UL;
+            const float hi_u = in ? ulut[k + 1] : 0.0f, lo_u = in ? ulut[k - 1] : 0.0f;
+            const float ddx = fmaf(D, hi_u, x0f) - fmaf(D, lo_u, x0f);
+            const float ddy = fmaf(D, hi_u, y0f) - fmaf(D, lo_u, y0f);
+            dxa[k] = ddx;
+            if (k >= 1) dxb[k - 1] = ddx;
+            dyt[k] = ddy;
+        }
+    }
+
 #pragma unroll 1
     for (int band = 0; band < GEO::NBANDS; ++band) {
         const int y_begin = band * kTileBand;
@@ -210,7 +228,7 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
         if (band != 0) {
             __syncthreads();   /* the band before has read its positions */
             constexpr int N4 = 2 * GWP / 4;
-            if (tid < 3 * N4) {
+            if (tid < (SPHERE ? 3 : 1) * N4) {
                 const int pl = tid / N4, c = tid - pl * N4;
                 float4 *dst = reinterpret_cast<float4 *>(pos + pl * PP) + c;
                 *dst = *reinterpret_cast<const float4 *>(pos + pl * PP + kTileBand * GWP + 4 * c);
@@ -245,13 +263,15 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
                 }
                 /* u of X = gx - 1, gx: table index X + 2; the pair is aligned in the first copy when gx is odd,
                  * in the second (one entry further) when it is even */
-                const F2 u = *reinterpret_cast<const F2 *>(sh ? uA : uB);
-                const float v = *vp;
+                F2 u = bc(0.0f);
+                float v = 0.0f;
+                if (SPHERE) {
+                    u = *reinterpret_cast<const F2 *>(sh ? uA : uB);
+                    v = *vp;
+                }
                 F2 qx, qy, qz;
                 if (!SPHERE) {
-                    qx = fma2(bc(D), u, bc(x0f));
-                    qy = bc(fmaf(D, v, y0f));
-                    qz = h;
+                    qx = qy = qz = h;
                 } else {
                     const F2 U = sub2(bc(1.0f), u);
                     const float V = 1.0f - v;
@@ -276,9 +296,13 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
 #undef ROW4
                 }
                 /* stored at column gx + shift + 2 (the +2 keeps the odd-start pad at a non-negative, even slot) */
-                *reinterpret_cast<F2 *>(o3) = qx;
-                *reinterpret_cast<F2 *>(o3 + PP) = qy;
-                *reinterpret_cast<F2 *>(o3 + 2 * PP) = qz;
+                if (SPHERE) {
+                    *reinterpret_cast<F2 *>(o3) = qx;
+                    *reinterpret_cast<F2 *>(o3 + PP) = qy;
+                    *reinterpret_cast<F2 *>(o3 + 2 * PP) = qz;
+                } else {
+                    *reinterpret_cast<F2 *>(o3) = qz;     /* flat: the height plane only */
+                }
             }
         }
         __syncthreads();
@@ -299,6 +323,17 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
              * so row g1 starts at x + odd + 2 = xc2 + 2 and row g0 (grid column x + 1) at xc2 + 4 - 2 odd. */
             const float *c0 = c1 - GWP + 2 - 2 * odd;
             F2 d1[3], e1[3], d2[3], e2[3];
+            if (!SPHERE) {
+                const F2 l1 = *reinterpret_cast<const F2 *>(c1), r1 = *reinterpret_cast<const F2 *>(c1 + 2);
+                const F2 l2 = *reinterpret_cast<const F2 *>(c1 + GWP), r2 = *reinterpret_cast<const F2 *>(c1 + GWP + 2);
+                const F2 m0 = *reinterpret_cast<const F2 *>(c0), m3 = *reinterpret_cast<const F2 *>(c0 + 3 * GWP);
+                const F2 m1 = make_float2(l1.y, r1.x), m2 = make_float2(l2.y, r2.x);
+                const F2 ddx = *reinterpret_cast<const F2 *>(odd ? dxb + xc2 : dxa + xc2 + 2);
+                const float *dyp = dyt + y_begin + ry + 2;
+                d1[0] = d2[0] = ddx;          d1[1] = d2[1] = bc(0.0f);   d1[2] = sub2(r1, l1);  d2[2] = sub2(r2, l2);
+                e1[0] = e2[0] = bc(0.0f);     e1[1] = bc(dyp[0]);         e2[1] = bc(dyp[1]);
+                e1[2] = sub2(m2, m0);         e2[2] = sub2(m3, m1);
+            } else
 #pragma unroll
             for (int cpt = 0; cpt < 3; ++cpt) {
                 const F2 l1 = *reinterpret_cast<const F2 *>(c1 + cpt * PP);                 /* g1: x, x+1 */
@@ -317,9 +352,16 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
                 const F2 *d = half ? d2 : d1, *e = half ? e2 : e1;
-                F2 nx = fma2(d[1], e[2], neg(mul2(d[2], e[1])));
-                F2 ny = fma2(d[2], e[0], neg(mul2(d[0], e[2])));
-                F2 nz = fma2(d[0], e[1], neg(mul2(d[1], e[0])));
+                F2 nx, ny, nz;
+                if (SPHERE) {
+                    nx = fma2(d[1], e[2], neg(mul2(d[2], e[1])));
+                    ny = fma2(d[2], e[0], neg(mul2(d[0], e[2])));
+                    nz = fma2(d[0], e[1], neg(mul2(d[1], e[0])));
+                } else {   /* the same cross product with its exact zeros removed (d.y = e.x = 0) */
+                    nx = neg(mul2(d[2], e[1]));
+                    ny = neg(mul2(d[0], e[2]));
+                    nz = mul2(d[0], e[1]);
+                }
                 const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
                 nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
                 const F2 tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
