@@ -176,6 +176,7 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
     const float s = rq.smooth;
     const float w00 = rq.w2t[0], w01 = rq.w2t[1], w02 = rq.w2t[2];
     const float w10 = rq.w2t[3], w11 = rq.w2t[4], w12 = rq.w2t[5];
+    const bool w2t_identity = w00 == 1.0f && w01 == 0.0f && w02 == 0.0f && w10 == 0.0f && w11 == 1.0f && w12 == 0.0f;
 
     /* Thread -> (column, row lane) of both phases.  A warp's lanes must not straddle two rows inside a
      * half-warp: the two rows' 8-byte accesses would then share banks (2.5 instead of 2 wavefronts per
@@ -364,8 +365,13 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
                 }
                 const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
                 nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);
-                const F2 tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
-                const F2 ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
+                /* worldToTangentFrame; the identity of a flat terrain (NormalProducer.cpp:279-280) returns nx, ny
+                 * themselves (up to the sign of a zero, which the unorm8 conversion does not see) */
+                F2 tx = nx, ty = ny;
+                if (SPHERE || !w2t_identity) {
+                    tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
+                    ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
+                }
                 /* unorm8: round(clamp(v * 0.5 + 0.5, 0, 1) * 255), NaN -> 0 */
                 const F2 r = mul2(make_float2(__saturatef(fmaf(tx.x, 0.5f, 0.5f)), __saturatef(fmaf(tx.y, 0.5f, 0.5f))), bc(255.0f));
                 const F2 g = mul2(make_float2(__saturatef(fmaf(ty.x, 0.5f, 0.5f)), __saturatef(fmaf(ty.y, 0.5f, 0.5f))), bc(255.0f));
