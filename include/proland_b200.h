@@ -283,6 +283,29 @@ int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *bl
 int pl_residual_upsample(pl_ctx *ctx, pl_pool *pool, int src_slot, int dst_slot, int tile_size,
                          int tx, int ty);
 
+/* ---- the step before the path: building residual files ----
+ * One level of HeightMipmap::buildResiduals (preprocess/terrain/HeightMipmap.cpp:255-324) for n tiles:
+ *   residual      = heights - upsample(parent approximation)        computeResidual   :449-497
+ *   stored int16  = short(roundf(residual))                          encodeResidual    :499-512
+ *   approximation = upsample(parent approximation) + stored int16    computeApproxTile :514-559
+ * The upsample is ResidualProducer::upsample's (same taps, same CPU evaluation order), so the
+ * approximation equals, bit for bit, what the run-time producer reconstructs from the file.
+ * heights / approx: F32 residual pools (tiles of tile_size + 5 texels in the lower-left corner of the
+ * slot, heights already divided by the file's scale); resid: an I16 residual pool.  The approximation of a
+ * level-0 tile is the tile itself (getApproxTile :420-431): upload it to the approx pool.
+ * max_residual / max_err (n floats each, or NULL): max |residual before rounding|, max |heights - approximation|. */
+typedef struct pl_resid_enc_req {
+    int32_t tile_slot;      /* heights pool: the tile to encode                    */
+    int32_t parent_slot;    /* approx pool: the parent's approximation             */
+    int32_t approx_slot;    /* approx pool: receives this tile's approximation     */
+    int32_t resid_slot;     /* resid pool: receives the int16 residuals            */
+    int32_t tile_size;      /* min(topLevelSize << level, tileSize)                */
+    int32_t tx, ty;         /* the tile's coordinates (select the parent quadrant) */
+    int32_t pad_;
+} pl_resid_enc_req;         /* 32 bytes */
+int pl_residual_encode_batch(pl_ctx *ctx, pl_pool *heights, pl_pool *approx, pl_pool *resid, int n,
+                             const pl_resid_enc_req *reqs, float *max_residual, float *max_err);
+
 #ifdef __cplusplus
 }
 #endif

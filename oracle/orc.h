@@ -217,4 +217,9 @@ long orc_produce_quadtree(const orc_scene *s, int maxLevel, int nthreads,
 #ifdef __cplusplus
 }
 #endif
+/* ---------------------------------------------------------------- preprocess
+ * the residual-pyramid builder, one tile of one level (HeightMipmap.cpp:449-559), orc_preprocess.c */
+void orc_hm_encode_tile(const float *parentTile, const float *tile, int n, int tileSize, int tx, int ty,
+                        short *resid, float *approx, float *maxR, float *maxErr);
+
 #endif

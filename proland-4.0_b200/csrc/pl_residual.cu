@@ -573,6 +573,80 @@ int parse_tiff(const uint8_t *blob, uint32_t size, int want_w, InflateJob *job, 
     return 0;
 }
 
+/* ---- the builder's side: HeightMipmap::computeResidual / encodeResidual / computeApproxTile
+ * (preprocess/terrain/HeightMipmap.cpp:449-559), one CTA per tile ------------------------------- */
+
+/* the height the parent approximation predicts for texel (i, j): the same taps and CPU evaluation order
+ * as residual_upsample_kernel above (HeightMipmap.cpp:458-489 == ResidualProducer.cpp:349-380) */
+__device__ __forceinline__ float hm_predict(const float *parent, int pitch, int i, int j, int px, int py)
+{
+    const int cx = i / 2 + px, cy = j / 2 + py;
+#define P(a, b) parent[(a) + (b) * pitch]
+    float z;
+    if (j % 2 == 0) {
+        if (i % 2 == 0) {
+            z = P(cx, cy);
+        } else {
+            const float z0 = P(cx - 1, cy), z1 = P(cx, cy), z2 = P(cx + 1, cy), z3 = P(cx + 2, cy);
+            z = ((z1 + z2) * 9.0f - (z0 + z3)) / 16.0f;
+        }
+    } else {
+        if (i % 2 == 0) {
+            const float z0 = P(cx, cy - 1), z1 = P(cx, cy), z2 = P(cx, cy + 1), z3 = P(cx, cy + 2);
+            z = ((z1 + z2) * 9.0f - (z0 + z3)) / 16.0f;
+        } else {
+            z = 0.0f;
+            for (int dj = -1; dj <= 2; ++dj) {
+                const float f = (dj == -1 || dj == 2) ? -1 / 16.0f : 9 / 16.0f;
+                for (int di = -1; di <= 2; ++di) {
+                    const float g = (di == -1 || di == 2) ? -1 / 16.0f : 9 / 16.0f;
+                    z = z + (f * g) * P(cx + di, cy + dj);
+                }
+            }
+        }
+    }
+#undef P
+    return z;
+}
+
+__global__ void __launch_bounds__(256) residual_encode_kernel(const pl_resid_enc_req *jobs, const unsigned char *hbase,
+                                                              size_t hslot, int hpitch, unsigned char *abase, size_t aslot,
+                                                              int apitch, unsigned char *rbase, size_t rslot, int rpitch,
+                                                              float2 *stats)
+{
+    __shared__ float red_r[8], red_e[8];
+    const pl_resid_enc_req J = jobs[blockIdx.x];
+    const float *tile = reinterpret_cast<const float *>(hbase + (size_t) J.tile_slot * hslot);
+    const float *parent = reinterpret_cast<const float *>(abase + (size_t) J.parent_slot * aslot);
+    float *approx = reinterpret_cast<float *>(abase + (size_t) J.approx_slot * aslot);
+    short *resid = reinterpret_cast<short *>(rbase + (size_t) J.resid_slot * rslot);
+    const int w = J.tile_size + 5;
+    const int px = 1 + (J.tx % 2) * J.tile_size / 2, py = 1 + (J.ty % 2) * J.tile_size / 2;
+    float mr = 0.0f, me = 0.0f;
+    for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
+        const int j = k / w, i = k - j * w;
+        const float z = hm_predict(parent, apitch, i, j, px, py);
+        const float t = tile[i + j * hpitch];
+        const float diff = t - z;
+        mr = fmaxf(fabsf(diff), mr);
+        const short q = (short) (int) roundf(diff);          /* short(roundf(residual)): half away from zero */
+        const float a = z + (float) q;
+        me = fmaxf(fabsf(t - a), me);
+        resid[i + j * rpitch] = q;
+        approx[i + j * apitch] = a;
+    }
+    for (int s2 = 16; s2 > 0; s2 >>= 1) {
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, s2));
+        me = fmaxf(me, __shfl_xor_sync(0xffffffffu, me, s2));
+    }
+    if ((threadIdx.x & 31) == 0) { red_r[threadIdx.x >> 5] = mr; red_e[threadIdx.x >> 5] = me; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < 8; ++q) { mr = fmaxf(mr, red_r[q]); me = fmaxf(me, red_e[q]); }
+        stats[blockIdx.x] = make_float2(mr, me);
+    }
+}
+
 }  // namespace
 
 extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
@@ -680,5 +754,54 @@ extern "C" int pl_residual_upsample(pl_ctx *ctx, pl_pool *pool, int src_slot, in
     pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    return PL_OK;
+}
+
+/* HeightMipmap::buildResiduals for n tiles of one level (preprocess/terrain/HeightMipmap.cpp:255-324):
+ * residual = heights - upsample(parent approximation), rounded to int16; approximation = upsample +
+ * rounded residual -- what ResidualProducer reconstructs from the file. */
+extern "C" int pl_residual_encode_batch(pl_ctx *ctx, pl_pool *heights, pl_pool *approx, pl_pool *resid, int n,
+                                        const pl_resid_enc_req *reqs, float *max_residual, float *max_err)
+{
+    if (!ctx || !heights || !approx || !resid || n < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (n == 0) return PL_OK;
+    if (!reqs) return pl_set_error(PL_ERR_ARG, "reqs is NULL");
+    if (heights->kind != PL_POOL_RESID_F32 || approx->kind != PL_POOL_RESID_F32 || resid->kind != PL_POOL_RESID_I16)
+        return pl_set_error(PL_ERR_ARG, "pl_residual_encode_batch needs F32 height and approximation pools and an I16 residual pool");
+    for (int j = 0; j < n; ++j) {
+        const pl_resid_enc_req &q = reqs[j];
+        /* parent reads span [px - 1, (ts + 4) / 2 + px + 2] <= ts + 4: inside a parent tile of the same container */
+        if (q.tile_size < 2 || q.tile_size % 2 != 0 || q.tile_size + 5 > heights->tile_w || q.tile_size + 5 > approx->tile_w ||
+            q.tile_size + 5 > resid->tile_w || q.tx < 0 || q.ty < 0)
+            return pl_set_error(PL_ERR_ARG, "request %d: tile size %d does not fit the pools", j, q.tile_size);
+        if (q.tile_slot < 0 || q.tile_slot >= heights->capacity || q.parent_slot < 0 || q.parent_slot >= approx->capacity ||
+            q.approx_slot < 0 || q.approx_slot >= approx->capacity || q.resid_slot < 0 || q.resid_slot >= resid->capacity ||
+            q.approx_slot == q.parent_slot)
+            return pl_set_error(PL_ERR_ARG, "request %d: slot out of range", j);
+    }
+    PL_CUDA(cudaSetDevice(ctx->device));
+    void *dev = nullptr;
+    const size_t req_bytes = (sizeof(pl_resid_enc_req) * (size_t) n + 15) & ~(size_t) 15;
+    std::vector<uint8_t> stage(req_bytes + sizeof(float2) * (size_t) n, 0);
+    memcpy(stage.data(), reqs, sizeof(pl_resid_enc_req) * (size_t) n);
+    int rc = pl_stage_requests(ctx, stage.data(), stage.size(), &dev);
+    if (rc) return rc;
+    float2 *d_stats = reinterpret_cast<float2 *>(static_cast<unsigned char *>(dev) + req_bytes);
+    pl_timing_begin(ctx, PL_K_RESIDUAL, n);
+    residual_encode_kernel<<<n, 256, 0, ctx->stream>>>(static_cast<const pl_resid_enc_req *>(dev), heights->base, heights->slot_bytes,
+                                                       heights->pitch, approx->base, approx->slot_bytes, approx->pitch, resid->base,
+                                                       resid->slot_bytes, resid->pitch, d_stats);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    if (max_residual || max_err) {
+        std::vector<float2> st(n);
+        PL_CUDA(cudaMemcpyAsync(st.data(), d_stats, sizeof(float2) * (size_t) n, cudaMemcpyDeviceToHost, ctx->stream));
+        PL_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < n; ++j) {
+            if (max_residual) max_residual[j] = st[j].x;
+            if (max_err) max_err[j] = st[j].y;
+        }
+    }
     return PL_OK;
 }

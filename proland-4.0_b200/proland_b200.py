@@ -30,7 +30,7 @@ EXPORTS = [
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
-    "pl_residual_decode_batch", "pl_residual_upsample",
+    "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch",
 ]
 
 
@@ -85,7 +85,9 @@ NORM_REQ_DTYPE = np.dtype([("out_slot", "i4"), ("elev_slot", "i4"), ("parent_slo
                            ("corners", "f4", (12,)), ("verticals", "f4", (12,)),
                            ("norms", "f4", (4,)), ("w2t", "f4", (9,)), ("p2t", "f4", (9,)),
                            ("smooth", "f4"), ("pad_", "i4", (3,))])
-assert ELEV_REQ_DTYPE.itemsize == 64 and NORM_REQ_DTYPE.itemsize == 240
+RESID_ENC_DTYPE = np.dtype([("tile_slot", "i4"), ("parent_slot", "i4"), ("approx_slot", "i4"), ("resid_slot", "i4"),
+                            ("tile_size", "i4"), ("tx", "i4"), ("ty", "i4"), ("pad_", "i4")])
+assert ELEV_REQ_DTYPE.itemsize == 64 and NORM_REQ_DTYPE.itemsize == 240 and RESID_ENC_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -159,6 +161,8 @@ def lib():
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         L.pl_residual_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.pl_residual_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                               C.c_void_p, C.c_void_p]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
         L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -382,6 +386,16 @@ class Context:
         assert len(ereqs) == len(nreqs)
         check(lib().pl_pair_batch(self.h, C.byref(escene), C.byref(nscene), elev.h, norm.h,
                                   resid.h if resid else None, len(ereqs), _ptr(ereqs), _ptr(nreqs)))
+
+    def residual_encode(self, heights, approx, resid, reqs):
+        """one level of the residual-pyramid builder (pl_residual_encode_batch);
+        -> (max |residual|, max |heights - approximation|) per tile"""
+        reqs = np.ascontiguousarray(reqs, RESID_ENC_DTYPE)
+        mr = np.empty(len(reqs), np.float32)
+        me = np.empty(len(reqs), np.float32)
+        check(lib().pl_residual_encode_batch(self.h, heights.h, approx.h, resid.h, len(reqs), _ptr(reqs),
+                                             _ptr(mr), _ptr(me)))
+        return mr, me
 
     def normal_batch_dev(self, scene, norm, elev, n, dev_ptr):
         check(lib().pl_normal_batch_dev(self.h, C.byref(scene), norm.h, elev.h, n,

@@ -257,6 +257,25 @@ class Resid:
         return out
 
 
+def hm_encode_tile(parent, tile, tile_size, tx, ty):
+    """HeightMipmap computeResidual + encodeResidual + computeApproxTile for one tile (orc_preprocess.c).
+    parent, tile: (n, n) float32 with n = the container's tileSize + 5.
+    -> (int16 residuals (ts+5, ts+5), approximation (n, n), max |residual|, max |tile - approximation|)"""
+    parent = np.ascontiguousarray(parent, np.float32)
+    tile = np.ascontiguousarray(tile, np.float32)
+    n = tile.shape[0]
+    w = tile_size + 5
+    resid = np.zeros((w, w), np.int16)
+    approx = np.zeros((n, n), np.float32)
+    mr, me = C.c_float(), C.c_float()
+    L = lib()
+    L.orc_hm_encode_tile.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_hm_encode_tile(parent.ctypes.data, tile.ctypes.data, n, tile_size, tx, ty, resid.ctypes.data,
+                         approx.ctypes.data, C.byref(mr), C.byref(me))
+    return resid, approx, mr.value, me.value
+
+
 # --------------------------------------------------------------- driver ----
 
 def make_scene(*, W=101, gridMeshSize=24, rootQuadSize=100000.0, face=0, flip=0, noise_mode=1,

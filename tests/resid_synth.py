@@ -105,3 +105,25 @@ def container(min_level=3, max_level=5, tile_size=192, root=(0, 0, 0), scale=1.0
         body += b
     head = struct.pack("<6if", min_level, max_level, tile_size, root[0], root[1], root[2], scale)
     return head + struct.pack("<%dI" % len(offsets), *offsets) + body, tiles
+
+
+def container_from_tiles(tiles, min_level, max_level, tile_size, root=(0, 0, 0), scale=1.0, level=6):
+    """{tile id: (w, w) int16} -> file bytes, laid out like HeightMipmap::generate (offset table in id
+    order, all-zero tiles sharing the first all-zero blob, HeightMipmap.cpp:601-611).  The blob order in
+    the body is id order here (the reference writes Lebesgue order; readers only use the offset table)."""
+    nt = n_tiles(min_level, max_level)
+    body, offsets, zero = b"", [], None
+    for tid in range(nt):
+        t = np.ascontiguousarray(tiles[tid], np.int16)
+        if not t.any():
+            if zero is None:
+                b = tiff_blob(t, level)
+                zero = (len(body), len(body) + len(b))
+                body += b
+            offsets += list(zero)
+            continue
+        b = tiff_blob(t, level)
+        offsets += [len(body), len(body) + len(b)]
+        body += b
+    head = struct.pack("<6if", min_level, max_level, tile_size, root[0], root[1], root[2], scale)
+    return head + struct.pack("<%dI" % len(offsets), *offsets) + body

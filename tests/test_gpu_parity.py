@@ -450,3 +450,87 @@ def test_residual_root_composition_delta(plb, ctx, oracle, delta):
         ctx.residual_upsample(pool, 0, 0, 96)            # in place is not defined
     with pytest.raises(plb.PlError):
         ctx.residual_upsample(pool, 0, 1, 194)           # does not fit the pool
+
+
+# ------------------------------------------------- the step before the path: building residual files
+
+def _height_levels(rng, top=24, levels=5):
+    """int16 height fields of a square domain, level l = top * 2^l samples (+1), coarser levels are
+    point samples of the next finer one (HeightMipmap::buildMipmapLevel, HeightMipmap.cpp:199-253)"""
+    n = top << (levels - 1)
+    yy, xx = np.mgrid[0:n + 1, 0:n + 1] / n
+    base = 900 * np.sin(5 * xx) * np.cos(4 * yy) + 250 * np.sin(23 * xx + 2) * np.sin(17 * yy) + rng.normal(0, 6, xx.shape)
+    out = [np.rint(base).astype(np.int16)]
+    for _ in range(levels - 1):
+        out.insert(0, out[0][::2, ::2])
+    return out
+
+
+def _height_tile(field, ts, tx, ty, n):
+    """the (ts + 5)^2 tile with its 2-sample border, edge samples repeated, in an n x n float array"""
+    idx_x = np.clip(np.arange(-2, ts + 3) + tx * ts, 0, field.shape[1] - 1)
+    idx_y = np.clip(np.arange(-2, ts + 3) + ty * ts, 0, field.shape[0] - 1)
+    out = np.zeros((n, n), np.float32)
+    out[:ts + 5, :ts + 5] = field[np.ix_(idx_y, idx_x)].astype(np.float32)
+    return out
+
+
+def test_residual_pyramid_builder_and_round_trip(plb, ctx, oracle):
+    """pl_residual_encode_batch (HeightMipmap::buildResiduals on the device) against the oracle, level by
+    level, then the loop closed: the residuals go into a container in the reference's format, come back
+    through pl_residual_decode_batch, and ResidualProducer's composition upsample(parent) + residual
+    reproduces the builder's approximation of every tile bit for bit."""
+    rng = np.random.default_rng(11)
+    min_level, max_level, tile_size, n = 3, 4, 192, 197
+    fields = _height_levels(rng, 24, max_level + 1)
+    tiles_of = lambda l: 1 if l < min_level else 1 << (l - min_level)
+    ts_of = lambda l: rs.tile_width(min_level, tile_size, l) - 5
+    ids = {(l, tx, ty): rs.tile_id(min_level, l, tx, ty) for l in range(max_level + 1)
+           for ty in range(tiles_of(l)) for tx in range(tiles_of(l))}
+    nt = len(ids)
+    heights = ctx.pool(plb.POOL_RESID_F32, n, nt)
+    approx = ctx.pool(plb.POOL_RESID_F32, n, nt + 1)
+    resid = ctx.pool(plb.POOL_RESID_I16, n, nt)
+    want_approx, resid_tiles = {}, {}
+    for key, tid in ids.items():
+        heights.upload(tid, _height_tile(fields[key[0]], ts_of(key[0]), key[1], key[2], n))
+    # level 0: stored as is, and its own approximation (produceTile :567-578, getApproxTile :420-431)
+    t0 = _height_tile(fields[0], ts_of(0), 0, 0, n)
+    approx.upload(0, t0)
+    want_approx[(0, 0, 0)] = t0
+    resid_tiles[0] = np.rint(t0[:ts_of(0) + 5, :ts_of(0) + 5]).astype(np.int16)
+    for l in range(1, max_level + 1):
+        keys = [k for k in ids if k[0] == l]
+        reqs = np.zeros(len(keys), plb.RESID_ENC_DTYPE)
+        for i, (_, tx, ty) in enumerate(keys):
+            parent = (l - 1, tx // 2, ty // 2) if l > min_level else (l - 1, 0, 0)
+            reqs[i] = (ids[(l, tx, ty)], ids[parent], ids[(l, tx, ty)], ids[(l, tx, ty)], ts_of(l), tx, ty, 0)
+        mr, me = ctx.residual_encode(heights, approx, resid, reqs)
+        for i, key in enumerate(keys):
+            _, tx, ty = key
+            parent = (l - 1, tx // 2, ty // 2) if l > min_level else (l - 1, 0, 0)
+            r, a, omr, ome = oracle.hm_encode_tile(want_approx[parent], _height_tile(fields[l], ts_of(l), tx, ty, n),
+                                                   ts_of(l), tx, ty)
+            w = ts_of(l) + 5
+            assert np.array_equal(resid.download(ids[key])[:w, :w], r), key
+            assert np.array_equal(approx.download(ids[key])[:w, :w], a[:w, :w]), key
+            assert mr[i] == np.float32(omr) and me[i] == np.float32(ome) and ome <= 0.5, key
+            want_approx[key] = a
+            resid_tiles[ids[key]] = r
+    # the loop closed: container -> decode -> upsample(parent approximation) + residual == approximation
+    data = rs.container_from_tiles(resid_tiles, min_level, max_level, tile_size)
+    rd = oracle.Resid(data)
+    dec = ctx.pool(plb.POOL_RESID_F32, n, nt + 1)
+    dec.upload(0, want_approx[(0, 0, 0)])
+    for l in range(1, max_level + 1):
+        for key in [k for k in ids if k[0] == l]:
+            _, tx, ty = key
+            parent = (l - 1, tx // 2, ty // 2) if l > min_level else (l - 1, 0, 0)
+            ctx.residual_upsample(dec, ids[parent], nt, ts_of(l), tx, ty)           # into the spare slot
+            ctx.residual_decode(dec, [rd.blob(ids[key])], [ts_of(l) + 5], [ids[key]], add_slots=[nt], scale=1.0)
+            w = ts_of(l) + 5
+            assert np.array_equal(dec.download(ids[key])[:w, :w], want_approx[key][:w, :w]), key
+    # and the elevation the run-time path would start from stays within the quantisation error
+    fine = want_approx[(max_level, 1, 1)][2:195, 2:195]
+    truth = fields[max_level][192:385, 192:385].astype(np.float32)
+    assert np.abs(fine - truth).max() <= 0.5

@@ -208,3 +208,28 @@ def test_canonical_vs_strict_tolerance(oracle):
     assert hi - lo > 100
     assert max_dh <= 1e-5 * (hi - lo), (max_dh, hi - lo)
     assert max_dn <= 1
+
+
+def test_residual_builder_restatement_round_trips_through_the_reader():
+    """orc_hm_encode_tile (HeightMipmap.cpp:449-559) against the reader it feeds: the approximation the
+    builder carries equals upsample(parent) + residual * scale as ResidualProducer composes it
+    (orc_resid_upsample + the int16 tile), and |heights - approximation| <= 0.5 (rounding)."""
+    import numpy as np
+    import orc
+    rng = np.random.default_rng(7)
+    n, ts = 29, 24                       # a 24 + 5 container whose level-1 tiles are full size
+    yy, xx = np.mgrid[0:n, 0:n]
+    parent = (300 * np.sin(xx / 5.0) * np.cos(yy / 7.0)).astype(np.float32)
+    for tx, ty in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        tile = (parent[::1, ::1] * 0 + rng.normal(0, 40, (n, n))).astype(np.float32)
+        resid, approx, mr, me = orc.hm_encode_tile(parent, tile, ts, tx, ty)
+        assert resid.dtype == np.int16 and resid.shape == (ts + 5, ts + 5)
+        assert me <= 0.5 + 1e-3 and mr >= np.abs(resid).max() - 0.5
+        # the reader's side: upsample of the same parent quadrant, plus the stored integers
+        f = orc.ResidFile()
+        f.tileSize, f.minLevel = ts, 0
+        up = np.zeros((n, n), np.float32)
+        orc.lib().orc_resid_upsample(orc.C.byref(f), 1, tx, ty, parent.ctypes.data_as(orc.C.c_void_p),
+                                     up.ctypes.data_as(orc.C.c_void_p))
+        want = up[:ts + 5, :ts + 5] + resid.astype(np.float32)
+        assert np.array_equal(approx[:ts + 5, :ts + 5], want)
