@@ -306,6 +306,16 @@ typedef struct pl_resid_enc_req {
 int pl_residual_encode_batch(pl_ctx *ctx, pl_pool *heights, pl_pool *approx, pl_pool *resid, int n,
                              const pl_resid_enc_req *reqs, float *max_residual, float *max_err);
 
+/* HeightMipmap::generate + produceTile (HeightMipmap.cpp:99-130, 561-655): write a residual file in the
+ * format ResidualProducer reads -- header, offset table per tile id, one little-endian TIFF/DEFLATE blob
+ * per tile (levels below min_level first, then Lebesgue order per level), all-zero tiles sharing one
+ * blob.  tiles + tile_offsets[id]: the dense (w x w, w = getTileSize(level) + 5) int16 residuals of tile
+ * id (ResidualProducer::getTileId numbering).  zlib_level: -1 (zlib's default, what libtiff uses) .. 9.
+ * Host code only; PL_ERR_IO when the file cannot be written. */
+int pl_residual_write_file(const char *path, int min_level, int max_level, int tile_size, int root_level,
+                           int root_tx, int root_ty, float scale, const int16_t *tiles,
+                           const uint64_t *tile_offsets, int zlib_level);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,7 +30,7 @@ EXPORTS = [
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
-    "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch",
+    "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
 ]
 
 
@@ -161,6 +161,8 @@ def lib():
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         L.pl_residual_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.pl_residual_write_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                             C.c_void_p, C.c_void_p, C.c_int]
         L.pl_residual_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
@@ -240,6 +242,17 @@ def make_requests_range(scene, level, morton0, n, out_slot0=0, parent_slot0=0, p
     check(lib().pl_make_requests_range(C.byref(scene), level, morton0, n, out_slot0, parent_slot0,
                                        parent_morton0, _ptr(e), _ptr(q) if normals else None, nthreads))
     return e, q
+
+
+def residual_write_file(path, tiles, min_level, max_level, tile_size, root=(0, 0, 0), scale=1.0, zlib_level=-1):
+    """tiles: {tile id: (w, w) int16} -> a residual file in the reference's format (pl_residual_write_file)"""
+    ids = sorted(tiles)
+    flat = [np.ascontiguousarray(tiles[i], np.int16).ravel() for i in ids]
+    assert ids == list(range(len(ids)))
+    offs = np.concatenate([[0], np.cumsum([len(a) for a in flat[:-1]])]).astype(np.uint64)
+    buf = np.concatenate(flat)
+    check(lib().pl_residual_write_file(os.fsencode(path), min_level, max_level, tile_size, root[0], root[1], root[2],
+                                       C.c_float(scale), _ptr(buf), _ptr(offs), zlib_level))
 
 
 def morton_encode(tx, ty):

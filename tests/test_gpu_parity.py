@@ -518,7 +518,12 @@ def test_residual_pyramid_builder_and_round_trip(plb, ctx, oracle):
             want_approx[key] = a
             resid_tiles[ids[key]] = r
     # the loop closed: container -> decode -> upsample(parent approximation) + residual == approximation
-    data = rs.container_from_tiles(resid_tiles, min_level, max_level, tile_size)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        plb.residual_write_file(os.path.join(tmp, "DEM.dat"), resid_tiles, min_level, max_level, tile_size)
+        data = open(os.path.join(tmp, "DEM.dat"), "rb").read()
+    assert oracle.Resid(rs.container_from_tiles(resid_tiles, min_level, max_level, tile_size)).inflate(5)[0] == \
+        oracle.Resid(data).inflate(5)[0]
     rd = oracle.Resid(data)
     dec = ctx.pool(plb.POOL_RESID_F32, n, nt + 1)
     dec.upload(0, want_approx[(0, 0, 0)])

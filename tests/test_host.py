@@ -131,3 +131,42 @@ def test_sweep_plan_covers_the_planet_once(plb):
         parts = [sweep.units_of_rank(units, r, world) for r in range(world)]
         assert sorted(sum(parts, [])) == sorted(units) and len({len(p) for p in parts}) == 1
     assert [plb.morton_decode(plb.morton_encode(x, y)) for x, y in ((0, 0), (5, 9), (1023, 77))] == [(0, 0), (5, 9), (1023, 77)]
+
+
+def test_residual_file_writer_matches_the_reference_format(plb, tmp_path):
+    """pl_residual_write_file (HeightMipmap::generate / produceTile): the oracle's reader -- pinned on the
+    reference's own DEM.dat -- reads every tile back; all-zero tiles share one blob; the blobs of a level
+    lie in Lebesgue order; the header and the offset-table size are the reference's."""
+    import struct
+    import numpy as np
+    import orc
+    import resid_synth as rs
+    min_level, max_level, tile_size = 3, 5, 192
+    _, tiles = rs.container(min_level=min_level, max_level=max_level, tile_size=tile_size, zero_fraction=0.3, seed=5)
+    path = str(tmp_path / "DEM.dat")
+    plb.residual_write_file(path, tiles, min_level, max_level, tile_size, root=(0, 0, 0), scale=0.5)
+    data = open(path, "rb").read()
+    head = struct.unpack("<6if", data[:28])
+    assert head[:6] == (min_level, max_level, tile_size, 0, 0, 0) and head[6] == 0.5
+    nt = rs.n_tiles(min_level, max_level)
+    offs = np.frombuffer(data[28:28 + 8 * nt], "<u4").reshape(nt, 2)
+    assert 28 + 8 * nt + int(offs[:, 1].max()) == len(data)
+    rd = orc.Resid(data)
+    for tid, t in tiles.items():
+        raw, w, h = rd.inflate(tid)
+        assert (w, h) == t.shape and np.array_equal(np.frombuffer(raw, "<i2").reshape(t.shape), t), tid
+    zero_ids = [tid for tid, t in tiles.items() if not t.any()]
+    assert len(zero_ids) > 2 and len({tuple(offs[t]) for t in zero_ids}) == 1
+    # Lebesgue order inside a level: offsets grow along the Z curve (skipping the shared zero blob)
+    l = max_level - min_level
+    seen = []
+    for m in range(4 ** l):
+        tx = sum(((m >> (2 * b)) & 1) << b for b in range(l))
+        ty = sum(((m >> (2 * b + 1)) & 1) << b for b in range(l))
+        tid = rs.tile_id(min_level, max_level, tx, ty)
+        if tiles[tid].any():
+            seen.append(int(offs[tid, 0]))
+    assert seen == sorted(seen) and len(set(seen)) == len(seen)
+    with pytest.raises(plb.PlError) as e:
+        plb.residual_write_file(str(tmp_path / "no" / "such" / "dir.dat"), tiles, min_level, max_level, tile_size)
+    assert e.value.code == plb.PL_ERR_IO
