@@ -2,6 +2,8 @@
 
 #include <algorithm>
 #include <map>
+#include <unordered_map>
+#include <unordered_set>
 #include <stdexcept>
 
 namespace ork
@@ -52,22 +54,43 @@ struct Node
     std::vector<Task *> deps;   /* tasks or graphs this task waits for, over all graphs that hold it */
 };
 
+/* the primitive tasks below the roots, in the order the graphs list them (hashed lookup: the view is
+ * rebuilt every wave of every frame) */
+struct Flat
+{
+    std::vector<Node> nodes;
+    std::unordered_map<Task *, size_t> index;
+    std::unordered_set<Task *> seenGraphs;
+
+    Node &operator[](Task *t)
+    {
+        std::unordered_map<Task *, size_t>::iterator i = index.find(t);
+        if (i != index.end()) {
+            return nodes[i->second];
+        }
+        index.insert(std::make_pair(t, nodes.size()));
+        nodes.push_back(Node());
+        nodes.back().task = t;
+        return nodes.back();
+    }
+};
+
 /* primitive tasks below `t`, with their dependencies */
-void flatten(Task *t, std::set<Task *> &seenGraphs, std::map<Task *, Node> &nodes)
+void flatten(Task *t, Flat &nodes)
 {
     if (!t->isTaskGraph()) {
         Node &n = nodes[t];
         n.task = t;
         return;
     }
-    if (!seenGraphs.insert(t).second) {
+    if (!nodes.seenGraphs.insert(t).second) {
         return;
     }
     TaskGraph *g = static_cast<TaskGraph *>(t);
     const TaskGraph::TaskSet &ts = g->taskSet();
     for (TaskGraph::TaskSet::const_iterator i = ts.begin(); i != ts.end(); ++i) {
         Task *c = i->get();
-        flatten(c, seenGraphs, nodes);
+        flatten(c, nodes);
         const TaskGraph::TaskSet *deps = g->dependenciesOf(c);
         if (deps == NULL) {
             continue;
@@ -97,6 +120,31 @@ bool byContext(Task *a, Task *b)
 
 }  // namespace
 
+static void initAll(const std::vector<ptr<Task> > &roots, std::set<Task *> &initialized)
+{
+    for (;;) {
+        Flat nodes;
+        for (size_t i = 0; i < roots.size(); ++i) {
+            flatten(roots[i].get(), nodes);
+        }
+        bool any = false;
+        /* keep the tasks alive: an init may drop the last other reference to a sibling */
+        std::vector<ptr<Task> > todo;
+        for (std::vector<Node>::iterator n = nodes.nodes.begin(); n != nodes.nodes.end(); ++n) {
+            if (initialized.insert(n->task).second) {
+                todo.push_back(n->task);
+            }
+        }
+        for (size_t i = 0; i < todo.size(); ++i) {
+            todo[i]->init(initialized);
+            any = true;
+        }
+        if (!any) {
+            break;
+        }
+    }
+}
+
 void BatchScheduler::run(ptr<Task> task)
 {
     ++frame;
@@ -109,26 +157,28 @@ void BatchScheduler::run(ptr<Task> task)
         prefetch.pop_front();
     }
 
+    /* Task::init of every primitive task below the roots, once.  TaskGraph::init would walk the nested
+     * per-tile graphs recursively -- a tile's graph holds its parent's, which holds its parent's ...: every
+     * frame re-walked each ancestor chain once per descendant (60 % of the host time of a fly-through).  The
+     * flattened view visits every graph once; initialising a task may add tasks (CreateTile::start acquires
+     * the tiles it is made from), so flatten again until nothing new appears. */
     std::set<Task *> initialized;
-    for (size_t i = 0; i < roots.size(); ++i) {
-        roots[i]->init(initialized);
-    }
+    initAll(roots, initialized);
 
     for (;;) {
         /* flatten again every wave: finishing a task releases its inputs, restarting one re-acquires
          * them, both edit the graphs */
-        std::set<Task *> seen;
-        std::map<Task *, Node> nodes;
+        Flat nodes;
         for (size_t i = 0; i < roots.size(); ++i) {
-            flatten(roots[i].get(), seen, nodes);
+            flatten(roots[i].get(), nodes);
         }
         /* done tasks that completed before one of their inputs changed are stale */
         bool restarted = false;
-        for (std::map<Task *, Node>::iterator n = nodes.begin(); n != nodes.end(); ++n) {
-            Task *t = n->first;
+        for (std::vector<Node>::iterator n = nodes.nodes.begin(); n != nodes.nodes.end(); ++n) {
+            Task *t = n->task;
             if (!t->isDone()) continue;
-            for (size_t d = 0; d < n->second.deps.size(); ++d) {
-                if (n->second.deps[d]->getChangeDate() > t->getCompletionDate()) {
+            for (size_t d = 0; d < n->deps.size(); ++d) {
+                if (n->deps[d]->getChangeDate() > t->getCompletionDate()) {
                     t->setIsDone(false, 0, Task::DATA_CHANGED);
                     initialized.erase(t);
                     restarted = true;
@@ -138,22 +188,20 @@ void BatchScheduler::run(ptr<Task> task)
         }
         if (restarted) {
             /* restarted tasks re-acquire their input tiles (CreateTile::init -> start) */
-            for (size_t i = 0; i < roots.size(); ++i) {
-                roots[i]->init(initialized);
-            }
+            initAll(roots, initialized);
             continue;
         }
 
         std::vector<Task *> ready;
         size_t open = 0;
-        for (std::map<Task *, Node>::iterator n = nodes.begin(); n != nodes.end(); ++n) {
-            if (n->first->isDone()) continue;
+        for (std::vector<Node>::iterator n = nodes.nodes.begin(); n != nodes.nodes.end(); ++n) {
+            if (n->task->isDone()) continue;
             ++open;
             bool ok = true;
-            for (size_t d = 0; d < n->second.deps.size() && ok; ++d) {
-                ok = n->second.deps[d]->isDone();
+            for (size_t d = 0; d < n->deps.size() && ok; ++d) {
+                ok = n->deps[d]->isDone();
             }
-            if (ok) ready.push_back(n->first);
+            if (ok) ready.push_back(n->task);
         }
         if (open == 0) {
             break;
