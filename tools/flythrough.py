@@ -92,14 +92,21 @@ def run(frames=300, asynchronous=False, ntiles=1296, max_level=12, data_dir=None
     samplers = [ph.Sampler("elevationSampler", elevations, asynchronous), ph.Sampler("fragmentNormalSampler", normals, asynchronous)]
     split = ph.lib().plh_split_distance(2.0, 1024.0, math.radians(80.0))
     times, quads, made = [], [], []
+    parts = [0.0, 0.0, 0.0]     # quadtree update, samplers + scheduler, device sync
     launches0 = ph.lib().plh_device_launches(-1)
     for k, cam in enumerate(camera_path(frames)):
         before = elevations.counts()[0] + normals.counts()[0] + residuals.counts()[0]
         t0 = time.perf_counter()
         nq = terrain.update(*cam, split_dist=split)
+        t1 = time.perf_counter()
         ph.frame_update(sched, terrain, samplers)
+        t2 = time.perf_counter()
         ph.lib().plh_device_sync(-1)
-        times.append(time.perf_counter() - t0)
+        t3 = time.perf_counter()
+        times.append(t3 - t0)
+        parts[0] += t1 - t0
+        parts[1] += t2 - t1
+        parts[2] += t3 - t2
         quads.append(nq)
         made.append(elevations.counts()[0] + normals.counts()[0] + residuals.counts()[0] - before)
         if on_frame is not None:
@@ -116,6 +123,7 @@ def run(frames=300, asynchronous=False, ntiles=1296, max_level=12, data_dir=None
         "frame_ms_max": float(t.max() * 1e3), "quads_mean": float(np.mean(quads)), "quads_max": int(max(quads)),
         "tiles_per_frame_max": int(max(made)),
         "miss_rate": {n: s["misses"] / max(s["queries"], 1) for n, s in stats.items()},
+        "host_seconds": {"terrain_update": parts[0], "samplers_and_scheduler": parts[1], "device_sync": parts[2]},
         "kernel_launches": int(ph.lib().plh_device_launches(-1) - launches0),
         "tiles_per_launch": total / max(int(ph.lib().plh_device_launches(-1) - launches0), 1),
     }
