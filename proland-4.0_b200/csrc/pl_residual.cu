@@ -239,9 +239,6 @@ struct InflateJob {
     unsigned int compression;    /* 1 = stored strip, else zlib stream */
 };
 
-/* Events lane 0 hands to the warp */
-enum { EV_NONE = 0, EV_EOB = 1, EV_FLUSH = 2, EV_FAR = 3, EV_ERR = 4 };
-
 /* ring[flushed .. flushed + n) -> dst (n, flushed multiples of 16; both sides 16-byte aligned) */
 __device__ __forceinline__ void flush_ring(const unsigned char *ring, unsigned char *dst, unsigned int flushed, unsigned int n, int lane)
 {
@@ -250,12 +247,15 @@ __device__ __forceinline__ void flush_ring(const unsigned char *ring, unsigned c
     for (unsigned int q = lane; q < n / 16; q += 32) dst4[q] = src4[q];
 }
 
-/* One warp per tile.  Lane 0 decodes on its own -- literals and near matches (distance < kRing) go
- * straight into a ring of the last kRing output bytes in shared memory -- and wakes the other lanes only
- * for what a warp does better: building the code tables of a block, flushing kFlush finished bytes to the
- * dense stream in HBM with 16-byte stores, and the rare match that reaches behind the ring (its source
- * has been flushed by then and is read back from HBM).  The old kernel kept the output in HBM and paid an
- * L2 round trip for every match and two warp shuffles for every symbol. */
+/* One warp per tile, and ALL 32 LANES DECODE THE SAME STREAM IN LOCKSTEP: every lane carries the same bit
+ * buffer, reads the same table entries (shared-memory broadcasts) and so knows every symbol, length and
+ * distance without a shuffle.  The cost of a warp is its instruction count whatever the number of active
+ * lanes, so the redundancy is free -- and it removes what made one-lane decoding slow (measured: 161
+ * instructions per symbol): the divergence bookkeeping around every branch of a lane-0-only region, the
+ * hand-over of matches to the other lanes, the byte-by-byte match loop.  Lane 0 alone writes literals
+ * into a ring of the last kRing output bytes in shared memory; matches are copied by all lanes; finished
+ * kilobytes leave for the dense stream in HBM as 16-byte stores; a match that reaches behind the ring
+ * (rare) reads its source back from there. */
 __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const InflateJob *jobs, const unsigned char *in,
                                                                    unsigned char *out, size_t out_stride, int *status)
 {
@@ -270,7 +270,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
     const unsigned char *src = in + J.in_off;
     unsigned char *dst = out + (size_t) job * out_stride;
     const unsigned int cap = J.out_len;
-    const unsigned int FULL = 0xffffffffu;
     constexpr unsigned int M = kRing - 1;
 
     if (J.compression == 1) {   /* uncompressed strip */
@@ -280,94 +279,90 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
     }
 
     BitReader b;
-    if (lane == 0) br_init(b, src, J.in_len);
+    br_init(b, src, J.in_len);
     int err = INF_OK;
     unsigned int pos = 0, flushed = 0;     /* bytes produced / bytes already in HBM (a multiple of kFlush) */
-    if (lane == 0) {   /* zlib header: CM = 8, no preset dictionary, header checksum */
+    {   /* zlib header: CM = 8, no preset dictionary, header checksum */
         const unsigned int cmf = br_bits(b, 8), flg = br_bits(b, 8);
         if ((cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32) || ((cmf << 8) | flg) % 31 != 0) err = INF_BAD_HEADER;
     }
-    err = __shfl_sync(FULL, err, 0);
+
+    /* finished flush units of the ring -> HBM; the warp must have met since the last ring write */
+    auto flush = [&]() {
+        while (pos - flushed >= (unsigned int) kFlush) {
+            flush_ring(ring, dst, flushed, kFlush, lane);
+            flushed += kFlush;
+        }
+        __syncwarp();
+    };
 
     int last = 0;
     while (!err && !last) {
-        int type = 0;
-        if (lane == 0) {
-            last = (int) br_bits(b, 1);
-            type = (int) br_bits(b, 2);
-        }
-        last = __shfl_sync(FULL, last, 0);
-        type = __shfl_sync(FULL, type, 0);
+        last = (int) br_bits(b, 1);
+        const int type = (int) br_bits(b, 2);
 
         if (type == 0) {   /* stored block */
-            unsigned int len = 0, src_pos = 0;
-            if (lane == 0) {
-                br_drop(b, b.cnt & 7);                 /* to the byte boundary */
-                len = br_bits(b, 16);
-                const unsigned int nlen = br_bits(b, 16);
-                if ((len ^ nlen) != 0xffffu) err = INF_BAD_BLOCK;
-                src_pos = br_byte_pos(b);              /* next unread byte */
-                if (!err && src_pos + len > b.end) err = INF_OVERRUN_IN;
-                if (!err && pos + len > cap) err = INF_OVERRUN_OUT;
-            }
-            err = __shfl_sync(FULL, err, 0);
-            len = __shfl_sync(FULL, len, 0);
-            src_pos = __shfl_sync(FULL, src_pos, 0);
+            br_drop(b, b.cnt & 7);                 /* to the byte boundary */
+            const unsigned int len = br_bits(b, 16);
+            const unsigned int nlen = br_bits(b, 16);
+            if ((len ^ nlen) != 0xffffu) err = INF_BAD_BLOCK;
+            const unsigned int src_pos = br_byte_pos(b);              /* next unread byte */
+            if (!err && src_pos + len > b.end) err = INF_OVERRUN_IN;
+            if (!err && pos + len > cap) err = INF_OVERRUN_OUT;
             if (err) break;
             /* through the ring, a flush unit at a time (later matches may refer to these bytes) */
             unsigned int done = 0;
+            __syncwarp();
             while (done < len) {
                 const unsigned int piece = min(len - done, (unsigned int) kFlush - (pos - flushed));
                 for (unsigned int k = lane; k < piece; k += 32) ring[(pos + k) & M] = __ldg(src + src_pos + done + k);
                 pos += piece;
                 done += piece;
                 __syncwarp();
-                if (pos - flushed >= kFlush) {
-                    flush_ring(ring, dst, flushed, kFlush, lane);
-                    flushed += kFlush;
-                    __syncwarp();
-                }
+                flush();
             }
-            if (lane == 0) br_seek(b, src_pos + len);   /* restart the bit reader after the stored bytes */
+            br_seek(b, src_pos + len);   /* restart the bit reader after the stored bytes */
             continue;
         }
         if (type == 3) { err = INF_BAD_BLOCK; break; }
 
         int nlen = 288, ndist = 30;
+        __syncwarp();   /* nobody still reads the tables of the previous block */
         if (type == 1) {   /* fixed code */
             for (int s = lane; s < 288; s += 32) T.lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
             for (int s = lane; s < 32; s += 32) T.lens[288 + s] = 5;
             ndist = 30;
-        } else {           /* dynamic code: read the code lengths (lane 0) */
-            if (lane == 0) {
-                nlen = (int) br_bits(b, 5) + 257;
-                ndist = (int) br_bits(b, 5) + 1;
-                const int ncode = (int) br_bits(b, 4) + 4;
-                if (nlen > 286 || ndist > 30) err = INF_BAD_BLOCK;
-                for (int k = 0; k < 19; ++k) T.lens[k] = 0;
-                for (int k = 0; k < ncode; ++k) T.lens[kClOrder[k]] = (unsigned char) br_bits(b, 3);
+        } else {           /* dynamic code: read the code lengths */
+            nlen = (int) br_bits(b, 5) + 257;
+            ndist = (int) br_bits(b, 5) + 1;
+            const int ncode = (int) br_bits(b, 4) + 4;
+            if (nlen > 286 || ndist > 30) { err = INF_BAD_BLOCK; break; }
+            if (lane < 19) T.lens[lane] = 0;
+            __syncwarp();
+            for (int k = 0; k < ncode; ++k) {
+                const unsigned int v = br_bits(b, 3);
+                if (lane == 0) T.lens[kClOrder[k]] = (unsigned char) v;
             }
-            err = __shfl_sync(FULL, err, 0);
-            nlen = __shfl_sync(FULL, nlen, 0);
-            ndist = __shfl_sync(FULL, ndist, 0);
-            if (err) break;
             __syncwarp();
             /* the code-length code reuses the literal tables (7-bit codes fit the first-level table) */
             if (!build_code(T.lens, 19, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane)) { err = INF_BAD_CODE; break; }
-            if (lane == 0) {
+            {
                 /* the 19 code-length lengths are in use through the tables only, which are already
-                 * built, so lens[] is overwritten */
-                int idx = 0;
+                 * built, so lens[] is overwritten (by lane 0; every lane tracks the previous length) */
+                int idx = 0, prev_len = 0;
                 while (idx < nlen + ndist && !err) {
                     const int s = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
                     if (s < 0) { err = INF_BAD_CODE; break; }
                     if (s < 16) {
-                        T.lens[idx++] = (unsigned char) s;
+                        if (lane == 0) T.lens[idx] = (unsigned char) s;
+                        if (idx == 256 && s == 0) err = INF_BAD_CODE;   /* no end-of-block code */
+                        idx++;
+                        prev_len = s;
                     } else {
                         int prev = 0, rep;
                         if (s == 16) {
                             if (idx == 0) { err = INF_BAD_CODE; break; }
-                            prev = T.lens[idx - 1];
+                            prev = prev_len;
                             rep = 3 + (int) br_bits(b, 2);
                         } else if (s == 17) {
                             rep = 3 + (int) br_bits(b, 3);
@@ -375,12 +370,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
                             rep = 11 + (int) br_bits(b, 7);
                         }
                         if (idx + rep > nlen + ndist) { err = INF_BAD_CODE; break; }
-                        while (rep--) T.lens[idx++] = (unsigned char) prev;
+                        if (idx <= 256 && idx + rep > 256 && prev == 0) err = INF_BAD_CODE;   /* lens[256] == 0 */
+                        if (lane == 0)
+                            for (int q = 0; q < rep; ++q) T.lens[idx + q] = (unsigned char) prev;
+                        idx += rep;
+                        prev_len = prev;
                     }
                 }
-                if (!err && T.lens[256] == 0) err = INF_BAD_CODE;   /* no end-of-block code */
             }
-            err = __shfl_sync(FULL, err, 0);
             if (err) break;
             __syncwarp();
         }
@@ -394,62 +391,52 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
             if (!okd || !okl) { err = INF_BAD_CODE; break; }
         }
 
-        /* symbols of the block: lane 0 runs until it needs the warp */
+        /* symbols of the block */
         for (;;) {
-            int ev = EV_NONE;
-            unsigned int len = 0, dist = 0;
-            if (lane == 0) {
-                for (;;) {
-                    const int sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
-                    if (sym < 256) {
-                        if (sym < 0) { err = INF_BAD_CODE; ev = EV_ERR; break; }
-                        if (pos >= cap) { err = INF_OVERRUN_OUT; ev = EV_ERR; break; }
-                        ring[pos & M] = (unsigned char) sym;
-                        pos += 1;
-                    } else if (sym == 256) {
-                        ev = EV_EOB;
-                        break;
+            const int sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
+            if (sym < 256) {
+                if (sym < 0) { err = INF_BAD_CODE; break; }
+                if (pos >= cap) { err = INF_OVERRUN_OUT; break; }
+                if (lane == 0) ring[pos & M] = (unsigned char) sym;
+                pos += 1;
+            } else if (sym == 256) {
+                break;
+            } else {
+                if (sym > 285) { err = INF_BAD_CODE; break; }
+                const int li = sym - 257;
+                const unsigned int len = kLenBase[li] + br_bits(b, kLenExtra[li]);
+                const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
+                if (ds < 0 || ds > 29) { err = INF_BAD_CODE; break; }
+                const unsigned int dist = kDistBase[ds] + br_bits(b, kDistExtra[ds]);
+                if (dist > pos) { err = INF_BAD_DISTANCE; break; }
+                if (pos + len > cap) { err = INF_OVERRUN_OUT; break; }
+                __syncwarp();   /* lane 0's literals are in the ring */
+                if (dist < (unsigned int) kRing) {
+                    /* overlapping matches repeat their first `dist` bytes, all of which exist already */
+                    if (dist >= len) {
+                        for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = ring[(pos - dist + k) & M];
                     } else {
-                        if (sym > 285) { err = INF_BAD_CODE; ev = EV_ERR; break; }
-                        const int li = sym - 257;
-                        len = kLenBase[li] + br_bits(b, kLenExtra[li]);
-                        const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
-                        if (ds < 0 || ds > 29) { err = INF_BAD_CODE; ev = EV_ERR; break; }
-                        dist = kDistBase[ds] + br_bits(b, kDistExtra[ds]);
-                        if (dist > pos) { err = INF_BAD_DISTANCE; ev = EV_ERR; break; }
-                        if (pos + len > cap) { err = INF_OVERRUN_OUT; ev = EV_ERR; break; }
-                        if (dist >= (unsigned int) kRing) { ev = EV_FAR; break; }
-                        /* near match: byte by byte inside the ring (overlapping matches repeat naturally) */
-                        for (unsigned int k = 0; k < len; ++k) ring[(pos + k) & M] = ring[(pos + k - dist) & M];
-                        pos += len;
+                        for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = ring[(pos - dist + (k % dist)) & M];
                     }
-                    if (b.overrun) { err = INF_OVERRUN_IN; ev = EV_ERR; break; }
-                    if (pos - flushed >= (unsigned int) kFlush) { ev = EV_FLUSH; break; }
+                } else {
+                    /* the source lies at least kRing - 258 bytes behind pos: flushed long ago (dist > len) */
+                    for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = dst[pos - dist + k];
                 }
-                if (!err && b.overrun) { err = INF_OVERRUN_IN; ev = EV_ERR; }
-            }
-            ev = __shfl_sync(FULL, ev, 0);
-            pos = __shfl_sync(FULL, pos, 0);
-            if (ev == EV_ERR) { err = __shfl_sync(FULL, err, 0); break; }
-            __syncwarp();   /* lane 0's ring stores are visible to the other lanes */
-            if (ev == EV_FAR) {
-                len = __shfl_sync(FULL, len, 0);
-                dist = __shfl_sync(FULL, dist, 0);
-                /* the source lies at least kRing - 258 bytes behind pos: flushed long ago (dist > len) */
-                for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = dst[pos - dist + k];
                 pos += len;
+                __syncwarp();   /* the copy is complete before anybody writes behind it */
+            }
+            if (b.overrun) { err = INF_OVERRUN_IN; break; }
+            if (pos - flushed >= (unsigned int) kFlush) {
                 __syncwarp();
+                flush();
             }
-            while (pos - flushed >= (unsigned int) kFlush) {
-                flush_ring(ring, dst, flushed, kFlush, lane);
-                flushed += kFlush;
-            }
-            __syncwarp();   /* the flushed bytes are visible to later far matches of any lane */
-            if (ev == EV_EOB) break;
         }
+        if (!err && b.overrun) err = INF_OVERRUN_IN;
+        __syncwarp();
+        flush();
     }
-    err = __shfl_sync(FULL, err, 0);
     if (!err && pos != cap) err = INF_SHORT;
+    __syncwarp();
     if (!err) {   /* the tail: whole 16-byte words, then bytes */
         const unsigned int rest = pos - flushed, r16 = rest & ~15u;
         flush_ring(ring, dst, flushed, r16, lane);
