@@ -138,6 +138,7 @@ class PlanetSweep:
             nmax = 4 ** max(self.max_level - 2, 1)
             self._req_bufs = (np.zeros(nmax, pl.ELEV_REQ_DTYPE), np.zeros(nmax, pl.NORM_REQ_DTYPE))
         h2d = d2h = 0
+        self.stats_checksum = 0.0      # sum of every (zmin, zmax) read back: must not depend on the partition
         pending = []
         prof = [0.0] * 4 if os.environ.get("PL_E2E_PROFILE") else None
         for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
@@ -151,7 +152,9 @@ class PlanetSweep:
             t3 = t2
             if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile, collected three
                 if len(pending) == 3:                                    # read-backs later (ReadbackManager
-                    d2h += ctx.elev_stats_readback_end(pending.pop(0)).nbytes   # keeps several in flight)
+                    st = ctx.elev_stats_readback_end(pending.pop(0))     # keeps several in flight)
+                    d2h += st.nbytes
+                    self.stats_checksum += float(st.astype(np.float64).sum())
                 t3 = time.perf_counter()
                 pending.append(ctx.elev_stats_readback_begin(self.elev, s0, n))
             if prof is not None:
@@ -159,7 +162,9 @@ class PlanetSweep:
                 for j, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
                     prof[j] += dt
         for tk in pending:
-            d2h += ctx.elev_stats_readback_end(tk).nbytes
+            st = ctx.elev_stats_readback_end(tk)
+            d2h += st.nbytes
+            self.stats_checksum += float(st.astype(np.float64).sum())
         if prof is not None:
             print("e2e host profile (s): build requests %.3f, pair_batch %.3f, readback wait %.3f, "
                   "readback begin %.3f" % tuple(prof), file=sys.stderr)
@@ -310,8 +315,10 @@ def main():
             e2e = (e2e_s, h2d, d2h)
 
     t = torch.tensor([ms, e2e[0] if e2e else 0.0], dtype=torch.float64, device="cuda")
+    c = torch.tensor([sweep.stats_checksum if e2e else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
     ms_max, e2e_s_max = float(t[0]), float(t[1])
 
     if rank == 0:
@@ -346,7 +353,10 @@ def main():
         if e2e:
             line["e2e"] = {"value": total_pairs / e2e_s_max, "unit": "pairs/s",
                            "h2d_bytes_per_step": int(e2e[1]) * world, "d2h_bytes_per_step": int(e2e[2]) * world,
-                           "path": "host-built per-tile requests -> pl_pair_batch (HOST arrays), stats read back"}
+                           "path": "host-built per-tile requests -> pl_pair_batch (HOST arrays), stats read back",
+                           "stats_checksum": float(c[0]),
+                           "stats_checksum_of": "sum of the (zmin, zmax) of every tile of levels 8..10 read back "
+                                                "in the step: independent of the number of ranks"}
         if world == 1 and not args.no_cpu_baseline:
             n, dt, (csum, clo, chi) = cpu_sample(7)
             line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": os.cpu_count(),
