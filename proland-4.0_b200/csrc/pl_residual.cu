@@ -67,8 +67,8 @@ struct WarpTables {
 
 /* The bit reader of lane 0.  Input comes in ALIGNED 32-bit words, one word prefetched ahead of the bit
  * buffer so that the load latency overlaps the decoding of the 32 bits before it (byte loads on the
- * critical path were a third of the old kernel's time).  Bytes past the end of the strip read as zero;
- * consuming one of them sets `overrun`. */
+ * critical path were a third of the old kernel's time).  Consuming bits behind the end of the strip is
+ * detected by position (br_overrun), not by what those bits are. */
 struct BitReader {
     const unsigned char *src;    /* strip start */
     unsigned int end;            /* strip length in bytes */
@@ -78,18 +78,15 @@ struct BitReader {
     unsigned int nxt;
     unsigned long long buf;
     int cnt;
-    bool overrun;
 };
 
-/* word k of the stream: strip bytes [org + 4k, org + 4k + 4), zero beyond the end */
+/* word k of the stream: strip bytes [org + 4k, org + 4k + 4).  Words behind the end of the strip are
+ * not fetched (zero); inside the last word the bytes behind the end are whatever follows the strip in the
+ * packed blob buffer (the TIFF directory): a stream that consumes them has `overrun` set and is rejected */
 __device__ __forceinline__ unsigned int br_word(const BitReader &b, unsigned int k)
 {
     const int lo = b.org + 4 * (int) k;
-    if (lo >= (int) b.end) return 0u;
-    unsigned int w = __ldg(reinterpret_cast<const unsigned int *>(b.src + lo));
-    const int valid = (int) b.end - lo;          /* bytes of this word inside the strip (>= 1) */
-    if (valid < 4) w &= (1u << (8 * valid)) - 1u;
-    return w;
+    return lo < (int) b.end ? __ldg(reinterpret_cast<const unsigned int *>(b.src + lo)) : 0u;
 }
 /* start reading at strip offset t */
 __device__ __forceinline__ void br_seek(BitReader &b, unsigned int t)
@@ -105,10 +102,10 @@ __device__ __forceinline__ void br_seek(BitReader &b, unsigned int t)
 }
 __device__ __forceinline__ void br_init(BitReader &b, const unsigned char *src, unsigned int n)
 {
-    b.src = src; b.end = n; b.overrun = false;
+    b.src = src; b.end = n;
     br_seek(b, 0);
 }
-/* at least 33 valid bits afterwards (zero bits past the end; overrun noted when consumed) */
+/* at least 33 valid bits afterwards */
 __device__ __forceinline__ void br_fill(BitReader &b)
 {
     if (b.cnt <= 32) {
@@ -124,9 +121,6 @@ __device__ __forceinline__ void br_drop(BitReader &b, int n)
 {
     b.buf >>= n;
     b.cnt -= n;
-    /* bytes merged so far minus whole bytes still buffered must not pass the end; only possible once
-     * padding words have been merged (one compare on the hot path) */
-    if (b.merged > b.end && b.merged - (unsigned int) (b.cnt >> 3) > b.end) b.overrun = true;
 }
 __device__ __forceinline__ unsigned int br_bits(BitReader &b, int n)
 {
@@ -134,6 +128,13 @@ __device__ __forceinline__ unsigned int br_bits(BitReader &b, int n)
     const unsigned int v = br_peek(b, n);
     br_drop(b, n);
     return v;
+}
+/* bits were consumed behind the end of the strip: bytes merged so far minus whole bytes still buffered
+ * pass the end.  Checked at every flush and block end, not per symbol: a stream running on garbage stays
+ * bounded by the output capacity and the code tables, and is rejected at the next check */
+__device__ __forceinline__ bool br_overrun(const BitReader &b)
+{
+    return b.merged > b.end && b.merged - (unsigned int) (b.cnt >> 3) > b.end;
 }
 /* strip offset of the next unread byte (call at a byte boundary) */
 __device__ __forceinline__ unsigned int br_byte_pos(const BitReader &b) { return b.merged - (unsigned int) (b.cnt >> 3); }
@@ -425,13 +426,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
                 pos += len;
                 __syncwarp();   /* the copy is complete before anybody writes behind it */
             }
-            if (b.overrun) { err = INF_OVERRUN_IN; break; }
             if (pos - flushed >= (unsigned int) kFlush) {
+                if (br_overrun(b)) { err = INF_OVERRUN_IN; break; }
                 __syncwarp();
                 flush();
             }
         }
-        if (!err && b.overrun) err = INF_OVERRUN_IN;
+        if (br_overrun(b)) err = INF_OVERRUN_IN;      /* also overrides what the garbage decoded to */
         __syncwarp();
         flush();
     }
