@@ -65,7 +65,7 @@ struct WarpTables {
     unsigned char lens[320];
 };
 
-/* The bit reader of lane 0.  Input comes in ALIGNED 32-bit words, one word prefetched ahead of the bit
+/* The bit reader (every lane of the warp carries an identical copy).  Input comes in ALIGNED 32-bit words, one word prefetched ahead of the bit
  * buffer so that the load latency overlaps the decoding of the 32 bits before it (byte loads on the
  * critical path were a third of the old kernel's time).  Consuming bits behind the end of the strip is
  * detected by position (br_overrun), not by what those bits are. */
@@ -125,6 +125,13 @@ __device__ __forceinline__ void br_drop(BitReader &b, int n)
 __device__ __forceinline__ unsigned int br_bits(BitReader &b, int n)
 {
     if (b.cnt < n) br_fill(b);
+    const unsigned int v = br_peek(b, n);
+    br_drop(b, n);
+    return v;
+}
+/* n bits the caller knows are buffered (no refill test) */
+__device__ __forceinline__ unsigned int br_take(BitReader &b, int n)
+{
     const unsigned int v = br_peek(b, n);
     br_drop(b, n);
     return v;
@@ -392,12 +399,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
             if (!okd || !okl) { err = INF_BAD_CODE; break; }
         }
 
-        /* symbols of the block */
+        /* symbols of the block.  Bit budget: decode_sym leaves >= 33 - 15 = 18 bits, enough for the length
+         * extra bits (<= 5); one refill test before the distance code covers its 15 + 13 bits.  The output
+         * bound is tested where it matters -- before a flush unit leaves for HBM and at the end: the ring
+         * absorbs the at most kFlush + 258 bytes a corrupt stream can overshoot by in between. */
         for (;;) {
             const int sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
             if (sym < 256) {
                 if (sym < 0) { err = INF_BAD_CODE; break; }
-                if (pos >= cap) { err = INF_OVERRUN_OUT; break; }
                 if (lane == 0) ring[pos & M] = (unsigned char) sym;
                 pos += 1;
             } else if (sym == 256) {
@@ -405,12 +414,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
             } else {
                 if (sym > 285) { err = INF_BAD_CODE; break; }
                 const int li = sym - 257;
-                const unsigned int len = kLenBase[li] + br_bits(b, kLenExtra[li]);
+                const unsigned int len = kLenBase[li] + br_take(b, kLenExtra[li]);
                 const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
                 if (ds < 0 || ds > 29) { err = INF_BAD_CODE; break; }
-                const unsigned int dist = kDistBase[ds] + br_bits(b, kDistExtra[ds]);
+                const unsigned int dist = kDistBase[ds] + br_take(b, kDistExtra[ds]);
                 if (dist > pos) { err = INF_BAD_DISTANCE; break; }
-                if (pos + len > cap) { err = INF_OVERRUN_OUT; break; }
                 __syncwarp();   /* lane 0's literals are in the ring */
                 if (dist < (unsigned int) kRing) {
                     /* overlapping matches repeat their first `dist` bytes, all of which exist already */
@@ -427,14 +435,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
                 __syncwarp();   /* the copy is complete before anybody writes behind it */
             }
             if (pos - flushed >= (unsigned int) kFlush) {
+                if (pos > cap) { err = INF_OVERRUN_OUT; break; }
                 if (br_overrun(b)) { err = INF_OVERRUN_IN; break; }
                 __syncwarp();
                 flush();
             }
         }
+        if (!err && pos > cap) err = INF_OVERRUN_OUT;
         if (br_overrun(b)) err = INF_OVERRUN_IN;      /* also overrides what the garbage decoded to */
         __syncwarp();
-        flush();
+        if (!err) flush();                            /* never past the tile's capacity */
     }
     if (!err && pos != cap) err = INF_SHORT;
     __syncwarp();
