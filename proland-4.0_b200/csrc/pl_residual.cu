@@ -403,22 +403,28 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
          * extra bits (<= 5); one refill test before the distance code covers its 15 + 13 bits.  The output
          * bound is tested where it matters -- before a flush unit leaves for HBM and at the end: the ring
          * absorbs the at most kFlush + 258 bytes a corrupt stream can overshoot by in between. */
+        /* Malformed input is noted in `bad` and acted upon at the next flush or block end instead of
+         * branching out of the loop at every test (each early exit costs 4-5 instructions of reconvergence
+         * bookkeeping per symbol): table indices are clamped, the ring index is masked, so decoding garbage
+         * for at most one flush unit touches nothing outside the warp's own tables and ring. */
+        int bad = 0;     /* bit 0: bad code, bit 1: distance reaches before the start of the output */
         for (;;) {
             const int sym = decode_sym(b, T.lit_lut, kLitBits, T.lit_count, T.lit_sym);
             if (sym < 256) {
-                if (sym < 0) { err = INF_BAD_CODE; break; }
+                bad |= sym < 0 ? 1 : 0;
                 if (lane == 0) ring[pos & M] = (unsigned char) sym;
                 pos += 1;
             } else if (sym == 256) {
                 break;
             } else {
-                if (sym > 285) { err = INF_BAD_CODE; break; }
-                const int li = sym - 257;
+                bad |= sym > 285 ? 1 : 0;
+                const int li = min(sym - 257, 28);
                 const unsigned int len = kLenBase[li] + br_take(b, kLenExtra[li]);
-                const int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
-                if (ds < 0 || ds > 29) { err = INF_BAD_CODE; break; }
+                int ds = decode_sym(b, T.dist_lut, kDistBits, T.dist_count, T.dist_sym);
+                bad |= (ds < 0 || ds > 29) ? 1 : 0;
+                ds = min(max(ds, 0), 29);
                 const unsigned int dist = kDistBase[ds] + br_take(b, kDistExtra[ds]);
-                if (dist > pos) { err = INF_BAD_DISTANCE; break; }
+                bad |= dist > pos ? 2 : 0;
                 __syncwarp();   /* lane 0's literals are in the ring */
                 if (dist < (unsigned int) kRing) {
                     /* overlapping matches repeat their first `dist` bytes, all of which exist already */
@@ -427,7 +433,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
                     } else {
                         for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = ring[(pos - dist + (k % dist)) & M];
                     }
-                } else {
+                } else if (!bad) {
                     /* the source lies at least kRing - 258 bytes behind pos: flushed long ago (dist > len) */
                     for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = dst[pos - dist + k];
                 }
@@ -435,12 +441,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
                 __syncwarp();   /* the copy is complete before anybody writes behind it */
             }
             if (pos - flushed >= (unsigned int) kFlush) {
+                if (bad) break;
                 if (pos > cap) { err = INF_OVERRUN_OUT; break; }
                 if (br_overrun(b)) { err = INF_OVERRUN_IN; break; }
                 __syncwarp();
                 flush();
             }
         }
+        if (bad) err = (bad & 1) ? INF_BAD_CODE : INF_BAD_DISTANCE;
         if (!err && pos > cap) err = INF_OVERRUN_OUT;
         if (br_overrun(b)) err = INF_OVERRUN_IN;      /* also overrides what the garbage decoded to */
         __syncwarp();
