@@ -334,8 +334,13 @@ def main():
             if n_launch == 0:
                 continue
             gbs = per_tile[k] * n_tiles / (tot_ms * 1e-3) / 1e9 if tot_ms > 0 else 0.0
+            per_launch = n_tiles / max(n_launch, 1)
             roof[k] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                       "frac": gbs / peak, "traffic": TRAFFIC.get(k), "launches": n_launch,
+                       "frac": gbs / peak,
+                       # measured DRAM bytes (ncu --set full, profiles/) scaled to the average launch of this run
+                       "traffic": TRAFFIC[k] * per_launch if TRAFFIC.get(k) else None,
+                       "traffic_per_pair": TRAFFIC.get(k), "algorithmic_bytes_per_launch": per_tile[k] * per_launch,
+                       "tiles_per_launch": per_launch, "launches": n_launch,
                        "avg_launch_ms": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / ms_max,
                        "bytes_per_tile": per_tile[k], "peak_kind": peak_kind}
         dom = max(roof, key=lambda k: roof[k]["share_of_step"])
