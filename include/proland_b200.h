@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PL_ABI_VERSION 1
+#define PL_ABI_VERSION 2
 
 /* Error convention: the reference asserts / logs / returns NULL
  * (TileSampler.cpp:441-444, ResidualProducer.cpp:86-91); here each
@@ -60,9 +60,9 @@ int pl_device_sm_count(pl_ctx *ctx);
  * reference's hook is Ork's monitorTask("CreateElevationTile")).
  * pl_timing_collect synchronises, sums the elapsed time per kernel
  * {0 elevation, 1 normal, 2 request generation, 3 residual decode, 4 fused
- * elevation+normal} into the three PL_TIMING_KERNELS-entry arrays and resets
- * the record. */
-#define PL_TIMING_KERNELS 5
+ * elevation+normal, 5 ortho} into the three PL_TIMING_KERNELS-entry arrays and
+ * resets the record. */
+#define PL_TIMING_KERNELS 6
 int pl_timing_enable(pl_ctx *ctx, int on);
 int pl_timing_collect(pl_ctx *ctx, double *ms, uint64_t *launches, uint64_t *tiles);
 
@@ -77,7 +77,11 @@ typedef enum pl_pool_kind {
     PL_POOL_NORM_UN8x2 = 1, /* RG8 normals                                        */
     PL_POOL_NORM_UN8x4 = 2, /* RGBA8 normals (fine + coarse)                      */
     PL_POOL_RESID_F32 = 3,  /* float residual tiles (CPUTileStorage<float>)       */
-    PL_POOL_RESID_I16 = 4   /* raw int16 residual tiles as stored in the file     */
+    PL_POOL_RESID_I16 = 4,  /* raw int16 residual tiles as stored in the file     */
+    PL_POOL_ORTHO_UN8x4 = 5 /* RGBA8 ortho tiles and their byte residual tiles
+                               (OrthoProducer's GPUTileStorage / the CPUTileStorage<unsigned char>
+                               slots it uploads, ortho/OrthoProducer.cpp:296-318); a storage with
+                               fewer channels keeps the first ones                  */
 } pl_pool_kind;
 
 int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, pl_pool **out);
@@ -85,7 +89,7 @@ void pl_pool_destroy(pl_pool *pool);
 int pl_pool_capacity(const pl_pool *pool);
 int pl_pool_tile_w(const pl_pool *pool);
 /* bytes of one tile in the REFERENCE's layout (what download/upload move):
- * tile_w*tile_w*{12, 2, 4, 4, 2} */
+ * tile_w*tile_w*{12, 2, 4, 4, 2, 4} */
 size_t pl_pool_tile_bytes(const pl_pool *pool);
 /* bytes of one slot in HBM (padded) and the device base pointer */
 size_t pl_pool_slot_bytes(const pl_pool *pool);
@@ -315,6 +319,68 @@ int pl_residual_encode_batch(pl_ctx *ctx, pl_pool *heights, pl_pool *approx, pl_
 int pl_residual_write_file(const char *path, int min_level, int max_level, int tile_size, int root_level,
                            int root_tx, int root_ty, float scale, const int16_t *tiles,
                            const uint64_t *tile_offsets, int zlib_level);
+
+/* ------------------------------------------------------------------- ortho
+ * OrthoProducer: the colour twin of the elevation pass.  A tile is the 4-tap
+ * (9,3,3,1)/16 upsample of its parent's quadrant, plus a byte residual, plus a noise layer that
+ * modulates the colour directly or in HSV space
+ * (terrain/sources/proland/ortho/OrthoProducer.cpp:268-372 + demo/shaders/ortho/upsampleOrthoShader.glsl).
+ * Tiles are tile_w x tile_w RGBA8 with a 2-texel border (tile_w = tileSize + 4, e.g. 196);
+ * (tile_w - 4) must be a multiple of 8 (196 and 100 in every shipped archive). */
+
+/* createOrthoNoise (OrthoProducer.cpp:48-118): six tile_w x tile_w RGBA8 layers from the reference's
+ * LCG streams, stored on the device in their 4 rotations.  host_out (optional) receives the six
+ * unrotated layers, 6*tile_w*tile_w*4 bytes. */
+int pl_ortho_noise_init(pl_ctx *ctx, int tile_w, uint8_t *host_out);
+/* the six unrotated layers only (host code, no device needed) */
+int pl_ortho_noise_host(int tile_w, uint8_t *out);
+
+/* per-producer constants: the orthoProducer resource (OrthoProducer.cpp:440-560) */
+typedef struct pl_ortho_scene {
+    int32_t tile_w;            /* tileWidth uniform                                          */
+    int32_t channels;          /* channels of the residual tiles (1..4); a missing channel reads
+                                  0, a missing alpha 255 (GL texture swizzle defaults)       */
+    int32_t hsv;               /* hsv="true": noiseUVLH.w                                    */
+    int32_t face;              /* face="..." or the name's last digit                        */
+    float scale;               /* scale="..." (default 2): residualOSH.w                     */
+    float noise_color[4];      /* cnoise="..." / 255                                         */
+    float root_noise_color[4]; /* rnoise="..." / 255                                         */
+    int32_t n_amp;             /* noise="..." list (<= 32 levels)                            */
+    int32_t max_level;         /* maxLevel (-1: none): hasTile                               */
+    int32_t pad_;
+    float noise_amp[32];
+} pl_ortho_scene;
+
+/* per-tile uniforms, OrthoProducer.cpp:286-366 */
+typedef struct pl_ortho_req {
+    int32_t out_slot;       /* GPUSlot::l of the tile being produced                         */
+    int32_t parent_slot;    /* coarseLevelOSL.w, -1 at level 0                               */
+    int32_t resid_slot;     /* slot in the residual pool, -1: residualOSH = -1               */
+    int32_t dx, dy;         /* coarseLevelOSL.xy in texels: (t%2)*(tile_w-4)/2               */
+    int32_t noise_r;        /* noiseUVLH.x (.y = (noise_r+1)%4)                              */
+    int32_t noise_l;        /* noiseUVLH.z                                                   */
+    int32_t level;
+    float noise_color[4];   /* the noiseColor uniform (scaled by the level's amplitude)      */
+    int32_t tx, ty;
+    int32_t pad_[2];
+} pl_ortho_req;             /* 64 bytes */
+
+/* Fill one request exactly as OrthoProducer::doCreateTile does (host); slots are set to -1. */
+void pl_ortho_make_req(const pl_ortho_scene *scene, int level, int tx, int ty, int has_resid,
+                       pl_ortho_req *req);
+/* n tiles of one level, consecutive in Morton order from morton0, into slots out_slot0.. (parents as in
+ * pl_make_requests_range); nthreads host threads (<= 0: all).  No residuals. */
+int pl_ortho_make_requests_range(const pl_ortho_scene *scene, int level, uint64_t morton0, int n,
+                                 int out_slot0, int parent_slot0, uint64_t parent_morton0,
+                                 pl_ortho_req *reqs, int nthreads);
+
+/* The batched upsampleOrthoShader: n tiles, one CTA per tile; the parent quadrant (+ border) is staged
+ * in shared memory by bulk copies (cp.async.bulk, mbarrier-signalled).  reqs is HOST memory.
+ * ortho and resid are PL_POOL_ORTHO_UN8x4 pools of the same tile_w; resid may be NULL. */
+int pl_ortho_batch(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, pl_pool *resid, int n,
+                   const pl_ortho_req *reqs);
+int pl_ortho_batch_dev(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, pl_pool *resid, int n,
+                       const pl_ortho_req *dev_reqs);
 
 #ifdef __cplusplus
 }

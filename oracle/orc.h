@@ -214,6 +214,31 @@ void orc_produce_pair(const orc_scene *s, const float *noise, int level, int tx,
 long orc_produce_quadtree(const orc_scene *s, int maxLevel, int nthreads,
                           double *checksum, float *zmin, float *zmax);
 
+/* -------------------------------------------------------------------- ortho
+ * OrthoProducer, orc_ortho.c */
+typedef struct orc_ortho_params {
+    int tileWidth;           /* tileWidth uniform (storage tile size, e.g. 196)          */
+    int level;
+    int dx, dy;              /* coarseLevelOSL.xy in texels, -1 at level 0                */
+    int hasResidual;         /* residualOSH.x != -1                                       */
+    float residualScale;     /* residualOSH.w (scale, or -1 without residual)             */
+    int noiseR, noiseL;      /* noiseUVLH.x, .z                                           */
+    int hsv;                 /* noiseUVLH.w                                               */
+    float noiseColor[4];     /* noiseColor uniform (OrthoProducer.cpp:357-361)            */
+    float rootNoiseColor[4];
+} orc_ortho_params;
+/* OrthoProducer.cpp:48-118; out = 6*W*W*4 bytes */
+void orc_ortho_noise(int W, uint8_t *out);
+/* OrthoProducer.cpp:286-372 */
+void orc_ortho_uniforms(int W, int face, int level, int tx, int ty, const float *noiseAmp, int nAmp,
+                        const float noiseColor[4], const float rootNoiseColor[4], int hsv, float scale,
+                        int hasResidual, orc_ortho_params *p);
+/* upsampleOrthoShader.glsl:123-158 */
+void orc_ortho_tile(const orc_ortho_params *p, const uint8_t *parent, const uint8_t *residual, int channels,
+                    const uint8_t *noise, uint8_t *out);
+long orc_ortho_quadtree(int W, int face, int maxLevel, const float *noiseAmp, int nAmp, const float noiseColor[4],
+                        const float rootNoiseColor[4], int hsv, float scale, const uint8_t *noise, uint8_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,7 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->noise_rot) cudaFree(ctx->noise_rot);
+    if (ctx->ortho_noise_rot) cudaFree(ctx->ortho_noise_rot);
     for (auto &rb : ctx->readback) {
         if (rb.pinned) cudaFreeHost(rb.pinned);
         if (rb.done) cudaEventDestroy(rb.done);
@@ -374,6 +375,7 @@ static int elem_bytes(int kind)
     case PL_POOL_NORM_UN8x4: return 4;
     case PL_POOL_RESID_F32: return 4;
     case PL_POOL_RESID_I16: return 2;
+    case PL_POOL_ORTHO_UN8x4: return 4;
     default: return 0;
     }
 }
@@ -415,6 +417,14 @@ extern "C" int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, p
     case PL_POOL_RESID_I16:
         p->pitch = pl_round_up(tile_w, 8);
         p->slot_bytes = (size_t) pl_round_up(tile_w * p->pitch * 2, 128);
+        break;
+    case PL_POOL_ORTHO_UN8x4:
+        if ((tile_w - 4) % 8 != 0) {
+            delete p;
+            return pl_set_error(PL_ERR_ARG, "ortho tile_w - 4 must be a multiple of 8 (16-byte quadrant rows), got %d", tile_w);
+        }
+        p->pitch = tile_w * 4;
+        p->slot_bytes = (size_t) pl_round_up(tile_w * p->pitch, 128);
         break;
     }
     /* F32 residual pools carry one hidden scratch slot (index capacity, PL_SLOT_SCRATCH): the
@@ -508,6 +518,7 @@ extern "C" int pl_pool_download(pl_pool *p, int slot, void *host, size_t bytes)
     }
     case PL_POOL_NORM_UN8x2:
     case PL_POOL_NORM_UN8x4:
+    case PL_POOL_ORTHO_UN8x4:
         PL_CUDA(cudaMemcpyAsync(host, src, p->tile_bytes, cudaMemcpyDeviceToHost, s));
         PL_CUDA(cudaStreamSynchronize(s));
         break;
@@ -545,6 +556,7 @@ extern "C" int pl_pool_upload(pl_pool *p, int slot, const void *host, size_t byt
     }
     case PL_POOL_NORM_UN8x2:
     case PL_POOL_NORM_UN8x4:
+    case PL_POOL_ORTHO_UN8x4:
         PL_CUDA(cudaMemcpyAsync(dst, host, p->tile_bytes, cudaMemcpyHostToDevice, s));
         PL_CUDA(cudaStreamSynchronize(s));
         break;

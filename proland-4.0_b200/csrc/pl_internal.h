@@ -22,6 +22,8 @@
  *              last 16-byte bulk store of a tile stays inside its slot.
  * RESID_F32  : tile_w rows of pitch floats (pitch = tile_w rounded up to 4).
  * RESID_I16  : tile_w rows of pitch int16  (pitch = tile_w rounded up to 8).
+ * ORTHO_UN8x4: dense rows of tile_w*4 bytes (16-byte rows: (tile_w-4) % 8 == 0), slot stride
+ *              rounded up to 128.
  */
 struct pl_pool {
     pl_ctx *ctx;
@@ -48,6 +50,9 @@ struct pl_ctx {
     int noise_w;
     int noise_pitch;
     __half *noise_rot;
+    /* ortho noise (createOrthoNoise), 4 rotations x 6 layers of RGBA8 */
+    int ortho_noise_w;
+    uint32_t *ortho_noise_rot;
     /* device-side request generation (pl_requests.cu) */
     int *perlin_perm;
     float *perlin_g2;
@@ -93,7 +98,7 @@ int pl_set_error(int code, const char *fmt, ...);
     } while (0)
 
 /* kernel ids of pl_timing_collect */
-enum { PL_K_ELEVATION = 0, PL_K_NORMAL = 1, PL_K_GENREQ = 2, PL_K_RESIDUAL = 3, PL_K_PAIR = 4, PL_K_COUNT = PL_TIMING_KERNELS };
+enum { PL_K_ELEVATION = 0, PL_K_NORMAL = 1, PL_K_GENREQ = 2, PL_K_RESIDUAL = 3, PL_K_PAIR = 4, PL_K_ORTHO = 5, PL_K_COUNT = PL_TIMING_KERNELS };
 /* bracket a launch with events when timing is on: call begin before, end after */
 void pl_timing_begin(pl_ctx *ctx, int kernel, int tiles);
 void pl_timing_end(pl_ctx *ctx);
@@ -117,6 +122,10 @@ bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
                        const pl_pool *norm);
 int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
                    pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs);
+
+int pl_launch_ortho(pl_ctx *ctx, const pl_ortho_scene *sc, pl_pool *ortho, pl_pool *resid, int n,
+                    const pl_ortho_req *dev_reqs);
+void pl_host_ortho_noise(int W, uint8_t *out6);   /* createOrthoNoise, 6*W*W*4 bytes */
 
 /* host maths shared with the request builders (pl_hostmath.cpp) */
 void pl_host_dem_noise(int W, float *out6);      /* fp32, before the R16F rounding */

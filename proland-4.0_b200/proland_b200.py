@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PL_LIB", os.path.join(HERE, "libproland_b200.so"))
 
 PL_OK, PL_ERR_ARG, PL_ERR_POOL_FULL, PL_ERR_CUDA, PL_ERR_CORRUPT, PL_ERR_NO_DEVICE, PL_ERR_IO = range(7)
-POOL_ELEV, POOL_NORM2, POOL_NORM4, POOL_RESID_F32, POOL_RESID_I16 = range(5)
+POOL_ELEV, POOL_NORM2, POOL_NORM4, POOL_RESID_F32, POOL_RESID_I16, POOL_ORTHO = range(6)
 NOISE_PLAIN, NOISE_SLOPE = 0, 1
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
 
@@ -31,6 +31,7 @@ EXPORTS = [
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
+    "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev",
 ]
 
 
@@ -72,6 +73,17 @@ class SweepScene(C.Structure):
                 ("face", C.c_int32), ("n_amp", C.c_int32), ("pad_", C.c_int32),
                 ("noise_amp", C.c_float * 32)]
 
+
+class OrthoScene(C.Structure):
+    _fields_ = [("tile_w", C.c_int32), ("channels", C.c_int32), ("hsv", C.c_int32), ("face", C.c_int32),
+                ("scale", C.c_float), ("noise_color", C.c_float * 4), ("root_noise_color", C.c_float * 4),
+                ("n_amp", C.c_int32), ("max_level", C.c_int32), ("pad_", C.c_int32), ("noise_amp", C.c_float * 32)]
+
+
+ORTHO_REQ_DTYPE = np.dtype([("out_slot", "i4"), ("parent_slot", "i4"), ("resid_slot", "i4"), ("dx", "i4"), ("dy", "i4"),
+                            ("noise_r", "i4"), ("noise_l", "i4"), ("level", "i4"), ("noise_color", "f4", (4,)),
+                            ("tx", "i4"), ("ty", "i4"), ("pad_", "i4", (2,))])
+assert ORTHO_REQ_DTYPE.itemsize == 64 and C.sizeof(OrthoScene) == 192
 
 assert C.sizeof(ElevReq) == 64 and C.sizeof(NormReq) == 240 and C.sizeof(ElevScene) == 32
 
@@ -165,6 +177,14 @@ def lib():
                                              C.c_void_p, C.c_void_p, C.c_int]
         L.pl_residual_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p]
+        L.pl_ortho_noise_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.pl_ortho_noise_host.argtypes = [C.c_int, C.c_void_p]
+        L.pl_ortho_make_req.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.pl_ortho_make_req.restype = None
+        L.pl_ortho_make_requests_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                                   C.c_void_p, C.c_int]
+        L.pl_ortho_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pl_ortho_batch_dev.argtypes = L.pl_ortho_batch.argtypes
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
         L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -293,7 +313,7 @@ class Pool:
         W = self.tile_w
         return {POOL_ELEV: ((W, W, 3), np.float32), POOL_NORM2: ((W, W, 2), np.uint8),
                 POOL_NORM4: ((W, W, 4), np.uint8), POOL_RESID_F32: ((W, W), np.float32),
-                POOL_RESID_I16: ((W, W), np.int16)}[self.kind]
+                POOL_RESID_I16: ((W, W), np.int16), POOL_ORTHO: ((W, W, 4), np.uint8)}[self.kind]
 
     def download(self, slot):
         shape, dt = self._shape_dtype()
@@ -434,11 +454,11 @@ def _timing_enable(self, on=True):
 
 def _timing_collect(self):
     """-> {kernel name: (total ms, launches, tiles)} since the last collect (synchronises)."""
-    ms = np.zeros(5, np.float64)
-    cnt = np.zeros(5, np.uint64)
-    tiles = np.zeros(5, np.uint64)
+    ms = np.zeros(6, np.float64)
+    cnt = np.zeros(6, np.uint64)
+    tiles = np.zeros(6, np.uint64)
     check(lib().pl_timing_collect(self.h, _ptr(ms), _ptr(cnt), _ptr(tiles)))
-    names = ("elevation", "normal", "genreq", "residual", "pair")
+    names = ("elevation", "normal", "genreq", "residual", "pair", "ortho")
     return {n: (float(ms[i]), int(cnt[i]), int(tiles[i])) for i, n in enumerate(names)}
 
 
@@ -477,7 +497,68 @@ def _residual_upsample(self, pool, src_slot, dst_slot, tile_size, tx=0, ty=0):
     check(lib().pl_residual_upsample(self.h, pool.h, src_slot, dst_slot, tile_size, tx, ty))
 
 
+def ortho_scene(*, tile_w=196, channels=4, hsv=0, face=1, scale=2.0, cnoise=(255, 255, 255, 255),
+                rnoise=(127.5, 127.5, 127.5, 127.5), noise_amp=(), max_level=-1):
+    """The orthoProducer resource (OrthoProducer.cpp:440-512): cnoise / rnoise are the XML's 0..255 values
+    (divided by 255 as a float, `(float) atof(..) / 255`); a 3-value list keeps the default of the 4th."""
+    s = OrthoScene()
+    s.tile_w, s.channels, s.hsv, s.face, s.scale = tile_w, channels, int(hsv), face, scale
+    nc = [np.float32(1.0)] * 4
+    rc = [np.float32(0.5)] * 4
+    for i, v in enumerate(cnoise):
+        nc[i] = np.float32(v) / np.float32(255)
+    for i, v in enumerate(rnoise):
+        rc[i] = np.float32(v) / np.float32(255)
+    for i in range(4):
+        s.noise_color[i] = nc[i]
+        s.root_noise_color[i] = rc[i]
+    s.n_amp = len(noise_amp)
+    s.max_level = max_level
+    for i, a in enumerate(noise_amp):
+        s.noise_amp[i] = a
+    return s
+
+
+def ortho_noise_host(tile_w=196):
+    out = np.empty((6, tile_w, tile_w, 4), np.uint8)
+    check(lib().pl_ortho_noise_host(tile_w, _ptr(out)))
+    return out
+
+
+def ortho_make_reqs(scene, tiles, has_resid=None):
+    """tiles: iterable of (level, tx, ty) -> structured array of pl_ortho_req (slots = -1)."""
+    tiles = list(tiles)
+    out = np.zeros(len(tiles), ORTHO_REQ_DTYPE)
+    L = lib()
+    for i, (level, tx, ty) in enumerate(tiles):
+        hr = 0 if has_resid is None else int(bool(has_resid[i]))
+        L.pl_ortho_make_req(C.byref(scene), level, tx, ty, hr, C.c_void_p(out.ctypes.data + 64 * i))
+    return out
+
+
+def ortho_make_requests_range(scene, level, morton0, n, out_slot0=0, parent_slot0=0, parent_morton0=0, nthreads=0,
+                              out=None):
+    q = out[:n] if out is not None else np.zeros(n, ORTHO_REQ_DTYPE)
+    check(lib().pl_ortho_make_requests_range(C.byref(scene), level, morton0, n, out_slot0, parent_slot0,
+                                             parent_morton0, _ptr(q), nthreads))
+    return q
+
+
+def _ortho_noise_init(self, tile_w=196, want_host=False):
+    out = np.empty((6, tile_w, tile_w, 4), np.uint8) if want_host else None
+    check(lib().pl_ortho_noise_init(self.h, tile_w, _ptr(out) if want_host else None))
+    return out
+
+
+def _ortho_batch(self, scene, ortho, resid, reqs):
+    reqs = np.ascontiguousarray(reqs, ORTHO_REQ_DTYPE)
+    check(lib().pl_ortho_batch(self.h, C.byref(scene), ortho.h, resid.h if resid is not None else None, len(reqs),
+                               _ptr(reqs)))
+
+
 SLOT_SCRATCH = -2
+Context.ortho_noise_init = _ortho_noise_init
+Context.ortho_batch = _ortho_batch
 Context.residual_decode = _residual_decode
 Context.residual_upsample = _residual_upsample
 Context.force_generic = _force_generic

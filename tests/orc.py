@@ -61,6 +61,12 @@ class Scene(C.Structure):
                 ("resid", C.POINTER(ResidFile))]
 
 
+class OrthoParams(C.Structure):
+    _fields_ = [("tileWidth", C.c_int), ("level", C.c_int), ("dx", C.c_int), ("dy", C.c_int),
+                ("hasResidual", C.c_int), ("residualScale", C.c_float), ("noiseR", C.c_int), ("noiseL", C.c_int),
+                ("hsv", C.c_int), ("noiseColor", C.c_float * 4), ("rootNoiseColor", C.c_float * 4)]
+
+
 _lib = None
 _ref = None
 
@@ -308,3 +314,56 @@ def produce_quadtree(scene, max_level, nthreads=0):
     n = lib().orc_produce_quadtree(C.byref(scene), max_level, nthreads, C.byref(cs),
                                    C.byref(lo), C.byref(hi))
     return n, cs.value, lo.value, hi.value
+
+
+# ---------------------------------------------------------------- ortho ----
+
+def _u8(a):
+    return a.ctypes.data_as(c_u8_p) if a is not None else None
+
+
+def _f4(v):
+    return (C.c_float * 4)(*[float(x) for x in v])
+
+
+def ortho_noise(W=196):
+    out = np.empty((6, W, W, 4), np.uint8)
+    lib().orc_ortho_noise(C.c_int(W), _u8(out))
+    return out
+
+
+def ortho_uniforms(level, tx, ty, *, W=196, face=1, noise_amp=(), noise_color=(1, 1, 1, 1),
+                   root_noise_color=(0.5, 0.5, 0.5, 0.5), hsv=0, scale=2.0, has_residual=0):
+    p = OrthoParams()
+    amp = np.asarray(noise_amp, np.float32)
+    lib().orc_ortho_uniforms(C.c_int(W), C.c_int(face), C.c_int(level), C.c_int(tx), C.c_int(ty), _fp(amp),
+                             C.c_int(len(amp)), _f4(noise_color), _f4(root_noise_color), C.c_int(int(hsv)),
+                             C.c_float(scale), C.c_int(int(has_residual)), C.byref(p))
+    return p
+
+
+def ortho_tile(p, parent, residual, noise, channels=4):
+    """parent: (W, W, 4) uint8 or None; residual: (W, W, channels) uint8 or None -> (W, W, 4) uint8"""
+    W = p.tileWidth
+    out = np.empty((W, W, 4), np.uint8)
+    par = np.ascontiguousarray(parent, np.uint8) if parent is not None else None
+    res = np.ascontiguousarray(residual, np.uint8) if residual is not None else None
+    nz = np.ascontiguousarray(noise, np.uint8)
+    lib().orc_ortho_tile(C.byref(p), _u8(par), _u8(res), C.c_int(channels), _u8(nz), _u8(out))
+    return out
+
+
+def ortho_quadtree(max_level, *, W=196, face=1, noise_amp=(), noise_color=(1, 1, 1, 1),
+                   root_noise_color=(0.5, 0.5, 0.5, 0.5), hsv=0, scale=2.0, noise=None):
+    """All tiles of levels 0..max_level, level order, Morton order inside a level -> (n, W, W, 4) uint8"""
+    n = (4 ** (max_level + 1) - 1) // 3
+    out = np.empty((n, W, W, 4), np.uint8)
+    amp = np.asarray(noise_amp, np.float32)
+    nz = np.ascontiguousarray(noise if noise is not None else ortho_noise(W), np.uint8)
+    L = lib()
+    L.orc_ortho_quadtree.restype = C.c_long
+    done = L.orc_ortho_quadtree(C.c_int(W), C.c_int(face), C.c_int(max_level), _fp(amp), C.c_int(len(amp)),
+                                _f4(noise_color), _f4(root_noise_color), C.c_int(int(hsv)), C.c_float(scale),
+                                _u8(nz), _u8(out))
+    assert done == n
+    return out

@@ -1,0 +1,165 @@
+"""GPU parity of the ortho path (OrthoProducer / upsampleOrthoShader): pl_ortho_batch
+through the C ABI against the CPU oracle (oracle/orc_ortho.c), byte for byte."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORTHO = json.load(open(os.path.join(HERE, "golden", "ortho.json")))
+TERRAIN3 = dict(hsv=1, cnoise=(70, 80, 100), rnoise=(60, 150, 20), noise_amp=[255] * 17, face=1)
+
+
+def _sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def _gpu_quadtree(plb, ctx, sc, max_level):
+    """levels 0..max_level, one batch per level, slots in level order / Morton order inside a level"""
+    W = sc.tile_w
+    n = (4 ** (max_level + 1) - 1) // 3
+    pool = ctx.pool(plb.POOL_ORTHO, W, n)
+    ctx.ortho_noise_init(W)
+    off = [(4 ** l - 1) // 3 for l in range(max_level + 2)]
+    for l in range(max_level + 1):
+        reqs = plb.ortho_make_requests_range(sc, l, 0, 4 ** l, out_slot0=off[l], parent_slot0=off[l - 1] if l else 0)
+        ctx.ortho_batch(sc, pool, None, reqs)
+    ctx.sync()
+    return np.stack([pool.download(s) for s in range(n)])
+
+
+def _oracle_quadtree(oracle, sc, max_level):
+    return oracle.ortho_quadtree(max_level, W=sc.tile_w, face=sc.face, noise_amp=list(sc.noise_amp)[:sc.n_amp],
+                                 noise_color=list(sc.noise_color), root_noise_color=list(sc.root_noise_color),
+                                 hsv=sc.hsv, scale=sc.scale)
+
+
+def _assert_same(gpu, ref, what):
+    bad = np.argwhere(gpu != ref)
+    assert bad.size == 0, "%s: %d bytes differ from the oracle, first at %s: gpu %d, oracle %d" % (
+        what, len(bad), tuple(bad[0]), gpu[tuple(bad[0])], ref[tuple(bad[0])])
+
+
+def test_ortho_noise_on_device_matches_oracle(plb, ctx, oracle):
+    for W in (196, 100):
+        assert np.array_equal(ctx.ortho_noise_init(W, want_host=True), oracle.ortho_noise(W))
+
+
+def test_terrain3_hsv_quadtree(plb, ctx, oracle):
+    """terrain3/helloworld.xml:47-49: hsv noise, rnoise 60,150,20, cnoise 70,80,100, amplitudes 255: levels 0..4"""
+    sc = plb.ortho_scene(**TERRAIN3)
+    gpu = _gpu_quadtree(plb, ctx, sc, 4)
+    _assert_same(gpu, _oracle_quadtree(oracle, sc, 4), "terrain3 hsv")
+    assert [_sha(t) for t in gpu[:85]] == ORTHO["terrain3_hsv"]["levels_0_3_sha1"]
+
+
+@pytest.mark.parametrize("face", [1, 2, 5, 6])
+def test_plain_noise_quadtree_per_face(plb, ctx, oracle, face):
+    """hsv="false": noiseColor * scale * amplitude added per channel; the layer / rotation choice per cube face"""
+    sc = plb.ortho_scene(hsv=0, cnoise=(127.5, 40, 90, 10), noise_amp=[0, 255, 255, 128, 64], face=face, scale=2.0)
+    gpu = _gpu_quadtree(plb, ctx, sc, 3)
+    _assert_same(gpu, _oracle_quadtree(oracle, sc, 3), "plain noise, face %d" % face)
+
+
+def test_plain_golden(plb, ctx):
+    sc = plb.ortho_scene(hsv=0, cnoise=(127.5, 0, 0, 0), noise_amp=[0, 255, 255, 255, 255], face=3)
+    gpu = _gpu_quadtree(plb, ctx, sc, 3)
+    assert [_sha(t) for t in gpu] == ORTHO["plain"]["levels_0_3_sha1"]
+
+
+def test_tile_w_100(plb, ctx, oracle):
+    """the 100-texel storages of the land-cover producers (exercise2/helloworld.xml:43-52)"""
+    sc = plb.ortho_scene(tile_w=100, hsv=1, cnoise=(30, 200, 150, 90), noise_amp=[255, 200, 150, 100], face=2)
+    _assert_same(_gpu_quadtree(plb, ctx, sc, 3), _oracle_quadtree(oracle, sc, 3), "tile_w 100")
+
+
+@pytest.mark.parametrize("hsv,channels", [(0, 4), (0, 3), (1, 3), (1, 4), (0, 1)])
+def test_residual_tiles(plb, ctx, oracle, hsv, channels):
+    """byte residuals (OrthoCPUProducer tiles uploaded like OrthoProducer.cpp:296-318): random residuals with
+    1, 3 and 4 channels, on level 0 (no parent) and on children of a random parent, hsv and plain noise;
+    tiles without a residual in the same batch"""
+    W = 196
+    rng = np.random.default_rng(100 * hsv + channels)
+    sc = plb.ortho_scene(tile_w=W, channels=channels, hsv=hsv, cnoise=(70, 80, 100, 60), rnoise=(60, 150, 20, 99),
+                         noise_amp=[200, 255, 255], face=1, scale=2.0)
+    pool = ctx.pool(plb.POOL_ORTHO, W, 8)
+    rpool = ctx.pool(plb.POOL_ORTHO, W, 8)
+    nz = ctx.ortho_noise_init(W, want_host=True)
+    parent = rng.integers(0, 256, (W, W, 4), dtype=np.uint8)
+    parent[:50] = rng.integers(0, 256, 4, dtype=np.uint8)            # a flat area: delta == 0 pixels in the hsv branch
+    parent[50:60, :, :3] = 0                                         # black: maxVal == 0
+    pool.upload(0, parent)
+    tiles = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (1, 1, 1)]
+    has = [1, 1, 1, 0, 1, 1]
+    resid = []
+    for i, h in enumerate(has):
+        r = rng.integers(0, 256, (W, W, channels), dtype=np.uint8)
+        if i == 4:
+            r[:] = 128                                               # the neutral residual
+        if i == 5:
+            r = (128 + rng.integers(-6, 7, (W, W, channels))).astype(np.uint8)   # what real residual files hold
+        resid.append(r if h else None)
+        if h:
+            full = np.zeros((W, W, 4), np.uint8)
+            full[..., :channels] = r
+            full[..., channels:] = 37                                # garbage in the unused channels: must be ignored
+            rpool.upload(i, full)
+    reqs = plb.ortho_make_reqs(sc, tiles, has)
+    for i, q in enumerate(reqs):
+        q["out_slot"] = 1 + i
+        q["parent_slot"] = 0 if tiles[i][0] > 0 else -1
+        q["resid_slot"] = i if has[i] else -1
+    ctx.ortho_batch(sc, pool, rpool, reqs)
+    ctx.sync()
+    for i, (l, tx, ty) in enumerate(tiles):
+        p = oracle.ortho_uniforms(l, tx, ty, W=W, face=1, noise_amp=[200, 255, 255], noise_color=list(sc.noise_color),
+                                  root_noise_color=list(sc.root_noise_color), hsv=hsv, scale=2.0, has_residual=has[i])
+        want = oracle.ortho_tile(p, parent if l > 0 else None, resid[i], nz, channels=channels)
+        _assert_same(pool.download(1 + i), want, "tile %d %s hsv=%d channels=%d" % (i, tiles[i], hsv, channels))
+
+
+def test_ortho_errors(plb, ctx):
+    sc = plb.ortho_scene(**TERRAIN3)
+    with pytest.raises(plb.PlError) as e:
+        ctx.pool(plb.POOL_ORTHO, 197, 4)
+    assert e.value.code == plb.PL_ERR_ARG
+    pool = ctx.pool(plb.POOL_ORTHO, 196, 4)
+    reqs = plb.ortho_make_reqs(sc, [(0, 0, 0)])
+    reqs[0]["out_slot"] = 0
+    with pytest.raises(plb.PlError):                                  # noise not initialised
+        ctx.ortho_batch(sc, pool, None, reqs)
+    ctx.ortho_noise_init(196)
+    reqs[0]["out_slot"] = 4
+    with pytest.raises(plb.PlError):                                  # slot out of range
+        ctx.ortho_batch(sc, pool, None, reqs)
+    reqs[0]["out_slot"] = 0
+    reqs[0]["resid_slot"] = 1
+    with pytest.raises(plb.PlError):                                  # residual slot without a residual pool
+        ctx.ortho_batch(sc, pool, None, reqs)
+    reqs[0]["resid_slot"] = -1
+    ctx.ortho_batch(sc, pool, None, reqs)
+    ctx.ortho_batch(sc, pool, None, reqs[:0])                         # empty batch
+    ctx.sync()
+
+
+def test_ortho_idempotent_and_order_independent(plb, ctx):
+    """producing a level twice, or in two halves in the other order, gives the same bytes (tiles are
+    independent given their parents)"""
+    sc = plb.ortho_scene(**TERRAIN3)
+    a = _gpu_quadtree(plb, ctx, sc, 3)
+    W, n = 196, 85
+    pool = ctx.pool(plb.POOL_ORTHO, W, n)
+    off = [0, 1, 5, 21]
+    for l in range(4):
+        reqs = plb.ortho_make_requests_range(sc, l, 0, 4 ** l, out_slot0=off[l], parent_slot0=off[l - 1] if l else 0)
+        h = len(reqs) // 2
+        ctx.ortho_batch(sc, pool, None, reqs[h:])
+        ctx.ortho_batch(sc, pool, None, reqs[:h])
+        ctx.ortho_batch(sc, pool, None, reqs)
+    ctx.sync()
+    b = np.stack([pool.download(s) for s in range(n)])
+    assert np.array_equal(a, b)

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(plb):
     lib = plb.lib()
     for name in sorted(declared):
         assert hasattr(lib, name), "libproland_b200.so does not export " + name
-    assert lib.pl_abi_version() == 1
+    assert lib.pl_abi_version() == 2
 
 
 def test_no_device_is_an_error_not_a_fallback(plb):

@@ -233,3 +233,115 @@ def test_residual_builder_restatement_round_trips_through_the_reader():
                                      up.ctypes.data_as(orc.C.c_void_p))
         want = up[:ts + 5, :ts + 5] + resid.astype(np.float32)
         assert np.array_equal(approx[:ts + 5, :ts + 5], want)
+
+
+# ------------------------------------------------------------------ ortho ----
+
+ORTHO = json.load(open(os.path.join(HERE, "golden", "ortho.json")))
+TERRAIN3 = dict(hsv=1, noise_amp=[255] * 17, noise_color=[np.float32(v) / np.float32(255) for v in (70, 80, 100, 255)],
+                root_noise_color=[np.float32(v) / np.float32(255) for v in (60, 150, 20, 127.5)], face=1)
+
+
+def _sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def test_unorm8_fetch_times_255_is_exact():
+    """oracle/orc_ortho.c's premise: a texel c fetched as fp32 c/255 and multiplied by 255.0 is c again."""
+    c = np.arange(256, dtype=np.float32)
+    assert np.array_equal(c / np.float32(255) * np.float32(255), c)
+
+
+@pytest.mark.parametrize("W", [196, 100])
+def test_ortho_noise_structure_and_kats(oracle, W):
+    """createOrthoNoise (OrthoProducer.cpp:48-118): hand-derived first bytes, 128 corners, mirrored borders,
+    committed hashes."""
+    nz = oracle.ortho_noise(W)
+    assert [_sha(nz[l]) for l in range(6)] == ORTHO["noise_sha1_%d" % W]
+    # int(frandom(1234567) * 255) = int(0.943745792 * 255); border seeds 7654321 / 5647381 (SURVEY 8c)
+    assert nz[0, 4, 4, 0] == 240 and nz[0, 2, 4, 0] == 134 and nz[1, 2, 4, 0] == 166
+    for l in range(6):
+        for cy in (slice(0, 4), slice(W - 4, W)):
+            for cx in (slice(0, 4), slice(W - 4, W)):
+                assert (nz[l, cy, cx] == 128).all()
+        body = slice(4, W - 4)
+        assert np.array_equal(nz[l, 2:4, body], nz[l, 0:2, body][::-1, ::-1])              # bottom
+        assert np.array_equal(nz[l, W - 2:W, body], nz[l, W - 4:W - 2, body][::-1, ::-1])  # top
+        assert np.array_equal(nz[l, body, 0:2], nz[l, body, 2:4][::-1, ::-1])              # left
+        assert np.array_equal(nz[l, body, W - 4:W - 2], nz[l, body, W - 2:W][::-1, ::-1])  # right
+        assert nz[l].max() <= 254
+    # neighbouring tiles agree: a layer with the "top" bit clear and one with the "bottom" bit clear draw the
+    # shared strip from the same seed -> layer 0's top two rows equal layer 0's bottom rows 2..3 mirrored back
+    assert np.array_equal(nz[0, W - 2:W, 4:W - 4], nz[0, 2:4, 4:W - 4])
+
+
+def test_ortho_host_noise_matches_oracle(oracle, plb):
+    """the product's host generator (pl_ortho_noise_host, no device needed) against the oracle"""
+    for W in (196, 100):
+        assert np.array_equal(plb.ortho_noise_host(W), oracle.ortho_noise(W))
+
+
+def test_ortho_golden_tiles(oracle):
+    tiles = oracle.ortho_quadtree(3, W=196, **TERRAIN3)
+    assert [_sha(t) for t in tiles] == ORTHO["terrain3_hsv"]["levels_0_3_sha1"]
+    # level 0 without residual: rootNoiseColor modulated in HSV space -> a green-ish tile (rnoise 60,150,20)
+    assert tiles[0][..., 1].mean() > tiles[0][..., 0].mean() > tiles[0][..., 2].mean()
+
+
+def test_ortho_upsample_is_the_9331_filter(oracle):
+    """noise amplitude 0, no residual: a child is the pure (9,3,3,1)/16 upsample of its parent's quadrant,
+    a constant parent gives a constant child, a ramp stays monotone."""
+    W = 196
+    nz = oracle.ortho_noise(W)
+    p = oracle.ortho_uniforms(1, 1, 0, W=W, noise_amp=[0, 0], hsv=0)
+    assert (p.dx, p.dy) == (96, 0) and p.noiseColor[0] == 0.0
+    const = np.full((W, W, 4), 77, np.uint8)
+    assert (oracle.ortho_tile(p, const, None, nz) == 77).all()
+    rng = np.random.default_rng(5)
+    par = rng.integers(0, 256, (W, W, 4), dtype=np.uint8)
+    got = oracle.ortho_tile(p, par, None, nz).astype(np.int64)
+    P = par.astype(np.int64)
+    for (x, y) in [(0, 0), (1, 0), (0, 1), (1, 1), (100, 57), (195, 195), (194, 1)]:
+        px, py = ((x + 1) >> 1) + 96, (y + 1) >> 1
+        w = {0: (1, 3, 3, 9), 1: (3, 1, 9, 3), 2: (3, 9, 1, 3), 3: (9, 3, 3, 1)}[(x & 1) + 2 * (y & 1)]
+        want = (w[0] * P[py, px] + w[1] * P[py, px + 1] + w[2] * P[py + 1, px] + w[3] * P[py + 1, px + 1]) // 16
+        assert np.array_equal(got[y, x], want), (x, y)
+
+
+def test_ortho_residual_and_channels(oracle):
+    """residual 128 is neutral; a 3-channel residual reads alpha 255 -> (255 - 128) * scale added to alpha."""
+    W = 100
+    nz = oracle.ortho_noise(W)
+    p = oracle.ortho_uniforms(1, 0, 1, W=W, noise_amp=[0, 0], hsv=0, scale=2.0, has_residual=1)
+    par = np.random.default_rng(1).integers(0, 200, (W, W, 4), dtype=np.uint8)
+    p0 = oracle.ortho_uniforms(1, 0, 1, W=W, noise_amp=[0, 0], hsv=0, scale=2.0, has_residual=0)
+    base = oracle.ortho_tile(p0, par, None, nz)
+    neutral = oracle.ortho_tile(p, par, np.full((W, W, 4), 128, np.uint8), nz, channels=4)
+    assert np.array_equal(neutral, base)
+    rgb = oracle.ortho_tile(p, par, np.full((W, W, 3), 129, np.uint8), nz, channels=3)
+    assert np.array_equal(rgb[..., :3], np.minimum(base[..., :3].astype(int) + 2, 255))
+    assert (rgb[..., 3] == 255).all()
+
+
+def test_ortho_make_req_matches_oracle(oracle, plb):
+    """pl_ortho_make_req (host) against the oracle's statement of OrthoProducer.cpp:286-366"""
+    for hsv in (0, 1):
+        sc = plb.ortho_scene(hsv=hsv, cnoise=(70, 80, 100), rnoise=(60, 150, 20), noise_amp=[255, 200, 100, 50, 25],
+                             scale=2.0, face=4)
+        tiles = [(l, tx, ty) for l in range(7) for (tx, ty) in [(0, 0), ((1 << l) - 1, (1 << l) // 2), ((1 << l) // 3, (1 << l) - 1)]]
+        reqs = plb.ortho_make_reqs(sc, tiles)
+        for q, (l, tx, ty) in zip(reqs, tiles):
+            p = oracle.ortho_uniforms(l, tx, ty, W=196, face=4, noise_amp=[255, 200, 100, 50, 25],
+                                      noise_color=list(sc.noise_color), root_noise_color=list(sc.root_noise_color),
+                                      hsv=hsv, scale=2.0)
+            assert (q["noise_r"], q["noise_l"]) == (p.noiseR, p.noiseL)
+            assert np.array_equal(q["noise_color"], np.array(list(p.noiseColor), np.float32))
+            if l > 0:
+                assert (q["dx"], q["dy"]) == (p.dx, p.dy)
+    rng_reqs = plb.ortho_make_requests_range(sc, 6, 100, 5000, out_slot0=7, parent_slot0=3, parent_morton0=25)
+    one = plb.ortho_make_reqs(sc, [(6,) + plb.morton_decode(100 + 4321)])[0]
+    got = rng_reqs[4321]
+    assert got["out_slot"] == 7 + 4321 and got["parent_slot"] == 3 + ((100 + 4321) >> 2) - 25
+    for k in ("dx", "dy", "noise_r", "noise_l", "level", "tx", "ty"):
+        assert got[k] == one[k]
+    assert np.array_equal(got["noise_color"], one["noise_color"])
