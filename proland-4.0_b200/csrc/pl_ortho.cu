@@ -231,23 +231,49 @@ __device__ __forceinline__ void ob_bulk_load(void *dst, const void *src, uint32_
 /* RN(a / 255), RN(a / 6): q = a*y, r = a - b*q (exact), q' = q + r*y with y = RN(1/b) */
 __device__ __forceinline__ float div255(float a) { return plfp::div_rn(a, 255.0f, 1.0f / 255.0f); }
 __device__ __forceinline__ float div6(float a) { return plfp::div_rn(a, 6.0f, 1.0f / 6.0f); }
-__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
-
-/* the RGBA8 colour buffer write of result / 255 */
-__device__ __forceinline__ uint32_t to_unorm8(float result)
+/* min(max(v, 0), 1) in one instruction (NaN -> 0 like fmaxf(NaN, 0)) */
+__device__ __forceinline__ float clamp01(float v) { return __saturatef(v); }
+__device__ __forceinline__ float fma_sat(float a, float b, float c)
 {
-    return (uint32_t) __float2int_rn(clamp01(div255(result)) * 255.0f);
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+/* (float) byte K of w, minus BIAS, exactly and without the conversion unit: PRMT builds the float
+ * 2^23 + b (0x4B0000bb), one FADD removes 2^23 + BIAS */
+template <int K, int BIAS>
+__device__ __forceinline__ float byte_f(uint32_t w)
+{
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | K)) - (8388608.0f + (float) BIAS);
+}
+
+/* The RGBA8 colour buffer write of result / 255: clamp(RN(result / 255), 0, 1) * 255 rounded to nearest
+ * even.  The rounding is the FADD of 1.5 * 2^23 (the sum's ulp is 1): the byte is the low byte of the
+ * returned bits. */
+__device__ __forceinline__ uint32_t to_unorm8_bits(float result)
+{
+    const float q = result * (1.0f / 255.0f);
+    const float rem = fmaf(q, -255.0f, result);
+    const float f = fma_sat(1.0f / 255.0f, rem, q);
+    return __float_as_uint(f * 255.0f + 12582912.0f);
+}
+/* low bytes of four words -> one RGBA8 texel */
+__device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3)
+{
+    return __byte_perm(__byte_perm(b0, b1, 0x0040u), __byte_perm(b2, b3, 0x0040u), 0x5410u);
 }
 
 /* upsampleOrthoShader.glsl:141-151, the hsv branch: modulates r[0..2] in HSV space, r[3] directly */
-__device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const float nz[4])
+__device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const float nm[4] /* noise - 128 */)
 {
     const float R = div255(r[0]), G = div255(r[1]), B = div255(r[2]);
     const float minv = fminf(R, fminf(G, B)), maxv = fmaxf(R, fmaxf(G, B));
     const float delta = maxv - minv;
     float H = 0.0f, S = 0.0f, V = maxv;
     if (delta != 0.0f) {
-        S = __fdiv_rn(delta, maxv);
+        /* maxv <= 0 (only with residuals below -c) leaves the domain of the branch-free division */
+        S = maxv > 1e-30f ? plfp::div_rn(delta, maxv, plfp::rcp_rn(maxv)) : __fdiv_rn(delta, maxv);
         const float rd = plfp::rcp_rn(delta);
         const float half = delta * 0.5f;                       /* delta / 2.0, exact */
         const float dR = plfp::div_rn(div6(maxv - R) + half, delta, rd);
@@ -260,11 +286,12 @@ __device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const f
         if (H > 1.0f) H -= 1.0f;
     }
     constexpr float kEdge = 0.8f - 0.4f;
-    const float t = clamp01(plfp::div_rn(V - 0.4f, kEdge, 1.0f / kEdge));
+    const float e0 = V - 0.4f, tq = e0 * (1.0f / kEdge);
+    const float t = fma_sat(1.0f / kEdge, fmaf(tq, -kEdge, e0), tq);     /* clamp(RN(e0 / kEdge), 0, 1) */
     const float k = 1.0f - t * t * fmaf(-2.0f, t, 3.0f);
-    H *= 1.0f + div255(k * nc[0] * (nz[0] - 128.0f));
-    S *= 1.0f + div255(k * nc[1] * (nz[1] - 128.0f));
-    V *= 1.0f + div255(k * nc[2] * (nz[2] - 128.0f));
+    H *= 1.0f + div255(k * nc[0] * nm[0]);
+    S *= 1.0f + div255(k * nc[1] * nm[1]);
+    V *= 1.0f + div255(k * nc[2] * nm[2]);
     H = H - floorf(H);
     S = clamp01(S);
     V = clamp01(V);
@@ -286,7 +313,93 @@ __device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const f
     r[0] = oR * 255.0f;
     r[1] = oG * 255.0f;
     r[2] = oB * 255.0f;
-    r[3] = fmaf(nc[3], nz[3] - 128.0f, r[3]);
+    r[3] = fmaf(nc[3], nm[3], r[3]);
+}
+
+/* all rows of one tile.  PARENT = false only for level-0 tiles */
+template <bool HSV, bool RESID, bool PARENT>
+__device__ __forceinline__ void ortho_rows(const OrthoArgs &a, const uint32_t *win, const uint32_t *noise, const uint8_t *res,
+                                           uint8_t *out, const float nc[4], int tid)
+{
+    const int W = a.W, PW = a.PW;
+    /* item i = y * groups + k: four texels from column 4k of row y.  i advances by the CTA size, so
+     * (y, k) advance by its quotient and remainder with one conditional carry (no division in the loop) */
+    const int groups = W >> 2;
+    const int dy = kOrthoThreads / groups, dk = kOrthoThreads - dy * groups;
+    int y = tid / groups, k = tid - y * groups;
+    for (; y < W; y += dy, k += dk) {
+        if (k >= groups) {
+            k -= groups;
+            if (++y >= W) break;
+        }
+        const size_t texel = (size_t) y * W + 4 * k;
+        /* channels (0,2) in bytes 0 and 2 of cE, channels (1,3) in bytes 0 and 2 of cO (the other bytes are junk) */
+        uint32_t cE[4] = { 0, 0, 0, 0 }, cO[4] = { 0, 0, 0, 0 };
+        if (PARENT) {
+            const uint32_t *r0 = win + ((y + 1) >> 1) * PW + 2 * k;
+            const uint2 a01 = *(const uint2 *) r0, a23 = *(const uint2 *) (r0 + 2);
+            const uint2 b01 = *(const uint2 *) (r0 + PW), b23 = *(const uint2 *) (r0 + PW + 2);
+            const uint32_t wy0 = (y & 1) ? 3u : 1u, wy1 = 4u - wy0;
+            const uint32_t ta[4] = { a01.x, a01.y, a23.x, a23.y }, tb[4] = { b01.x, b01.y, b23.x, b23.y };
+            uint32_t vE[4], vO[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                /* two 16-bit lanes per register: bytes (0, 2) and (1, 3) of the texel */
+                vE[j] = wy0 * __byte_perm(ta[j], 0u, 0x4240u) + wy1 * __byte_perm(tb[j], 0u, 0x4240u);
+                vO[j] = wy0 * __byte_perm(ta[j], 0u, 0x4341u) + wy1 * __byte_perm(tb[j], 0u, 0x4341u);
+            }
+            /* texel 4k+p reads window columns 2k + (p+1)/2 and the next one; even x: weights (1,3), odd x: (3,1).
+             * A lane's sum is < 4096, so after >> 4 its byte is clean and only bits 12..15 hold the neighbour's */
+            cE[0] = (vE[0] + 3u * vE[1]) >> 4;  cO[0] = (vO[0] + 3u * vO[1]) >> 4;
+            cE[1] = (3u * vE[1] + vE[2]) >> 4;  cO[1] = (3u * vO[1] + vO[2]) >> 4;
+            cE[2] = (vE[1] + 3u * vE[2]) >> 4;  cO[2] = (vO[1] + 3u * vO[2]) >> 4;
+            cE[3] = (3u * vE[2] + vE[3]) >> 4;  cO[3] = (3u * vO[2] + vO[3]) >> 4;
+        }
+        const uint4 nz4 = __ldg((const uint4 *) (noise + texel));
+        const uint32_t nzw[4] = { nz4.x, nz4.y, nz4.z, nz4.w };
+        uint32_t rw[4] = { 0, 0, 0, 0 };
+        if (RESID && res) {
+            if (a.channels == 4) {
+                const uint4 r4 = __ldg((const uint4 *) (res + texel * 4));
+                rw[0] = r4.x; rw[1] = r4.y; rw[2] = r4.z; rw[3] = r4.w;
+            } else {
+                const uint4 r4 = __ldg((const uint4 *) (res + texel * 4));
+                /* a missing channel reads 0, a missing alpha 255 */
+                const uint32_t keep = (1u << (8 * a.channels)) - 1u;
+                rw[0] = (r4.x & keep) | 0xFF000000u; rw[1] = (r4.y & keep) | 0xFF000000u;
+                rw[2] = (r4.z & keep) | 0xFF000000u; rw[3] = (r4.w & keep) | 0xFF000000u;
+            }
+        }
+        uint32_t ow[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float c[4] = { byte_f<0, 0>(cE[p]), byte_f<0, 0>(cO[p]), byte_f<2, 0>(cE[p]), byte_f<2, 0>(cO[p]) };
+            /* noise - 128, residual - 128 */
+            const float nm[4] = { byte_f<0, 128>(nzw[p]), byte_f<1, 128>(nzw[p]), byte_f<2, 128>(nzw[p]), byte_f<3, 128>(nzw[p]) };
+            float r[4];
+            if (RESID && res) {
+                if (PARENT) {
+                    r[0] = fmaf(byte_f<0, 128>(rw[p]), a.scale, c[0]);
+                    r[1] = fmaf(byte_f<1, 128>(rw[p]), a.scale, c[1]);
+                    r[2] = fmaf(byte_f<2, 128>(rw[p]), a.scale, c[2]);
+                    r[3] = fmaf(byte_f<3, 128>(rw[p]), a.scale, c[3]);
+                } else {
+                    r[0] = byte_f<0, 0>(rw[p]); r[1] = byte_f<1, 0>(rw[p]); r[2] = byte_f<2, 0>(rw[p]); r[3] = byte_f<3, 0>(rw[p]);
+                }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) r[ch] = PARENT ? c[ch] : a.root255[ch];
+            }
+            if (HSV) {
+                hsv_noise(r, nc, nm);
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) r[ch] = fmaf(nc[ch], nm[ch], r[ch]);
+            }
+            ow[p] = pack4(to_unorm8_bits(r[0]), to_unorm8_bits(r[1]), to_unorm8_bits(r[2]), to_unorm8_bits(r[3]));
+        }
+        *(uint4 *) (out + texel * 4) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
 }
 
 template <bool HSV, bool RESID>
@@ -322,71 +435,8 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const OrthoArgs a)
     const uint8_t *res = resid_slot >= 0 ? a.resid + (long long) resid_slot * a.resid_slot_bytes : nullptr;
     if (has_parent) ob_mbar_wait(&bar, 0);
 
-    const int groups = W >> 2, items = W * groups;
-    for (int i = tid; i < items; i += kOrthoThreads) {
-        const int y = i / groups, k = i - y * groups;
-        const size_t texel = (size_t) y * W + 4 * k;
-        uint32_t cE[4] = { 0, 0, 0, 0 }, cO[4] = { 0, 0, 0, 0 };   /* channels (0,2) and (1,3) of the upsampled parent */
-        if (has_parent) {
-            const uint32_t *r0 = win + ((y + 1) >> 1) * PW + 2 * k;
-            const uint2 a01 = *(const uint2 *) r0, a23 = *(const uint2 *) (r0 + 2);
-            const uint2 b01 = *(const uint2 *) (r0 + PW), b23 = *(const uint2 *) (r0 + PW + 2);
-            const uint32_t wy0 = (y & 1) ? 3u : 1u, wy1 = 4u - wy0;
-            const uint32_t ta[4] = { a01.x, a01.y, a23.x, a23.y }, tb[4] = { b01.x, b01.y, b23.x, b23.y };
-            uint32_t vE[4], vO[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                vE[j] = wy0 * (ta[j] & 0x00FF00FFu) + wy1 * (tb[j] & 0x00FF00FFu);
-                vO[j] = wy0 * ((ta[j] >> 8) & 0x00FF00FFu) + wy1 * ((tb[j] >> 8) & 0x00FF00FFu);
-            }
-            /* texel 4k+p reads window columns 2k + (p+1)/2 and the next one; even x: weights (1,3), odd x: (3,1) */
-            cE[0] = ((vE[0] + 3u * vE[1]) >> 4) & 0x00FF00FFu;  cO[0] = ((vO[0] + 3u * vO[1]) >> 4) & 0x00FF00FFu;
-            cE[1] = ((3u * vE[1] + vE[2]) >> 4) & 0x00FF00FFu;  cO[1] = ((3u * vO[1] + vO[2]) >> 4) & 0x00FF00FFu;
-            cE[2] = ((vE[1] + 3u * vE[2]) >> 4) & 0x00FF00FFu;  cO[2] = ((vO[1] + 3u * vO[2]) >> 4) & 0x00FF00FFu;
-            cE[3] = ((3u * vE[2] + vE[3]) >> 4) & 0x00FF00FFu;  cO[3] = ((3u * vO[2] + vO[3]) >> 4) & 0x00FF00FFu;
-        }
-        const uint4 nz4 = __ldg((const uint4 *) (noise + texel));
-        const uint32_t nzw[4] = { nz4.x, nz4.y, nz4.z, nz4.w };
-        uint32_t rw[4] = { 0, 0, 0, 0 };
-        if (RESID && res) {
-            if (a.channels == 4) {
-                const uint4 r4 = __ldg((const uint4 *) (res + texel * 4));
-                rw[0] = r4.x; rw[1] = r4.y; rw[2] = r4.z; rw[3] = r4.w;
-            } else {
-#pragma unroll
-                for (int p = 0; p < 4; ++p) rw[p] = __ldg((const uint32_t *) (res + (texel + p) * 4));
-            }
-            /* a missing channel reads 0, a missing alpha 255 */
-            const uint32_t keep = a.channels >= 4 ? 0xFFFFFFFFu : (1u << (8 * a.channels)) - 1u;
-            const uint32_t fill = a.channels >= 4 ? 0u : 0xFF000000u;
-#pragma unroll
-            for (int p = 0; p < 4; ++p) rw[p] = (rw[p] & keep) | fill;
-        }
-        uint32_t ow[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const float c[4] = { (float) (cE[p] & 0xFFFFu), (float) (cO[p] & 0xFFFFu), (float) (cE[p] >> 16), (float) (cO[p] >> 16) };
-            float r[4], nz[4];
-#pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                nz[ch] = (float) ((nzw[p] >> (8 * ch)) & 0xFFu);
-                if (RESID && res) {
-                    const float rv = (float) ((rw[p] >> (8 * ch)) & 0xFFu);
-                    r[ch] = has_parent ? fmaf(rv - 128.0f, a.scale, c[ch]) : rv;
-                } else {
-                    r[ch] = has_parent ? c[ch] : a.root255[ch];
-                }
-            }
-            if (HSV) {
-                hsv_noise(r, nc, nz);
-            } else {
-#pragma unroll
-                for (int ch = 0; ch < 4; ++ch) r[ch] = fmaf(nc[ch], nz[ch] - 128.0f, r[ch]);
-            }
-            ow[p] = to_unorm8(r[0]) | (to_unorm8(r[1]) << 8) | (to_unorm8(r[2]) << 16) | (to_unorm8(r[3]) << 24);
-        }
-        *(uint4 *) (out + texel * 4) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-    }
+    if (has_parent) ortho_rows<HSV, RESID, true>(a, win, noise, res, out, nc, tid);
+    else ortho_rows<HSV, RESID, false>(a, win, noise, res, out, nc, tid);
 }
 
 }  // namespace
@@ -426,9 +476,14 @@ static int check_ortho_args(pl_ctx *ctx, const pl_ortho_scene *sc, const pl_pool
 {
     if (!ctx || !sc || !ortho) return pl_set_error(PL_ERR_ARG, "NULL argument");
     if (n < 0) return pl_set_error(PL_ERR_ARG, "n = %d", n);
-    if (ortho->kind != PL_POOL_ORTHO_UN8x4 || ortho->ctx != ctx || ortho->tile_w != sc->tile_w)
+    /* an RGBA8 normal pool has the same layout (dense 4-byte texels): a host layer that creates its
+     * RGBA8 storages before knowing their producer passes one */
+    auto rgba8 = [](const pl_pool *p) {
+        return (p->kind == PL_POOL_ORTHO_UN8x4 || p->kind == PL_POOL_NORM_UN8x4) && (p->tile_w - 4) % 8 == 0;
+    };
+    if (!rgba8(ortho) || ortho->ctx != ctx || ortho->tile_w != sc->tile_w)
         return pl_set_error(PL_ERR_ARG, "ortho pool: wrong kind, context or tile_w (scene %d)", sc->tile_w);
-    if (resid && (resid->kind != PL_POOL_ORTHO_UN8x4 || resid->ctx != ctx || resid->tile_w != sc->tile_w))
+    if (resid && (!rgba8(resid) || resid->ctx != ctx || resid->tile_w != sc->tile_w))
         return pl_set_error(PL_ERR_ARG, "ortho residual pool: wrong kind, context or tile_w");
     if (sc->channels < 1 || sc->channels > 4) return pl_set_error(PL_ERR_ARG, "channels = %d", sc->channels);
     if (!ctx->ortho_noise_rot || ctx->ortho_noise_w != sc->tile_w)

@@ -61,7 +61,7 @@ void DeviceContext::shutdown()
 }
 
 DeviceContext::DeviceContext(int device, pl_ctx *ctx) :
-    Object("DeviceContext"), device(device), ctx(ctx), noiseWidth(0), depth(0)
+    Object("DeviceContext"), device(device), ctx(ctx), noiseWidth(0), orthoNoiseWidth(0), depth(0)
 {
 }
 
@@ -75,6 +75,15 @@ void DeviceContext::ensureNoise(int tileWidth)
     if (noiseWidth != tileWidth) {
         check(pl_noise_init(ctx, tileWidth, NULL));
         noiseWidth = tileWidth;
+    }
+}
+
+void DeviceContext::ensureOrthoNoise(int tileWidth)
+{
+    if (orthoNoiseWidth != tileWidth) {
+        flush();
+        check(pl_ortho_noise_init(ctx, tileWidth, NULL));
+        orthoNoiseWidth = tileWidth;
     }
 }
 

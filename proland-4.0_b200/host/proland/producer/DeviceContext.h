@@ -56,6 +56,8 @@ public:
     /* createDemNoise is cached per tile width in the reference (demNoiseFactory,
      * ElevationProducer.cpp:135); one width per context here */
     void ensureNoise(int tileWidth);
+    /* createOrthoNoise, cached per tile width (orthoNoiseFactory, OrthoProducer.cpp:120) */
+    void ensureOrthoNoise(int tileWidth);
 
     void addSource(BatchSource *s);
     void removeSource(BatchSource *s);
@@ -75,7 +77,7 @@ private:
     DeviceContext(int device, pl_ctx *ctx);
     int device;
     pl_ctx *ctx;
-    int noiseWidth;
+    int noiseWidth, orthoNoiseWidth;
     int depth;
     std::vector<BatchSource *> sources;
 };

@@ -59,7 +59,8 @@ void GPUTileStorage::init(int tileSize, int nTiles, TextureInternalFormat intern
     case RGB32F:
     case RGBA32F: kind = PL_POOL_ELEV_F32x3; break;      /* (zf, zc, zm); the 4th channel of RGBA32F is always 0 */
     case RG8: kind = PL_POOL_NORM_UN8x2; break;
-    case RGBA8: kind = PL_POOL_NORM_UN8x4; break;
+    case RGBA8: kind = PL_POOL_NORM_UN8x4; break;          /* normals (fine + coarse) or ortho colours */
+    case RGB8: kind = PL_POOL_ORTHO_UN8x4; break;          /* ortho colours; stored as RGBA8, alpha unused */
     case R32F: kind = PL_POOL_RESID_F32; break;
     default: kind = PL_POOL_RESID_I16; break;
     }
@@ -83,6 +84,7 @@ const char *GPUTileStorage::getInternalFormatName() const
     case RGBA32F: return "RGBA32F";
     case RG8: return "RG8";
     case RGBA8: return "RGBA8";
+    case RGB8: return "RGB8";
     case R32F: return "R32F";
     default: return "R16I";
     }
@@ -95,6 +97,7 @@ int GPUTileStorage::getComponents() const
     case RGBA32F: return 4;
     case RG8: return 2;
     case RGBA8: return 4;
+    case RGB8: return 3;
     default: return 1;
     }
 }
@@ -107,7 +110,7 @@ size_t GPUTileStorage::getTileBytes() const
 bool GPUTileStorage::parseInternalFormat(const std::string &name, TextureInternalFormat *f)
 {
     static const struct { const char *n; TextureInternalFormat f; } table[] = {
-        { "RGB32F", RGB32F }, { "RGBA32F", RGBA32F }, { "RG8", RG8 }, { "RGBA8", RGBA8 }, { "R32F", R32F }, { "R16I", R16I }
+        { "RGB32F", RGB32F }, { "RGBA32F", RGBA32F }, { "RG8", RG8 }, { "RGBA8", RGBA8 }, { "R32F", R32F }, { "R16I", R16I }, { "RGB8", RGB8 }
     };
     for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); ++i) {
         if (name == table[i].n) {
@@ -122,6 +125,10 @@ bool GPUTileStorage::parseFilter(const std::string &name, TextureFilter *f)
 {
     if (name == "NEAREST") { *f = NEAREST; return true; }
     if (name == "LINEAR") { *f = LINEAR; return true; }
+    /* mipmapped ortho storages (terrain3/helloworld.xml:43-45): the producers fetch level 0 at texel
+     * centres, where every filter returns the texel */
+    if (name == "LINEAR_MIPMAP_LINEAR" || name == "LINEAR_MIPMAP_NEAREST") { *f = LINEAR; return true; }
+    if (name == "NEAREST_MIPMAP_NEAREST" || name == "NEAREST_MIPMAP_LINEAR") { *f = NEAREST; return true; }
     return false;
 }
 

@@ -22,7 +22,7 @@ namespace proland
 {
 
 /* the internal formats the tile-production path uses */
-enum TextureInternalFormat { RGB32F, RGBA32F, RG8, RGBA8, R32F, R16I };
+enum TextureInternalFormat { RGB32F, RGBA32F, RG8, RGBA8, R32F, R16I, RGB8 };
 enum TextureFilter { NEAREST, LINEAR };
 
 PROLAND_API class GPUTileStorage : public TileStorage

@@ -10,6 +10,7 @@
 #include "ork/BatchScheduler.h"
 #include "proland/dem/ElevationProducer.h"
 #include "proland/dem/NormalProducer.h"
+#include "proland/ortho/OrthoProducer.h"
 #include "proland/dem/ResidualProducer.h"
 #include "proland/producer/CPUTileStorage.h"
 #include "proland/producer/GPUTileStorage.h"
@@ -88,7 +89,7 @@ bool isStorage(const std::string &n)
 bool isKnown(const std::string &n)
 {
     return isStorage(n) || n == "multithreadScheduler" || n == "tileCache" || n == "residualProducer" ||
-           n == "elevationProducer" || n == "normalProducer";
+           n == "elevationProducer" || n == "normalProducer" || n == "orthoProducer";
 }
 
 }  // namespace
@@ -218,11 +219,11 @@ ptr<Object> ResourceManager::createStorage(const XmlElement *e)
         getIntParameter(e, "nTiles", &nTiles);
         TextureInternalFormat tf;
         if (!GPUTileStorage::parseInternalFormat(getParameter(e, "internalformat"), &tf)) {
-            fail(e, "internalformat must be RGB32F, RGBA32F (elevations), RG8 or RGBA8 (normals) on this path");
+            fail(e, "internalformat must be RGB32F, RGBA32F (elevations), RG8, RGBA8 (normals) or RGB8, RGBA8 (ortho) on this path");
         }
         TextureFilter minf = NEAREST, magf = NEAREST;
         if (e->Attribute("min") != NULL && !GPUTileStorage::parseFilter(e->Attribute("min"), &minf)) {
-            fail(e, "min filter must be NEAREST or LINEAR (tile storages of this path are not mipmapped)");
+            fail(e, "min filter must be NEAREST, LINEAR or one of their MIPMAP variants");
         }
         if (e->Attribute("mag") != NULL && !GPUTileStorage::parseFilter(e->Attribute("mag"), &magf)) {
             fail(e, "mag filter must be NEAREST or LINEAR");
@@ -345,6 +346,66 @@ ptr<Object> ResourceManager::create(const std::string &name, const XmlElement *e
         if (e->Attribute("gridSize") != NULL) getIntParameter(e, "gridSize", &gridSize);
         const bool deform = e->Attribute("deform") != NULL && strcmp(e->Attribute("deform"), "sphere") == 0;
         return new NormalProducer(cache, elevations, gridSize, deform);
+    }
+    if (e->name == "orthoProducer") {
+        /* OrthoProducer.cpp:440-512 */
+        checkParameters(e, "name,cache,residuals,face,upsampleProg,rnoise,cnoise,noise,hsv,scale,maxLevel,");
+        ptr<TileCache> cache = loadResource(getParameter(e, "cache")).cast<TileCache>();
+        if (cache == NULL) fail(e, "cache is not a TileCache");
+        ptr<TileProducer> residuals;
+        if (e->Attribute("residuals") != NULL) {
+            residuals = loadResource(getParameter(e, "residuals")).cast<TileProducer>();
+            if (residuals == NULL) fail(e, "residuals is not a TileProducer");
+        }
+        if (e->Attribute("upsampleProg") != NULL) {
+            std::string prog = getParameter(e, "upsampleProg");
+            while (!prog.empty() && prog[prog.size() - 1] == ';') prog.erase(prog.size() - 1);
+            if (prog != "upsampleOrthoShader") fail(e, "unknown upsampleProg '" + prog + "' (upsampleOrthoShader;)");
+        }
+        float rootNoiseColor[4] = { 0.5f, 0.5f, 0.5f, 0.5f };
+        float noiseColor[4] = { 1.0f, 1.0f, 1.0f, 1.0f };
+        const char *colorAttr[2] = { "rnoise", "cnoise" };
+        float *colors[2] = { rootNoiseColor, noiseColor };
+        for (int k = 0; k < 2; ++k) {
+            if (e->Attribute(colorAttr[k]) == NULL) continue;
+            /* four items always: a missing one is atof("") = 0 (OrthoProducer.cpp:462-481) */
+            const std::string c = std::string(e->Attribute(colorAttr[k])) + ",";
+            std::string::size_type start = 0;
+            for (int i = 0; i < 4; ++i) {
+                const std::string::size_type index = c.find(',', start);
+                const std::string item = index == std::string::npos ? std::string() : c.substr(start, index - start);
+                colors[k][i] = (float) atof(item.c_str()) / 255;
+                start = index == std::string::npos ? c.size() : index + 1;
+            }
+        }
+        std::vector<float> noiseAmp;
+        if (e->Attribute("noise") != NULL) {
+            const std::string noiseAmps = std::string(e->Attribute("noise")) + ",";
+            std::string::size_type start = 0, index;
+            while ((index = noiseAmps.find(',', start)) != std::string::npos) {
+                float value = 0.0f;
+                sscanf(noiseAmps.substr(start, index - start).c_str(), "%f", &value);
+                noiseAmp.push_back(value);
+                start = index + 1;
+            }
+        }
+        const bool hsv = e->Attribute("hsv") != NULL && strcmp(e->Attribute("hsv"), "true") == 0;
+        float scale = 2.0f;
+        int maxLevel = -1;
+        if (e->Attribute("scale") != NULL) getFloatParameter(e, "scale", &scale);
+        if (e->Attribute("maxLevel") != NULL) getIntParameter(e, "maxLevel", &maxLevel);
+        int face = 1;
+        if (e->Attribute("face") != NULL) {
+            getIntParameter(e, "face", &face);
+        } else if (!name.empty() && name[name.size() - 1] >= '1' && name[name.size() - 1] <= '6') {
+            face = name[name.size() - 1] - '0';
+        }
+        for (size_t i = 0; i < e->children.size(); ++i) {
+            if (Logger::WARNING_LOGGER != NULL) {
+                Logger::WARNING_LOGGER->log("RESOURCE", "Unknown scene node element '" + e->children[i].name + "'");
+            }
+        }
+        return new OrthoProducer(cache, residuals, rootNoiseColor, noiseColor, noiseAmp, hsv, scale, maxLevel, face);
     }
     fail(e, "not a resource of the tile-production path");
     return NULL;

@@ -163,3 +163,66 @@ def test_ortho_idempotent_and_order_independent(plb, ctx):
     ctx.sync()
     b = np.stack([pool.download(s) for s in range(n)])
     assert np.array_equal(a, b)
+
+
+# ------------------------------------------------- through the C++ host layer (proland::OrthoProducer)
+
+@pytest.fixture(scope="module")
+def ph():
+    import proland_host
+    if not os.path.exists(proland_host.LIB_PATH):
+        proland_host.build()
+    return proland_host
+
+
+TERRAIN3_XML = """<?xml version="1.0" ?>
+<archive>
+    <multithreadScheduler name="defaultScheduler" nthreads="3" fps="0"/>
+    <tileCache name="groundOrthoGpu" scheduler="defaultScheduler">
+        <gpuTileStorage tileSize="196" nTiles="512"
+            internalformat="%s" format="RGB" type="UNSIGNED_BYTE" min="LINEAR_MIPMAP_LINEAR" mag="LINEAR"
+            anisotropy="16"/>
+    </tileCache>
+    <orthoProducer name="groundOrthoGpu%d" cache="groundOrthoGpu"
+        hsv="true" rnoise="60,150,20" cnoise="70,80,100"
+        noise="255,255,255,255,255,255,255,255,255,255,255,255,255,255,255,255,255"/>
+</archive>"""
+
+
+@pytest.mark.parametrize("fmt,face", [("RGB8", 1), ("RGBA8", 5)])
+def test_terrain3_archive_through_the_host_layer(ph, plb, oracle, fmt, face):
+    """terrain3/helloworld.xml:42-49 verbatim (storage + orthoProducer): XML -> TileCache -> OrthoProducer ->
+    BatchScheduler -> pl_ortho_batch; one launch per quadtree level; every tile equals the oracle's.
+    rnoise / cnoise with three items: the fourth is atof("") / 255 = 0 (OrthoProducer.cpp:462-481)."""
+    kw = dict(W=196, face=face, noise_amp=[255] * 17, hsv=1, scale=2.0,
+              noise_color=[np.float32(v) / np.float32(255) for v in (70, 80, 100, 0)],
+              root_noise_color=[np.float32(v) / np.float32(255) for v in (60, 150, 20, 0)])
+    ref = oracle.ortho_quadtree(3, **kw)
+    with ph.Scene(TERRAIN3_XML % (fmt, face)) as scene:
+        ortho = scene.producer("groundOrthoGpu%d" % face)
+        assert (ortho.type, ortho.task_type) == ("OrthoProducer", "CreateOrthoTile")
+        assert ortho.info()["border"] == 2 and ortho.info()["gpu"] and ortho.info()["tile_size"] == 196
+        assert ortho.has_tile(20, 0, 0)
+        launches0 = ph.lib().plh_device_launches(-1)
+        tiles = [ortho.get_tile(3, tx, ty) for ty in range(8) for tx in range(8)]
+        scene.scheduler("defaultScheduler").run(tiles)
+        assert all(t.done for t in tiles)
+        assert ortho.counts() == (85, 4)
+        assert ph.lib().plh_device_launches(-1) - launches0 == 4
+        nch = 3 if fmt == "RGB8" else 4
+        for t in tiles:
+            want = ref[21 + plb.morton_encode(t.tx, t.ty)]
+            assert np.array_equal(t.download()[..., :nch], want[..., :nch]), (t.tx, t.ty)
+        root = ortho.find_tile(0, 0, 0, include_cache=True, done=True)
+        assert root is not None and np.array_equal(root.download()[..., :nch], ref[0][..., :nch])
+        for t in tiles:
+            ortho.put_tile(t)
+        assert scene.cache("groundOrthoGpu").stats()["used"] == 0
+
+
+def test_ortho_producer_max_level(ph):
+    xml = TERRAIN3_XML % ("RGBA8", 1)
+    xml = xml.replace('hsv="true"', 'hsv="true" maxLevel="7"')
+    with ph.Scene(xml) as scene:
+        ortho = scene.producer("groundOrthoGpu1")
+        assert ortho.has_tile(7, 3, 3) and not ortho.has_tile(8, 3, 3)
