@@ -264,27 +264,42 @@ __device__ __forceinline__ uint32_t pack4(uint32_t b0, uint32_t b1, uint32_t b2,
     return __byte_perm(__byte_perm(b0, b1, 0x0040u), __byte_perm(b2, b3, 0x0040u), 0x5410u);
 }
 
-/* upsampleOrthoShader.glsl:141-151, the hsv branch: modulates r[0..2] in HSV space, r[3] directly */
+/* upsampleOrthoShader.glsl:141-151, the hsv branch: modulates r[0..2] in HSV space, r[3] directly.
+ * Branch-free: neighbouring texels take different arms of rgb_to_hsv / hsv_to_rgb, so every arm is
+ * evaluated and the result selected -- operation for operation what the taken arm of the oracle computes.
+ *  - delta == 0: the divisions run on a substitute divisor 1 and H, S are selected to 0
+ *  - S == 0 needs no arm of its own: V*(1 - 0), V*fma(-0, f, 1) are V exactly
+ * MAYBE_NEG (residual variants): maxVal <= 0 with delta != 0 is possible (a residual below -parent) and
+ * leaves the domain of the branch-free division: those texels take the IEEE operator. */
+template <bool MAYBE_NEG>
 __device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const float nm[4] /* noise - 128 */)
 {
     const float R = div255(r[0]), G = div255(r[1]), B = div255(r[2]);
     const float minv = fminf(R, fminf(G, B)), maxv = fmaxf(R, fmaxf(G, B));
     const float delta = maxv - minv;
-    float H = 0.0f, S = 0.0f, V = maxv;
-    if (delta != 0.0f) {
-        /* maxv <= 0 (only with residuals below -c) leaves the domain of the branch-free division */
-        S = maxv > 1e-30f ? plfp::div_rn(delta, maxv, plfp::rcp_rn(maxv)) : __fdiv_rn(delta, maxv);
-        const float rd = plfp::rcp_rn(delta);
-        const float half = delta * 0.5f;                       /* delta / 2.0, exact */
-        const float dR = plfp::div_rn(div6(maxv - R) + half, delta, rd);
-        const float dG = plfp::div_rn(div6(maxv - G) + half, delta, rd);
-        const float dB = plfp::div_rn(div6(maxv - B) + half, delta, rd);
-        if (R == maxv) H = dB - dG;
-        else if (G == maxv) H = (float) (1.0 / 3.0) + dR - dB;
-        else H = (float) (2.0 / 3.0) + dG - dR;                /* B == maxv */
-        if (H < 0.0f) H += 1.0f;
-        if (H > 1.0f) H -= 1.0f;
+    const bool grey = delta == 0.0f;
+    const float dsafe = grey ? 1.0f : delta;
+    float msafe = maxv;
+    if (MAYBE_NEG) msafe = maxv > 1e-30f ? maxv : 1.0f;
+    else msafe = grey ? 1.0f : maxv;             /* without residuals rgb >= 0: delta != 0 implies maxv > 0 */
+    float S = plfp::div_rn(delta, msafe, plfp::rcp_rn(msafe));
+    if (MAYBE_NEG) {
+        if (!(maxv > 1e-30f)) S = __fdiv_rn(delta, maxv);
     }
+    const float rd = plfp::rcp_rn(dsafe);
+    const float half = delta * 0.5f;                       /* delta / 2.0, exact */
+    const float dR = plfp::div_rn(div6(maxv - R) + half, dsafe, rd);
+    const float dG = plfp::div_rn(div6(maxv - G) + half, dsafe, rd);
+    const float dB = plfp::div_rn(div6(maxv - B) + half, dsafe, rd);
+    const float hR = dB - dG;
+    const float hG = (float) (1.0 / 3.0) + dR - dB;
+    const float hB = (float) (2.0 / 3.0) + dG - dR;
+    float H = R == maxv ? hR : (G == maxv ? hG : hB);      /* one of the three is maxVal */
+    H = H < 0.0f ? H + 1.0f : H;
+    H = H > 1.0f ? H - 1.0f : H;
+    H = grey ? 0.0f : H;
+    S = grey ? 0.0f : S;
+    float V = maxv;
     constexpr float kEdge = 0.8f - 0.4f;
     const float e0 = V - 0.4f, tq = e0 * (1.0f / kEdge);
     const float t = fma_sat(1.0f / kEdge, fmaf(tq, -kEdge, e0), tq);     /* clamp(RN(e0 / kEdge), 0, 1) */
@@ -295,21 +310,20 @@ __device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const f
     H = H - floorf(H);
     S = clamp01(S);
     V = clamp01(V);
-    float oR = V, oG = V, oB = V;
-    if (S != 0.0f) {
-        const float vh = H * 6.0f;
-        const float vi = floorf(vh);
-        const float f = vh - vi;
-        const float v1 = V * (1.0f - S);
-        const float v2 = V * fmaf(-S, f, 1.0f);
-        const float v3 = V * fmaf(-S, 1.0f - f, 1.0f);
-        if (vi == 0.0f) { oR = V; oG = v3; oB = v1; }
-        else if (vi == 1.0f) { oR = v2; oG = V; oB = v1; }
-        else if (vi == 2.0f) { oR = v1; oG = V; oB = v3; }
-        else if (vi == 3.0f) { oR = v1; oG = v2; oB = V; }
-        else if (vi == 4.0f) { oR = v3; oG = v1; oB = V; }
-        else { oR = V; oG = v1; oB = v2; }
-    }
+    const float vh = H * 6.0f;
+    const float vi = floorf(vh);
+    const float f = vh - vi;
+    const float v1 = V * (1.0f - S);
+    const float v2 = V * fmaf(-S, f, 1.0f);
+    const float v3 = V * fmaf(-S, 1.0f - f, 1.0f);
+    /* sector:  0        1        2        3        4        other
+     *   R      V        v2       v1       v1       v3       V
+     *   G      v3       V        V        v2       v1       v1
+     *   B      v1       v1       v3       V        V        v2     */
+    const bool s0 = vi == 0.0f, s1 = vi == 1.0f, s2 = vi == 2.0f, s3 = vi == 3.0f, s4 = vi == 4.0f;
+    const float oR = s1 ? v2 : ((s2 || s3) ? v1 : (s4 ? v3 : V));
+    const float oG = s0 ? v3 : ((s1 || s2) ? V : (s3 ? v2 : v1));
+    const float oB = (s0 || s1) ? v1 : (s2 ? v3 : ((s3 || s4) ? V : v2));
     r[0] = oR * 255.0f;
     r[1] = oG * 255.0f;
     r[2] = oB * 255.0f;
@@ -391,7 +405,7 @@ __device__ __forceinline__ void ortho_rows(const OrthoArgs &a, const uint32_t *w
                 for (int ch = 0; ch < 4; ++ch) r[ch] = PARENT ? c[ch] : a.root255[ch];
             }
             if (HSV) {
-                hsv_noise(r, nc, nm);
+                hsv_noise<RESID>(r, nc, nm);
             } else {
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) r[ch] = fmaf(nc[ch], nm[ch], r[ch]);
