@@ -382,6 +382,18 @@ int pl_ortho_batch(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, pl_
 int pl_ortho_batch_dev(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, pl_pool *resid, int n,
                        const pl_ortho_req *dev_reqs);
 
+/* OrthoCPUProducer::doCreateTile, the TIFF branch (ortho/OrthoCPUProducer.cpp:205-232): n blobs of an ortho
+ * residual file (written by ColorMipmap::produceTile, preprocess/terrain/ColorMipmap.cpp:296-325: one
+ * little-endian TIFF, one DEFLATE strip of tile_w * tile_w * channels bytes, channels = 1..4 samples of 8 bits),
+ * inflated on the device into slots out_slots[j] of an RGBA8 pool (channels the file does not have are written as
+ * 0).  blobs / offsets / sizes are HOST memory, as for pl_residual_decode_batch; the file handling (header of 7
+ * ints, offset table, tile id = tx + ty * 2^level + (4^level - 1) / 3, OrthoCPUProducer.cpp:84-118,243-246)
+ * stays with the caller.  *channels (optional) receives the sample count of the blobs (all must agree): the value
+ * for pl_ortho_scene.channels.  DXT-compressed files (flags & 1) are consumed by the GL texture unit in the
+ * reference and are not supported: PL_ERR_CORRUPT. */
+int pl_ortho_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
+                          const uint32_t *sizes, const int32_t *out_slots, int *channels);
+
 #ifdef __cplusplus
 }
 #endif

@@ -236,6 +236,8 @@ void orc_ortho_uniforms(int W, int face, int level, int tx, int ty, const float 
 /* upsampleOrthoShader.glsl:123-158 */
 void orc_ortho_tile(const orc_ortho_params *p, const uint8_t *parent, const uint8_t *residual, int channels,
                     const uint8_t *noise, uint8_t *out);
+/* OrthoCPUProducer.cpp:68-118,160-246: one tile of an ortho residual file -> W*W*channels bytes; returns W or < 0 */
+int orc_ortho_cpu_read(const uint8_t *file, size_t size, int level, int tx, int ty, uint8_t *out, int *channels);
 long orc_ortho_quadtree(int W, int face, int maxLevel, const float *noiseAmp, int nAmp, const float noiseColor[4],
                         const float rootNoiseColor[4], int hsv, float scale, const uint8_t *noise, uint8_t *out);
 

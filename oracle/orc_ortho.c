@@ -245,3 +245,37 @@ long orc_ortho_quadtree(int W, int face, int maxLevel, const float *noiseAmp, in
     }
     return done;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * OrthoCPUProducer (ortho/OrthoCPUProducer.cpp:68-118, 160-246): the reader of ortho residual files.
+ *   header  : 7 int32 (maxLevel, tileSize, channels, rootLevel, rootTx, rootTy, flags); flags & 1 = DXT
+ *             blobs, flags & 2 = no border
+ *   offsets : ntiles x (begin, end) int64 relative to the end of the table, ntiles = (4^(maxLevel+1) - 1) / 3
+ *   blob    : tile id = tx + ty * 2^level + (4^level - 1) / 3; a TIFF whose single strip inflates to
+ *             (tileSize + 2 border)^2 * channels bytes (TIFFReadEncodedStrip)
+ * Returns the tile width, or < 0: -1 bad header / level, -2 DXT file (not decoded on the CPU either: the
+ * reference hands those bytes to the GL texture unit), -3 corrupt blob. */
+int orc_ortho_cpu_read(const uint8_t *file, size_t size, int level, int tx, int ty, uint8_t *out, int *channels)
+{
+    if (size < 28) return -1;
+    int32_t h[7];
+    memcpy(h, file, 28);
+    const int maxLevel = h[0], tileSize = h[1], ch = h[2], flags = h[6];
+    if (level < 0 || level > maxLevel || ch < 1 || ch > 4) return -1;
+    if (flags & 1) return -2;
+    const int border = (flags & 2) ? 0 : 2;
+    const long ntiles = ((1L << (maxLevel * 2 + 2)) - 1) / 3;
+    const size_t header = 28 + (size_t) ntiles * 16;
+    if (size < header) return -1;
+    const int tileid = tx + ty * (1 << level) + ((1 << (2 * level)) - 1) / 3;
+    int64_t range[2];
+    memcpy(range, file + 28 + (size_t) tileid * 16, 16);
+    if (range[0] < 0 || range[1] < range[0] || header + (size_t) range[1] > size) return -3;
+    const int w = tileSize + 2 * border;
+    int tw = 0, th = 0;
+    const long got = orc_tiff_inflate(file + header + range[0], (uint32_t) (range[1] - range[0]), out,
+                                      (size_t) w * w * ch, &tw, &th);
+    if (got != (long) w * w * ch || tw != w || th != w) return -3;
+    if (channels) *channels = ch;
+    return w;
+}

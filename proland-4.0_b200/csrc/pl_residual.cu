@@ -497,6 +497,22 @@ __global__ void __launch_bounds__(256) residual_store_kernel(const StoreJob *job
     }
 }
 
+/* dense bytes (w x w x channels, what TIFFReadEncodedStrip hands OrthoCPUProducer, OrthoCPUProducer.cpp:226-231)
+ * -> RGBA8 texels of an ortho pool; channels the file does not have are written as 0 */
+__global__ void __launch_bounds__(256) ortho_store_kernel(const StoreJob *jobs, const unsigned char *dense, size_t dense_stride,
+                                                          unsigned char *pool, size_t slot_bytes)
+{
+    const StoreJob J = jobs[blockIdx.x];
+    const unsigned char *src = dense + (size_t) blockIdx.x * dense_stride;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(pool + (size_t) J.out_slot * slot_bytes);
+    const int w = J.width, ch = J.add_slot;      /* add_slot carries the sample count here */
+    for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
+        uint32_t t = 0;
+        for (int c = 0; c < ch; ++c) t |= (uint32_t) src[(size_t) k * ch + c] << (8 * c);
+        dst[k] = t;
+    }
+}
+
 /* ResidualProducer::upsample (ResidualProducer.cpp:342-384): the (ts + 5)^2 tile of the next root
  * level from the quadrant (tx%2, ty%2) of its parent, in the CPU evaluation order of the reference
  * (NOT the GLSL mdot order): ((z1 + z2) * 9 - (z0 + z3)) / 16 on the axes, and for odd/odd texels the
@@ -541,7 +557,11 @@ inline unsigned int rd16(const uint8_t *p) { return (unsigned int) p[0] | ((unsi
 inline unsigned int rd32(const uint8_t *p) { return rd16(p) | (rd16(p + 2) << 16); }
 
 /* the first IFD of a little-endian baseline TIFF with one strip */
-int parse_tiff(const uint8_t *blob, uint32_t size, int want_w, InflateJob *job, uint64_t base)
+/* sample_bytes: bytes per texel the caller expects (2: the int16 residuals, stored as 2 x 8-bit or 1 x 16-bit
+ * samples); 0: byte tiles with 1..4 samples of 8 bits (ColorMipmap::produceTile, preprocess/terrain/
+ * ColorMipmap.cpp:312-325), *spp_out receives the sample count */
+int parse_tiff(const uint8_t *blob, uint32_t size, int want_w, InflateJob *job, uint64_t base, int sample_bytes = 2,
+               int *spp_out = nullptr)
 {
     if (size < 8 || blob[0] != 'I' || blob[1] != 'I' || rd16(blob + 2) != 42) return -1;
     const uint32_t ifd = rd32(blob + 4);
@@ -557,8 +577,16 @@ int parse_tiff(const uint8_t *blob, uint32_t size, int want_w, InflateJob *job, 
         case 256: w = val; break;
         case 257: h = val; break;
         case 258:   /* BitsPerSample: two shorts fit the value field; more than two are an offset */
-            bps = count <= 2 ? rd16(e + 8) : 0;
-            if (count == 2 && rd16(e + 10) != bps) bps = 0;
+            if (count <= 2) {
+                bps = rd16(e + 8);
+                if (count == 2 && rd16(e + 10) != bps) bps = 0;
+            } else {
+                const uint32_t off = rd32(e + 8);
+                if (type != 3 || count > 4 || (uint64_t) off + 2ull * count > size) return -8;
+                bps = rd16(blob + off);
+                for (unsigned int s = 1; s < count; ++s)
+                    if (rd16(blob + off + 2 * s) != bps) bps = 0;
+            }
             break;
         case 259: comp = val; break;
         case 273: soff = val; break;
@@ -569,12 +597,18 @@ int parse_tiff(const uint8_t *blob, uint32_t size, int want_w, InflateJob *job, 
         }
     }
     if ((int) w != want_w || h != w) return -4;
-    if (spp * bps != 16 || predictor != 1) return -5;
+    if (predictor != 1) return -5;
+    if (sample_bytes == 0) {
+        if (bps != 8 || spp < 1 || spp > 4) return -5;
+    } else if (spp * bps != 8u * (unsigned) sample_bytes) {
+        return -5;
+    }
+    if (spp_out) *spp_out = (int) spp;
     if (comp != 1 && comp != 8 && comp != 32946) return -6;
     if ((uint64_t) soff + slen > size) return -7;
     job->in_off = base + soff;
     job->in_len = slen;
-    job->out_len = w * w * 2;
+    job->out_len = w * w * (sample_bytes == 0 ? spp : (uint32_t) sample_bytes);
     job->compression = comp;
     return 0;
 }
@@ -655,14 +689,16 @@ __global__ void __launch_bounds__(256) residual_encode_kernel(const pl_resid_enc
 
 }  // namespace
 
-extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
-                                        const uint32_t *sizes, const int32_t *widths, const int32_t *out_slots,
-                                        const int32_t *add_slots, float scale)
+static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
+                        const uint32_t *sizes, const int32_t *widths, const int32_t *out_slots,
+                        const int32_t *add_slots, float scale, int *channels_out)
 {
     if (!ctx || !out || n < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
     if (n == 0) return PL_OK;
-    if (!blobs || !offsets || !sizes || !widths || !out_slots) return pl_set_error(PL_ERR_ARG, "NULL argument");
-    if (out->kind != PL_POOL_RESID_F32 && out->kind != PL_POOL_RESID_I16)
+    if (!blobs || !offsets || !sizes || !out_slots) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    const bool ortho = out->kind == PL_POOL_ORTHO_UN8x4 || out->kind == PL_POOL_NORM_UN8x4;
+    if (!ortho && !widths) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (!ortho && out->kind != PL_POOL_RESID_F32 && out->kind != PL_POOL_RESID_I16)
         return pl_set_error(PL_ERR_ARG, "out is not a residual pool");
     if (add_slots && out->kind != PL_POOL_RESID_F32) return pl_set_error(PL_ERR_ARG, "add_slots needs an F32 pool");
     PL_CUDA(cudaSetDevice(ctx->device));
@@ -674,21 +710,29 @@ extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const 
     uint64_t total = 0;
     int max_w = 0;
     for (int j = 0; j < n; ++j) {
-        if (widths[j] < 1 || widths[j] > out->tile_w) return pl_set_error(PL_ERR_ARG, "tile %d: width %d exceeds the pool tile", j, widths[j]);
+        const int wj = ortho ? out->tile_w : widths[j];
+        if (wj < 1 || wj > out->tile_w) return pl_set_error(PL_ERR_ARG, "tile %d: width %d exceeds the pool tile", j, wj);
         const int os = out_slots[j] == PL_SLOT_SCRATCH ? out->capacity : out_slots[j];
         const int as = !add_slots ? -1 : (add_slots[j] == PL_SLOT_SCRATCH ? out->capacity : add_slots[j]);
         if (os < 0 || os > out->capacity || as > out->capacity || (os == out->capacity && out->kind != PL_POOL_RESID_F32))
             return pl_set_error(PL_ERR_ARG, "tile %d: slot out of range", j);
         packed_off[j] = total;
         total += ((uint64_t) sizes[j] + 7) & ~7ull;
-        const int rc = parse_tiff(blobs + offsets[j], sizes[j], widths[j], &jobs[j], packed_off[j]);
-        if (rc) return pl_set_error(PL_ERR_CORRUPT, "tile %d: not a single-strip 16-bit TIFF blob (code %d)", j, rc);
-        sjobs[j].width = widths[j];
+        int spp = 0;
+        const int rc = parse_tiff(blobs + offsets[j], sizes[j], wj, &jobs[j], packed_off[j], ortho ? 0 : 2, &spp);
+        if (rc) return pl_set_error(PL_ERR_CORRUPT, "tile %d: not a single-strip %s TIFF blob of width %d (code %d)", j,
+                                    ortho ? "8-bit" : "16-bit", wj, rc);
+        if (ortho && os >= out->capacity) return pl_set_error(PL_ERR_ARG, "tile %d: slot out of range", j);
+        if (ortho && channels_out) {
+            if (j > 0 && *channels_out != spp) return pl_set_error(PL_ERR_CORRUPT, "tile %d: %d channels, tile 0 has %d", j, spp, *channels_out);
+            *channels_out = spp;
+        }
+        sjobs[j].width = wj;
         sjobs[j].out_slot = os;
-        sjobs[j].add_slot = as < 0 ? -1 : as;
-        if (widths[j] > max_w) max_w = widths[j];
+        sjobs[j].add_slot = ortho ? spp : (as < 0 ? -1 : as);
+        if (wj > max_w) max_w = wj;
     }
-    const size_t dense_stride = ((size_t) max_w * max_w * 2 + 15) & ~(size_t) 15;
+    const size_t dense_stride = ((size_t) max_w * max_w * (ortho ? 4 : 2) + 15) & ~(size_t) 15;
     const size_t bytes_in = (size_t) total + 16;
 
     /* staging: pinned host buffer -> device, one async copy */
@@ -721,7 +765,9 @@ extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const 
         inflate_kernel<<<(n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, ctx->stream>>>(n, d_jobs, d_in, d_dense,
                                                                                                 dense_stride, d_status);
         PL_CUDA(cudaGetLastError());
-        if (out->kind == PL_POOL_RESID_F32)
+        if (ortho)
+            ortho_store_kernel<<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes);
+        else if (out->kind == PL_POOL_RESID_F32)
             residual_store_kernel<true><<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes, out->pitch, scale);
         else
             residual_store_kernel<false><<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes, out->pitch, scale);
@@ -737,6 +783,27 @@ extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const 
                 return pl_set_error(PL_ERR_CORRUPT, "tile %d: DEFLATE stream is corrupt (inflate code %d)", j, status[j]);
     }
     return PL_OK;
+}
+
+extern "C" int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
+                                        const uint32_t *sizes, const int32_t *widths, const int32_t *out_slots,
+                                        const int32_t *add_slots, float scale)
+{
+    if (out && (out->kind == PL_POOL_ORTHO_UN8x4 || out->kind == PL_POOL_NORM_UN8x4))
+        return pl_set_error(PL_ERR_ARG, "out is not a residual pool (byte tiles: pl_ortho_decode_batch)");
+    return decode_batch(ctx, out, n, blobs, offsets, sizes, widths, out_slots, add_slots, scale, nullptr);
+}
+
+/* OrthoCPUProducer::doCreateTile, the TIFF branch (ortho/OrthoCPUProducer.cpp:205-232) */
+extern "C" int pl_ortho_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
+                                     const uint32_t *sizes, const int32_t *out_slots, int *channels)
+{
+    if (out && out->kind != PL_POOL_ORTHO_UN8x4 && out->kind != PL_POOL_NORM_UN8x4)
+        return pl_set_error(PL_ERR_ARG, "out is not an RGBA8 pool");
+    int ch = 0;
+    const int rc = decode_batch(ctx, out, n, blobs, offsets, sizes, nullptr, out_slots, nullptr, 1.0f, &ch);
+    if (rc == PL_OK && channels && n > 0) *channels = ch;
+    return rc;
 }
 
 extern "C" int pl_residual_upsample(pl_ctx *ctx, pl_pool *pool, int src_slot, int dst_slot, int tile_size, int tx, int ty)

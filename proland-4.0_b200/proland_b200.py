@@ -31,7 +31,7 @@ EXPORTS = [
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
-    "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev",
+    "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch",
 ]
 
 
@@ -185,6 +185,8 @@ def lib():
                                                    C.c_void_p, C.c_int]
         L.pl_ortho_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.pl_ortho_batch_dev.argtypes = L.pl_ortho_batch.argtypes
+        L.pl_ortho_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.POINTER(C.c_int)]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
         L.pl_timing_collect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -556,7 +558,20 @@ def _ortho_batch(self, scene, ortho, resid, reqs):
                                _ptr(reqs)))
 
 
+def _ortho_decode(self, pool, blobs, out_slots):
+    """blobs: list of bytes (one TIFF blob per byte tile) -> the blobs' channel count"""
+    n = len(blobs)
+    buf = np.frombuffer(b"".join(blobs), np.uint8)
+    sizes = np.array([len(b) for b in blobs], np.uint32)
+    offs = np.concatenate([[0], np.cumsum(sizes[:-1], dtype=np.uint64)]).astype(np.uint64)
+    out_slots = np.ascontiguousarray(out_slots, np.int32)
+    ch = C.c_int(0)
+    check(lib().pl_ortho_decode_batch(self.h, pool.h, n, _ptr(buf), _ptr(offs), _ptr(sizes), _ptr(out_slots), C.byref(ch)))
+    return ch.value
+
+
 SLOT_SCRATCH = -2
+Context.ortho_decode = _ortho_decode
 Context.ortho_noise_init = _ortho_noise_init
 Context.ortho_batch = _ortho_batch
 Context.residual_decode = _residual_decode

@@ -367,3 +367,15 @@ def ortho_quadtree(max_level, *, W=196, face=1, noise_amp=(), noise_color=(1, 1,
                                 _u8(nz), _u8(out))
     assert done == n
     return out
+
+
+def ortho_cpu_read(file_bytes, level, tx, ty, W=196, max_channels=4):
+    """OrthoCPUProducer's reader on a whole file image -> (W, W, channels) uint8, or the negative error code"""
+    buf = np.frombuffer(file_bytes, np.uint8)
+    out = np.empty(W * W * max_channels, np.uint8)
+    ch = C.c_int(0)
+    rc = lib().orc_ortho_cpu_read(_u8(buf), C.c_size_t(len(file_bytes)), C.c_int(level), C.c_int(tx), C.c_int(ty),
+                                  _u8(out), C.byref(ch))
+    if rc < 0:
+        return rc
+    return out[:rc * rc * ch.value].reshape(rc, rc, ch.value).copy()

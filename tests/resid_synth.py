@@ -127,3 +127,64 @@ def container_from_tiles(tiles, min_level, max_level, tile_size, root=(0, 0, 0),
         body += b
     head = struct.pack("<6if", min_level, max_level, tile_size, root[0], root[1], root[2], scale)
     return head + struct.pack("<%dI" % len(offsets), *offsets) + body
+
+
+# ------------------------------------------------------------------------------------- ortho residual files
+
+def ortho_tiff_blob(tile, level=6, compression=32946):
+    """tile: (w, w, channels) uint8 -> the TIFF ColorMipmap::produceTile writes
+    (preprocess/terrain/ColorMipmap.cpp:312-325): channels x 8-bit samples, contiguous, one DEFLATE strip.
+    With more than two samples the BitsPerSample values do not fit the tag's value field and sit at an offset,
+    as libtiff writes them."""
+    tile = np.ascontiguousarray(tile, np.uint8)
+    w, ch = tile.shape[0], tile.shape[2]
+    raw = tile.tobytes()
+    strip = raw if compression == 1 else zlib.compress(raw, level)
+    strip_len = len(strip)
+    if len(strip) % 2:
+        strip += b"\0"
+    extra = b""
+    bps_val = 8 | (8 << 16) if ch == 2 else 8
+    extra_off = 8 + len(strip)
+    if ch > 2:
+        extra = struct.pack("<%dH" % ch, *([8] * ch))
+        bps_val = extra_off
+    ifd_off = extra_off + len(extra)
+    tags = [(256, 4, 1, w), (257, 4, 1, w), (258, 3, ch, bps_val), (259, 3, 1, compression),
+            (262, 3, 1, 1 if ch == 1 else 2), (273, 4, 1, 8), (274, 3, 1, 4), (277, 3, 1, ch),
+            (279, 4, 1, strip_len), (284, 3, 1, 1)]
+    out = b"II*\0" + struct.pack("<I", ifd_off) + strip + extra + struct.pack("<H", len(tags))
+    for tag, typ, cnt, val in tags:
+        out += struct.pack("<HHII", tag, typ, cnt, val)
+    return out + struct.pack("<I", 0)
+
+
+def ortho_container(tiles, max_level, tile_size=192, channels=3, root=(0, 0, 0), flags=0, level=6):
+    """tiles: {(level, tx, ty): (w, w, channels) uint8} for every tile of levels 0..max_level -> file bytes in the
+    format OrthoCPUProducer reads (OrthoCPUProducer.cpp:84-118): 7 int32, (begin, end) int64 per tile id, blobs."""
+    ntiles = (4 ** (max_level + 1) - 1) // 3
+    blobs, offs = [], []
+    pos = 0
+    for tid in range(ntiles):
+        l = 0
+        while (4 ** (l + 1) - 1) // 3 <= tid:
+            l += 1
+        k = tid - (4 ** l - 1) // 3
+        tx, ty = k % (1 << l), k // (1 << l)
+        b = ortho_tiff_blob(tiles[(l, tx, ty)], level)
+        blobs.append(b)
+        offs.append((pos, pos + len(b)))
+        pos += len(b)
+    head = struct.pack("<7i", max_level, tile_size, channels, root[0], root[1], root[2], flags)
+    table = b"".join(struct.pack("<qq", a, b) for a, b in offs)
+    return head + table + b"".join(blobs)
+
+
+def ortho_container_blob(file_bytes, level, tx, ty):
+    """what the host side does before the decode call: header, offset table, tile id -> the blob's bytes"""
+    max_level = struct.unpack_from("<i", file_bytes, 0)[0]
+    ntiles = (4 ** (max_level + 1) - 1) // 3
+    header = 28 + 16 * ntiles
+    tid = tx + ty * (1 << level) + (4 ** level - 1) // 3
+    a, b = struct.unpack_from("<qq", file_bytes, 28 + 16 * tid)
+    return file_bytes[header + a:header + b]

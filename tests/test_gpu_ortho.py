@@ -226,3 +226,95 @@ def test_ortho_producer_max_level(ph):
     with ph.Scene(xml) as scene:
         ortho = scene.producer("groundOrthoGpu1")
         assert ortho.has_tile(7, 3, 3) and not ortho.has_tile(8, 3, 3)
+
+
+# ------------------------------------------------------------- OrthoCPUProducer: residual files on the device
+
+def _ortho_file(channels, max_level=1, seed=3, W=196):
+    import resid_synth as rs
+    rng = np.random.default_rng(seed)
+    tiles = {}
+    for l in range(max_level + 1):
+        for ty in range(1 << l):
+            for tx in range(1 << l):
+                t = (128 + rng.integers(-9, 10, (W, W, channels))).astype(np.uint8)
+                t[:40] = 128
+                tiles[(l, tx, ty)] = t
+    return tiles, rs.ortho_container(tiles, max_level, W - 4, channels)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+def test_ortho_decode_batch_matches_oracle_reader(plb, ctx, oracle, channels):
+    """pl_ortho_decode_batch (OrthoCPUProducer.cpp:205-232 on the device) against the oracle's reader of the same
+    file, byte for byte, for 1..4 channel files; unused channels of the RGBA8 slot are 0"""
+    import resid_synth as rs
+    tiles, data = _ortho_file(channels)
+    keys = sorted(tiles)
+    pool = ctx.pool(plb.POOL_ORTHO, 196, len(keys))
+    got_ch = ctx.ortho_decode(pool, [rs.ortho_container_blob(data, *k) for k in keys], list(range(len(keys))))
+    assert got_ch == channels
+    for slot, k in enumerate(keys):
+        got = pool.download(slot)
+        want = oracle.ortho_cpu_read(data, *k)
+        assert np.array_equal(got[..., :channels], want), k
+        assert (got[..., channels:] == 0).all()
+
+
+def test_ortho_decode_errors(plb, ctx):
+    import resid_synth as rs
+    tiles, data = _ortho_file(3)
+    pool = ctx.pool(plb.POOL_ORTHO, 196, 2)
+    good = rs.ortho_container_blob(data, 0, 0, 0)
+    bad = bytearray(good)
+    bad[40:60] = b"\xff" * 20                                       # garbage in the DEFLATE stream
+    with pytest.raises(plb.PlError) as e:
+        ctx.ortho_decode(pool, [bytes(bad)], [0])
+    assert e.value.code == plb.PL_ERR_CORRUPT
+    with pytest.raises(plb.PlError) as e:                           # a 100-texel tile into a 196-texel pool
+        ctx.ortho_decode(pool, [rs.ortho_tiff_blob(np.zeros((100, 100, 3), np.uint8))], [0])
+    assert e.value.code == plb.PL_ERR_CORRUPT
+    # an elevation residual blob is 2 x 8-bit samples per texel (ResidualProducer's int16): a legal 2-channel byte tile
+    assert ctx.ortho_decode(pool, [rs.tiff_blob(np.full((196, 196), 0x0201, np.int16))], [0]) == 2
+    assert (pool.download(0) == np.array([1, 2, 0, 0], np.uint8)).all()
+    with pytest.raises(plb.PlError):
+        ctx.ortho_decode(pool, [good], [2])                         # slot out of range
+    rpool = ctx.pool(plb.POOL_RESID_I16, 197, 2)
+    with pytest.raises(plb.PlError):                                # the residual entry point refuses byte pools and v.v.
+        ctx.residual_decode(pool, [good], [196], [0])
+    with pytest.raises(plb.PlError):
+        ctx.ortho_decode(rpool, [good], [0])
+    assert ctx.ortho_decode(pool, [good], [1]) == 3
+
+
+@pytest.mark.parametrize("hsv", [0, 1])
+def test_ortho_file_to_tiles(plb, ctx, oracle, hsv):
+    """the whole ortho chain of earth-like archives: residual file -> device decode -> OrthoProducer pass with
+    residuals on every tile of levels 0..2, against the oracle fed by its own reader"""
+    import resid_synth as rs
+    W, L = 196, 2
+    tiles, data = _ortho_file(3, max_level=L, seed=11)
+    keys = [(l, tx, ty) for l in range(L + 1) for ty in range(1 << l) for tx in range(1 << l)]
+    n = len(keys)
+    sc = plb.ortho_scene(tile_w=W, channels=3, hsv=hsv, cnoise=(70, 80, 100, 60), rnoise=(60, 150, 20, 99),
+                         noise_amp=[0, 30, 60], face=2, scale=2.0)
+    pool, rpool = ctx.pool(plb.POOL_ORTHO, W, n), ctx.pool(plb.POOL_ORTHO, W, n)
+    nz = ctx.ortho_noise_init(W, want_host=True)
+    assert ctx.ortho_decode(rpool, [rs.ortho_container_blob(data, *k) for k in keys], list(range(n))) == 3
+    slot = {k: i for i, k in enumerate(keys)}
+    for l in range(L + 1):
+        lk = [k for k in keys if k[0] == l]
+        reqs = plb.ortho_make_reqs(sc, lk, [1] * len(lk))
+        for q, k in zip(reqs, lk):
+            q["out_slot"] = slot[k]
+            q["resid_slot"] = slot[k]
+            q["parent_slot"] = slot[(l - 1, k[1] // 2, k[2] // 2)] if l else -1
+        ctx.ortho_batch(sc, pool, rpool, reqs)
+    ctx.sync()
+    ref = {}
+    for k in keys:
+        l, tx, ty = k
+        p = oracle.ortho_uniforms(l, tx, ty, W=W, face=2, noise_amp=[0, 30, 60], noise_color=list(sc.noise_color),
+                                  root_noise_color=list(sc.root_noise_color), hsv=hsv, scale=2.0, has_residual=1)
+        parent = ref[(l - 1, tx // 2, ty // 2)] if l else None
+        ref[k] = oracle.ortho_tile(p, parent, oracle.ortho_cpu_read(data, *k), nz, channels=3)
+        _assert_same(pool.download(slot[k]), ref[k], "tile %s" % (k,))

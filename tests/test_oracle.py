@@ -345,3 +345,33 @@ def test_ortho_make_req_matches_oracle(oracle, plb):
     for k in ("dx", "dy", "noise_r", "noise_l", "level", "tx", "ty"):
         assert got[k] == one[k]
     assert np.array_equal(got["noise_color"], one["noise_color"])
+
+
+def _ortho_file(channels, max_level=1, seed=3):
+    import resid_synth as rs
+    rng = np.random.default_rng(seed)
+    tiles = {}
+    for l in range(max_level + 1):
+        for ty in range(1 << l):
+            for tx in range(1 << l):
+                t = (128 + rng.integers(-9, 10, (196, 196, channels))).astype(np.uint8)
+                t[:40] = 128                                        # long runs: DEFLATE matches far behind
+                tiles[(l, tx, ty)] = t
+    return tiles, rs.ortho_container(tiles, max_level, 192, channels)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4])
+def test_ortho_cpu_reader(oracle, channels):
+    """OrthoCPUProducer's reader (OrthoCPUProducer.cpp:84-118,160-246) on a file in ColorMipmap's format: tile id,
+    offset table, TIFF strip; the blob python's zlib inflates is what the oracle returns"""
+    import resid_synth as rs
+    tiles, data = _ortho_file(channels)
+    for key, want in tiles.items():
+        got = oracle.ortho_cpu_read(data, *key)
+        assert np.array_equal(got, want), key
+        blob = rs.ortho_container_blob(data, *key)
+        assert blob[:4] == b"II*\0"
+    assert oracle.ortho_cpu_read(data, 2, 0, 0) == -1               # level > maxLevel
+    dxt = bytearray(data)
+    dxt[24] = 1                                                     # flags & 1: DXT blobs are not TIFFs
+    assert oracle.ortho_cpu_read(bytes(dxt), 0, 0, 0) == -2
