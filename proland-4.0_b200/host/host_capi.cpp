@@ -14,6 +14,7 @@
 #include "proland/dem/ElevationProducer.h"
 #include "proland/dem/NormalProducer.h"
 #include "proland/dem/ResidualProducer.h"
+#include "proland/ortho/OrthoCPUProducer.h"
 #include "proland/ortho/OrthoProducer.h"
 #include "proland/producer/TileCache.h"
 #include "proland/producer/TileProducer.h"
@@ -306,6 +307,7 @@ int plh_producer_counts(void *prod, unsigned long long out[2])
     if (ElevationProducer *e = dynamic_cast<ElevationProducer *>(p)) { out[0] = e->getTileCount(); out[1] = e->getBatchCount(); }
     else if (NormalProducer *n = dynamic_cast<NormalProducer *>(p)) { out[0] = n->getTileCount(); out[1] = n->getBatchCount(); }
     else if (OrthoProducer *o = dynamic_cast<OrthoProducer *>(p)) { out[0] = o->getTileCount(); out[1] = o->getBatchCount(); }
+    else if (OrthoCPUProducer *c = dynamic_cast<OrthoCPUProducer *>(p)) { out[0] = c->getTileCount(); }
     else if (ResidualProducer *r = dynamic_cast<ResidualProducer *>(p)) { out[0] = r->getTileCount(); }
     else return -1;
     return 0;

@@ -42,13 +42,14 @@ void ElevationProducer::init(ptr<TileCache> cache, ptr<TileProducer> residualTil
     this->context = storage->getContext();
     /* demNoiseFactory->get(tileWidth), ElevationProducer.cpp:176 */
     context->ensureNoise(tileWidth);
-    context->addSource(this);
+    BatchSourceRegistration registration(context.get(), this);
     if (residualTiles != NULL) {
         GPUTileStorage *rs = dynamic_cast<GPUTileStorage *>(residualTiles->getCache()->getStorage().get());
         if (rs == NULL || rs->getInternalFormat() != R32F || rs->getContext() != context) {
             throw std::invalid_argument("ElevationProducer: residual tiles must live in a float storage of the same device");
         }
     }
+    registration.commit();
 }
 
 ElevationProducer::~ElevationProducer()

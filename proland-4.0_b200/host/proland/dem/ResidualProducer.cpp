@@ -36,7 +36,7 @@ void ResidualProducer::init(ptr<TileCache> cache, const char *name, int deltaLev
         throw std::invalid_argument("ResidualProducer: bad tile storage");
     }
     context = storage->getContext();
-    context->addSource(this);
+    BatchSourceRegistration registration(context.get(), this);
 
     if (strlen(name) == 0) {
         /* no file: all-zero residuals of any level (ResidualProducer.cpp:76-84) */
@@ -49,6 +49,7 @@ void ResidualProducer::init(ptr<TileCache> cache, const char *name, int deltaLev
         this->rootTy = 0;
         this->scale = 1.0;
         this->header = 0;
+        registration.commit();
         return;
     }
 
@@ -102,6 +103,7 @@ void ResidualProducer::init(ptr<TileCache> cache, const char *name, int deltaLev
         }
     }
     assert(fileData == NULL || this->deltaLevel <= minLevel);
+    registration.commit();
 }
 
 ResidualProducer::~ResidualProducer()

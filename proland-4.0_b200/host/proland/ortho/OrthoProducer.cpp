@@ -60,7 +60,7 @@ void OrthoProducer::init(ptr<TileCache> cache, ptr<TileProducer> residualTiles, 
     }
     /* orthoNoiseFactory->get(tileWidth), OrthoProducer.cpp:155 */
     context->ensureOrthoNoise(tileWidth);
-    context->addSource(this);
+    BatchSourceRegistration registration(context.get(), this);
     if (residualTiles != NULL) {
         GPUTileStorage *rs = dynamic_cast<GPUTileStorage *>(residualTiles->getCache()->getStorage().get());
         if (rs == NULL || (rs->getInternalFormat() != RGBA8 && rs->getInternalFormat() != RGB8) ||
@@ -71,6 +71,7 @@ void OrthoProducer::init(ptr<TileCache> cache, ptr<TileProducer> residualTiles, 
         scene.channels = rs->getComponents();
         assert(storage->getComponents() >= scene.channels);
     }
+    registration.commit();
 }
 
 OrthoProducer::~OrthoProducer()

@@ -45,6 +45,30 @@ private:
     int channels;
 };
 
+/* CPUTileStorage<unsigned char> (`cpuByteTileStorage`): the ortho residual tile pool.  In the reference
+ * OrthoProducer::doCreateTile uploads CPUSlot::data into residualTexture for every tile
+ * (ortho/OrthoProducer.cpp:296-318); here the decoded bytes stay on the device in an RGBA8 pool
+ * (PL_POOL_ORTHO_UN8x4 / _NORM_UN8x4; a tile with fewer channels uses the first bytes of each texel). */
+template <>
+PROLAND_API class CPUTileStorage<unsigned char> : public GPUTileStorage
+{
+public:
+    typedef GPUTileStorage::GPUSlot CPUSlot;
+
+    CPUTileStorage(int tileSize, int channels, int capacity, ptr<DeviceContext> context = NULL) :
+        GPUTileStorage(tileSize, capacity, channels == 4 ? RGBA8 : RGB8, NEAREST, NEAREST, context), channels(channels)
+    {
+        if (channels < 1 || channels > 4) {
+            throw std::invalid_argument("cpuByteTileStorage: 1 to 4 channels");
+        }
+    }
+    int getChannels() { return channels; }
+    virtual int getComponents() const { return channels; }
+
+private:
+    int channels;
+};
+
 }  // namespace proland
 
 #endif

@@ -87,6 +87,19 @@ void DeviceContext::ensureOrthoNoise(int tileWidth)
     }
 }
 
+BatchSourceRegistration::BatchSourceRegistration(DeviceContext *context, BatchSource *source) :
+    context(context), source(source), committed(false)
+{
+    context->addSource(source);
+}
+
+BatchSourceRegistration::~BatchSourceRegistration()
+{
+    if (!committed) {
+        context->removeSource(source);
+    }
+}
+
 void DeviceContext::addSource(BatchSource *s)
 {
     sources.push_back(s);

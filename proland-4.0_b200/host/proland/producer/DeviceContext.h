@@ -38,6 +38,24 @@ public:
     virtual void flushBatch() = 0;
 };
 
+class DeviceContext;
+
+/* Registers a producer with its context for the length of an init(); unless commit() is reached the
+ * registration is undone -- a constructor that throws runs no destructor, and the context must not keep a
+ * pointer to the dead object. */
+class BatchSourceRegistration
+{
+public:
+    BatchSourceRegistration(DeviceContext *context, BatchSource *source);
+    ~BatchSourceRegistration();
+    void commit() { committed = true; }
+
+private:
+    DeviceContext *context;
+    BatchSource *source;
+    bool committed;
+};
+
 class DeviceContext : public Object
 {
 public:

@@ -52,7 +52,7 @@ public:
 
     TextureInternalFormat getInternalFormat() const { return internalf; }
     const char *getInternalFormatName() const;
-    int getComponents() const;
+    virtual int getComponents() const;
     /* LINEAR only when both min and mag are: what a texel fetch at +0.25 sees */
     TextureFilter getFilter() const { return (minFilter == LINEAR && magFilter == LINEAR) ? LINEAR : NEAREST; }
     ptr<DeviceContext> getContext() const { return context; }

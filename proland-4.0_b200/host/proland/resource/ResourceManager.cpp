@@ -10,6 +10,7 @@
 #include "ork/BatchScheduler.h"
 #include "proland/dem/ElevationProducer.h"
 #include "proland/dem/NormalProducer.h"
+#include "proland/ortho/OrthoCPUProducer.h"
 #include "proland/ortho/OrthoProducer.h"
 #include "proland/dem/ResidualProducer.h"
 #include "proland/producer/CPUTileStorage.h"
@@ -83,13 +84,13 @@ void getFloatParameter(const XmlElement *e, const char *name, float *out)
 
 bool isStorage(const std::string &n)
 {
-    return n == "gpuTileStorage" || n == "cpuFloatTileStorage";
+    return n == "gpuTileStorage" || n == "cpuFloatTileStorage" || n == "cpuByteTileStorage";
 }
 
 bool isKnown(const std::string &n)
 {
     return isStorage(n) || n == "multithreadScheduler" || n == "tileCache" || n == "residualProducer" ||
-           n == "elevationProducer" || n == "normalProducer" || n == "orthoProducer";
+           n == "elevationProducer" || n == "normalProducer" || n == "orthoProducer" || n == "orthoCpuProducer";
 }
 
 }  // namespace
@@ -235,6 +236,9 @@ ptr<Object> ResourceManager::createStorage(const XmlElement *e)
     getIntParameter(e, "tileSize", &tileSize);
     getIntParameter(e, "channels", &channels);
     getIntParameter(e, "capacity", &capacity);
+    if (e->name == "cpuByteTileStorage") {
+        return new CPUTileStorage<unsigned char>(tileSize, channels, capacity, context);
+    }
     return new CPUTileStorage<float>(tileSize, channels, capacity, context);
 }
 
@@ -346,6 +350,15 @@ ptr<Object> ResourceManager::create(const std::string &name, const XmlElement *e
         if (e->Attribute("gridSize") != NULL) getIntParameter(e, "gridSize", &gridSize);
         const bool deform = e->Attribute("deform") != NULL && strcmp(e->Attribute("deform"), "sphere") == 0;
         return new NormalProducer(cache, elevations, gridSize, deform);
+    }
+    if (e->name == "orthoCpuProducer") {
+        /* OrthoCPUProducer.cpp:248-266 */
+        checkParameters(e, "name,cache,file,");
+        ptr<TileCache> cache = loadResource(getParameter(e, "cache")).cast<TileCache>();
+        if (cache == NULL) fail(e, "cache is not a TileCache");
+        std::string file;
+        if (e->Attribute("file") != NULL) file = findFile(getParameter(e, "file"));
+        return new OrthoCPUProducer(cache, file.c_str());
     }
     if (e->name == "orthoProducer") {
         /* OrthoProducer.cpp:440-512 */

@@ -157,7 +157,7 @@ class Producer:
     def tile_shape(self):
         w = self.info()["tile_size"]
         return {"ElevationProducer": ((w, w, 3), np.float32), "ResidualProducer": ((w, w), np.float32),
-                "OrthoProducer": ((w, w, 4), np.uint8), "NormalProducer": None}.get(self.type) or ((w, w, self._norm_channels), np.uint8)
+                "OrthoProducer": ((w, w, 4), np.uint8), "OrthoCPUProducer": ((w, w, 4), np.uint8), "NormalProducer": None}.get(self.type) or ((w, w, self._norm_channels), np.uint8)
 
     _norm_channels = 2
 

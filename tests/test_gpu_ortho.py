@@ -318,3 +318,78 @@ def test_ortho_file_to_tiles(plb, ctx, oracle, hsv):
         parent = ref[(l - 1, tx // 2, ty // 2)] if l else None
         ref[k] = oracle.ortho_tile(p, parent, oracle.ortho_cpu_read(data, *k), nz, channels=3)
         _assert_same(pool.download(slot[k]), ref[k], "tile %s" % (k,))
+
+
+ORTHO_FILE_XML = """<?xml version="1.0" ?>
+<archive>
+    <multithreadScheduler name="defaultScheduler" nthreads="3" fps="0"/>
+    <tileCache name="groundOrthoCpu" scheduler="defaultScheduler">
+        <cpuByteTileStorage tileSize="196" channels="%d" capacity="64"/>
+    </tileCache>
+    <orthoCpuProducer name="groundOrthoCpu2" cache="groundOrthoCpu" file="RGB2.dat"/>
+    <tileCache name="groundOrthoGpu" scheduler="defaultScheduler">
+        <gpuTileStorage tileSize="196" nTiles="128"
+            internalformat="RGBA8" format="RGBA" type="UNSIGNED_BYTE" min="LINEAR_MIPMAP_LINEAR" mag="LINEAR"
+            anisotropy="16"/>
+    </tileCache>
+    <orthoProducer name="groundOrthoGpu2" cache="groundOrthoGpu" residuals="groundOrthoCpu2"
+        cnoise="70,80,100,60" rnoise="60,150,20,99" noise="0,30,60,90" scale="2" hsv="%s"/>
+</archive>"""
+
+
+@pytest.mark.parametrize("channels,hsv", [(3, "true"), (4, "false")])
+def test_ortho_file_archive_through_the_host_layer(ph, plb, oracle, tmp_path, channels, hsv):
+    """an earth-style ortho archive (preprocess/helloworld.xml:61-64 + an orthoProducer with residuals): XML ->
+    cpuByteTileStorage + orthoCpuProducer (file mapped, blobs inflated on the device) -> orthoProducer.  The file
+    has levels 0..2; level-3 tiles have no residual (OrthoCPUProducer::hasTile) and are pure upsample + noise."""
+    W, L = 196, 2
+    tiles, data = _ortho_file(channels, max_level=L, seed=5)
+    (tmp_path / "RGB2.dat").write_bytes(data)
+    amp = [0, 30, 60, 90]
+    nz = oracle.ortho_noise(W)
+    ncol = [np.float32(v) / np.float32(255) for v in (70, 80, 100, 60)]
+    rcol = [np.float32(v) / np.float32(255) for v in (60, 150, 20, 99)]
+    ref = {}
+    chain = [(0, 0, 0), (1, 1, 0), (2, 3, 1), (3, 6, 2)]
+    for (l, tx, ty) in chain:
+        has = l <= L
+        p = oracle.ortho_uniforms(l, tx, ty, W=W, face=2, noise_amp=amp, noise_color=ncol, root_noise_color=rcol,
+                                  hsv=int(hsv == "true"), scale=2.0, has_residual=int(has))
+        parent = ref[(l - 1, tx // 2, ty // 2)] if l else None
+        res = oracle.ortho_cpu_read(data, l, tx, ty) if has else None
+        ref[(l, tx, ty)] = oracle.ortho_tile(p, parent, res, nz, channels=channels)
+    with ph.Scene(ORTHO_FILE_XML % (channels, hsv), data_dir=str(tmp_path)) as scene:
+        ortho, cpu = scene.producer("groundOrthoGpu2"), scene.producer("groundOrthoCpu2")
+        assert (cpu.type, cpu.task_type) == ("OrthoCPUProducer", "CreateOrthoCPUTile")
+        assert cpu.info()["border"] == 2 and ortho.info()["referenced"] == 1
+        assert cpu.has_tile(2, 0, 0) and not cpu.has_tile(3, 0, 0) and ortho.has_tile(3, 0, 0)
+        t = ortho.get_tile(3, 6, 2)
+        scene.scheduler("defaultScheduler").run([t])
+        assert t.done and ortho.counts()[0] == 4 and cpu.counts()[0] == 3
+        assert np.array_equal(t.download(), ref[(3, 6, 2)])
+        for key in chain[:-1]:
+            a = ortho.find_tile(*key, include_cache=True, done=True)
+            assert a is not None and np.array_equal(a.download(), ref[key]), key
+        r = cpu.find_tile(2, 3, 1, include_cache=True, done=True)
+        assert r is not None and np.array_equal(r.download()[..., :channels], tiles[(2, 3, 1)])
+        ortho.put_tile(t)
+        assert scene.cache("groundOrthoGpu").stats()["used"] == 0 and scene.cache("groundOrthoCpu").stats()["used"] == 0
+
+
+def test_ortho_cpu_producer_missing_file_and_dxt(ph, tmp_path):
+    """a missing file: error log + a producer without tiles (maxLevel = -1, OrthoCPUProducer.cpp:80-85);
+    a DXT file is refused at load time"""
+    ph.lib().plh_quiet_errors(1)
+    try:
+        with ph.Scene(ORTHO_FILE_XML % (3, "false"), data_dir=str(tmp_path)) as scene:
+            assert not scene.producer("groundOrthoCpu2").has_tile(0, 0, 0)
+        _, data = _ortho_file(3, max_level=0)
+        dxt = bytearray(data)
+        dxt[24] = 1
+        (tmp_path / "RGB2.dat").write_bytes(bytes(dxt))
+        scene = ph.Scene(ORTHO_FILE_XML % (3, "false"), data_dir=str(tmp_path))
+        with pytest.raises(ph.HostError):                           # resources load on first use
+            scene.producer("groundOrthoCpu2")
+        scene.close()
+    finally:
+        ph.lib().plh_quiet_errors(0)
