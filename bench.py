@@ -203,6 +203,47 @@ def gpu_fingerprint(pl, ctx, max_level, face=1):
     return out
 
 
+ORTHO_BYTES = 196 * 196 * 4 + 100 * 100 * 4     # RGBA8 tile written + parent quadrant read
+
+
+def ortho_lines(pl, ctx, torch, stream, peak, peak_kind, max_level=7, reps=3):
+    """The ortho path (OrthoProducer) beside the headline: terrain3's hsv scene and a plain-noise
+    scene, the full quadtree of levels 0..max_level of one face through pl_ortho_batch (host-built requests inside the
+    timed region).  Auxiliary numbers: they do not enter `value`."""
+    off = [(4 ** l - 1) // 3 for l in range(max_level + 2)]
+    total = off[max_level + 1]
+    ctx.ortho_noise_init(196)
+    pool = ctx.pool(pl.POOL_ORTHO, 196, total)
+    out = {}
+    scenes = {"ortho_hsv": pl.ortho_scene(hsv=1, cnoise=(70, 80, 100), rnoise=(60, 150, 20), noise_amp=[255] * 17, face=1),
+              "ortho_plain": pl.ortho_scene(hsv=0, cnoise=(127.5, 0, 0, 0), noise_amp=[0] + [255] * 16, face=3)}
+    for name, sc in scenes.items():
+        def sweep():
+            for l in range(max_level + 1):
+                ctx.ortho_batch(sc, pool, None, pl.ortho_make_requests_range(sc, l, 0, 4 ** l, out_slot0=off[l],
+                                                                             parent_slot0=off[l - 1] if l else 0))
+        sweep()
+        ctx.sync()
+        ctx.timing_collect()
+        ctx.timing_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            sweep()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        k_ms, launches, tiles = ctx.timing_collect()["ortho"]
+        ctx.timing_enable(False)
+        gbs = ORTHO_BYTES * tiles / (k_ms * 1e-3) / 1e9
+        out[name] = {"tiles_per_s": total / (ms * 1e-3), "tiles_per_sweep": total, "ms_per_sweep": ms,
+                     "launches_per_sweep": launches // reps,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                  "bytes_per_tile": ORTHO_BYTES, "peak_kind": peak_kind}}
+    pool.close()
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -375,6 +416,9 @@ def main():
                               "checksum_rel_err": abs(gsum - csum) / max(abs(csum), 1e-30),
                               "zmin_equal": glo == clo, "zmax_equal": ghi == chi,
                               "height_range_m": [clo, chi]}
+        if world == 1 and not args.no_cpu_baseline:
+            with torch.cuda.stream(stream):
+                line["other_paths"] = ortho_lines(pl, ctx, torch, stream, peak, peak_kind)
         print(json.dumps(line), flush=True)
 
     ctx.close()
