@@ -393,3 +393,33 @@ def test_ortho_cpu_producer_missing_file_and_dxt(ph, tmp_path):
         scene.close()
     finally:
         ph.lib().plh_quiet_errors(0)
+
+
+def test_ortho_seams_at_scale(plb, ctx):
+    """size-independent property at a size the oracle does not reach: all 1 024 tiles of level 5 (and their 341
+    ancestors) of terrain3's scene -- every pair of neighbouring tiles agrees, byte for byte, on the 4 texels
+    they share (the 2-texel border convention, src/terrain/doc/overview.txt:81-88)"""
+    sc = plb.ortho_scene(**TERRAIN3)
+    L, W = 5, 196
+    n = (4 ** (L + 1) - 1) // 3
+    pool = ctx.pool(plb.POOL_ORTHO, W, n)
+    ctx.ortho_noise_init(W)
+    off = [(4 ** l - 1) // 3 for l in range(L + 2)]
+    for l in range(L + 1):
+        ctx.ortho_batch(sc, pool, None, plb.ortho_make_requests_range(sc, l, 0, 4 ** l, out_slot0=off[l],
+                                                                      parent_slot0=off[l - 1] if l else 0))
+    ctx.sync()
+    side = 1 << L
+    row = None
+    seams = 0
+    for ty in range(side):
+        cur = [pool.download(off[L] + plb.morton_encode(tx, ty)) for tx in range(side)]
+        for tx in range(side - 1):
+            assert np.array_equal(cur[tx][:, W - 4:], cur[tx + 1][:, :4]), (tx, ty)
+            seams += 1
+        if row is not None:
+            for tx in range(side):
+                assert np.array_equal(row[tx][W - 4:, :], cur[tx][:4, :]), (tx, ty)
+                seams += 1
+        row = cur
+    assert seams == 2 * side * (side - 1)

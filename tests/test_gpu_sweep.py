@@ -112,3 +112,51 @@ def test_subtree_sweep_with_residual_params_d4(plb, ctx, oracle):
         s = slot0 + (m - first)
         assert np.array_equal(elev.download(s), e), (tx, ty)
         assert np.array_equal(norm.download(s), nrm), (tx, ty)
+
+
+def test_elevation_seams_at_scale(plb, ctx):
+    """size-independent property at a size the oracle does not reach: the 4 096 tiles of level 6 of config 1's
+    terrain (pl_produce_range, fused kernel) -- every pair of neighbouring tiles holds the same zf and zm on the 5
+    texel columns / rows they share (the 2-texel border convention that makes tiles self-contained,
+    src/terrain/doc/overview.txt:81-88,137-142).  The RG8 normals of the vertices both tiles own agree to within one
+    unorm8 step, and almost always exactly: a tile evaluates positions relative to its own origin in fp32, so the
+    last bit of a component can fall on the other side of a rounding boundary (the oracle shows the same: 1 byte
+    of 93 120 at level 4)."""
+    amp = [-140, -100, -15, -8, 5, 2.5, 1.5, 1, 0.5, 0.25, 0.1, 0.05]
+    L = 6
+    off = [(4 ** l - 1) // 3 for l in range(L + 2)]
+    sc = plb.sweep_scene(noise_amp=amp, face=0, root_quad_size=100000.0, sphere=0, want_stats=1)
+    elev = ctx.pool(plb.POOL_ELEV, 101, off[L + 1])
+    norm = ctx.pool(plb.POOL_NORM2, 97, off[L + 1])
+    ctx.noise_init(101)
+    for l in range(L + 1):
+        ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    ctx.sync()
+    side = 1 << L
+    row = None
+    seams = 0
+    ndiff = [0, 0]      # normal bytes compared / differing
+
+    def normals_close(u, v):
+        d = np.abs(u.astype(np.int16) - v.astype(np.int16))
+        ndiff[0] += d.size
+        ndiff[1] += int((d != 0).sum())
+        return d.max() <= 1
+
+    for ty in range(side):
+        cur = [(elev.download(off[L] + plb.morton_encode(tx, ty)), norm.download(off[L] + plb.morton_encode(tx, ty)))
+               for tx in range(side)]
+        for tx in range(side - 1):
+            (a, na), (b, nb) = cur[tx], cur[tx + 1]
+            assert np.array_equal(a[:, 96:101, 0], b[:, 0:5, 0]) and np.array_equal(a[:, 96:101, 2], b[:, 0:5, 2]), (tx, ty)
+            assert normals_close(na[:, 96], nb[:, 0]), (tx, ty)       # normal texel 96 of a tile is texel 0 of the next
+            seams += 1
+        if row is not None:
+            for tx in range(side):
+                (a, na), (b, nb) = row[tx], cur[tx]
+                assert np.array_equal(a[96:101, :, 0], b[0:5, :, 0]) and np.array_equal(a[96:101, :, 2], b[0:5, :, 2]), (tx, ty)
+                assert normals_close(na[96, :], nb[0, :]), (tx, ty)
+                seams += 1
+        row = cur
+    assert seams == 2 * side * (side - 1)
+    assert ndiff[1] <= 1e-3 * ndiff[0], ndiff

@@ -375,3 +375,34 @@ def test_ortho_cpu_reader(oracle, channels):
     dxt = bytearray(data)
     dxt[24] = 1                                                     # flags & 1: DXT blobs are not TIFFs
     assert oracle.ortho_cpu_read(bytes(dxt), 0, 0, 0) == -2
+
+
+# ------------------------------------------------ the border convention: neighbouring tiles agree on their overlap
+
+def test_tile_seams_of_the_oracle(oracle, plb):
+    """src/terrain/doc/overview.txt:81-88,137-142: tiles carry a 2-texel border so that they are self-contained --
+    two neighbouring tiles of a level must hold the same values on the texels they share (5 columns of an
+    elevation tile, 4 of an ortho tile).  This only works because createDemNoise / createOrthoNoise mirror their
+    border strips and the layer / rotation choice puts the same seed on both sides of an edge
+    (ElevationProducer.cpp:50-128,345-376; OrthoProducer.cpp:48-118,321-352): the oracle's restatement of all
+    of that is what this pins."""
+    import quadtree as qt
+    ref = qt.oracle_quadtree(oracle, 3, noise_amp=FRACTAL)
+    for ty in range(8):
+        for tx in range(8):
+            a = ref[(3, tx, ty)][0]
+            if tx < 7:
+                assert np.array_equal(a[:, 96:101, 0], ref[(3, tx + 1, ty)][0][:, 0:5, 0]), (tx, ty)
+            if ty < 7:
+                assert np.array_equal(a[96:101, :, 0], ref[(3, tx, ty + 1)][0][0:5, :, 0]), (tx, ty)
+    W = 196
+    for hsv in (0, 1):
+        tiles = oracle.ortho_quadtree(3, W=W, face=1, noise_amp=[255] * 5, noise_color=[0.3, 0.3, 0.4, 0.2],
+                                      root_noise_color=[0.2, 0.6, 0.1, 0.5], hsv=hsv)
+        for ty in range(8):
+            for tx in range(8):
+                a = tiles[21 + plb.morton_encode(tx, ty)]
+                if tx < 7:
+                    assert np.array_equal(a[:, W - 4:], tiles[21 + plb.morton_encode(tx + 1, ty)][:, :4]), (hsv, tx, ty)
+                if ty < 7:
+                    assert np.array_equal(a[W - 4:, :], tiles[21 + plb.morton_encode(tx, ty + 1)][:4, :]), (hsv, tx, ty)
