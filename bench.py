@@ -20,6 +20,7 @@ only gathers per-rank counters).  Total work is fixed as N grows -> "strong".
   torchrun ... bench.py --gpus N ...          (one rank per GPU)
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -303,9 +304,21 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL writes its banner / debug lines to stdout by default: stdout carries the ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the communicator is created: stdout carries the ONE
+        # JSON line only, so the creation (init + a first collective) runs with fd 1 pointing at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            ctypes.CDLL(None).fflush(None)      # the banner sits in C stdio's buffer when stdout is a pipe
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:

@@ -1,0 +1,163 @@
+"""Gathering finished tiles and statistics over NCCL / NVLink (north star: "NCCL is used only to gather finished
+tiles or statistics"; SURVEY 8e: measured as a separate number, not part of the production path).
+
+Every rank produces its contiguous Morton range of each level of one planet face (levels below the first
+level that splits evenly are replicated) into a pool laid out for the WHOLE quadtree, so that the tiles of a level
+form one slab per pool and a rank's share is one contiguous piece of it.  Then, for the deepest level:
+
+  stats      all_gather of the per-tile (zmin, zmax) pairs (8 B per tile)            TileSamplerZ's consumers
+  normals    in-place all_gather of the RG8 normal slab (18 848 B per tile)           a renderer on every GPU
+  elevations in-place all_gather of the elevation slab (126 048 B per tile)
+
+timed with CUDA events on the launching stream (max over ranks), reported as bytes received per rank and second.
+Afterwards rank 0 produces the whole level by itself and compares: the gathered slabs must be bit-identical.
+
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/gather_tiles.py [--level 7]
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "proland-4.0_b200"))
+sys.path.insert(0, ROOT)
+import proland_b200 as pl
+
+PLANET = [-3250, -1590, -1125, -795, -561, -397, -140, -100, 15, 8, 5, 2.5, 1.5, 1, 0.5, 0.25, 0.1, 0.05]
+
+
+def split_level(world):
+    """the first level whose tile count splits evenly over the ranks"""
+    l = 0
+    while 4 ** l < world or 4 ** l % world:
+        l += 1
+    return l
+
+
+def rank_range(level, rank, world):
+    """(morton0, n) of the tiles of `level` a rank produces; whole levels above the split level"""
+    if level < split_level(world):
+        return 0, 4 ** level
+    n = 4 ** level // world
+    return rank * n, n
+
+
+class _DeviceBytes:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--level", type=int, default=7)
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)                   # NCCL's version banner goes to stderr: stdout is the one JSON line
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.all_reduce(torch.zeros(1, device="cuda"))
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        ctypes.CDLL(None).fflush(None)          # the banner sits in C stdio's buffer when stdout is a pipe
+        os.dup2(saved, 1)
+        os.close(saved)
+    L = a.level
+    off = [(4 ** l - 1) // 3 for l in range(L + 2)]
+    with pl.Context(local) as ctx:
+        stream = torch.cuda.Stream()
+        ctx.set_stream(stream.cuda_stream)
+        elev = ctx.pool(pl.POOL_ELEV, 101, off[L + 1])
+        norm = ctx.pool(pl.POOL_NORM2, 97, off[L + 1])
+        ctx.noise_init(101)
+        sc = pl.sweep_scene(noise_amp=PLANET, face=3, root_quad_size=12720000.0, sphere=1, want_stats=1)
+
+        def produce(r, w):
+            for l in range(L + 1):
+                m0, n = rank_range(l, r, w)
+                ctx.produce_range(sc, elev, norm, l, m0, n, off[l] + m0, off[l - 1] + (m0 >> 2) if l else 0, m0 >> 2)
+
+        def slab(pool):
+            base = pl.lib().pl_pool_device_ptr(pool.h) + off[L] * pool.slot_bytes
+            return torch.as_tensor(_DeviceBytes(base, 4 ** L * pool.slot_bytes), device="cuda")
+
+        with torch.cuda.stream(stream):
+            produce(rank, world)
+            ctx.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(a.reps):
+                produce(rank, world)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            prod_ms = e0.elapsed_time(e1) / a.reps
+
+            m0, n = rank_range(L, rank, world)
+            results = {}
+            # statistics: what TileSamplerZ reads back, 8 bytes per tile
+            mine = torch.from_numpy(ctx.elev_stats_range(elev, off[L] + m0, n)).cuda()
+            allst = torch.empty((4 ** L, 2), dtype=torch.float32, device="cuda")
+            for name, out, inp in (("stats", allst, mine),):
+                dist.all_gather_into_tensor(out, inp)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(a.reps):
+                    dist.all_gather_into_tensor(out, inp)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                results[name] = e0.elapsed_time(e1) / a.reps
+            for name, pool in (("normals", norm), ("elevations", elev)):
+                full = slab(pool)
+                part = full[m0 * pool.slot_bytes:(m0 + n) * pool.slot_bytes]
+                dist.all_gather_into_tensor(full, part)          # in place: a rank's share is already where it belongs
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(a.reps):
+                    dist.all_gather_into_tensor(full, part)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                results[name] = e0.elapsed_time(e1) / a.reps
+            t = torch.tensor([prod_ms] + [results[k] for k in ("stats", "normals", "elevations")], dtype=torch.float64,
+                             device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            # parity of the gather: every rank now holds the whole level; rank 0 produces it alone and compares
+            got_n, got_e = slab(norm).clone(), slab(elev).clone()
+            sums = torch.stack([got_n.sum(dtype=torch.int64), got_e.sum(dtype=torch.int64)])
+            allsums = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(allsums, sums)
+            identical = all(bool(torch.equal(s, allsums[0])) for s in allsums)
+            if rank == 0:
+                for r in range(world):
+                    produce(r, world)
+                ctx.sync()
+                identical = identical and bool(torch.equal(slab(norm), got_n)) and bool(torch.equal(slab(elev), got_e))
+                st = ctx.elev_stats_range(elev, off[L], 4 ** L)
+                identical = identical and np.array_equal(st, allst.cpu().numpy())
+        if rank == 0:
+            tiles = 4 ** L
+            recv = lambda pool_bytes: (world - 1) / world * tiles * pool_bytes
+            line = {"workload": "gather of the %d finished tiles of level %d of one planet face, %d ranks, "
+                                "in-place NCCL all_gather" % (tiles, L, world),
+                    "n_gpus": world, "production_ms": float(t[0]),
+                    "production_pairs_per_s": sum(rank_range(l, 0, world)[1] for l in range(L + 1)) * world / (float(t[0]) * 1e-3),
+                    "identical_to_single_gpu": bool(identical)}
+            for i, (k, b) in enumerate((("stats", 8), ("normals", norm.slot_bytes), ("elevations", elev.slot_bytes))):
+                ms = float(t[1 + i])
+                line[k] = {"ms": ms, "bytes_received_per_rank": recv(b), "GBps_per_rank": recv(b) / (ms * 1e-3) / 1e9}
+            print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
