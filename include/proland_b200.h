@@ -100,6 +100,20 @@ void *pl_pool_device_ptr(pl_pool *pool);
 int pl_pool_download(pl_pool *pool, int slot, void *host, size_t bytes);
 int pl_pool_upload(pl_pool *pool, int slot, const void *host, size_t bytes);
 
+/* Peers: the copies of a pool on the other GPUs of one box (one process per GPU).  pl_pool_export gives the
+ * PL_IPC_HANDLE_BYTES-byte CUDA IPC handle of the pool's memory; after the processes have exchanged them (any
+ * transport: torch.distributed.all_gather in tools/gather_tiles.py) pl_pool_attach_peers(handles of all n ranks in
+ * rank order, own rank) maps the others' pools (peer access over NVLink).  With pl_pool_push_to_peers(norm, 1) the
+ * fused elevation + normal kernel stores every finished RG8 normal tile into the same slot of every peer's pool
+ * as well: the "gather finished tiles" step of a multi-GPU sweep rides on the producing kernel, tile
+ * by tile, instead of a collective after it.  Slot numbering must be the same on all ranks; a consumer reads the
+ * tiles after the producer's stream has been synchronised and the ranks have met (a barrier).  All pools of the
+ * group must have the same kind, tile_w and capacity. */
+#define PL_IPC_HANDLE_BYTES 64
+int pl_pool_export(pl_pool *pool, void *handle64);
+int pl_pool_attach_peers(pl_pool *pool, int n, const void *handles, int self);
+int pl_pool_push_to_peers(pl_pool *pool, int on);
+
 /* ------------------------------------------------------------------- noise */
 
 /* createDemNoise (ElevationProducer.cpp:50-133): builds the six W x W layers

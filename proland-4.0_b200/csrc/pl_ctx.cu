@@ -476,9 +476,49 @@ extern "C" void pl_pool_destroy(pl_pool *p)
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
+    for (int i = 0; i < p->npeers; ++i) cudaIpcCloseMemHandle(p->peer_base[i]);
     if (p->base) cudaFree(p->base);
     if (p->stats) cudaFree(p->stats);
     delete p;
+}
+
+/* ---- peers: the copies of a pool on the other GPUs of the box ---------------------------------- */
+
+extern "C" int pl_pool_export(pl_pool *p, void *handle64)
+{
+    if (!p || !handle64) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PL_IPC_HANDLE_BYTES, "handle size");
+    PL_CUDA(cudaSetDevice(p->ctx->device));
+    cudaIpcMemHandle_t h;
+    PL_CUDA(cudaIpcGetMemHandle(&h, p->base));
+    memcpy(handle64, &h, sizeof(h));
+    return PL_OK;
+}
+
+extern "C" int pl_pool_attach_peers(pl_pool *p, int n, const void *handles, int self)
+{
+    if (!p || !handles || n < 1 || n > pl_pool::kMaxPeers + 1 || self < 0 || self >= n)
+        return pl_set_error(PL_ERR_ARG, "pl_pool_attach_peers: %d handles, self %d (at most %d GPUs)", n, self, pl_pool::kMaxPeers + 1);
+    if (p->npeers) return pl_set_error(PL_ERR_ARG, "peers are already attached");
+    PL_CUDA(cudaSetDevice(p->ctx->device));
+    for (int i = 0; i < n; ++i) {
+        if (i == self) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *) handles + (size_t) i * PL_IPC_HANDLE_BYTES, sizeof(h));
+        void *ptr = nullptr;
+        PL_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        p->peer_base[p->npeers++] = (uint8_t *) ptr;
+    }
+    return PL_OK;
+}
+
+extern "C" int pl_pool_push_to_peers(pl_pool *p, int on)
+{
+    if (!p) return pl_set_error(PL_ERR_ARG, "pool is NULL");
+    if (on && p->kind != PL_POOL_NORM_UN8x2) return pl_set_error(PL_ERR_ARG, "only RG8 normal pools push their tiles");
+    if (on && !p->npeers) return pl_set_error(PL_ERR_ARG, "no peers attached");
+    p->push = on ? 1 : 0;
+    return PL_OK;
 }
 
 extern "C" int pl_pool_capacity(const pl_pool *p) { return p ? p->capacity : 0; }

@@ -36,6 +36,12 @@ struct pl_pool {
     size_t tile_bytes;  /* reference layout */
     uint8_t *base;      /* device */
     float2 *stats;      /* ELEV only: per-slot (zmin, zmax) */
+    /* peer copies of this pool on the other GPUs of the box (pl_pool_attach_peers): device pointers into
+     * their memory, mapped through CUDA IPC; kernels that push finished tiles store to them over NVLink */
+    enum { kMaxPeers = 7 };
+    int npeers;
+    int push;              /* NORM pools: the fused kernel also stores every tile into the peers */
+    uint8_t *peer_base[kMaxPeers];
     CUtensorMap tm_parent; /* ELEV only: 3-D map over the zf/zc/zm planes, box = parent window */
     int box_w, box_h;
 };

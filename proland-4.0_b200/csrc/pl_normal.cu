@@ -264,6 +264,8 @@ int pl_norm_fill_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_po
     a.nbands = a.W / kBandRows > 0 ? a.W / kBandRows : 1;
     a.max_rows = a.W - (a.nbands - 1) * kBandRows;
     a.norm_slot_bytes = (long long) norm->slot_bytes;
+    a.npeers = norm->push ? norm->npeers : 0;
+    for (int p = 0; p < a.npeers; ++p) a.peer_delta[p] = (long long) (norm->peer_base[p] - norm->base);
     return PL_OK;
 }
 

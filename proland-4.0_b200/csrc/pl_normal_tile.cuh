@@ -30,6 +30,10 @@ struct NormArgs {
     int parent_linear;       /* normal storage filter (parent coarse normal fetch) */
     int nbands, max_rows;    /* bands per tile, rows of the largest band */
     long long norm_slot_bytes;
+    /* push of finished normal tiles to the peer GPUs (pl_pool_attach_peers): byte distance from this GPU's
+     * normal pool to each peer's mapping of its own */
+    int npeers;
+    long long peer_delta[7];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -162,9 +166,9 @@ __device__ __forceinline__ int row_shift(int g) { return ((g + 3) >> 1) & 1; }
 /* Normals of one tile.  zs: the tile's zm plane (EW rows of pitch EPITCH) in shared memory; pos: 3
  * position planes of POS_ROWS x GWP; ulut: the two uv tables; out: the tile's RG8 texels in HBM.
  * All threads of the CTA call this; it contains __syncthreads(). */
-template <int TW, bool SPHERE, bool LINEAR, int NT>
+template <int TW, bool SPHERE, bool LINEAR, int NT, bool PUSH = false>
 __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const float *ulut, const pl_norm_req &rq,
-                                            unsigned short *out, const int tid)
+                                            unsigned short *out, const int tid, const NormArgs *peers = nullptr)
 {
     using namespace plf2;
     using GEO = NGeo<TW>;
@@ -384,6 +388,21 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
             if (px1) o[1] = (unsigned short) rg[0][1];
             if (px0 && py1) o[W] = (unsigned short) rg[1][0];
             if (px1 && py1) o[W + 1] = (unsigned short) rg[1][1];
+        }
+    }
+    if (PUSH) {
+        /* The finished tile also goes into every peer's copy of the pool: the gather of finished tiles rides on
+         * the kernel that makes them, tile by tile, instead of a collective after it.  The texels are read back
+         * from this GPU's L2 (they were stored a moment ago) and leave as 16-byte stores, 512 contiguous bytes
+         * per warp instruction: NVLink moves those at full packet size, the 2-byte stores of the producing loop
+         * it would not.  The 16-byte tail may run into the slot's padding, never into the next slot. */
+        __syncthreads();
+        constexpr int N16 = (W * W * 2 + 15) / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(out);
+        for (int i = tid; i < N16; i += NT) {
+            const uint4 v = __ldcg(src + i);
+            for (int p = 0; p < peers->npeers; ++p)
+                reinterpret_cast<uint4 *>(reinterpret_cast<char *>(out) + peers->peer_delta[p])[i] = v;
         }
     }
 }

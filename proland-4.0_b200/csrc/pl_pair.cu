@@ -45,7 +45,7 @@ struct PairSmem {
     static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
 };
 
-template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR>
+template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false>
 __global__ void __launch_bounds__(kPairThreads, 3)
 tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
 {
@@ -78,7 +78,7 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
 
     /* normals from the shared zm plane */
     unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
-    plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads>(zs, work, ulut, nrq, out, tid);
+    plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH>(zs, work, ulut, nrq, out, tid, &na);
 }
 
 template <int RESID>
@@ -88,6 +88,12 @@ int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const pl
     void (*kern)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
         na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true> : tile_pair_kernel<101, 4, RESID, true, false>)
                   : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true> : tile_pair_kernel<101, 4, RESID, false, false>);
+    if (na.npeers > 0) {
+        /* finished normal tiles also go to the peer GPUs (fractal scenes: the variants without residuals) */
+        if (RESID != 0) return pl_set_error(PL_ERR_ARG, "pushing tiles to peers is built for scenes without residuals");
+        kern = na.sphere ? (na.linear ? tile_pair_kernel<101, 4, 0, true, true, true> : tile_pair_kernel<101, 4, 0, true, false, true>)
+                         : (na.linear ? tile_pair_kernel<101, 4, 0, false, true, true> : tile_pair_kernel<101, 4, 0, false, false, true>);
+    }
     PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SM::BYTES));
     pl_timing_begin(ctx, PL_K_PAIR, n);
     kern<<<n, kPairThreads, SM::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);

@@ -25,6 +25,7 @@ EXPORTS = [
     "pl_timing_collect", "pl_pool_create",
     "pl_pool_destroy", "pl_pool_capacity", "pl_pool_tile_w", "pl_pool_tile_bytes",
     "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload",
+    "pl_pool_export", "pl_pool_attach_peers", "pl_pool_push_to_peers",
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
@@ -136,6 +137,9 @@ def lib():
         for f in (L.pl_pool_capacity, L.pl_pool_tile_w, L.pl_pool_tile_bytes, L.pl_pool_slot_bytes,
                   L.pl_pool_device_ptr):
             f.argtypes = [C.c_void_p]
+        L.pl_pool_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.pl_pool_attach_peers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.pl_pool_push_to_peers.argtypes = [C.c_void_p, C.c_int]
         L.pl_pool_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.pl_pool_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.pl_noise_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -310,6 +314,20 @@ class Pool:
         if self.h:
             lib().pl_pool_destroy(self.h)
             self.h = None
+
+    def export(self):
+        """the 64-byte CUDA IPC handle of the pool's memory (pl_pool_export)"""
+        h = np.zeros(64, np.uint8)
+        check(lib().pl_pool_export(self.h, _ptr(h)))
+        return h
+
+    def attach_peers(self, handles, self_rank):
+        """handles: (world, 64) uint8, the exported handles of all ranks in rank order"""
+        hs = np.ascontiguousarray(handles, np.uint8)
+        check(lib().pl_pool_attach_peers(self.h, len(hs), _ptr(hs), self_rank))
+
+    def push_to_peers(self, on=True):
+        check(lib().pl_pool_push_to_peers(self.h, int(on)))
 
     def _shape_dtype(self):
         W = self.tile_w

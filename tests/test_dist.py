@@ -53,3 +53,27 @@ def test_partition_and_gather_world2():
     assert total == 8388606 - 6 * 21          # every subtree tile exactly once across the ranks
     assert tmax == 101.0                      # max over ranks
     assert ids == sorted(f * 16 + m for f in range(1, 7) for m in range(16))
+
+
+def test_gather_partition_covers_every_level_once():
+    """tools/gather_tiles.py: contiguous Morton ranges per rank -- above the split level every tile of a level belongs to
+    exactly one rank, a rank's range of level l + 1 is the children of its range of level l (parents stay local), and a
+    rank's share is one contiguous piece of the level's slab (what makes the all_gather in place)"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gather_tiles", os.path.join(ROOT, "tools", "gather_tiles.py"))
+    gt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gt)
+    for world in (1, 2, 4, 8):
+        ls = gt.split_level(world)
+        assert 4 ** ls % world == 0 and (ls == 0 or 4 ** (ls - 1) % world or 4 ** (ls - 1) < world)
+        for level in range(ls, 8):
+            ranges = [gt.rank_range(level, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and sum(n for _, n in ranges) == 4 ** level
+            for (m0, n), (m1, _) in zip(ranges, ranges[1:]):
+                assert m0 + n == m1
+            for r in range(world):
+                m0, n = ranges[r]
+                c0, cn = gt.rank_range(level + 1, r, world)
+                assert (c0, cn) == (4 * m0, 4 * n)
+        for level in range(ls):
+            assert all(gt.rank_range(level, r, world) == (0, 4 ** level) for r in range(world))

@@ -160,3 +160,24 @@ def test_elevation_seams_at_scale(plb, ctx):
         row = cur
     assert seams == 2 * side * (side - 1)
     assert ndiff[1] <= 1e-3 * ndiff[0], ndiff
+
+
+def test_gather_and_push_between_two_gpus():
+    """tools/gather_tiles.py on 2 GPUs (skipped on a single-GPU box): the in-place NCCL all_gather of finished tiles
+    and statistics, and the fused kernel's push of finished normal tiles into the peer's pool (CUDA IPC + NVLink
+    stores), both bit-identical to single-GPU production"""
+    import json
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "gather_tiles.py"), "--level", "5", "--reps", "2"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert out.stdout.strip().startswith("{"), "stdout must be the JSON line only"
+    assert line["identical_to_single_gpu"] is True
+    assert line["push_from_the_kernel"]["identical_on_every_rank"] is True

@@ -144,6 +144,34 @@ def main():
                 identical = identical and bool(torch.equal(slab(norm), got_n)) and bool(torch.equal(slab(elev), got_e))
                 st = ctx.elev_stats_range(elev, off[L], 4 ** L)
                 identical = identical and np.array_equal(st, allst.cpu().numpy())
+
+            # ---- the same gather WITHOUT a collective: the fused kernel stores every finished normal tile into the
+            # peers' pools over NVLink while it produces (pl_pool_attach_peers / pl_pool_push_to_peers)
+            push = None
+            if world > 1:
+                mine_h = torch.from_numpy(norm.export()).cuda()
+                handles = [torch.zeros_like(mine_h) for _ in range(world)]
+                dist.all_gather(handles, mine_h)
+                norm.attach_peers(torch.stack(handles).cpu().numpy(), rank)
+                slab(norm).zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                norm.push_to_peers(True)
+                produce(rank, world)
+                ctx.sync()
+                dist.barrier()
+                torch.cuda.synchronize()
+                pushed_ok = bool(torch.equal(slab(norm), got_n))        # every rank holds the whole level again
+                e0.record(stream)
+                for _ in range(a.reps):
+                    produce(rank, world)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                dist.barrier()
+                norm.push_to_peers(False)
+                tp = torch.tensor([e0.elapsed_time(e1) / a.reps, 0.0 if pushed_ok else 1.0], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+                push = (float(tp[0]), float(tp[1]) == 0.0)
         if rank == 0:
             tiles = 4 ** L
             recv = lambda pool_bytes: (world - 1) / world * tiles * pool_bytes
@@ -155,6 +183,15 @@ def main():
             for i, (k, b) in enumerate((("stats", 8), ("normals", norm.slot_bytes), ("elevations", elev.slot_bytes))):
                 ms = float(t[1 + i])
                 line[k] = {"ms": ms, "bytes_received_per_rank": recv(b), "GBps_per_rank": recv(b) / (ms * 1e-3) / 1e9}
+            if push:
+                per_rank_tiles = sum(rank_range(l, 0, world)[1] for l in range(L + 1))
+                sent = (world - 1) * per_rank_tiles * 97 * 97 * 2
+                line["push_from_the_kernel"] = {
+                    "what": "production of levels 0..%d with every finished RG8 normal tile also stored into the peers' "
+                            "pools by the fused kernel (no collective)" % L,
+                    "production_ms": push[0], "extra_ms_vs_plain_production": push[0] - float(t[0]),
+                    "all_gather_of_the_normals_ms": float(t[2]), "bytes_sent_per_rank": sent,
+                    "identical_on_every_rank": push[1]}
             print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
