@@ -468,6 +468,7 @@ struct StoreJob {
     int width;       /* w of this tile */
     int out_slot;
     int add_slot;    /* -1: none */
+    int channels;    /* byte tiles (pl_ortho_decode_batch): samples per texel in the dense stream */
 };
 
 /* dense int16 (w x w) -> pitched pool rows; ResidualProducer.cpp:321-338 */
@@ -505,7 +506,7 @@ __global__ void __launch_bounds__(256) ortho_store_kernel(const StoreJob *jobs, 
     const StoreJob J = jobs[blockIdx.x];
     const unsigned char *src = dense + (size_t) blockIdx.x * dense_stride;
     uint32_t *dst = reinterpret_cast<uint32_t *>(pool + (size_t) J.out_slot * slot_bytes);
-    const int w = J.width, ch = J.add_slot;      /* add_slot carries the sample count here */
+    const int w = J.width, ch = J.channels;
     for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
         uint32_t t = 0;
         for (int c = 0; c < ch; ++c) t |= (uint32_t) src[(size_t) k * ch + c] << (8 * c);
@@ -729,7 +730,8 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
         }
         sjobs[j].width = wj;
         sjobs[j].out_slot = os;
-        sjobs[j].add_slot = ortho ? spp : (as < 0 ? -1 : as);
+        sjobs[j].add_slot = ortho || as < 0 ? -1 : as;
+        sjobs[j].channels = spp;
         if (wj > max_w) max_w = wj;
     }
     const size_t dense_stride = ((size_t) max_w * max_w * (ortho ? 4 : 2) + 15) & ~(size_t) 15;
