@@ -72,6 +72,62 @@ def run(ctx, torch, stream, sc, max_level, reps, peak, peak_kind):
             "sha1_levels_0_6": h.hexdigest()[:16], "levels_0_3_sha1": first}
 
 
+def run_residuals(ctx, torch, stream, peak, peak_kind, level=6, reps=3):
+    """ortho residual files on the device: 4^level TIFF/DEFLATE blobs of 196 x 196 x 3 bytes (64 distinct synthetic
+    tiles, zlib level 6, cycled) through pl_ortho_decode_batch, then that level produced WITH its residuals
+    (algorithmic bytes per tile: + 196*196*4 of residual read)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import resid_synth as rs
+    rng = np.random.default_rng(20240612)
+    distinct = []
+    for _ in range(64):
+        base = rng.integers(-6, 7, (W // 4 + 1, W // 4 + 1, 3))
+        t = 128 + np.kron(base, np.ones((4, 4, 1), np.int64))[:W, :W] + rng.integers(-3, 4, (W, W, 3))
+        distinct.append(t.astype(np.uint8))
+    blobs64 = [rs.ortho_tiff_blob(t, 6) for t in distinct]
+    n = 4 ** level
+    blobs = [blobs64[i % 64] for i in range(n)]
+    in_bytes = sum(len(b) for b in blobs)
+    off = [(4 ** l - 1) // 3 for l in range(level + 2)]
+    pool = ctx.pool(pl.POOL_ORTHO, W, off[level + 1])
+    rpool = ctx.pool(pl.POOL_ORTHO, W, n)
+    out = {}
+    assert ctx.ortho_decode(rpool, blobs, list(range(n))) == 3
+    ctx.timing_collect()
+    ctx.timing_enable(True)
+    for _ in range(reps):
+        ctx.ortho_decode(rpool, blobs, list(range(n)))
+    ms = ctx.timing_collect()["residual"][0] / reps
+    ctx.timing_enable(False)
+    assert np.array_equal(rpool.download(5)[..., :3], distinct[5])
+    out["decode"] = {"tiles": n, "tiles_per_s": n / (ms * 1e-3), "ms_per_batch": ms,
+                     "compressed_MBps": in_bytes / (ms * 1e-3) / 1e6, "decoded_GBps": n * W * W * 3 / (ms * 1e-3) / 1e9,
+                     "compression_ratio": n * W * W * 3 / in_bytes}
+    for name, hsv in (("hsv", 1), ("plain", 0)):
+        sc = pl.ortho_scene(channels=3, hsv=hsv, cnoise=(70, 80, 100), rnoise=(60, 150, 20), noise_amp=[255] * 17, face=1)
+        for l in range(level):
+            ctx.ortho_batch(sc, pool, None, pl.ortho_make_requests_range(sc, l, 0, 4 ** l, out_slot0=off[l],
+                                                                         parent_slot0=off[l - 1] if l else 0))
+        reqs = pl.ortho_make_requests_range(sc, level, 0, n, out_slot0=off[level], parent_slot0=off[level - 1])
+        reqs["resid_slot"] = np.arange(n)
+        ctx.ortho_batch(sc, pool, rpool, reqs)
+        ctx.sync()
+        ctx.timing_collect()
+        ctx.timing_enable(True)
+        for _ in range(reps):
+            ctx.ortho_batch(sc, pool, rpool, reqs)
+        k_ms = ctx.timing_collect()["ortho"][0] / reps
+        ctx.timing_enable(False)
+        by = TILE_BYTES + W * W * 4
+        gbs = by * n / (k_ms * 1e-3) / 1e9
+        out[name] = {"tiles": n, "tiles_per_s": n / (k_ms * 1e-3), "ms_per_batch": k_ms,
+                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                                  "bytes_per_tile": by, "peak_kind": peak_kind}}
+    pool.close()
+    rpool.close()
+    return out
+
+
 def main():
     import torch
     ap = argparse.ArgumentParser()
@@ -90,6 +146,7 @@ def main():
         plain = pl.ortho_scene(hsv=0, cnoise=(127.5, 0, 0, 0), noise_amp=[0] + [255] * 16, face=3)
         out["terrain3_hsv"] = run(ctx, torch, stream, hsv, a.max_level, a.reps, peak, peak_kind)
         out["plain"] = run(ctx, torch, stream, plain, a.max_level, a.reps, peak, peak_kind)
+        out["with_residuals"] = run_residuals(ctx, torch, stream, peak, peak_kind)
     out["terrain3_hsv"]["golden_ok"] = out["terrain3_hsv"].pop("levels_0_3_sha1") == golden["terrain3_hsv"]["levels_0_3_sha1"]
     out["plain"]["golden_ok"] = out["plain"].pop("levels_0_3_sha1") == golden["plain"]["levels_0_3_sha1"]
     # CPU baseline: the oracle (a port, OpenMP over the tiles of a level) on a bounded sample
