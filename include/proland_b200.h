@@ -396,6 +396,13 @@ int pl_ortho_batch(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, pl_
 int pl_ortho_batch_dev(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, pl_pool *resid, int n,
                        const pl_ortho_req *dev_reqs);
 
+/* pl_produce_range for ortho tiles: the requests of a Morton range are generated on the device (no per-tile data
+ * crosses the PCIe bus), then the ortho kernel runs on them.  No residuals.  The generated requests are the ones
+ * pl_ortho_make_requests_range builds on the host, byte for byte (pl_debug_download_requests returns them in its
+ * elevation-request array: both request types are 64 bytes). */
+int pl_ortho_produce_range(pl_ctx *ctx, const pl_ortho_scene *scene, pl_pool *ortho, int level, uint64_t morton0, int n,
+                           int out_slot0, int parent_slot0, uint64_t parent_morton0);
+
 /* OrthoCPUProducer::doCreateTile, the TIFF branch (ortho/OrthoCPUProducer.cpp:205-232): n blobs of an ortho
  * residual file (written by ColorMipmap::produceTile, preprocess/terrain/ColorMipmap.cpp:296-325: one
  * little-endian TIFF, one DEFLATE strip of tile_w * tile_w * channels bytes, channels = 1..4 samples of 8 bits),

@@ -123,33 +123,10 @@ extern "C" int pl_ortho_noise_init(pl_ctx *ctx, int W, uint8_t *host_out)
 
 /* --------------------------------------------------------------- host: requests */
 
-static void ortho_fill_req(const PerlinView T, const pl_ortho_scene *sc, int level, int tx, int ty, int has_resid,
-                           pl_ortho_req *q)
-{
-    const int half = (sc->tile_w - 4) / 2;
-    q->out_slot = -1;
-    q->parent_slot = -1;
-    q->resid_slot = -1;                     /* the caller fills in the residual tile's slot when has_resid */
-    (void) has_resid;
-    q->dx = (tx % 2) * half;
-    q->dy = (ty % 2) * half;
-    noise_select(T, level, tx, ty, sc->face, &q->noise_r, &q->noise_l);
-    q->level = level;
-    const float rs = level < sc->n_amp ? sc->noise_amp[level] : 0.0f;
-    if (sc->hsv) {   /* noiseColor * (rs, rs, rs, scale * rs) / 255 */
-        for (int c = 0; c < 3; ++c) q->noise_color[c] = sc->noise_color[c] * rs / 255.0f;
-        q->noise_color[3] = sc->noise_color[3] * (sc->scale * rs) / 255.0f;
-    } else {         /* noiseColor * scale * rs / 255 */
-        for (int c = 0; c < 4; ++c) q->noise_color[c] = sc->noise_color[c] * sc->scale * rs / 255.0f;
-    }
-    q->tx = tx;
-    q->ty = ty;
-    q->pad_[0] = q->pad_[1] = 0;
-}
-
 extern "C" void pl_ortho_make_req(const pl_ortho_scene *sc, int level, int tx, int ty, int has_resid, pl_ortho_req *req)
 {
-    ortho_fill_req(pl_host_perlin(), sc, level, tx, ty, has_resid, req);
+    (void) has_resid;   /* the caller fills in the residual tile's slot */
+    ortho_fill_req(pl_host_perlin(), sc, level, tx, ty, req);
 }
 
 extern "C" int pl_ortho_make_requests_range(const pl_ortho_scene *sc, int level, uint64_t morton0, int n, int out_slot0,
@@ -162,7 +139,7 @@ extern "C" int pl_ortho_make_requests_range(const pl_ortho_scene *sc, int level,
         int tx, ty;
         morton_decode(m, &tx, &ty);
         pl_ortho_req *q = reqs + i;
-        ortho_fill_req(T, sc, level, tx, ty, 0, q);
+        ortho_fill_req(T, sc, level, tx, ty, q);
         q->out_slot = out_slot0 + i;
         q->parent_slot = level > 0 ? parent_slot0 + (int) ((m >> 2) - parent_morton0) : -1;
     };

@@ -126,6 +126,29 @@ PL_HD void elev_fill_req(const PerlinView T, int tile_w, float root_quad_size, c
     req->pad_[0] = req->pad_[1] = 0;
 }
 
+/* the uniforms of one ortho tile, OrthoProducer.cpp:286-366 (slots are left at -1) */
+PL_HD void ortho_fill_req(const PerlinView T, const pl_ortho_scene *sc, int level, int tx, int ty, pl_ortho_req *q)
+{
+    const int half = (sc->tile_w - 4) / 2;
+    q->out_slot = -1;
+    q->parent_slot = -1;
+    q->resid_slot = -1;
+    q->dx = (tx % 2) * half;
+    q->dy = (ty % 2) * half;
+    noise_select(T, level, tx, ty, sc->face, &q->noise_r, &q->noise_l);
+    q->level = level;
+    const float rs = level < sc->n_amp ? sc->noise_amp[level] : 0.0f;
+    if (sc->hsv) {   /* noiseColor * (rs, rs, rs, scale * rs) / 255 */
+        for (int c = 0; c < 3; ++c) q->noise_color[c] = sc->noise_color[c] * rs / 255.0f;
+        q->noise_color[3] = sc->noise_color[3] * (sc->scale * rs) / 255.0f;
+    } else {         /* noiseColor * scale * rs / 255 */
+        for (int c = 0; c < 4; ++c) q->noise_color[c] = sc->noise_color[c] * sc->scale * rs / 255.0f;
+    }
+    q->tx = tx;
+    q->ty = ty;
+    q->pad_[0] = q->pad_[1] = 0;
+}
+
 struct PlV3 { double x, y, z; };
 PL_HD PlV3 v3_unit(PlV3 v, double *len)
 {

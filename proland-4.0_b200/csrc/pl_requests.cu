@@ -186,6 +186,78 @@ extern "C" int pl_make_requests_range(const pl_sweep_scene *sc, int level, uint6
     return PL_OK;
 }
 
+/* ---- the same for ortho tiles: requests generated on the device, then the ortho kernel ---------------- */
+
+namespace {
+
+struct GenOrthoArgs {
+    PerlinView perlin;
+    pl_ortho_req *req;
+    pl_ortho_scene sc;
+    int level, n;
+    unsigned long long morton0, parent_morton0;
+    int out_slot0, parent_slot0;
+};
+
+__global__ void __launch_bounds__(128) gen_ortho_requests_kernel(const GenOrthoArgs g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const unsigned long long m = g.morton0 + (unsigned long long) i;
+    int tx, ty;
+    morton_decode(m, &tx, &ty);
+    pl_ortho_req q;
+    ortho_fill_req(g.perlin, &g.sc, g.level, tx, ty, &q);
+    q.out_slot = g.out_slot0 + i;
+    q.parent_slot = g.level > 0 ? g.parent_slot0 + (int) ((m >> 2) - g.parent_morton0) : -1;
+    g.req[i] = q;
+}
+
+}  // namespace
+
+extern "C" int pl_ortho_produce_range(pl_ctx *ctx, const pl_ortho_scene *sc, pl_pool *ortho, int level, uint64_t morton0,
+                                      int n, int out_slot0, int parent_slot0, uint64_t parent_morton0)
+{
+    if (!ctx || !sc || !ortho) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (level < 0 || level > 24) return pl_set_error(PL_ERR_ARG, "level %d out of range", level);
+    if (n < 0 || morton0 + (uint64_t) n > (1ull << (2 * level))) return pl_set_error(PL_ERR_ARG, "Morton range exceeds level %d", level);
+    if (out_slot0 < 0 || out_slot0 + n > ortho->capacity)
+        return pl_set_error(PL_ERR_POOL_FULL, "slots [%d,%d) exceed the pool capacity", out_slot0, out_slot0 + n);
+    if (sc->n_amp < 0 || sc->n_amp > 32) return pl_set_error(PL_ERR_ARG, "n_amp out of range");
+    if (level > 0 && n > 0) {
+        const uint64_t p_first = morton0 >> 2, p_last = (morton0 + n - 1) >> 2;
+        if (p_first < parent_morton0) return pl_set_error(PL_ERR_ARG, "parent range starts after the first parent");
+        const int64_t s_first = (int64_t) parent_slot0 + (int64_t) (p_first - parent_morton0);
+        const int64_t s_last = (int64_t) parent_slot0 + (int64_t) (p_last - parent_morton0);
+        if (s_first < 0 || s_last >= ortho->capacity) return pl_set_error(PL_ERR_ARG, "parent slots out of range");
+        if (s_first < (int64_t) out_slot0 + n && s_last >= out_slot0)
+            return pl_set_error(PL_ERR_ARG, "parent slots overlap the output slots");
+    }
+    if (n == 0) return PL_OK;
+    PL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_perlin(ctx)) != PL_OK) return rc;
+    if ((rc = ensure_gen_buffers(ctx, n)) != PL_OK) return rc;
+    static_assert(sizeof(pl_ortho_req) == sizeof(pl_elev_req), "the generated ortho requests reuse the elevation request buffer");
+    GenOrthoArgs g;
+    g.perlin.perm = ctx->perlin_perm;
+    g.perlin.g2 = ctx->perlin_g2;
+    g.req = reinterpret_cast<pl_ortho_req *>(ctx->gen_ereq);
+    g.sc = *sc;
+    g.level = level;
+    g.n = n;
+    g.morton0 = morton0;
+    g.parent_morton0 = parent_morton0;
+    g.out_slot0 = out_slot0;
+    g.parent_slot0 = parent_slot0;
+    pl_timing_begin(ctx, PL_K_GENREQ, n);
+    gen_ortho_requests_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return pl_ortho_batch_dev(ctx, sc, ortho, nullptr, n, g.req);
+}
+
 extern "C" int pl_debug_download_requests(pl_ctx *ctx, int n, pl_elev_req *elev_reqs, pl_norm_req *norm_reqs)
 {
     if (!ctx || n < 0 || n > ctx->gen_cap) return pl_set_error(PL_ERR_ARG, "bad argument");

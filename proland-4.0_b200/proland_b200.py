@@ -32,7 +32,7 @@ EXPORTS = [
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
-    "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch",
+    "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
 ]
 
 
@@ -189,6 +189,8 @@ def lib():
                                                    C.c_void_p, C.c_int]
         L.pl_ortho_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.pl_ortho_batch_dev.argtypes = L.pl_ortho_batch.argtypes
+        L.pl_ortho_produce_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                             C.c_uint64]
         L.pl_ortho_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.POINTER(C.c_int)]
         L.pl_timing_enable.argtypes = [C.c_void_p, C.c_int]
@@ -588,7 +590,13 @@ def _ortho_decode(self, pool, blobs, out_slots):
     return ch.value
 
 
+def _ortho_produce_range(self, scene, ortho, level, morton0, n, out_slot0, parent_slot0=0, parent_morton0=0):
+    check(lib().pl_ortho_produce_range(self.h, C.byref(scene), ortho.h, level, morton0, n, out_slot0, parent_slot0,
+                                       parent_morton0))
+
+
 SLOT_SCRATCH = -2
+Context.ortho_produce_range = _ortho_produce_range
 Context.ortho_decode = _ortho_decode
 Context.ortho_noise_init = _ortho_noise_init
 Context.ortho_batch = _ortho_batch

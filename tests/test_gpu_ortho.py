@@ -423,3 +423,35 @@ def test_ortho_seams_at_scale(plb, ctx):
                 seams += 1
         row = cur
     assert seams == 2 * side * (side - 1)
+
+
+def test_ortho_produce_range_device_requests(plb, ctx, oracle):
+    """pl_ortho_produce_range: the requests of a Morton range generated on the device are the host's, byte for byte,
+    and the tiles are the oracle's"""
+    sc = plb.ortho_scene(**dict(TERRAIN3, face=6))
+    L, W = 4, 196
+    off = [(4 ** l - 1) // 3 for l in range(L + 2)]
+    pool = ctx.pool(plb.POOL_ORTHO, W, off[L + 1])
+    ctx.ortho_noise_init(W)
+    launches0 = ctx.launches
+    for l in range(L + 1):
+        ctx.ortho_produce_range(sc, pool, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    ctx.sync()
+    assert ctx.launches - launches0 == 2 * (L + 1)              # request generation + the ortho kernel per level
+    dev, _ = ctx.last_requests(4 ** L)
+    host = plb.ortho_make_requests_range(sc, L, 0, 4 ** L, out_slot0=off[L], parent_slot0=off[L - 1])
+    assert dev.tobytes() == host.tobytes()
+    ref = _oracle_quadtree(oracle, sc, L)
+    _assert_same(np.stack([pool.download(s) for s in range(off[L + 1])]), ref, "device-generated requests")
+    # a partial range in the middle of a level, parents elsewhere
+    pool2 = ctx.pool(plb.POOL_ORTHO, W, 200)
+    for s in range(16):
+        pool2.upload(100 + s, ref[off[2] + s])
+    ctx.ortho_produce_range(sc, pool2, 3, 20, 24, 7, 100 + 5, 5)
+    ctx.sync()
+    for i in range(24):
+        assert np.array_equal(pool2.download(7 + i), ref[off[3] + 20 + i]), i
+    with pytest.raises(plb.PlError):
+        ctx.ortho_produce_range(sc, pool2, 3, 60, 8, 0, 100, 0)         # Morton range exceeds the level
+    with pytest.raises(plb.PlError):
+        ctx.ortho_produce_range(sc, pool2, 3, 0, 8, 196, 100, 0)        # slots exceed the pool

@@ -64,8 +64,21 @@ def run(ctx, torch, stream, sc, max_level, reps, peak, peak_kind):
         h.update(t.tobytes())
         if s < 85:
             first.append(hashlib.sha1(t.tobytes()).hexdigest()[:16])
+    # the same sweep with the requests generated on the device (pl_ortho_produce_range)
+    def sweep_dev():
+        for l in range(max_level + 1):
+            ctx.ortho_produce_range(sc, pool, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    sweep_dev()
+    ctx.sync()
+    e0.record(stream)
+    for _ in range(reps):
+        sweep_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1) / reps
     pool.close()
     return {"tiles_per_sweep": total, "tiles_per_s": total / (ms * 1e-3), "ms_per_sweep": ms, "wall_ms_per_sweep": wall * 1e3,
+            "device_requests": {"tiles_per_s": total / (ms_dev * 1e-3), "ms_per_sweep": ms_dev},
             "kernel": {"launches_per_sweep": launches // reps, "ms_per_sweep": k_ms / reps,
                        "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                                     "bytes_per_tile": TILE_BYTES, "peak_kind": peak_kind}},
