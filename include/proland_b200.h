@@ -1,6 +1,7 @@
 /*
  * proland_b200.h -- C ABI of the B200-native terrain tile-production path
- * (ElevationProducer -> NormalProducer, fed by ResidualProducer).
+ * (ElevationProducer -> NormalProducer, fed by ResidualProducer; and its colour
+ * twin OrthoProducer, fed by OrthoCPUProducer).
  *
  * Plain C, plain pointers and sizes.  This is the boundary a Proland build
  * binds instead of its GLSL draw calls; INTEGRATION.md shows the C++ side.
