@@ -181,3 +181,28 @@ def test_gather_and_push_between_two_gpus():
     assert out.stdout.strip().startswith("{"), "stdout must be the JSON line only"
     assert line["identical_to_single_gpu"] is True
     assert line["push_from_the_kernel"]["identical_on_every_rank"] is True
+
+
+def test_peer_api_errors_on_one_gpu(plb, ctx):
+    """pl_pool_export / attach_peers / push_to_peers argument checking (the two-GPU behaviour is in
+    test_gather_and_push_between_two_gpus)"""
+    norm = ctx.pool(plb.POOL_NORM2, 97, 4)
+    elev = ctx.pool(plb.POOL_ELEV, 101, 4)
+    h = norm.export()
+    assert h.shape == (64,) and h.any()
+    with pytest.raises(plb.PlError):                      # nobody attached yet
+        norm.push_to_peers(True)
+    norm.attach_peers(h[None, :], 0)                      # a group of one: no peers
+    with pytest.raises(plb.PlError):
+        norm.push_to_peers(True)
+    with pytest.raises(plb.PlError):                      # self outside the group
+        elev.attach_peers(h[None, :], 1)
+    with pytest.raises(plb.PlError):                      # only RG8 normal pools push
+        elev.push_to_peers(True)
+    norm.push_to_peers(False)
+    # production is unaffected
+    sc = plb.sweep_scene(noise_amp=[-140, -100], face=0, root_quad_size=100000.0, sphere=0, want_stats=1)
+    ctx.noise_init(101)
+    ctx.produce_range(sc, elev, norm, 0, 0, 1, 0, 0, 0)
+    ctx.sync()
+    assert norm.download(0).any()
