@@ -379,8 +379,13 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
                 /* unorm8: round(clamp(v * 0.5 + 0.5, 0, 1) * 255), NaN -> 0 */
                 const F2 r = mul2(make_float2(__saturatef(fmaf(tx.x, 0.5f, 0.5f)), __saturatef(fmaf(tx.y, 0.5f, 0.5f))), bc(255.0f));
                 const F2 g = mul2(make_float2(__saturatef(fmaf(ty.x, 0.5f, 0.5f)), __saturatef(fmaf(ty.y, 0.5f, 0.5f))), bc(255.0f));
-                rg[half][0] = (unsigned int) __float2int_rn(r.x) + ((unsigned int) __float2int_rn(g.x) << 8);
-                rg[half][1] = (unsigned int) __float2int_rn(r.y) + ((unsigned int) __float2int_rn(g.y) << 8);
+                /* round to nearest even by adding 1.5 * 2^23 (the sum's ulp is 1; scalar adds: ptxas would contract a
+                 * packed multiply + add into one FFMA2, a single rounding): the byte is the low byte of the sum's
+                 * bits, one PRMT packs r | g << 8.  No conversion instruction (XU pipe) per texel. */
+                const unsigned int rx = __float_as_uint(r.x + 12582912.0f), ry = __float_as_uint(r.y + 12582912.0f);
+                const unsigned int gx = __float_as_uint(g.x + 12582912.0f), gy = __float_as_uint(g.y + 12582912.0f);
+                rg[half][0] = __byte_perm(rx, gx, 0x0040u);
+                rg[half][1] = __byte_perm(ry, gy, 0x0040u);
             }
             unsigned short *o = ob - odd;
             const bool px0 = x >= 0, px1 = x + 1 < W, py1 = ry + 1 < rows;
