@@ -170,14 +170,24 @@ __device__ __forceinline__ void do_quad2(const QuadCtx &k, const int ip, const i
                 r01A = t1.x; r11A = t1.y; r01B = t1.z; r11B = t1.w;
             }
         } else {
+            /* int16 -> float without the conversion unit: flipping the sign bit makes the value an unsigned
+             * s + 32768, PRMT plants its two bytes in the mantissa of 2^23 (0x4B00hhll), one FADD removes
+             * 2^23 + 32768: exactly (float) s */
             const short *rp = static_cast<const short *>(k.resid) + off;
-            const short4 t0 = __ldg(reinterpret_cast<const short4 *>(rp));
-            r00A = (float) t0.x * k.resid_scale; r10A = (float) t0.y * k.resid_scale;
-            r00B = (float) t0.z * k.resid_scale; r10B = (float) t0.w * k.resid_scale;
+            const uint2 t0 = __ldg(reinterpret_cast<const uint2 *>(rp));
+            const unsigned int a0 = t0.x ^ 0x80008000u, b0 = t0.y ^ 0x80008000u;
+            constexpr float kBias = 8388608.0f + 32768.0f;
+            r00A = (__uint_as_float(__byte_perm(a0, 0x4B000000u, 0x7410u)) - kBias) * k.resid_scale;
+            r10A = (__uint_as_float(__byte_perm(a0, 0x4B000000u, 0x7432u)) - kBias) * k.resid_scale;
+            r00B = (__uint_as_float(__byte_perm(b0, 0x4B000000u, 0x7410u)) - kBias) * k.resid_scale;
+            r10B = (__uint_as_float(__byte_perm(b0, 0x4B000000u, 0x7432u)) - kBias) * k.resid_scale;
             if (!TAIL) {
-                const short4 t1 = __ldg(reinterpret_cast<const short4 *>(rp + k.resid_pitch));
-                r01A = (float) t1.x * k.resid_scale; r11A = (float) t1.y * k.resid_scale;
-                r01B = (float) t1.z * k.resid_scale; r11B = (float) t1.w * k.resid_scale;
+                const uint2 t1 = __ldg(reinterpret_cast<const uint2 *>(rp + k.resid_pitch));
+                const unsigned int a1 = t1.x ^ 0x80008000u, b1 = t1.y ^ 0x80008000u;
+                r01A = (__uint_as_float(__byte_perm(a1, 0x4B000000u, 0x7410u)) - kBias) * k.resid_scale;
+                r11A = (__uint_as_float(__byte_perm(a1, 0x4B000000u, 0x7432u)) - kBias) * k.resid_scale;
+                r01B = (__uint_as_float(__byte_perm(b1, 0x4B000000u, 0x7410u)) - kBias) * k.resid_scale;
+                r11B = (__uint_as_float(__byte_perm(b1, 0x4B000000u, 0x7432u)) - kBias) * k.resid_scale;
             }
         }
     }
