@@ -265,13 +265,16 @@ __device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const f
     }
     const float rd = plfp::rcp_rn(dsafe);
     const float half = delta * 0.5f;                       /* delta / 2.0, exact */
-    const float dR = plfp::div_rn(div6(maxv - R) + half, dsafe, rd);
-    const float dG = plfp::div_rn(div6(maxv - G) + half, dsafe, rd);
-    const float dB = plfp::div_rn(div6(maxv - B) + half, dsafe, rd);
-    const float hR = dB - dG;
-    const float hG = (float) (1.0 / 3.0) + dR - dB;
-    const float hB = (float) (2.0 / 3.0) + dG - dR;
-    float H = R == maxv ? hR : (G == maxv ? hG : hB);      /* one of the three is maxVal */
+    /* H = offset + del[a] - del[b] with (offset, a, b) = (0, B, G) when R is the maximum, (1/3, R, B) when G is,
+     * (2/3, G, R) otherwise: only two of the shader's three del terms are ever used, so the two channels are
+     * selected first and their terms evaluated once (0 + x is exact: the R branch's "del.z - del.y" is unchanged) */
+    const bool rmax = R == maxv, gmax = G == maxv;
+    const float ca = rmax ? B : (gmax ? R : G);
+    const float cb = rmax ? G : (gmax ? B : R);
+    const float hoff = rmax ? 0.0f : (gmax ? (float) (1.0 / 3.0) : (float) (2.0 / 3.0));
+    const float da = plfp::div_rn(div6(maxv - ca) + half, dsafe, rd);
+    const float db = plfp::div_rn(div6(maxv - cb) + half, dsafe, rd);
+    float H = hoff + da - db;
     H = H < 0.0f ? H + 1.0f : H;
     H = H > 1.0f ? H - 1.0f : H;
     H = grey ? 0.0f : H;
