@@ -362,7 +362,8 @@ typedef struct pl_ortho_scene {
     float root_noise_color[4]; /* rnoise="..." / 255                                         */
     int32_t n_amp;             /* noise="..." list (<= 32 levels)                            */
     int32_t max_level;         /* maxLevel (-1: none): hasTile                               */
-    int32_t pad_;
+    int32_t out_channels;      /* channels of the ortho storage: 0 or 4 = RGBA8; 1..3 (RGB8, RG8,
+                                  R8): the alpha channel is not computed and its byte written as 0  */
     float noise_amp[32];
 } pl_ortho_scene;
 

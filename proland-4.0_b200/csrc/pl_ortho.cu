@@ -311,7 +311,7 @@ __device__ __forceinline__ void hsv_noise(float r[4], const float nc[4], const f
 }
 
 /* all rows of one tile.  PARENT = false only for level-0 tiles */
-template <bool HSV, bool RESID, bool PARENT>
+template <bool HSV, bool RESID, bool PARENT, bool ALPHA>
 __device__ __forceinline__ void ortho_rows(const OrthoArgs &a, const uint32_t *win, const uint32_t *noise, const uint8_t *res,
                                            uint8_t *out, const float nc[4], int tid)
 {
@@ -390,13 +390,17 @@ __device__ __forceinline__ void ortho_rows(const OrthoArgs &a, const uint32_t *w
 #pragma unroll
                 for (int ch = 0; ch < 4; ++ch) r[ch] = fmaf(nc[ch], nm[ch], r[ch]);
             }
-            ow[p] = pack4(to_unorm8_bits(r[0]), to_unorm8_bits(r[1]), to_unorm8_bits(r[2]), to_unorm8_bits(r[3]));
+            if (ALPHA) {
+                ow[p] = pack4(to_unorm8_bits(r[0]), to_unorm8_bits(r[1]), to_unorm8_bits(r[2]), to_unorm8_bits(r[3]));
+            } else {   /* the storage keeps no alpha (RGB8, RG8, R8): its maths is dead code here, the byte is 0 */
+                ow[p] = pack4(to_unorm8_bits(r[0]), to_unorm8_bits(r[1]), to_unorm8_bits(r[2]), 0u) & 0x00FFFFFFu;
+            }
         }
         *(uint4 *) (out + texel * 4) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
 }
 
-template <bool HSV, bool RESID>
+template <bool HSV, bool RESID, bool ALPHA>
 __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const OrthoArgs a)
 {
     extern __shared__ __align__(128) uint8_t ortho_smem[];
@@ -429,8 +433,8 @@ __global__ void __launch_bounds__(kOrthoThreads) ortho_kernel(const OrthoArgs a)
     const uint8_t *res = resid_slot >= 0 ? a.resid + (long long) resid_slot * a.resid_slot_bytes : nullptr;
     if (has_parent) ob_mbar_wait(&bar, 0);
 
-    if (has_parent) ortho_rows<HSV, RESID, true>(a, win, noise, res, out, nc, tid);
-    else ortho_rows<HSV, RESID, false>(a, win, noise, res, out, nc, tid);
+    if (has_parent) ortho_rows<HSV, RESID, true, ALPHA>(a, win, noise, res, out, nc, tid);
+    else ortho_rows<HSV, RESID, false, ALPHA>(a, win, noise, res, out, nc, tid);
 }
 
 }  // namespace
@@ -453,8 +457,13 @@ int pl_launch_ortho(pl_ctx *ctx, const pl_ortho_scene *sc, pl_pool *ortho, pl_po
     for (int c = 0; c < 4; ++c) a.root255[c] = sc->root_noise_color[c] * 255.0f;
     const size_t smem = (size_t) a.PW * a.PW * 4;
     if (smem > 227 * 1024) return pl_set_error(PL_ERR_ARG, "ortho tile_w %d needs %zu bytes of shared memory", a.W, smem);
-    void (*kern)(const OrthoArgs) = sc->hsv ? (resid ? ortho_kernel<true, true> : ortho_kernel<true, false>)
-                                            : (resid ? ortho_kernel<false, true> : ortho_kernel<false, false>);
+    /* out_channels 1..3: the storage has no alpha channel (RGB8 in terrain3/helloworld.xml:43): it is not computed */
+    const bool alpha = !(sc->out_channels >= 1 && sc->out_channels <= 3);
+    void (*kern)(const OrthoArgs) =
+        alpha ? (sc->hsv ? (resid ? ortho_kernel<true, true, true> : ortho_kernel<true, false, true>)
+                         : (resid ? ortho_kernel<false, true, true> : ortho_kernel<false, false, true>))
+              : (sc->hsv ? (resid ? ortho_kernel<true, true, false> : ortho_kernel<true, false, false>)
+                         : (resid ? ortho_kernel<false, true, false> : ortho_kernel<false, false, false>));
     if (smem > 40 * 1024) PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     pl_timing_begin(ctx, PL_K_ORTHO, n);
     kern<<<n, kOrthoThreads, smem, ctx->stream>>>(a);

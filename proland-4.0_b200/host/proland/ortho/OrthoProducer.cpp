@@ -55,6 +55,7 @@ void OrthoProducer::init(ptr<TileCache> cache, ptr<TileProducer> residualTiles, 
     }
     scene.n_amp = (int) noiseAmp.size();
     scene.max_level = maxLevel;
+    scene.out_channels = storage->getComponents();
     for (size_t i = 0; i < noiseAmp.size(); ++i) {
         scene.noise_amp[i] = noiseAmp[i];
     }

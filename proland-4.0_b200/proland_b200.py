@@ -78,7 +78,7 @@ class SweepScene(C.Structure):
 class OrthoScene(C.Structure):
     _fields_ = [("tile_w", C.c_int32), ("channels", C.c_int32), ("hsv", C.c_int32), ("face", C.c_int32),
                 ("scale", C.c_float), ("noise_color", C.c_float * 4), ("root_noise_color", C.c_float * 4),
-                ("n_amp", C.c_int32), ("max_level", C.c_int32), ("pad_", C.c_int32), ("noise_amp", C.c_float * 32)]
+                ("n_amp", C.c_int32), ("max_level", C.c_int32), ("out_channels", C.c_int32), ("noise_amp", C.c_float * 32)]
 
 
 ORTHO_REQ_DTYPE = np.dtype([("out_slot", "i4"), ("parent_slot", "i4"), ("resid_slot", "i4"), ("dx", "i4"), ("dy", "i4"),
@@ -520,7 +520,7 @@ def _residual_upsample(self, pool, src_slot, dst_slot, tile_size, tx=0, ty=0):
 
 
 def ortho_scene(*, tile_w=196, channels=4, hsv=0, face=1, scale=2.0, cnoise=(255, 255, 255, 255),
-                rnoise=(127.5, 127.5, 127.5, 127.5), noise_amp=(), max_level=-1):
+                rnoise=(127.5, 127.5, 127.5, 127.5), noise_amp=(), max_level=-1, out_channels=0):
     """The orthoProducer resource (OrthoProducer.cpp:440-512): cnoise / rnoise are the XML's 0..255 values
     (divided by 255 as a float, `(float) atof(..) / 255`); a 3-value list keeps the default of the 4th."""
     s = OrthoScene()
@@ -536,6 +536,7 @@ def ortho_scene(*, tile_w=196, channels=4, hsv=0, face=1, scale=2.0, cnoise=(255
         s.root_noise_color[i] = rc[i]
     s.n_amp = len(noise_amp)
     s.max_level = max_level
+    s.out_channels = out_channels
     for i, a in enumerate(noise_amp):
         s.noise_amp[i] = a
     return s

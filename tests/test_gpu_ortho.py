@@ -71,6 +71,17 @@ def test_plain_golden(plb, ctx):
     assert [_sha(t) for t in gpu] == ORTHO["plain"]["levels_0_3_sha1"]
 
 
+@pytest.mark.parametrize("hsv", [0, 1])
+def test_rgb8_storage_skips_alpha(plb, ctx, oracle, hsv):
+    """out_channels = 3 (an RGB8 storage, terrain3/helloworld.xml:43): the colour channels are the oracle's, the
+    alpha byte is not computed and reads 0"""
+    kw = dict(hsv=hsv, cnoise=(70, 80, 100, 90), rnoise=(60, 150, 20, 200), noise_amp=[255] * 6, face=4)
+    gpu = _gpu_quadtree(plb, ctx, plb.ortho_scene(out_channels=3, **kw), 3)
+    ref = _oracle_quadtree(oracle, plb.ortho_scene(**kw), 3)
+    _assert_same(gpu[..., :3], ref[..., :3], "rgb8 hsv=%d" % hsv)
+    assert (gpu[..., 3] == 0).all()
+
+
 def test_tile_w_100(plb, ctx, oracle):
     """the 100-texel storages of the land-cover producers (exercise2/helloworld.xml:43-52)"""
     sc = plb.ortho_scene(tile_w=100, hsv=1, cnoise=(30, 200, 150, 90), noise_amp=[255, 200, 150, 100], face=2)

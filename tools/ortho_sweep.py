@@ -159,6 +159,12 @@ def main():
         plain = pl.ortho_scene(hsv=0, cnoise=(127.5, 0, 0, 0), noise_amp=[0] + [255] * 16, face=3)
         out["terrain3_hsv"] = run(ctx, torch, stream, hsv, a.max_level, a.reps, peak, peak_kind)
         out["plain"] = run(ctx, torch, stream, plain, a.max_level, a.reps, peak, peak_kind)
+        # the same scenes on a storage without alpha (terrain3's is RGB8): the alpha channel is not computed
+        for name, kw in (("terrain3_hsv_rgb8", dict(hsv=1, cnoise=(70, 80, 100), rnoise=(60, 150, 20), noise_amp=[255] * 17, face=1)),
+                         ("plain_rgb8", dict(hsv=0, cnoise=(127.5, 0, 0, 0), noise_amp=[0] + [255] * 16, face=3))):
+            r = run(ctx, torch, stream, pl.ortho_scene(out_channels=3, **kw), a.max_level, a.reps, peak, peak_kind)
+            r.pop("levels_0_3_sha1")
+            out[name] = r
         out["with_residuals"] = run_residuals(ctx, torch, stream, peak, peak_kind)
     out["terrain3_hsv"]["golden_ok"] = out["terrain3_hsv"].pop("levels_0_3_sha1") == golden["terrain3_hsv"]["levels_0_3_sha1"]
     out["plain"]["golden_ok"] = out["plain"].pop("levels_0_3_sha1") == golden["plain"]["levels_0_3_sha1"]
