@@ -29,6 +29,8 @@
 
 PerlinView pl_host_perlin();   /* pl_hostmath.cu */
 
+static_assert(sizeof(pl_ortho_req) == 64 && sizeof(pl_ortho_scene) == 192, "the layouts proland_b200.py mirrors");
+
 /* ------------------------------------------------------------------ host: noise */
 
 namespace {
