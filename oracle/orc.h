@@ -18,10 +18,17 @@
  *     src/terrain/examples/terrain4/DEM.dat (sha1 KATs) via stock zlib.
  *   - 4x4 upsample filter : pinned against the reference's own CPU restatement
  *     (CPUElevationProducer.cpp:194-245, re-stated in orc_cpu_elevation_tile).
- *   - GLSL evaluation order, fp16 rounding mode of the R16F upload, unorm8
- *     rounding, clamp-to-edge, Ork's vec3d::normalize : taken from the
- *     OpenGL 3.3 spec; the reference's GL path cannot run here -> those parts
- *     are "parity unpinned" and carried as stated tolerances.
+ *   - the float arithmetic of the three shaders (orc_upsample_tile, orc_normal_tile, orc_ortho_tile): pinned
+ *     on the reference's own GLSL text, compiled unchanged as C++ behind oracle/ref_shim/glsl_shim.h
+ *     (oracle/_ref/libref_glsl.so, oracle/ref_glsl_wrap.cpp).  The non-contracted build of this restatement
+ *     (liborc_strict.so) equals it BIT FOR BIT on every case of tests/glsl_cases.py (all shader variants, the
+ *     deep chains of BASELINE configs 1-4, four normal formats, ortho hsv / plain / residuals); the hashes are
+ *     committed (tests/golden/glsl.json).  The canonical build (liborc.so, a*b+c fused -- the order the CUDA
+ *     kernels share) differs from the text only by that contraction, which GLSL 3.30 leaves to the
+ *     implementation: measured in tests/test_glsl_pin.py, <= 1e-5 of the height range, <= 1 unorm8 step.
+ *   - what GL itself does around the shaders stays taken from the OpenGL 3.3 spec (no GL here): fp16 rounding
+ *     of the R16F upload, unorm8 rounding, clamp-to-edge, LINEAR weights with 8 subtexel bits, and Ork's
+ *     vec3d::normalize.
  */
 #ifndef ORC_H
 #define ORC_H

@@ -12,6 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORC_DIR = os.path.join(ROOT, "oracle")
 ORC_SO = os.path.join(ORC_DIR, "liborc.so")
 REF_SO = os.path.join(ORC_DIR, "_ref", "libref_noise.so")
+GLSL_SO = os.path.join(ORC_DIR, "_ref", "libref_glsl.so")
+STRICT_SO = os.path.join(ORC_DIR, "liborc_strict.so")
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)
@@ -113,8 +115,77 @@ def ref():
     return _ref
 
 
+_strict = None
+_glsl = None
+
+
+def strict():
+    """The non-contracted reading of the restatement (liborc_strict.so): every a*b+c is two roundings.  It is
+    the reading that must equal the reference's shader text compiled as plain IEEE fp32 (glsl()) bit for bit."""
+    global _strict
+    if _strict is None:
+        if not os.path.exists(STRICT_SO):
+            build()
+        _strict = C.CDLL(STRICT_SO)
+    return _strict
+
+
+def glsl():
+    """The reference's own GLSL shaders compiled unchanged as C++ (oracle/_ref/libref_glsl.so, oracle/Makefile),
+    or None when oracle/_ref was not built."""
+    global _glsl
+    if _glsl is None:
+        if not os.path.exists(GLSL_SO):
+            return None
+        _glsl = C.CDLL(GLSL_SO)
+    return _glsl
+
+
 def _fp(a):
     return a.ctypes.data_as(c_float_p)
+
+
+def _fpn(a):
+    return _fp(np.ascontiguousarray(a, np.float32)) if a is not None else None
+
+
+UPSAMPLE_VARIANT = {"A": 0, "B": 1, "C": 2, "D": 3, "D_NO_CLAMP": 4}   # SURVEY 2b
+NORMAL_VARIANT = {"flat": 0, "sphere": 1, "demo": 2}
+
+
+def glsl_upsample_tile(variant, p, parent, resid, noise, parent_filter=1, subtexel_bits=8):
+    """upsampleShader.glsl (the reference's text) on one tile -> (W, W, 3) float32"""
+    out = np.empty((p.W, p.W, 3), np.float32)
+    par = np.ascontiguousarray(parent, np.float32) if parent is not None else None
+    res = np.ascontiguousarray(resid, np.float32) if resid is not None else None
+    rc = glsl().ref_glsl_upsample_tile(C.c_int(UPSAMPLE_VARIANT[variant]), C.byref(p), _fpn(par), C.c_int(parent_filter),
+                                       _fpn(res), _fp(noise), C.c_int(subtexel_bits), _fp(out))
+    assert rc == 0
+    return out
+
+
+def glsl_normal_tile(variant, p, elev, parent=None, subtexel_bits=8):
+    """normalShader.glsl (the reference's text) on one tile -> (W, W, 4) float32, the fragment's `data`"""
+    out = np.empty((p.W, p.W, 4), np.float32)
+    el = np.ascontiguousarray(elev, np.float32)
+    par = np.ascontiguousarray(parent, np.float32) if parent is not None else None
+    rc = glsl().ref_glsl_normal_tile(C.c_int(NORMAL_VARIANT[variant]), C.byref(p), _fp(el), _fpn(par),
+                                     C.c_int(subtexel_bits), _fp(out))
+    assert rc == 0
+    return out
+
+
+def glsl_ortho_tile(variant, p, parent, residual, noise, channels=4, parent_filter=0):
+    """upsampleOrthoShader.glsl (the reference's text) on one tile -> (W, W, 4) float32 `data`"""
+    W = p.tileWidth
+    out = np.empty((W, W, 4), np.float32)
+    par = np.ascontiguousarray(parent, np.uint8) if parent is not None else None
+    res = np.ascontiguousarray(residual, np.uint8) if residual is not None else None
+    nz = np.ascontiguousarray(noise, np.uint8)
+    rc = glsl().ref_glsl_ortho_tile(C.c_int(variant), C.byref(p), _u8(par), C.c_int(parent_filter), _u8(res),
+                                    C.c_int(channels), _u8(nz), _fp(out))
+    assert rc == 0
+    return out
 
 
 # ---------------------------------------------------------------- noise ----
@@ -150,12 +221,12 @@ def elev_uniforms(level, tx, ty, *, W=101, gridMeshSize=24, rootQuadSize=100000.
     return p
 
 
-def upsample_tile(p, parent, resid, noise):
+def upsample_tile(p, parent, resid, noise, L=None):
     W = p.W
     out = np.empty((W, W, 3), np.float32)
-    par = _fp(np.ascontiguousarray(parent, np.float32)) if parent is not None else None
-    res = _fp(np.ascontiguousarray(resid, np.float32)) if resid is not None else None
-    lib().orc_upsample_tile(C.byref(p), par, res, _fp(noise), _fp(out))
+    par = np.ascontiguousarray(parent, np.float32) if parent is not None else None
+    res = np.ascontiguousarray(resid, np.float32) if resid is not None else None
+    (L or lib()).orc_upsample_tile(C.byref(p), _fpn(par), _fpn(res), _fp(noise), _fp(out))
     return out
 
 
@@ -186,10 +257,11 @@ def normal_uniforms(level, tx, ty, *, W=97, gridMeshSize=24, components=2, signe
     return p
 
 
-def normal_tile(p, elev, parent=None):
+def normal_tile(p, elev, parent=None, L=None):
     out = np.empty((p.W, p.W, 4), np.float32)
-    par = _fp(np.ascontiguousarray(parent, np.float32)) if parent is not None else None
-    lib().orc_normal_tile(C.byref(p), _fp(np.ascontiguousarray(elev, np.float32)), par, _fp(out))
+    par = np.ascontiguousarray(parent, np.float32) if parent is not None else None
+    el = np.ascontiguousarray(elev, np.float32)
+    (L or lib()).orc_normal_tile(C.byref(p), _fp(el), _fpn(par), _fp(out))
     return out
 
 
@@ -342,14 +414,14 @@ def ortho_uniforms(level, tx, ty, *, W=196, face=1, noise_amp=(), noise_color=(1
     return p
 
 
-def ortho_tile(p, parent, residual, noise, channels=4):
+def ortho_tile(p, parent, residual, noise, channels=4, L=None):
     """parent: (W, W, 4) uint8 or None; residual: (W, W, channels) uint8 or None -> (W, W, 4) uint8"""
     W = p.tileWidth
     out = np.empty((W, W, 4), np.uint8)
     par = np.ascontiguousarray(parent, np.uint8) if parent is not None else None
     res = np.ascontiguousarray(residual, np.uint8) if residual is not None else None
     nz = np.ascontiguousarray(noise, np.uint8)
-    lib().orc_ortho_tile(C.byref(p), _u8(par), _u8(res), C.c_int(channels), _u8(nz), _u8(out))
+    (L or lib()).orc_ortho_tile(C.byref(p), _u8(par), _u8(res), C.c_int(channels), _u8(nz), _u8(out))
     return out
 
 
