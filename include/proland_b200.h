@@ -195,7 +195,19 @@ typedef struct pl_norm_scene {
     int32_t elev_filter;   /* min/mag filter of the elevation storage             */
     int32_t parent_filter; /* min/mag filter of the normal storage                */
     int32_t sphere;        /* deform="sphere"                                     */
+    int32_t arith;         /* PL_ARITH_EXACT (0, default) or PL_ARITH_FAST: see below */
+    int32_t pad_;
 } pl_norm_scene;
+/* The arithmetic contract of the NORMAL pass (elevations are always bit-exact: children are built from them).
+ *   PL_ARITH_EXACT  every operation of normalShader.glsl in the canonical fp32 order with IEEE division and square
+ *                   root: tiles are bit-identical to the oracle.
+ *   PL_ARITH_FAST   the tolerance contract: a normal byte differs from the canonical evaluation by at most ONE
+ *                   unorm8 step (0.45 degrees at worst; BASELINE's "within a stated angular tolerance"), and fewer
+ *                   than 1e-3 of the bytes of a tile set differ.  MUFU.RCP / MUFU.RSQ seeds, one reciprocal per grid
+ *                   point, bilinear forms evaluated by row (pl_normal_tile.cuh).  Levels below R/64 quad size
+ *                   (smoothstep < 1) keep the exact position code.  Served by the specialised kernels (97-texel
+ *                   RG8 tiles); other geometries ignore it and stay exact. */
+enum { PL_ARITH_EXACT = 0, PL_ARITH_FAST = 1 };
 
 /* per-tile uniforms, NormalProducer.cpp:196-283 (fp64 on the host -> fp32) */
 typedef struct pl_norm_req {

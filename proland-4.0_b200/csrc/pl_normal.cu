@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads) normal_kernel_generic(const NormArgs
  * Specialised kernel: compile-time geometry, one CTA per tile; the per-tile
  * device code lives in pl_normal_tile.cuh (shared with pl_pair.cu).
  * ------------------------------------------------------------------------ */
-template <int TW, bool SPHERE, bool LINEAR>
+template <int TW, bool SPHERE, bool LINEAR, bool FAST>
 __global__ void __launch_bounds__(kTileThreads, 3) normal_kernel_fast(const NormArgs a)
 {
     using GEO = NGeo<TW>;
@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) normal_kernel_fast(const Norm
     float *zs = reinterpret_cast<float *>(smem_raw) + 4;             /* the tile's zm plane: EW x EPITCH, behind 4 guard floats */
     float *pos = zs + GEO::EPLANE;                                   /* 3 planes of POS_ROWS x GWP */
     float *ulut = pos + 3 * GEO::POS_PLANE;                          /* 2 x ULUT */
+    float *rowtab = ulut + 2 * GEO::ULUT;                            /* PL_ARITH_FAST: row_table of a band */
     __shared__ uint64_t bar;
     __shared__ pl_norm_req rq;
 
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) normal_kernel_fast(const Norm
     mbar_wait(&bar, 0);
 
     unsigned short *out = reinterpret_cast<unsigned short *>(a.norm + (size_t) rq.out_slot * a.norm_slot_bytes);
-    normal_tile<TW, SPHERE, LINEAR, kTileThreads>(zs, pos, ulut, rq, out, tid);
+    normal_tile<TW, SPHERE, LINEAR, kTileThreads, false, FAST>(zs, pos, ulut, rq, out, tid, nullptr, rowtab);
 }
 
 }  // namespace
@@ -263,6 +264,7 @@ int pl_norm_fill_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_po
     a.parent_linear = sc->parent_filter == PL_FILTER_LINEAR;
     a.nbands = a.W / kBandRows > 0 ? a.W / kBandRows : 1;
     a.max_rows = a.W - (a.nbands - 1) * kBandRows;
+    a.fast = sc->arith == PL_ARITH_FAST;
     a.norm_slot_bytes = (long long) norm->slot_bytes;
     a.npeers = norm->push ? norm->npeers : 0;
     for (int p = 0; p < a.npeers; ++p) a.peer_delta[p] = (long long) (norm->peer_base[p] - norm->base);
@@ -283,8 +285,11 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
         /* the geometry of every shipped archive: compile-time specialisation */
         using GEO = NGeo<97>;
         const size_t fsmem = GEO::SMEM;
-        void (*kern)(NormArgs) = a.sphere ? (a.linear ? normal_kernel_fast<97, true, true> : normal_kernel_fast<97, true, false>)
-                                          : (a.linear ? normal_kernel_fast<97, false, true> : normal_kernel_fast<97, false, false>);
+        void (*kern)(NormArgs) =
+            a.fast ? (a.sphere ? (a.linear ? normal_kernel_fast<97, true, true, true> : normal_kernel_fast<97, true, false, true>)
+                               : (a.linear ? normal_kernel_fast<97, false, true, true> : normal_kernel_fast<97, false, false, true>))
+                   : (a.sphere ? (a.linear ? normal_kernel_fast<97, true, true, false> : normal_kernel_fast<97, true, false, false>)
+                               : (a.linear ? normal_kernel_fast<97, false, true, false> : normal_kernel_fast<97, false, false, false>));
         PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem));
         pl_timing_begin(ctx, PL_K_NORMAL, n);
         kern<<<n, kTileThreads, fsmem, ctx->stream>>>(a);

@@ -29,6 +29,7 @@ struct NormArgs {
     int grid;                /* tileSDF.y */
     int parent_linear;       /* normal storage filter (parent coarse normal fetch) */
     int nbands, max_rows;    /* bands per tile, rows of the largest band */
+    int fast;                /* pl_norm_scene.arith == PL_ARITH_FAST */
     long long norm_slot_bytes;
     /* push of finished normal tiles to the peer GPUs (pl_pool_attach_peers): byte distance from this GPU's
      * normal pool to each peer's mapping of its own */
@@ -146,7 +147,8 @@ struct NGeo {
     static constexpr int POS_ROWS = kTileBand + 2;    /* grid rows a band touches */
     static constexpr int POS_PLANE = POS_ROWS * GWP;
     static constexpr int ULUT = (GW + 4) & ~1;        /* u of X = -2 .. W+1, twice (second copy one entry further) */
-    static constexpr size_t SMEM = 16 + (size_t) EPLANE * 4 + (size_t) 3 * POS_PLANE * 4 + (size_t) 2 * ULUT * 4;   /* 16: guard floats in front of the zm plane */
+    static constexpr int ROWTAB = POS_ROWS * 16;      /* PL_ARITH_FAST: 16 floats per grid row of a band (row_table) */
+    static constexpr size_t SMEM = 16 + (size_t) EPLANE * 4 + (size_t) 3 * POS_PLANE * 4 + (size_t) 2 * ULUT * 4 + (size_t) ROWTAB * 4;   /* 16: guard floats in front of the zm plane */
     static_assert(EPITCH % 2 == 0 && EPITCH >= GW + 3, "paired loads stay inside a staged row");
     static_assert(kTileBand % 4 == 0, "the row-shift pattern restarts with every band");
     static_assert((LAST_ROWS + 1) / 2 * 2 + 2 <= POS_ROWS, "the last band's blocks stay inside the position rows");
@@ -166,9 +168,23 @@ __device__ __forceinline__ int row_shift(int g) { return ((g + 3) >> 1) & 1; }
 /* Normals of one tile.  zs: the tile's zm plane (EW rows of pitch EPITCH) in shared memory; pos: 3
  * position planes of POS_ROWS x GWP; ulut: the two uv tables; out: the tile's RG8 texels in HBM.
  * All threads of the CTA call this; it contains __syncthreads(). */
-template <int TW, bool SPHERE, bool LINEAR, int NT, bool PUSH = false>
+/* PL_ARITH_FAST (pl_norm_scene.arith, template FAST): the tolerance contract of the normal pass.  Elevations stay
+ * bit-exact (children are built from them); the normal tile -- a terminal, unorm8-quantised product -- may differ
+ * from the canonical evaluation by at most ONE unorm8 step on < 1e-3 of its bytes (tests/test_gpu_fast.py):
+ *   - world positions on a sphere (levels whose smoothstep factor is exactly 1, i.e. quad size <= R/64: level >= 7
+ *     on a planet; the others keep the exact code): the shader's
+ *         alphaPrime = alpha*L / dot(alpha, L);  p = C*alphaPrime + h * (N*alphaPrime)
+ *     is p = (C*(alpha*L) + h * N*(alpha*L)) / dot(alpha, L): the three numerators and the denominator are
+ *     bilinear in (u, v), so a grid ROW carries their values at the row's two ends (row_table: 7 start values,
+ *     7 differences) and a grid point costs 7 fused lerps, ONE reciprocal (MUFU.RCP + one Newton step) shared by
+ *     the three components, 3 fma and 3 multiplies -- 15 packed instructions per pair of points instead of 56
+ *   - normalisation by MUFU.RSQ, folded with the unorm8 scale into the tangent-frame product:
+ *         byte = round(127.5 * rsqrt(n.n) * dot(w2t_row, n) + 127.5)
+ *     (no IEEE square root, no reciprocal, no clamp: |t| <= 1 + 1e-6 keeps the magic-add rounding inside 0..255) */
+template <int TW, bool SPHERE, bool LINEAR, int NT, bool PUSH = false, bool FAST = false>
 __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const float *ulut, const pl_norm_req &rq,
-                                            unsigned short *out, const int tid, const NormArgs *peers = nullptr)
+                                            unsigned short *out, const int tid, const NormArgs *peers = nullptr,
+                                            float *rowtab = nullptr)
 {
     using namespace plf2;
     using GEO = NGeo<TW>;
@@ -198,6 +214,7 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
     const int pc2 = 2 * pc;
     const bool pc_ok = rl0 < PR;
     const float *uA = ulut + pc2, *uB = ulut + UL + pc2;
+    const F2 uFA = *reinterpret_cast<const F2 *>(uA), uFB = *reinterpret_cast<const F2 *>(uB);
     /* normal phase: thread = (block column, block row lane) */
     int kl0, xc;
     if (tid < CMAIN * KR) { kl0 = tid / CMAIN; xc = tid - kl0 * CMAIN; }
@@ -221,6 +238,34 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
             if (k >= 1) dxb[k - 1] = ddx;
             dyt[k] = ddy;
         }
+    }
+
+    /* FAST sphere positions: the rows' end values of the 7 bilinear forms (see above).  Corner c of the patch has
+     * weight alpha_c = (U V, u V, U v, u v)_c; with Q_c = L_c * (N column c | C column c | 1):
+     *   row start A = V Q_0 + v Q_2 (u = 0), row end B = V Q_1 + v Q_3 (u = 1), point = A + u (B - A).
+     * Layout of a row: [A_n0 A_n1 A_n2 A_c0][A_c1 A_c2 A_den -][d_n0 d_n1 d_n2 d_c0][d_c1 d_c2 d_den -] */
+    const bool fastpos = FAST && SPHERE && s == 1.0f;
+    auto row_table = [&](int band) {
+        const int y_begin = band * kTileBand;
+        const int rows = band == GEO::NBANDS - 1 ? GEO::LAST_ROWS : kTileBand;
+        const int r = (band == 0 ? 0 : 2) + tid;
+        if (r < rows + 2) {
+            const float v = ulut[y_begin + r + 1], V = 1.0f - v;
+            float *t = rowtab + r * 16;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const float *M = k < 3 ? rq.verticals + 4 * k : rq.corners + 4 * (k - 3);
+                const float q0 = k < 6 ? rq.norms[0] * M[0] : rq.norms[0], q1 = k < 6 ? rq.norms[1] * M[1] : rq.norms[1];
+                const float q2 = k < 6 ? rq.norms[2] * M[2] : rq.norms[2], q3 = k < 6 ? rq.norms[3] * M[3] : rq.norms[3];
+                const float A = fmaf(v, q2, V * q0), B = fmaf(v, q3, V * q1);
+                t[k] = A;
+                t[8 + k] = B - A;
+            }
+        }
+    };
+    if (fastpos) {
+        row_table(0);
+        __syncthreads();
     }
 
 #pragma unroll 1
@@ -249,8 +294,9 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
             const float *zrow = zs + (y_begin + r + 1) * EPITCH + pc2;   /* row Y + 2 of the tile, column pc2 */
             const float *vp = ulut + y_begin + r + 1;                    /* Y = y_begin + r - 1 */
             float *o3 = pos + r * GWP + pc2 + 2;
+            const float4 *rt = reinterpret_cast<const float4 *>(rowtab + r * 16);
             if (pc_ok)
-            for (; r < r_hi; r += PR, zrow += PR * EPITCH, vp += PR, o3 += PR * GWP) {
+            for (; r < r_hi; r += PR, zrow += PR * EPITCH, vp += PR, o3 += PR * GWP, rt += PR * 4) {
                 const int sh = row_shift(r);
                 /* grid points gx, gx+1 with gx = pc2 - sh (X = gx - 1, gx): elevation texels (gx + 1, Y + 2),
                  * (gx + 2, Y + 2).  Column -1 / GW of a shifted or last pair is a pad: it reads inside the
@@ -270,13 +316,25 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
                  * in the second (one entry further) when it is even */
                 F2 u = bc(0.0f);
                 float v = 0.0f;
-                if (SPHERE) {
+                if (SPHERE && FAST && fastpos) {
+                    u = sh ? uFA : uFB;            /* the thread's columns never change: both pairs live in registers */
+                } else if (SPHERE) {
                     u = *reinterpret_cast<const F2 *>(sh ? uA : uB);
                     v = *vp;
                 }
                 F2 qx, qy, qz;
                 if (!SPHERE) {
                     qx = qy = qz = h;
+                } else if (FAST && fastpos) {
+                    const float4 A0 = rt[0], A1 = rt[1], D0 = rt[2], D1 = rt[3];
+                    const F2 den = fma2(u, bc(D1.z), bc(A1.z));
+                    const F2 r0 = make_float2(plfp::rcp_seed(den.x), plfp::rcp_seed(den.y));
+                    const F2 rden = fma2(r0, fma2(r0, neg(den), bc(1.0f)), r0);
+                    const F2 nx = fma2(u, bc(D0.x), bc(A0.x)), ny = fma2(u, bc(D0.y), bc(A0.y)), nz = fma2(u, bc(D0.z), bc(A0.z));
+                    const F2 cx = fma2(u, bc(D0.w), bc(A0.w)), cy = fma2(u, bc(D1.x), bc(A1.x)), cz = fma2(u, bc(D1.y), bc(A1.y));
+                    qx = mul2(fma2(h, nx, cx), rden);
+                    qy = mul2(fma2(h, ny, cy), rden);
+                    qz = mul2(fma2(h, nz, cz), rden);
                 } else {
                     const F2 U = sub2(bc(1.0f), u);
                     const float V = 1.0f - v;
@@ -311,6 +369,7 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
             }
         }
         __syncthreads();
+        if (FAST && fastpos && band + 1 < GEO::NBANDS) row_table(band + 1);   /* read after the next band's barriers */
 
         /* ---- normals of the band: a 2 x 2 block of texels per thread ------------- */
         /* thread = (block column xc, block row lane kl0): columns fixed, block rows advance by KR per pass */
@@ -366,6 +425,21 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
                     nx = neg(mul2(d[2], e[1]));
                     ny = neg(mul2(d[0], e[2]));
                     nz = mul2(d[0], e[1]);
+                }
+                if (FAST) {
+                    const F2 n2 = plf2::dot3(nx, ny, nz, nx, ny, nz);
+                    const F2 i2 = mul2(make_float2(plfp::rsqrt_seed(n2.x), plfp::rsqrt_seed(n2.y)), bc(127.5f));
+                    F2 tx = nx, ty = ny;
+                    if (SPHERE || !w2t_identity) {
+                        tx = plf2::dot3(bc(w00), bc(w01), bc(w02), nx, ny, nz);
+                        ty = plf2::dot3(bc(w10), bc(w11), bc(w12), nx, ny, nz);
+                    }
+                    const F2 r = fma2(tx, i2, bc(127.5f)), g = fma2(ty, i2, bc(127.5f));
+                    const unsigned int rx = __float_as_uint(r.x + 12582912.0f), ry = __float_as_uint(r.y + 12582912.0f);
+                    const unsigned int gx = __float_as_uint(g.x + 12582912.0f), gy = __float_as_uint(g.y + 12582912.0f);
+                    rg[half][0] = __byte_perm(rx, gx, 0x0040u);
+                    rg[half][1] = __byte_perm(ry, gy, 0x0040u);
+                    continue;
                 }
                 const F2 inv = rcp_rn2(sqrt_rn2(plf2::dot3(nx, ny, nz, nx, ny, nz)));
                 nx = mul2(nx, inv); ny = mul2(ny, inv); nz = mul2(nz, inv);

@@ -17,7 +17,8 @@
  * pl_normal_tile.cuh): results are bit-identical.
  *
  * Shared memory of a CTA: [guard 96 B | zm plane 42 016 B | elevation windows + tables, reused as the
- * position planes of the normal phase 27 456 B | uv tables 816 B] = 70.3 KB -> 3 CTAs per SM.
+ * position planes of the normal phase 27 456 B | uv tables 816 B | row table (PL_ARITH_FAST) 1 408 B] = 71.7 KB
+ * -> 3 CTAs per SM.
  */
 #include "pl_elevation_tile.cuh"
 #include "pl_normal_tile.cuh"
@@ -40,12 +41,12 @@ struct PairSmem {
     static constexpr int ELEV = plelev::ElevSmem<TW, TG>::FLOATS;
     static constexpr int POS = 3 * NG::POS_PLANE;
     static constexpr int WORK = ((ELEV > POS ? ELEV : POS) + 3) & ~3;           /* elevation scratch, then positions */
-    static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT) * 4;
+    static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT + NG::ROWTAB) * 4;
     static_assert(EG::PITCH == NG::EPITCH && EG::PLANE == NG::EPLANE, "both passes agree on the plane layout");
     static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
 };
 
-template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false>
+template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false>
 __global__ void __launch_bounds__(kPairThreads, 3)
 tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
 {
@@ -54,6 +55,7 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
     float *zs = reinterpret_cast<float *>(smem_raw) + SM::GUARD;   /* zm plane behind the guard floats */
     float *work = zs + plelev::Geo<TW, TG>::PLANE;
     float *ulut = work + SM::WORK;
+    float *rowtab = ulut + 2 * SM::NG::ULUT;   /* PL_ARITH_FAST: the row table of a band of the normal phase */
     __shared__ uint64_t bar;
     __shared__ pl_norm_req nrq;
 
@@ -78,7 +80,7 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
 
     /* normals from the shared zm plane */
     unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
-    plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH>(zs, work, ulut, nrq, out, tid, &na);
+    plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH, FAST>(zs, work, ulut, nrq, out, tid, &na, rowtab);
 }
 
 template <int RESID>
@@ -88,6 +90,9 @@ int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const pl
     void (*kern)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
         na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true> : tile_pair_kernel<101, 4, RESID, true, false>)
                   : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true> : tile_pair_kernel<101, 4, RESID, false, false>);
+    if (na.fast && na.npeers == 0)
+        kern = na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true, false, true> : tile_pair_kernel<101, 4, RESID, true, false, false, true>)
+                         : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true, false, true> : tile_pair_kernel<101, 4, RESID, false, false, false, true>);
     if (na.npeers > 0) {
         /* finished normal tiles also go to the peer GPUs (fractal scenes: the variants without residuals) */
         if (RESID != 0) return pl_set_error(PL_ERR_ARG, "pushing tiles to peers is built for scenes without residuals");

@@ -110,7 +110,7 @@ void NormalProducer::beginCreateTile()
 
 pl_norm_scene NormalProducer::scene() const
 {
-    pl_norm_scene sc;
+    pl_norm_scene sc = pl_norm_scene();
     sc.tile_w = storage->getTileSize();
     sc.grid = (storage->getTileSize() - 1) / gridMeshSize;
     sc.elev_border = elevationTiles->getBorder();

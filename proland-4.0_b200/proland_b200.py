@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("PL_LIB", os.path.join(HERE, "libproland_b200.so"))
 PL_OK, PL_ERR_ARG, PL_ERR_POOL_FULL, PL_ERR_CUDA, PL_ERR_CORRUPT, PL_ERR_NO_DEVICE, PL_ERR_IO = range(7)
 POOL_ELEV, POOL_NORM2, POOL_NORM4, POOL_RESID_F32, POOL_RESID_I16, POOL_ORTHO = range(6)
 NOISE_PLAIN, NOISE_SLOPE = 0, 1
+ARITH_EXACT, ARITH_FAST = 0, 1     # pl_norm_scene.arith: the normal pass's arithmetic contract
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
 
 # every symbol include/proland_b200.h declares (tests check the .so exports them all)
@@ -58,7 +59,8 @@ class ElevReq(C.Structure):
 
 class NormScene(C.Structure):
     _fields_ = [("tile_w", C.c_int32), ("grid", C.c_int32), ("elev_border", C.c_int32),
-                ("elev_filter", C.c_int32), ("parent_filter", C.c_int32), ("sphere", C.c_int32)]
+                ("elev_filter", C.c_int32), ("parent_filter", C.c_int32), ("sphere", C.c_int32),
+                ("arith", C.c_int32), ("pad_", C.c_int32)]
 
 
 class NormReq(C.Structure):
@@ -246,10 +248,10 @@ def norm_make_reqs(tiles, scene, *, root_quad_size=100000.0, components=2):
 
 def sweep_scene(*, noise_amp, face=0, root_quad_size=100000.0, tile_w=101, grid_size=24, flip=0,
                 noise_mode=NOISE_SLOPE, no_clamp=0, want_stats=0, sphere=0,
-                elev_filter=FILTER_LINEAR):
+                elev_filter=FILTER_LINEAR, arith=ARITH_EXACT):
     s = SweepScene()
     s.elev = elev_scene(tile_w, grid_size, flip, noise_mode, no_clamp, want_stats)
-    s.norm = norm_scene(tile_w - 4, grid_size, 2, elev_filter, FILTER_LINEAR, sphere)
+    s.norm = norm_scene(tile_w - 4, grid_size, 2, elev_filter, FILTER_LINEAR, sphere, arith)
     s.root_quad_size = root_quad_size
     s.face = face
     s.n_amp = len(noise_amp)
@@ -620,6 +622,6 @@ def elev_scene(tile_w=101, grid_size=24, flip=0, noise_mode=NOISE_SLOPE, no_clam
 
 
 def norm_scene(tile_w=97, grid_size=24, elev_border=2, elev_filter=FILTER_LINEAR,
-               parent_filter=FILTER_LINEAR, sphere=0):
+               parent_filter=FILTER_LINEAR, sphere=0, arith=ARITH_EXACT):
     return NormScene(tile_w, (tile_w - 1) // grid_size, elev_border, elev_filter, parent_filter,
-                     sphere)
+                     sphere, arith, 0)

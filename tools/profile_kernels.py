@@ -15,7 +15,8 @@ import proland_b200 as pl
 AMP = [-3250, -1590, -1125, -795, -561, -397, -140, -100, 15, 8, 5, 2.5, 1.5, 1, 0.5, 0.25, 0.1, 0.05]
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 with pl.Context(0) as ctx:
-    sc = pl.sweep_scene(noise_amp=AMP, face=3, root_quad_size=12720000.0, sphere=1, want_stats=1)
+    arith = pl.ARITH_FAST if os.environ.get("PL_ARITH", "exact") == "fast" else pl.ARITH_EXACT
+    sc = pl.sweep_scene(noise_amp=AMP, face=3, root_quad_size=12720000.0, sphere=1, want_stats=1, arith=arith)
     off = [sum(4 ** k for k in range(l)) for l in range(10)]
     elev = ctx.pool(pl.POOL_ELEV, 101, off[8] + 16384)
     norm = ctx.pool(pl.POOL_NORM2, 97, off[8] + 16384)
