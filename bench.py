@@ -245,20 +245,34 @@ def ortho_lines(pl, ctx, torch, stream, peak, peak_kind, max_level=7, reps=3):
     return out
 
 
+def host_cores():
+    """Host threads the CPU arm may use: every core of the box (sched_getaffinity when it is narrower).  torchrun
+    exports OMP_NUM_THREADS=1 to its workers; the arm passes this count to the oracle explicitly
+    (omp_set_num_threads), which overrides the environment."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank):
+    """--impl reference: the reference's algorithm for the path on the box's host cores (the oracle port, OpenMP over
+    the tiles of a level).  One step = face 1 of the same planet, levels 0..7: 21 845 pairs, 98 % of them in levels
+    5..7 (1 024 / 4 096 / 16 384 independent tiles per level: saturates any core count up to a few hundred)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    level = 6            # 5461 pairs per step: a few seconds on the box's cores
-    for _ in range(args.warmup):
-        cpu_sample(min(level, 4))
+    cores = host_cores()
+    level = 7
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(5, nthreads=cores)
     t_total, n_total = 0.0, 0
     for _ in range(args.steps):
-        n, dt, _ = cpu_sample(level)
+        n, dt, _ = cpu_sample(level, nthreads=cores)
         t_total += dt
         n_total += n
     value = n_total / t_total
-    sample = "face 1 of the planet, levels 0..%d (%d pairs) per step" % (level, n_total // max(args.steps, 1))
+    sample = ("face 1 of the planet, levels 0..%d (%d pairs) per step, %d OpenMP threads"
+              % (level, n_total // max(args.steps, 1), cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
@@ -267,6 +281,7 @@ def run_reference(args, rank):
                                    "(bounded CPU sample per step)", "tile_w": 101, "normal_w": 97},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                              "sample": sample},
+            "threads": cores, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
