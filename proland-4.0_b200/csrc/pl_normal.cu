@@ -233,10 +233,15 @@ __global__ void __launch_bounds__(kTileThreads, 3) normal_kernel_fast(const Norm
         bulk_load(zs, src, bytes, &bar);
     }
     normal_uv_tables<TW, kTileThreads>(ulut, tid);
+    if (FAST && SPHERE) normal_reg_qtab(rowtab, rq, tid);
     __syncthreads();
     mbar_wait(&bar, 0);
 
     unsigned short *out = reinterpret_cast<unsigned short *>(a.norm + (size_t) rq.out_slot * a.norm_slot_bytes);
+    if (FAST && normal_reg_ok(rq, SPHERE)) {
+        normal_tile_reg<TW, SPHERE, LINEAR, kTileThreads>(zs, pos, rowtab, ulut, rq, out, tid);
+        return;
+    }
     normal_tile<TW, SPHERE, LINEAR, kTileThreads, false, FAST>(zs, pos, ulut, rq, out, tid, nullptr, rowtab);
 }
 

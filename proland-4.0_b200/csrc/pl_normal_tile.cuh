@@ -486,6 +486,216 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
     }
 }
 
+/* ------------------------------------------------------------------------
+ * PL_ARITH_FAST, register form (normal_tile_reg): the normal pass of a tile WITHOUT position planes in
+ * shared memory and without a CTA barrier.  The banded form above is bound by the shared-memory pipe
+ * (profiles/pair_r2b_*: 74 % of its peak -- every position is stored once and loaded 4.5 times) and by the
+ * barriers between its phases.  Here a warp owns a strip of texel rows and walks down it; a lane owns FOUR
+ * adjacent grid columns (25 lanes cover the 99 grid columns of a tile) and keeps the world positions of the last
+ * three grid rows in registers:
+ *   - vertical neighbours (up - down) come from the lane's own registers,
+ *   - horizontal neighbours are the lane's own columns, except the pair right of its last column, which comes
+ *     from the next lane by SHFL (6 per grid row instead of 6 STS.64 + 18 LDS.64 per 2x2 block),
+ *   - the row table (the 7 bilinear forms of the FAST position, see normal_tile) is built by the warp for its own
+ *     rows (__syncwarp only) from the 28 corner values normal_reg_qtab prepares once per tile; the tangent-frame
+ *     rotation is folded into them: W (N a) x W (N b) = W (a x b) for the rotation W = worldToTangentFrame, so
+ *     the positions are evaluated IN the tangent frame and the cross product needs no matrix product afterwards,
+ *   - flat terrains: only the height is a position; the x difference per column and the y difference per row are
+ *     the same fp32 expressions as in the banded form (bit-identical results to it).
+ * Heights are fetched exactly as in the banded form (same operations, same order).
+ * Used when the tile qualifies (sphere: smoothstep factor exactly 1; flat: identity tangent frame); other tiles of
+ * a FAST scene take the banded form.
+ * ------------------------------------------------------------------------ */
+template <int TW, int NT>
+struct RGeo {
+    static constexpr int NWARP = NT / 32;
+    static constexpr int BASE = TW / NWARP, REM = TW - BASE * NWARP;   /* texel rows per warp: BASE, the first REM warps one more */
+    static constexpr int TROWS = BASE + 3;                             /* grid rows of a warp's strip */
+    static constexpr int TAB = NWARP * TROWS * 16;                     /* floats: 16 per grid row */
+    static constexpr int LANES = (TW + 2 + 3) / 4;                     /* lanes that own grid columns */
+    static_assert(LANES <= 32 && 4 * LANES + 1 <= NGeo<TW>::EPITCH, "one warp spans the tile; reads stay inside a staged row");
+};
+
+/* The 28 corner values of the 7 bilinear forms, once per tile (any 28 threads; visible after the next barrier):
+ * q[k][c] = L_c * (W N)[k][c] (k = 0..2), L_c * (W C)[k-3][c] (k = 3..5), L_c (k = 6) for patch corner c */
+__device__ __forceinline__ void normal_reg_qtab(float *qtab, const pl_norm_req &rq, const int t)
+{
+    if (t < 28) {
+        const int k = t >> 2, c = t & 3;
+        float m = 1.0f;
+        if (k < 6) {
+            const float *M = k < 3 ? rq.verticals : rq.corners;
+            const float *w = rq.w2t + 3 * (k < 3 ? k : k - 3);
+            m = fmaf(w[2], M[8 + c], fmaf(w[1], M[4 + c], w[0] * M[c]));
+        }
+        qtab[t] = rq.norms[c] * m;
+    }
+}
+
+template <int NC> struct RegRow { plf2::F2 p[NC][2]; };   /* positions of the lane's 4 grid columns: [component][columns 0,1 | 2,3] */
+
+__device__ __forceinline__ bool normal_reg_ok(const pl_norm_req &rq, const bool sphere)
+{
+    if (sphere) return rq.smooth == 1.0f;
+    return rq.w2t[0] == 1.0f && rq.w2t[1] == 0.0f && rq.w2t[2] == 0.0f && rq.w2t[3] == 0.0f && rq.w2t[4] == 1.0f && rq.w2t[5] == 0.0f;
+}
+
+template <int TW, bool SPHERE, bool LINEAR, int NT>
+__device__ __forceinline__ void normal_tile_reg(const float *zs, float *tab, const float *qtab, const float *ulut,
+                                                const pl_norm_req &rq, unsigned short *out, const int tid)
+{
+    using namespace plf2;
+    using GEO = NGeo<TW>;
+    using RG = RGeo<TW, NT>;
+    constexpr int W = GEO::W, EP = GEO::EPITCH, NC = SPHERE ? 3 : 1;
+    const int lane = tid & 31, wid = tid >> 5;
+    const int lc = min(lane, RG::LANES - 1);           /* lanes past the last column group repeat it (their stores are off) */
+    const int y0 = wid * RG::BASE + min(wid, RG::REM);  /* first texel row of the warp's strip */
+    const int n = RG::BASE + (wid < RG::REM ? 1 : 0);   /* texel rows of the strip; grid rows y0 .. y0 + n + 1 */
+    float *wt = tab + wid * (RG::TROWS * 16);
+
+    if (SPHERE) {
+        /* row table of the strip: [den A, den D, n0 A, n0 D][c0 A, c0 D, n1 A, n1 D][c1 A, c1 D, n2 A, n2 D][c2 A, c2 D, -, -]
+         * (value at u = 0 and difference to u = 1 of each form, in the order a grid point consumes them) */
+        if (lane < n + 2) {
+            const float v = ulut[y0 + lane + 1], V = 1.0f - v;   /* grid row g = y0 + lane is Y = g - 1 */
+            const float4 *q4 = reinterpret_cast<const float4 *>(qtab);
+            float *t = wt + lane * 16;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                const float4 q = q4[k];
+                const float A = fmaf(v, q.z, V * q.x), B = fmaf(v, q.w, V * q.y);
+                const int at = k == 6 ? 0 : (k < 3 ? 2 + 4 * k : 4 + 4 * (k - 3));
+                t[at] = A;
+                t[at + 1] = B - A;
+            }
+        }
+        __syncwarp();
+    }
+
+    /* the lane's grid columns gx = 4 lc + j (X = gx - 1): u = ulut[gx + 1] */
+    const F2 u01 = make_float2(ulut[4 * lc + 1], ulut[4 * lc + 2]), u23 = make_float2(ulut[4 * lc + 3], ulut[4 * lc + 4]);
+    /* flat: x difference of the horizontal neighbours of texel x = 4 lc + j (see normal_tile) */
+    F2 ddxA = bc(0.0f), ddxB = bc(0.0f);
+    const float Dq = rq.deform[2], x0f = rq.deform[0], y0f = rq.deform[1];
+    if (!SPHERE) {
+        float dd[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int x = 4 * lc + j;
+            dd[j] = fmaf(Dq, ulut[min(x + 3, GEO::ULUT - 1)], x0f) - fmaf(Dq, ulut[x + 1], x0f);
+        }
+        ddxA = make_float2(dd[0], dd[1]);
+        ddxB = make_float2(dd[2], dd[3]);
+    }
+
+    /* texels of the lane: x = 4 lane + (0, 1 | 2, 3) = centres at grid columns 4 lane + (1, 2 | 3, 4) */
+    const bool ok0 = 4 * lane < W, ok1 = 4 * lane + 1 < W, ok2 = 4 * lane + 2 < W, ok3 = 4 * lane + 3 < W;
+    const float *zp = zs + y0 * EP + 4 * lc;            /* zm row g, columns gx .. gx + 4 */
+    const float *rtp = wt;
+    unsigned short *o = out + y0 * W + 4 * lane;
+
+    /* world positions of the lane's four points of the next grid row (rows g, g + 1 of the zm plane; both are
+     * loaded here: carrying row g + 1 over to the next step costs more registers than its two loads) */
+    auto positions = [&](RegRow<NC> &up) {
+        const float4 zn = *reinterpret_cast<const float4 *>(zp + EP);
+        const float zn4 = zp[EP + 4];
+        F2 h01, h23;
+        if (!LINEAR) {
+            h01 = make_float2(zn.y, zn.z);
+            h23 = make_float2(zn.w, zn4);
+        } else {
+            const float4 zq = *reinterpret_cast<const float4 *>(zp);
+            const float z4 = zp[4];
+            h01 = fma2(bc(0.5625f), make_float2(zn.y, zn.z), fma2(bc(0.1875f), make_float2(zn.x, zn.y),
+                       fma2(bc(0.1875f), make_float2(zq.y, zq.z), mul2(bc(0.0625f), make_float2(zq.x, zq.y)))));
+            h23 = fma2(bc(0.5625f), make_float2(zn.w, zn4), fma2(bc(0.1875f), make_float2(zn.z, zn.w),
+                       fma2(bc(0.1875f), make_float2(zq.w, z4), mul2(bc(0.0625f), make_float2(zq.z, zq.w)))));
+        }
+        zp += EP;
+        if (SPHERE) {
+            const float4 *rt = reinterpret_cast<const float4 *>(rtp);
+            rtp += 16;
+            const float4 T0 = rt[0], T1 = rt[1], T2 = rt[2], T3 = rt[3];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const F2 u = p ? u23 : u01, h = p ? h23 : h01;
+                const F2 den = fma2(u, bc(T0.y), bc(T0.x));
+                const F2 r0 = make_float2(plfp::rcp_seed(den.x), plfp::rcp_seed(den.y));
+                const F2 rden = fma2(r0, fma2(r0, neg(den), bc(1.0f)), r0);
+                up.p[0][p] = mul2(fma2(h, fma2(u, bc(T0.w), bc(T0.z)), fma2(u, bc(T1.y), bc(T1.x))), rden);
+                up.p[NC > 1 ? 1 : 0][p] = mul2(fma2(h, fma2(u, bc(T1.w), bc(T1.z)), fma2(u, bc(T2.y), bc(T2.x))), rden);
+                up.p[NC > 2 ? 2 : 0][p] = mul2(fma2(h, fma2(u, bc(T2.w), bc(T2.z)), fma2(u, bc(T3.y), bc(T3.x))), rden);
+            }
+        } else {
+            up.p[0][0] = h01;
+            up.p[0][1] = h23;
+        }
+    };
+
+    /* normals of one texel row: centre grid row `mid`, the rows below `dn` and above `up`.  Texel pair A (centres at
+     * the lane's columns 1, 2) needs the lane's own registers only; pair B (columns 3, 4) takes column 4 -- the next
+     * lane's column 0 -- by SHFL: the centre row's pair for the x difference, and the finished y difference */
+    auto normals = [&](const int y, const RegRow<NC> &dn, const RegRow<NC> &mid, const RegRow<NC> &up) {
+        F2 ddy = bc(0.0f);
+        if (!SPHERE) ddy = bc(fmaf(Dq, ulut[y + 3], y0f) - fmaf(Dq, ulut[y + 1], y0f));
+        unsigned int rg[4];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            F2 d[NC], e[NC];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                if (p == 0) {
+                    d[k] = sub2(mid.p[k][1], mid.p[k][0]);
+                    e[k] = make_float2(up.p[k][0].y - dn.p[k][0].y, up.p[k][1].x - dn.p[k][1].x);
+                } else {
+                    const F2 r = make_float2(__shfl_down_sync(0xffffffffu, mid.p[k][0].x, 1), __shfl_down_sync(0xffffffffu, mid.p[k][0].y, 1));
+                    const float e4 = __shfl_down_sync(0xffffffffu, up.p[k][0].x - dn.p[k][0].x, 1);
+                    d[k] = sub2(r, mid.p[k][1]);
+                    e[k] = make_float2(up.p[k][1].y - dn.p[k][1].y, e4);
+                }
+            }
+            F2 nx, ny, nz;
+            if (SPHERE) {
+                nx = fma2(d[NC > 1 ? 1 : 0], e[NC > 2 ? 2 : 0], neg(mul2(d[NC > 2 ? 2 : 0], e[NC > 1 ? 1 : 0])));
+                ny = fma2(d[NC > 2 ? 2 : 0], e[0], neg(mul2(d[0], e[NC > 2 ? 2 : 0])));
+                nz = fma2(d[0], e[NC > 1 ? 1 : 0], neg(mul2(d[NC > 1 ? 1 : 0], e[0])));
+            } else {   /* d = (ddx, 0, dz), e = (0, ddy, ez): the cross product with its exact zeros removed */
+                const F2 ddx = p ? ddxB : ddxA;
+                nx = neg(mul2(d[0], ddy));
+                ny = neg(mul2(ddx, e[0]));
+                nz = mul2(ddx, ddy);
+            }
+            const F2 n2 = plf2::dot3(nx, ny, nz, nx, ny, nz);
+            const F2 i2 = mul2(make_float2(plfp::rsqrt_seed(n2.x), plfp::rsqrt_seed(n2.y)), bc(127.5f));
+            const F2 r = fma2(nx, i2, bc(127.5f)), g = fma2(ny, i2, bc(127.5f));
+            rg[2 * p] = __byte_perm(__float_as_uint(r.x + 12582912.0f), __float_as_uint(g.x + 12582912.0f), 0x0040u);
+            rg[2 * p + 1] = __byte_perm(__float_as_uint(r.y + 12582912.0f), __float_as_uint(g.y + 12582912.0f), 0x0040u);
+        }
+        if (ok0) o[0] = (unsigned short) rg[0];
+        if (ok1) o[1] = (unsigned short) rg[1];
+        if (ok2) o[2] = (unsigned short) rg[2];
+        if (ok3) o[3] = (unsigned short) rg[3];
+        o += W;
+    };
+
+    RegRow<NC> S0, S1, S2;
+    positions(S0);
+    positions(S1);
+    int y = y0;
+    const int y_end = y0 + n;
+#pragma unroll 1
+    for (; y + 3 <= y_end; y += 3) {
+        positions(S2); normals(y, S0, S1, S2);
+        positions(S0); normals(y + 1, S1, S2, S0);
+        positions(S1); normals(y + 2, S2, S0, S1);
+    }
+    if (y < y_end) {
+        positions(S2); normals(y, S0, S1, S2);
+        if (y + 1 < y_end) { positions(S0); normals(y + 1, S1, S2, S0); }
+    }
+}
+
 /* uv / (tileSDF.x - 1.0) for X = -2 .. (X = -2 and W+1 are pads of odd-start pairs), twice: the second
  * copy starts one entry further, so that a pair starting at an odd index is an aligned pair there */
 template <int TW, int NT>

@@ -30,7 +30,6 @@ int pl_norm_fill_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_po
 
 namespace {
 
-constexpr int kPairThreads = 256;
 
 template <int TW, int TG>
 struct PairSmem {
@@ -44,13 +43,20 @@ struct PairSmem {
     static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT + NG::ROWTAB) * 4;
     static_assert(EG::PITCH == NG::EPITCH && EG::PLANE == NG::EPLANE, "both passes agree on the plane layout");
     static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
+    static_assert(WORK >= plnorm::RGeo<TW - 4, 224>::TAB && NG::ROWTAB >= 28, "row tables of the register form fit");
 };
 
+/* threads of a CTA: 256 under PL_ARITH_EXACT; 224 under PL_ARITH_FAST -- 7 warps x 3 CTAs leave 96 registers per
+ * thread, which the register form of the normal pass needs (three grid rows of positions live in registers), and the
+ * 663 quad pairs of an elevation tile are 3 passes of 224 threads (97 % of the lanes busy) as they are 3 passes of 256 */
+template <bool FAST> struct PairThreads { static constexpr int N = FAST ? 224 : 256; };
+
 template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false>
-__global__ void __launch_bounds__(kPairThreads, 3)
+__global__ void __launch_bounds__(PairThreads<FAST>::N, 3)
 tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
 {
     using SM = PairSmem<TW, TG>;
+    constexpr int kPairThreads = PairThreads<FAST>::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *zs = reinterpret_cast<float *>(smem_raw) + SM::GUARD;   /* zm plane behind the guard floats */
     float *work = zs + plelev::Geo<TW, TG>::PLANE;
@@ -73,6 +79,7 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
     }
     plnorm::normal_uv_tables<TW - 4, kPairThreads>(ulut, tid);
     __syncthreads();
+    if (FAST && SPHERE) plnorm::normal_reg_qtab(rowtab, nrq, tid);   /* visible after the elevation phase's barriers */
 
     /* elevation: planes to HBM, zm also to shared memory */
     plelev::elevation_tile<TW, TG, RESID, kPairThreads, true>(&tm, ea, erq, work, &bar, 0, zs, tid);
@@ -80,6 +87,11 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
 
     /* normals from the shared zm plane */
     unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
+    if (FAST && !PUSH && plnorm::normal_reg_ok(nrq, SPHERE)) {
+        /* the register form: no position planes, no barriers; its row tables live in the elevation scratch */
+        plnorm::normal_tile_reg<TW - 4, SPHERE, LINEAR, kPairThreads>(zs, work, rowtab, ulut, nrq, out, tid);
+        return;
+    }
     plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH, FAST>(zs, work, ulut, nrq, out, tid, &na, rowtab);
 }
 
@@ -101,7 +113,8 @@ int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const pl
     }
     PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SM::BYTES));
     pl_timing_begin(ctx, PL_K_PAIR, n);
-    kern<<<n, kPairThreads, SM::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
+    const int threads = na.fast && na.npeers == 0 ? PairThreads<true>::N : PairThreads<false>::N;
+    kern<<<n, threads, SM::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
     pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
