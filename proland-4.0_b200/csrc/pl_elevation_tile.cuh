@@ -378,9 +378,23 @@ struct ElevSmem {
 /* One tile: stage the parent window (TMA), build the tables, run the quad loop, reduce the statistics.
  * smem: ElevSmem<TW,TG>::FLOATS floats, 128-byte aligned; bar: an mbarrier initialised with count 1 whose
  * current phase parity is `parity`.  All NT threads of the CTA call this; it contains __syncthreads(). */
+/* defer_stats: the caller has a barrier of its own right after this call: the per-warp statistics are left in shared
+ * memory and the caller finishes them with elevation_stats_finish after that barrier (one barrier less per tile) */
+template <int TW, int TG, int NT>
+__device__ __forceinline__ void elevation_stats_finish(const ElevArgs &a, const pl_elev_req &rq, const float *smem)
+{
+    using SM = ElevSmem<TW, TG>;
+    const float *red_lo = smem + SM::FLOATS - 64, *red_hi = red_lo + 32;
+    float lo = red_lo[0], hi = red_hi[0];
+#pragma unroll
+    for (int q = 1; q < NT / 32; ++q) { lo = fminf(lo, red_lo[q]); hi = fmaxf(hi, red_hi[q]); }
+    a.stats[rq.out_slot] = make_float2(lo, hi);
+}
+
 template <int TW, int TG, int RESID, int NT, bool ZS>
 __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const ElevArgs &a, const pl_elev_req &rq, float *smem,
-                                               uint64_t *bar, const uint32_t parity, float *zms, const int tid)
+                                               uint64_t *bar, const uint32_t parity, float *zms, const int tid,
+                                               const bool defer_stats = false)
 {
     using GEO = Geo<TW, TG>;
     using SM = ElevSmem<TW, TG>;
@@ -391,7 +405,7 @@ __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const Elev
     float *lat = winB + SM::WIN;
     int *lutx = reinterpret_cast<int *>(lat + ((SM::LAT + 3) & ~3));
     int *luty = lutx + QW;
-    float *red_lo = reinterpret_cast<float *>(luty + QW), *red_hi = red_lo + 32;
+    float *red_lo = reinterpret_cast<float *>(luty + QW), *red_hi = red_lo + 32;   /* = smem + SM::FLOATS - 64 (elevation_stats_finish) */
 
     const bool has_parent = rq.parent_slot >= 0;
 
@@ -484,6 +498,7 @@ __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const Elev
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, s));
         }
         if ((tid & 31) == 0) { red_lo[tid >> 5] = lo; red_hi[tid >> 5] = hi; }
+        if (defer_stats) return;
         __syncthreads();
         if (tid == 0) {
 #pragma unroll

@@ -668,9 +668,10 @@ __device__ __forceinline__ void normal_tile_reg(const float *zs, float *tab, con
             }
             const F2 n2 = plf2::dot3(nx, ny, nz, nx, ny, nz);
             const F2 i2 = mul2(make_float2(plfp::rsqrt_seed(n2.x), plfp::rsqrt_seed(n2.y)), bc(127.5f));
-            const F2 r = fma2(nx, i2, bc(127.5f)), g = fma2(ny, i2, bc(127.5f));
-            rg[2 * p] = __byte_perm(__float_as_uint(r.x + 12582912.0f), __float_as_uint(g.x + 12582912.0f), 0x0040u);
-            rg[2 * p + 1] = __byte_perm(__float_as_uint(r.y + 12582912.0f), __float_as_uint(g.y + 12582912.0f), 0x0040u);
+            /* round to nearest by the 1.5 * 2^23 magic add (the sum's ulp is 1), byte = low byte of the sum's bits */
+            const F2 r = add2(fma2(nx, i2, bc(127.5f)), bc(12582912.0f)), g = add2(fma2(ny, i2, bc(127.5f)), bc(12582912.0f));
+            rg[2 * p] = __byte_perm(__float_as_uint(r.x), __float_as_uint(g.x), 0x0040u);
+            rg[2 * p + 1] = __byte_perm(__float_as_uint(r.y), __float_as_uint(g.y), 0x0040u);
         }
         if (ok0) o[0] = (unsigned short) rg[0];
         if (ok1) o[1] = (unsigned short) rg[1];

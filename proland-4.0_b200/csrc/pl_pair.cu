@@ -43,7 +43,7 @@ struct PairSmem {
     static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT + NG::ROWTAB) * 4;
     static_assert(EG::PITCH == NG::EPITCH && EG::PLANE == NG::EPLANE, "both passes agree on the plane layout");
     static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
-    static_assert(WORK >= plnorm::RGeo<TW - 4, 224>::TAB && NG::ROWTAB >= 28, "row tables of the register form fit");
+    static_assert(ELEV - 64 >= plnorm::RGeo<TW - 4, 224>::TAB && NG::ROWTAB >= 28, "row tables of the register form fit in front of the statistics");
 };
 
 /* threads of a CTA: 256 under PL_ARITH_EXACT; 224 under PL_ARITH_FAST -- 7 warps x 3 CTAs leave 96 registers per
@@ -82,13 +82,17 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
     if (FAST && SPHERE) plnorm::normal_reg_qtab(rowtab, nrq, tid);   /* visible after the elevation phase's barriers */
 
     /* elevation: planes to HBM, zm also to shared memory */
-    plelev::elevation_tile<TW, TG, RESID, kPairThreads, true>(&tm, ea, erq, work, &bar, 0, zs, tid);
+    unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
+    const bool reg_form = FAST && !PUSH && plnorm::normal_reg_ok(nrq, SPHERE);
+    plelev::elevation_tile<TW, TG, RESID, kPairThreads, true>(&tm, ea, erq, work, &bar, 0, zs, tid, reg_form);
     __syncthreads();   /* zm plane complete; the elevation scratch is free */
 
     /* normals from the shared zm plane */
-    unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
-    if (FAST && !PUSH && plnorm::normal_reg_ok(nrq, SPHERE)) {
-        /* the register form: no position planes, no barriers; its row tables live in the elevation scratch */
+    if (reg_form) {
+        /* the register form: no position planes, no barriers; its row tables live in the elevation scratch (the
+         * first RGeo::TAB floats of it: the per-warp statistics at its end stay intact and are finished here,
+         * behind the barrier above instead of one of their own) */
+        if (tid == kPairThreads - 32 && ea.want_stats) plelev::elevation_stats_finish<TW, TG, kPairThreads>(ea, erq, work);
         plnorm::normal_tile_reg<TW - 4, SPHERE, LINEAR, kPairThreads>(zs, work, rowtab, ulut, nrq, out, tid);
         return;
     }
