@@ -283,6 +283,9 @@ int pl_debug_force_generic(pl_ctx *ctx, int on);
 /* tests / profiling: make pl_produce_range and pl_pair_batch[_dev] launch the elevation and the normal
  * pass as two kernels instead of the fused one (same results, bit for bit) */
 int pl_debug_no_fuse(pl_ctx *ctx, int on);
+/* tests / profiling: which DEFLATE decoder pl_residual_decode_batch / pl_ortho_decode_batch run: 0 = chosen by the batch
+ * size (default), 1 = the warp-per-stream kernel (small batches), 2 = the tokenizer + resolver pair (large batches) */
+int pl_debug_inflate_path(pl_ctx *ctx, int path);
 /* tests: the smallest request staging ring to allocate (default 32 MB); a small ring makes the FIFO
  * wrap around and grow within a few batches */
 int pl_debug_stage_ring(pl_ctx *ctx, size_t min_bytes);

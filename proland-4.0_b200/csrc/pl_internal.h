@@ -67,6 +67,7 @@ struct pl_ctx {
     int gen_cap;
     int force_generic;   /* tests: run the runtime-geometry kernels even for the shipped geometry */
     int no_fuse;         /* tests / profiling: pl_produce_range launches the two passes separately */
+    int inflate_path;    /* tests / profiling: 0 = by batch size, 1 = warp-per-stream decoder, 2 = tokenizer + resolver */
     /* per-launch CUDA-event timing (pl_timing_*): events on the launching stream */
     int timing;
     struct TimedLaunch { cudaEvent_t a, b; int kernel; int tiles; };

@@ -40,11 +40,30 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kRing = 4096;      /* bytes of recent output per warp in shared memory (a power of two) */
-constexpr int kFlush = 1024;     /* ... of which finished units of this size go to HBM */
-constexpr int kLitBits = 10;     /* first-level table of the literal/length code */
-constexpr int kDistBits = 8;     /* first-level table of the distance code */
+/* ------------------------------------------------------------------------
+ * DEFLATE on the device in two kernels.
+ *
+ * A DEFLATE stream is one serial chain: the position of every code depends on all codes before it.  The round-1
+ * kernel gave a whole warp to one stream (32 lanes decoding redundantly, matches copied through a 4 KB ring in
+ * shared memory): 104 warp instructions per symbol, issue-bound at 445 K tiles/s, and half of the matches of a
+ * 197 x 197 int16 tile reach further back than any ring that fits (zlib's window is 32 KB), i.e. an L2 round trip
+ * on the chain per match.  Splitting the warp into lane groups (one stream per 8 / 4 lanes) was measured SLOWER
+ * (264 K / 214 K tiles/s): groups diverge at every literal/match branch and the warp runs them one after the other.
+ * What the batch offers instead is thousands of independent streams, so:
+ *
+ *   inflate_tokens_kernel   ONE LANE PER STREAM does the serial part only -- Huffman decoding -- with uniform
+ *       control flow (one symbol per lane and iteration, the match branch is predicated work, block headers fall on
+ *       the same iteration for streams written with the same zlib settings).  A lane keeps its bit buffer in
+ *       registers and its code tables in shared memory (2.5 KB: 64 streams per SM) and writes 32-bit TOKENS:
+ *       up to three literal bytes, or (length, distance).  Nothing on its chain waits for HBM.
+ *   lz_resolve_kernel       ONE WARP PER STREAM turns tokens into bytes, 32 tokens at a time: a warp scan gives
+ *       every token its output offset; then, 32 output bytes per step, each lane finds the token its byte belongs
+ *       to (binary search over the 32 offsets by SHFL) and fetches the byte the match points at.  The copies of a
+ *       step are independent loads in flight together -- throughput, not a chain; a source inside the step itself
+ *       (runs: distance < 32) is resolved by passing values between lanes.  The warp then converts its finished
+ *       tile into the pool's layout (what residual_store_kernel did as a third launch).
+ * ------------------------------------------------------------------------ */
+constexpr int kTokLanes = 32;              /* streams per CTA of the tokenizer */
 
 enum {
     INF_OK = 0,
@@ -57,18 +76,29 @@ enum {
     INF_SHORT = 7
 };
 
-struct WarpTables {
-    unsigned short lit_lut[1 << kLitBits];   /* (symbol << 4) | code length, 0 = not in the table */
-    unsigned short dist_lut[1 << kDistBits];
-    unsigned short lit_count[16], lit_sym[288];   /* canonical decode (codes longer than the table) */
-    unsigned short dist_count[16], dist_sym[32];
-    unsigned char lens[320];
+/* A canonical prefix code is decoded WITHOUT a look-up table: with v = the next 15 bits of the stream, first bit on
+ * top, the code's length is the smallest l with v < lim[l] (canonical codes, left-justified, grow with their length)
+ * and its symbol is sym[off[l] + (v >> (15 - l))].  lim[] and off[] of the literal/length and of the distance code
+ * live in REGISTERS (60 of them: the kernel runs few warps per SM, registers are free), the comparison chain is
+ * straight-line code every lane executes alike -- no table misses, no divergence, and a stream needs only its sorted
+ * symbols in shared memory: 1 KB instead of the 2.6 KB of first-level tables, i.e. 2.5 x the streams per SM.
+ * The trailing pad makes the stride an odd number of words, so that the 32 lanes of a warp touching the same field
+ * of their own tables hit 32 different banks. */
+struct LaneTables {
+    unsigned short lit_sym[288];             /* symbols sorted by (code length, value) */
+    unsigned short dist_sym[32];
+    unsigned short lim[16];                  /* build_code -> registers; the code-length code is decoded from here */
+    short off[16];
+    unsigned short cnt[16];                  /* build_code scratch */
+    unsigned int pad_;
 };
+constexpr int kLensBytes = 320;             /* code lengths of a block header: per stream, in global scratch (read and
+                                             * written by the header phase only, a few hundred accesses per block) */
+static_assert(sizeof(LaneTables) % 8 == 4, "odd word stride");
 
-/* The bit reader (every lane of the warp carries an identical copy).  Input comes in ALIGNED 32-bit words, one word prefetched ahead of the bit
- * buffer so that the load latency overlaps the decoding of the 32 bits before it (byte loads on the
- * critical path were a third of the old kernel's time).  Consuming bits behind the end of the strip is
- * detected by position (br_overrun), not by what those bits are. */
+/* The bit reader of a stream.  Input comes in ALIGNED 32-bit words, one word prefetched ahead of the bit
+ * buffer so that the load latency overlaps the decoding of the 32 bits before it.  Consuming bits behind the end
+ * of the strip is detected by position (br_overrun), not by what those bits are. */
 struct BitReader {
     const unsigned char *src;    /* strip start */
     unsigned int end;            /* strip length in bytes */
@@ -116,7 +146,7 @@ __device__ __forceinline__ void br_fill(BitReader &b)
         b.nxt = br_word(b, b.k);
     }
 }
-__device__ __forceinline__ unsigned int br_peek(const BitReader &b, int n) { return (unsigned int) (b.buf & ((1ull << n) - 1)); }
+__device__ __forceinline__ unsigned int br_peek(const BitReader &b, int n) { return (unsigned int) b.buf & ((1u << n) - 1u); }   /* n <= 16 */
 __device__ __forceinline__ void br_drop(BitReader &b, int n)
 {
     b.buf >>= n;
@@ -137,8 +167,7 @@ __device__ __forceinline__ unsigned int br_take(BitReader &b, int n)
     return v;
 }
 /* bits were consumed behind the end of the strip: bytes merged so far minus whole bytes still buffered
- * pass the end.  Checked at every flush and block end, not per symbol: a stream running on garbage stays
- * bounded by the output capacity and the code tables, and is rejected at the next check */
+ * pass the end */
 __device__ __forceinline__ bool br_overrun(const BitReader &b)
 {
     return b.merged > b.end && b.merged - (unsigned int) (b.cnt >> 3) > b.end;
@@ -146,7 +175,323 @@ __device__ __forceinline__ bool br_overrun(const BitReader &b)
 /* strip offset of the next unread byte (call at a byte boundary) */
 __device__ __forceinline__ unsigned int br_byte_pos(const BitReader &b) { return b.merged - (unsigned int) (b.cnt >> 3); }
 
+/* The tables of a canonical prefix code from lens[0..n) (one lane, serial): symbols sorted by (length, value), and
+ * lim[] / off[] as described at LaneTables.  Returns false for an over-subscribed code. */
+__device__ bool build_code(const unsigned char *lens, int n, unsigned short *count, unsigned short *lim, short *off,
+                           unsigned short *sym)
+{
+    for (int l = 0; l < 16; ++l) count[l] = 0;
+    for (int s = 0; s < n; ++s) count[lens[s]]++;
+    int left = 1;
+    for (int l = 1; l < 16; ++l) {
+        left <<= 1;
+        left -= count[l];
+        if (left < 0) return false;
+    }
+    /* canonical codes in order of (length, value): code = first code of the length + rank */
+    unsigned int code = 0, idx = 0;
+    for (int l = 1; l < 16; ++l) {
+        code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
+        const unsigned int c = count[l];
+        lim[l] = (unsigned short) min((code + c) << (15 - l), 0xffffu);
+        off[l] = (short) ((int) idx - (int) code);
+        idx += c;
+    }
+    /* the slot of a symbol is the running offset of its length: count[] becomes those offsets */
+    unsigned int run = 0;
+    for (int l = 1; l < 16; ++l) { const unsigned int c = count[l]; count[l] = (unsigned short) run; run += c; }
+    for (int s = 0; s < n; ++s) {
+        const int l = lens[s];
+        if (l) sym[count[l]++] = (unsigned short) s;
+    }
+    return true;
+}
+
+struct CodeRegs { unsigned int lim[16]; int dlt[16]; int off1; };   /* dlt[k] = off[k + 1] - off[k] */
+
+__device__ __forceinline__ void load_code(CodeRegs &c, const unsigned short *lim, const short *off)
+{
+#pragma unroll
+    for (int k = 1; k < 16; ++k) { c.lim[k] = lim[k]; c.dlt[k] = k < 15 ? (int) off[k + 1] - (int) off[k] : 0; }
+    c.lim[0] = 0; c.dlt[0] = 0;
+    c.off1 = off[1];
+}
+
+/* one symbol of a code held in registers; MAXL: the longest code the alphabet allows.  -1: not a code.
+ * The 15 comparisons are independent of each other (a mask m_k = -1 where v >= lim[k]); the length and the symbol
+ * offset are sums over the masks (off[l] = off[1] + sum of the differences below l), added as trees: the decode
+ * is on the per-symbol dependency chain of a latency-bound kernel, so its DEPTH counts, not its instruction count */
+template <int MAXL, int NSYM>
+__device__ __forceinline__ int decode_sym(BitReader &b, const CodeRegs &c, const unsigned short *sym)
+{
+    if (b.cnt < 32) br_fill(b);
+    const unsigned int v = __brev((unsigned int) b.buf) >> 17;   /* the next 15 bits, first bit on top */
+    const unsigned int nv = ~v;                                  /* lim + nv = lim - v - 1: negative iff v >= lim */
+    int m[16], t[16];
+#pragma unroll
+    for (int k = 1; k <= MAXL; ++k) {
+        m[k] = (int) (c.lim[k] + nv) >> 31;
+        t[k] = m[k] & c.dlt[k];
+    }
+    m[0] = 0; t[0] = 0;
+#pragma unroll
+    for (int k = MAXL + 1; k < 16; ++k) { m[k] = 0; t[k] = 0; }
+    const int ms = ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7])) + (((m[8] + m[9]) + (m[10] + m[11])) + ((m[12] + m[13]) + (m[14] + m[15])));
+    const int ts = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7])) + (((t[8] + t[9]) + (t[10] + t[11])) + ((t[12] + t[13]) + (t[14] + t[15])));
+    int l = 1 - ms;
+    const int o = c.off1 + ts;
+    const bool bad = l > MAXL;
+    l = bad ? MAXL : l;
+    br_drop(b, l);
+    const int s = sym[min(max(o + (int) (v >> (15 - l)), 0), NSYM - 1)];
+    return bad ? -1 : s;
+}
+/* the code-length code of a block header (<= 7 bits), decoded from the arrays in shared memory */
+__device__ __forceinline__ int decode_cl(BitReader &b, const unsigned short *lim, const short *off, const unsigned short *sym)
+{
+    if (b.cnt < 32) br_fill(b);
+    const unsigned int v = __brev((unsigned int) b.buf) >> 17;
+    int l = 1;
+#pragma unroll
+    for (int k = 1; k <= 7; ++k)
+        if (v >= lim[k]) l = k + 1;
+    if (l > 7) { br_drop(b, 7); return -1; }
+    br_drop(b, l);
+    return sym[min(max(off[l] + (int) (v >> (15 - l)), 0), 18)];
+}
+
+__constant__ unsigned short kLenBase[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
+__constant__ unsigned char kLenExtra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
+__constant__ unsigned short kDistBase[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577 };
+__constant__ unsigned char kDistExtra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
+__constant__ unsigned char kClOrder[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
+
+struct InflateJob {
+    unsigned long long in_off;   /* strip start in the device blob buffer */
+    unsigned int in_len;
+    unsigned int out_len;        /* expected: w * w * 2 */
+    unsigned int compression;    /* 1 = stored strip, else zlib stream */
+};
+
+/* Tokens (32 bits): bits 31:30 = n > 0: n literal bytes in bits 7:0, 15:8, 23:16 (output order);
+ *                   bits 31:30 = 0: a match, length - 3 in bits 7:0, distance - 1 in bits 29:15.
+ * A stream of L output bytes has at most L / 2 + 2 tokens (the worst case alternates single literals with matches
+ * of length 3). */
+struct TokenInfo {
+    unsigned int ntok;       /* tokens written */
+    unsigned int out_len;    /* bytes they expand to */
+    int status;
+    int stored;              /* 1: uncompressed strip, no tokens: the resolver copies the strip */
+};
+
+/* ---- kernel 1: Huffman decoding, one lane per stream -------------------------------------------------- */
+__global__ void __launch_bounds__(kTokLanes) inflate_tokens_kernel(int n, const InflateJob *jobs, const unsigned char *in,
+                                                                    unsigned int *tokens, size_t tok_stride, TokenInfo *info,
+                                                                    unsigned char *lens_scratch)
+{
+    extern __shared__ __align__(16) unsigned char tok_smem[];
+    __shared__ unsigned int len_tab[32], dist_tab[32];   /* base | extra bits << 16 (constant memory would serialise over the lanes) */
+    if (threadIdx.x < 29) len_tab[threadIdx.x] = kLenBase[threadIdx.x] | ((unsigned int) kLenExtra[threadIdx.x] << 16);
+    if (threadIdx.x < 30) dist_tab[threadIdx.x] = kDistBase[threadIdx.x] | ((unsigned int) kDistExtra[threadIdx.x] << 16);
+    __syncthreads();
+    const int job = blockIdx.x * kTokLanes + threadIdx.x;
+    const bool real = job < n;
+    LaneTables &T = reinterpret_cast<LaneTables *>(tok_smem)[threadIdx.x];
+    InflateJob J;
+    J.in_off = 0; J.in_len = 0; J.out_len = 0; J.compression = 1;
+    if (real) J = jobs[job];
+    unsigned int *tok = tokens + (size_t) (real ? job : 0) * tok_stride;
+    unsigned char *lens = lens_scratch + (size_t) (real ? job : 0) * kLensBytes;
+    const unsigned int cap = J.out_len;
+    const unsigned int tok_cap = (unsigned int) tok_stride;
+
+    /* The lanes of a warp must stay CONVERGED: a warp instruction then advances 32 streams.  Left to itself the
+     * compiler reconverges lanes that broke out of nested loops only behind those loops (measured: every lane ran
+     * alone, 2 960 warp instructions per symbol step).  So the decoder is a state machine with one flat loop; every
+     * iteration starts with a warp vote, which is also a reconvergence point: a lane either parses a block header
+     * (streams written with the same zlib settings reach them on the same iteration), decodes ONE symbol, or idles. */
+    enum { ST_HEADER = 0, ST_SYMBOLS = 1, ST_DONE = 2 };
+    CodeRegs LC, DC;        /* the literal/length and the distance code of the current block */
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { LC.lim[k] = DC.lim[k] = 0; LC.dlt[k] = DC.dlt[k] = 0; }   /* a header loads the real ones */
+    LC.off1 = DC.off1 = 0;
+    int state = ST_HEADER;
+    int err = INF_OK;
+    BitReader b;
+    unsigned int pos = 0, ntok = 0;
+    unsigned int lit_acc = 0, lit_n = 0;      /* pending literal token */
+    int last = 0;
+    if (!real || J.compression == 1) {
+        state = ST_DONE;                       /* uncompressed strip: nothing to decode, the resolver copies it */
+        b.src = in; b.end = 0; b.org = 0; b.k = 0; b.merged = 0; b.nxt = 0; b.buf = 0; b.cnt = 0;
+    } else {
+        br_init(b, in + J.in_off, J.in_len);
+        /* zlib header: CM = 8, no preset dictionary, header checksum */
+        const unsigned int cmf = br_bits(b, 8), flg = br_bits(b, 8);
+        if ((cmf & 15) != 8 || (cmf >> 4) > 7 || (flg & 32) || ((cmf << 8) | flg) % 31 != 0) { err = INF_BAD_HEADER; state = ST_DONE; }
+    }
+
+    while (__any_sync(0xffffffffu, state != ST_DONE)) {
+        if (state == ST_HEADER) {
+            /* ---- a block header: stored bytes, or the code tables of the block ---- */
+            last = (int) br_bits(b, 1);
+            const int type = (int) br_bits(b, 2);
+            if (type == 0) {   /* stored block: its bytes become literal tokens */
+                br_drop(b, b.cnt & 7);                 /* to the byte boundary */
+                const unsigned int len = br_bits(b, 16);
+                const unsigned int nlen = br_bits(b, 16);
+                const unsigned int src_pos = br_byte_pos(b);              /* next unread byte */
+                if ((len ^ nlen) != 0xffffu) err = INF_BAD_BLOCK;
+                else if (src_pos + len > b.end) err = INF_OVERRUN_IN;
+                else if (pos + len > cap || ntok + len / 3 + 2 > tok_cap) err = INF_OVERRUN_OUT;
+                if (!err) {
+                    for (unsigned int k = 0; k < len; ++k) {
+                        lit_acc |= (unsigned int) __ldg(b.src + src_pos + k) << (8 * lit_n);
+                        if (++lit_n == 3) {
+                            tok[ntok++] = (3u << 30) | lit_acc;
+                            lit_acc = 0; lit_n = 0;
+                        }
+                    }
+                    pos += len;
+                    br_seek(b, src_pos + len);   /* restart the bit reader after the stored bytes */
+                    if (last) state = ST_DONE;
+                }
+            } else if (type == 3) {
+                err = INF_BAD_BLOCK;
+            } else {
+                int nlen = 288, ndist = 30;
+                if (type == 1) {   /* fixed code */
+                    for (int s = 0; s < 288; ++s) lens[s] = s < 144 ? 8 : (s < 256 ? 9 : (s < 280 ? 7 : 8));
+                    for (int s = 0; s < 32; ++s) lens[288 + s] = 5;
+                } else {           /* dynamic code: read the code lengths */
+                    nlen = (int) br_bits(b, 5) + 257;
+                    ndist = (int) br_bits(b, 5) + 1;
+                    const int ncode = (int) br_bits(b, 4) + 4;
+                    if (nlen > 286 || ndist > 30) err = INF_BAD_BLOCK;
+                    if (!err) {
+                        for (int s = 0; s < 19; ++s) lens[s] = 0;
+                        for (int k = 0; k < ncode; ++k) lens[kClOrder[k]] = (unsigned char) br_bits(b, 3);
+                        /* the code-length code reuses the literal tables (its codes have at most 7 bits) */
+                        if (!build_code(lens, 19, T.cnt, T.lim, T.off, T.lit_sym)) err = INF_BAD_CODE;
+                    }
+                    int idx = 0, prev_len = 0;
+                    while (!err && idx < nlen + ndist) {
+                        const int s = decode_cl(b, T.lim, T.off, T.lit_sym);
+                        if (s < 0) {
+                            err = INF_BAD_CODE;
+                        } else if (s < 16) {
+                            lens[idx] = (unsigned char) s;
+                            if (idx == 256 && s == 0) err = INF_BAD_CODE;   /* no end-of-block code */
+                            idx++;
+                            prev_len = s;
+                        } else {
+                            int prev = 0, rep;
+                            if (s == 16) {
+                                if (idx == 0) err = INF_BAD_CODE;
+                                prev = prev_len;
+                                rep = 3 + (int) br_bits(b, 2);
+                            } else if (s == 17) {
+                                rep = 3 + (int) br_bits(b, 3);
+                            } else {
+                                rep = 11 + (int) br_bits(b, 7);
+                            }
+                            if (idx + rep > nlen + ndist) err = INF_BAD_CODE;
+                            if (idx <= 256 && idx + rep > 256 && prev == 0) err = INF_BAD_CODE;   /* lens[256] == 0 */
+                            if (!err)
+                                for (int q = 0; q < rep; ++q) lens[idx + q] = (unsigned char) prev;
+                            idx += rep;
+                            prev_len = prev;
+                        }
+                    }
+                }
+                /* distance lengths follow the literal/length lengths in lens[]; incomplete distance codes (a single
+                 * distance code) are legal, over-subscription is not */
+                if (!err) {
+                    if (!build_code(lens + (type == 1 ? 288 : nlen), ndist, T.cnt, T.lim, T.off, T.dist_sym)) err = INF_BAD_CODE;
+                    load_code(DC, T.lim, T.off);
+                    if (!build_code(lens, nlen, T.cnt, T.lim, T.off, T.lit_sym)) err = INF_BAD_CODE;
+                    load_code(LC, T.lim, T.off);
+                }
+                state = ST_SYMBOLS;
+            }
+            if (err) state = ST_DONE;
+        } else if (state == ST_SYMBOLS) {
+            /* ---- one symbol.  Bit budget: decode_sym leaves >= 33 - 15 = 18 bits, enough for the length extra
+             * bits (<= 5); the distance decode refills for its 15 + 13 bits ---- */
+            const int sym = decode_sym<15, 288>(b, LC, T.lit_sym);
+            if (sym == 256) {
+                if (br_overrun(b)) err = INF_OVERRUN_IN;
+                state = last ? ST_DONE : ST_HEADER;
+            } else if (sym < 0 || sym > 285) {
+                err = INF_BAD_CODE;
+            } else if (ntok + 2 > tok_cap) {
+                err = INF_OVERRUN_OUT;
+            } else if (sym < 256) {
+                lit_acc |= (unsigned int) sym << (8 * lit_n);
+                pos += 1;
+                if (++lit_n == 3) {
+                    tok[ntok++] = (3u << 30) | lit_acc;
+                    lit_acc = 0; lit_n = 0;
+                }
+            } else {
+                const unsigned int le = len_tab[sym - 257];
+                const unsigned int len = (le & 0xffffu) + br_take(b, (int) (le >> 16));
+                const int ds = decode_sym<15, 32>(b, DC, T.dist_sym);
+                const unsigned int de = dist_tab[min(max(ds, 0), 29)];
+                const unsigned int dist = (de & 0xffffu) + br_take(b, (int) (de >> 16));
+                if (ds < 0 || ds > 29) err = INF_BAD_CODE;
+                else if (dist > pos) err = INF_BAD_DISTANCE;
+                else {
+                    if (lit_n) {
+                        tok[ntok++] = (lit_n << 30) | lit_acc;
+                        lit_acc = 0; lit_n = 0;
+                    }
+                    tok[ntok++] = ((dist - 1u) << 15) | (len - 3u);
+                    pos += len;
+                }
+            }
+            if (pos > cap) err = INF_OVERRUN_OUT;
+            if (err) state = ST_DONE;
+        }
+    }
+    if (!real) return;
+    TokenInfo ti;
+    if (J.compression == 1) {
+        ti.ntok = 0; ti.out_len = J.in_len; ti.stored = 1;
+        ti.status = J.in_len == cap ? INF_OK : INF_SHORT;
+    } else {
+        if (!err && lit_n) {
+            if (ntok >= tok_cap) err = INF_OVERRUN_OUT;
+            else tok[ntok++] = (lit_n << 30) | lit_acc;
+        }
+        if (!err && pos != cap) err = INF_SHORT;
+        ti.ntok = ntok; ti.out_len = pos; ti.status = err; ti.stored = 0;
+    }
+    info[job] = ti;
+}
+
+
+/* ------------------------------------------------------------------------
+ * Small batches: ONE WARP PER STREAM (the round-1 kernel).  The two-kernel decoder above needs tens of thousands of
+ * streams to fill the chip (a lane per stream); below ~6 000 streams its tokenizer's fixed chain time (11 ms: 17 K
+ * symbols of 1 300 cycles each) loses against 2.2 us per tile of this kernel.  Output: the dense stream + TokenInfo
+ * with stored = 2, i.e. lz_resolve_kernel only moves the finished tile into the pool.
+ * ------------------------------------------------------------------------ */
+namespace warpinf {
+constexpr int kWarpsPerCta = 4;
+constexpr int kRing = 4096;      /* bytes of recent output per warp in shared memory (a power of two) */
+constexpr int kFlush = 1024;     /* ... of which finished units of this size go to HBM */
+constexpr int kLitBits = 10;     /* first-level table of the literal/length code */
+constexpr int kDistBits = 8;     /* first-level table of the distance code */
 __device__ __forceinline__ unsigned int bitrev(unsigned int v, int n) { return __brev(v) >> (32 - n); }
+
+struct WarpTables {
+    unsigned short lit_lut[1 << kLitBits];   /* (symbol << 4) | code length, 0 = not in the table */
+    unsigned short dist_lut[1 << kDistBits];
+    unsigned short lit_count[16], lit_sym[288];   /* canonical decode (codes longer than the table) */
+    unsigned short dist_count[16], dist_sym[32];
+    unsigned char lens[320];
+};
 
 /* Build count/symbol arrays and the first-level table of a canonical prefix code from
  * lens[0..n) (all 32 lanes; lane 0 does the short serial parts).  Returns false for an
@@ -234,19 +579,6 @@ __device__ __forceinline__ int decode_sym(BitReader &b, const unsigned short *lu
     return slow_decode(b, count, sym);
 }
 
-__constant__ unsigned short kLenBase[29] = { 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258 };
-__constant__ unsigned char kLenExtra[29] = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0 };
-__constant__ unsigned short kDistBase[30] = { 1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577 };
-__constant__ unsigned char kDistExtra[30] = { 0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13 };
-__constant__ unsigned char kClOrder[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
-
-struct InflateJob {
-    unsigned long long in_off;   /* strip start in the device blob buffer */
-    unsigned int in_len;
-    unsigned int out_len;        /* expected: w * w * 2 */
-    unsigned int compression;    /* 1 = stored strip, else zlib stream */
-};
-
 /* ring[flushed .. flushed + n) -> dst (n, flushed multiples of 16; both sides 16-byte aligned) */
 __device__ __forceinline__ void flush_ring(const unsigned char *ring, unsigned char *dst, unsigned int flushed, unsigned int n, int lane)
 {
@@ -264,8 +596,8 @@ __device__ __forceinline__ void flush_ring(const unsigned char *ring, unsigned c
  * into a ring of the last kRing output bytes in shared memory; matches are copied by all lanes; finished
  * kilobytes leave for the dense stream in HBM as 16-byte stores; a match that reaches behind the ring
  * (rare) reads its source back from there. */
-__global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const InflateJob *jobs, const unsigned char *in,
-                                                                   unsigned char *out, size_t out_stride, int *status)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_warp_kernel(int n, const InflateJob *jobs, const unsigned char *in,
+                                                                        unsigned char *out, size_t out_stride, TokenInfo *info)
 {
     __shared__ WarpTables tables[kWarpsPerCta];
     __shared__ __align__(16) unsigned char rings[kWarpsPerCta][kRing];
@@ -282,7 +614,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
 
     if (J.compression == 1) {   /* uncompressed strip */
         for (unsigned int k = lane; k < min(J.in_len, cap); k += 32) dst[k] = __ldg(src + k);
-        if (lane == 0) status[job] = J.in_len == cap ? INF_OK : INF_SHORT;
+        if (lane == 0) { TokenInfo ti; ti.ntok = 0; ti.out_len = cap; ti.status = J.in_len == cap ? INF_OK : INF_SHORT; ti.stored = 2; info[job] = ti; }
         return;
     }
 
@@ -461,8 +793,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_kernel(int n, const
         flush_ring(ring, dst, flushed, r16, lane);
         for (unsigned int k = r16 + lane; k < rest; k += 32) dst[flushed + k] = ring[(flushed + k) & M];
     }
-    if (lane == 0) status[job] = err;
+    if (lane == 0) { TokenInfo ti; ti.ntok = 0; ti.out_len = pos; ti.status = err; ti.stored = 2; info[job] = ti; }
 }
+
+}  // namespace warpinf
 
 struct StoreJob {
     int width;       /* w of this tile */
@@ -471,46 +805,128 @@ struct StoreJob {
     int channels;    /* byte tiles (pl_ortho_decode_batch): samples per texel in the dense stream */
 };
 
-/* dense int16 (w x w) -> pitched pool rows; ResidualProducer.cpp:321-338 */
-template <bool F32>
-__global__ void __launch_bounds__(256) residual_store_kernel(const StoreJob *jobs, const unsigned char *dense, size_t dense_stride,
-                                                             unsigned char *pool, size_t slot_bytes, int pitch, float scale)
-{
-    const StoreJob J = jobs[blockIdx.x];
-    const short *src = reinterpret_cast<const short *>(dense + (size_t) blockIdx.x * dense_stride);
-    const int w = J.width;
-    for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
-        const int j = k / w, i = k - j * w;
-        const short z = src[k];
-        if (F32) {
-            float *dst = reinterpret_cast<float *>(pool + (size_t) J.out_slot * slot_bytes);
-            const float zs = (float) z * scale;
-            float v = zs;
-            if (J.add_slot >= 0) {
-                const float *add = reinterpret_cast<const float *>(pool + (size_t) J.add_slot * slot_bytes);
-                v = add[(size_t) j * pitch + i] + zs;
-            }
-            dst[(size_t) j * pitch + i] = v;
-        } else {
-            short *dst = reinterpret_cast<short *>(pool + (size_t) J.out_slot * slot_bytes);
-            dst[(size_t) j * pitch + i] = z;
-        }
-    }
-}
+/* what the resolver's warp does with its finished tile */
+enum { STORE_I16 = 0, STORE_F32 = 1, STORE_ORTHO = 2 };
 
-/* dense bytes (w x w x channels, what TIFFReadEncodedStrip hands OrthoCPUProducer, OrthoCPUProducer.cpp:226-231)
- * -> RGBA8 texels of an ortho pool; channels the file does not have are written as 0 */
-__global__ void __launch_bounds__(256) ortho_store_kernel(const StoreJob *jobs, const unsigned char *dense, size_t dense_stride,
-                                                          unsigned char *pool, size_t slot_bytes)
+/* ---- kernel 2: tokens -> bytes, one warp per stream; then the tile into the pool's layout --------------- */
+constexpr int kResolveWarps = 4;
+constexpr int kWarpPathBelow = 6000;     /* batches smaller than this take the warp-per-stream decoder (see warpinf) */
+
+template <int STORE>
+__global__ void __launch_bounds__(kResolveWarps * 32) lz_resolve_kernel(int n, const InflateJob *jobs, const unsigned char *in,
+                                                                        const unsigned int *tokens, size_t tok_stride,
+                                                                        const TokenInfo *info, unsigned char *dense, size_t dense_stride,
+                                                                        int *status, const StoreJob *sjobs, unsigned char *pool,
+                                                                        size_t slot_bytes, int pitch, float scale)
 {
-    const StoreJob J = jobs[blockIdx.x];
-    const unsigned char *src = dense + (size_t) blockIdx.x * dense_stride;
-    uint32_t *dst = reinterpret_cast<uint32_t *>(pool + (size_t) J.out_slot * slot_bytes);
-    const int w = J.width, ch = J.channels;
-    for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
-        uint32_t t = 0;
-        for (int c = 0; c < ch; ++c) t |= (uint32_t) src[(size_t) k * ch + c] << (8 * c);
-        dst[k] = t;
+    const int lane = threadIdx.x & 31;
+    const int job = blockIdx.x * kResolveWarps + (threadIdx.x >> 5);
+    if (job >= n) return;
+    const TokenInfo ti = info[job];
+    unsigned char *dst = dense + (size_t) job * dense_stride;
+    int err = ti.status;
+    if (!err && ti.stored == 2) {
+        /* the dense stream is complete already (inflate_warp_kernel) */
+    } else if (!err && ti.stored) {
+        const unsigned char *src = in + jobs[job].in_off;
+        for (unsigned int k = lane; k < ti.out_len; k += 32) dst[k] = __ldg(src + k);
+    } else if (!err) {
+        const unsigned int *tok = tokens + (size_t) job * tok_stride;
+        unsigned int pos = 0;       /* bytes finished */
+        for (unsigned int t0 = 0; t0 < ti.ntok; t0 += 32) {
+            const bool have = t0 + lane < ti.ntok;
+            const unsigned int tw = have ? __ldg(tok + t0 + lane) : 0u;
+            const unsigned int kind = tw >> 30;
+            const unsigned int olen = !have ? 0u : (kind ? kind : (tw & 0xffu) + 3u);
+            /* exclusive scan of the output lengths */
+            unsigned int incl = olen;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            const unsigned int excl = incl - olen;
+            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+            for (unsigned int s = 0; s < total; s += 32) {
+                const unsigned int q = s + lane;           /* output byte of this lane within the batch */
+                /* the token that covers q: the last one whose offset is <= q (empty tokens sit at the end) */
+                int t = 0;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const unsigned int oc = __shfl_sync(0xffffffffu, excl, t + d);
+                    if (oc <= q) t += d;
+                }
+                const unsigned int tt = __shfl_sync(0xffffffffu, tw, t);
+                const unsigned int te = __shfl_sync(0xffffffffu, excl, t);
+                const bool active = q < total;
+                const unsigned int r = q - te;            /* byte within the token */
+                unsigned int val = 0;
+                bool done = true;
+                int from = 0;                              /* lane of this step that produces the source byte */
+                if (active) {
+                    if (tt >> 30) {
+                        val = (tt >> (8 * r)) & 0xffu;
+                    } else {
+                        const unsigned int dist = ((tt >> 15) & 0x7fffu) + 1u;
+                        if (dist > pos + q) {
+                            err = INF_BAD_DISTANCE;        /* before the start of the output */
+                        } else if (dist > lane) {
+                            /* written by an earlier step (or batch): the stores of those are visible after the __syncwarp below */
+                            val = __ldcg(dst + (pos + q - dist));
+                        } else {
+                            done = false;                  /* produced in this very step, by lane - dist */
+                            from = lane - (int) dist;
+                        }
+                    }
+                }
+                /* runs: pass values down the lanes until every byte of the step is known (a source lane is always lower) */
+                while (__any_sync(0xffffffffu, !done)) {
+                    const unsigned int v = __shfl_sync(0xffffffffu, val, from);
+                    const int d = __shfl_sync(0xffffffffu, done ? 1 : 0, from);
+                    if (!done && d) { val = v; done = true; }
+                }
+                if (active) dst[pos + q] = (unsigned char) val;
+                __syncwarp();
+            }
+            pos += total;
+        }
+        if (!err && pos != ti.out_len) err = INF_SHORT;
+    }
+    err = (int) __reduce_max_sync(0xffffffffu, (unsigned int) err);   /* any lane's error is the stream's */
+    if (lane == 0) status[job] = err;
+    if (err) return;
+    __syncwarp();
+
+    /* the finished tile -> the pool (ResidualProducer.cpp:321-338; OrthoCPUProducer.cpp:226-231) */
+    const StoreJob S = sjobs[job];
+    const int w = S.width;
+    if (STORE == STORE_ORTHO) {
+        uint32_t *o = reinterpret_cast<uint32_t *>(pool + (size_t) S.out_slot * slot_bytes);
+        const int ch = S.channels;
+        for (int k = lane; k < w * w; k += 32) {
+            uint32_t t = 0;
+            for (int c = 0; c < ch; ++c) t |= (uint32_t) __ldcg(dst + (size_t) k * ch + c) << (8 * c);
+            o[k] = t;
+        }
+    } else {
+        const short *src = reinterpret_cast<const short *>(dst);
+        for (int k = lane; k < w * w; k += 32) {
+            const int j = k / w, i = k - j * w;
+            const short z = __ldcg(src + k);
+            if (STORE == STORE_F32) {
+                float *o = reinterpret_cast<float *>(pool + (size_t) S.out_slot * slot_bytes);
+                const float zs = (float) z * scale;
+                float v = zs;
+                if (S.add_slot >= 0) {
+                    const float *add = reinterpret_cast<const float *>(pool + (size_t) S.add_slot * slot_bytes);
+                    v = add[(size_t) j * pitch + i] + zs;
+                }
+                o[(size_t) j * pitch + i] = v;
+            } else {
+                short *o = reinterpret_cast<short *>(pool + (size_t) S.out_slot * slot_bytes);
+                o[(size_t) j * pitch + i] = z;
+            }
+        }
     }
 }
 
@@ -747,8 +1163,15 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
         memcpy(stage.data() + job_off + sizeof(InflateJob) * n, sjobs.data(), sizeof(StoreJob) * n);
         int rc = pl_stage_requests(ctx, stage.data(), stage.size(), &dev);
         if (rc) return rc;
-        /* scratch for the dense streams + status */
-        const size_t scratch = dense_stride * n + sizeof(int) * n;
+        /* scratch: the dense streams, status words, token streams and their counts */
+        size_t max_out = 0;
+        for (int j = 0; j < n; ++j) max_out = jobs[j].out_len > max_out ? jobs[j].out_len : max_out;
+        const size_t tok_stride = (max_out / 2 + 4 + 3) & ~(size_t) 3;                  /* tokens per stream (see TokenInfo) */
+        const size_t off_status = dense_stride * n;
+        const size_t off_info = (off_status + sizeof(int) * n + 15) & ~(size_t) 15;
+        const size_t off_tok = (off_info + sizeof(TokenInfo) * n + 15) & ~(size_t) 15;
+        const size_t off_lens = off_tok + tok_stride * sizeof(unsigned int) * n;
+        const size_t scratch = off_lens + (size_t) kLensBytes * n;
         if (scratch > ctx->resid_scratch_bytes) {
             PL_CUDA(cudaStreamSynchronize(ctx->stream));
             if (ctx->resid_scratch) cudaFree(ctx->resid_scratch);
@@ -761,18 +1184,34 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
         const InflateJob *d_jobs = reinterpret_cast<const InflateJob *>(d_in + job_off);
         const StoreJob *d_sjobs = reinterpret_cast<const StoreJob *>(d_in + job_off + sizeof(InflateJob) * n);
         unsigned char *d_dense = static_cast<unsigned char *>(ctx->resid_scratch);
-        int *d_status = reinterpret_cast<int *>(d_dense + dense_stride * n);
+        int *d_status = reinterpret_cast<int *>(d_dense + off_status);
+        TokenInfo *d_info = reinterpret_cast<TokenInfo *>(d_dense + off_info);
+        unsigned int *d_tok = reinterpret_cast<unsigned int *>(d_dense + off_tok);
+        unsigned char *d_lens = d_dense + off_lens;
 
+        const size_t tsmem = sizeof(LaneTables) * kTokLanes;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PL_CUDA(cudaFuncSetAttribute(inflate_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) tsmem));
+            attr_set = true;
+        }
         pl_timing_begin(ctx, PL_K_RESIDUAL, n);
-        inflate_kernel<<<(n + kWarpsPerCta - 1) / kWarpsPerCta, kWarpsPerCta * 32, 0, ctx->stream>>>(n, d_jobs, d_in, d_dense,
-                                                                                                dense_stride, d_status);
-        PL_CUDA(cudaGetLastError());
-        if (ortho)
-            ortho_store_kernel<<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes);
-        else if (out->kind == PL_POOL_RESID_F32)
-            residual_store_kernel<true><<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes, out->pitch, scale);
+        if (ctx->inflate_path == 1 || (ctx->inflate_path == 0 && n < kWarpPathBelow))
+            warpinf::inflate_warp_kernel<<<(n + warpinf::kWarpsPerCta - 1) / warpinf::kWarpsPerCta, warpinf::kWarpsPerCta * 32, 0, ctx->stream>>>(
+                n, d_jobs, d_in, d_dense, dense_stride, d_info);
         else
-            residual_store_kernel<false><<<n, 256, 0, ctx->stream>>>(d_sjobs, d_dense, dense_stride, out->base, out->slot_bytes, out->pitch, scale);
+            inflate_tokens_kernel<<<(n + kTokLanes - 1) / kTokLanes, kTokLanes, tsmem, ctx->stream>>>(n, d_jobs, d_in, d_tok, tok_stride, d_info, d_lens);
+        PL_CUDA(cudaGetLastError());
+        const int rgrid = (n + kResolveWarps - 1) / kResolveWarps;
+        if (ortho)
+            lz_resolve_kernel<STORE_ORTHO><<<rgrid, kResolveWarps * 32, 0, ctx->stream>>>(n, d_jobs, d_in, d_tok, tok_stride, d_info, d_dense, dense_stride,
+                                                                                      d_status, d_sjobs, out->base, out->slot_bytes, out->pitch, scale);
+        else if (out->kind == PL_POOL_RESID_F32)
+            lz_resolve_kernel<STORE_F32><<<rgrid, kResolveWarps * 32, 0, ctx->stream>>>(n, d_jobs, d_in, d_tok, tok_stride, d_info, d_dense, dense_stride,
+                                                                                    d_status, d_sjobs, out->base, out->slot_bytes, out->pitch, scale);
+        else
+            lz_resolve_kernel<STORE_I16><<<rgrid, kResolveWarps * 32, 0, ctx->stream>>>(n, d_jobs, d_in, d_tok, tok_stride, d_info, d_dense, dense_stride,
+                                                                                    d_status, d_sjobs, out->base, out->slot_bytes, out->pitch, scale);
         PL_CUDA(cudaGetLastError());
         pl_timing_end(ctx);
         ctx->launches += 2;
@@ -784,6 +1223,13 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
             if (status[j] != INF_OK)
                 return pl_set_error(PL_ERR_CORRUPT, "tile %d: DEFLATE stream is corrupt (inflate code %d)", j, status[j]);
     }
+    return PL_OK;
+}
+
+extern "C" int pl_debug_inflate_path(pl_ctx *ctx, int path)
+{
+    if (!ctx || path < 0 || path > 2) return pl_set_error(PL_ERR_ARG, "bad argument");
+    ctx->inflate_path = path;
     return PL_OK;
 }
 

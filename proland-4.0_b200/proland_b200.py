@@ -31,7 +31,7 @@ EXPORTS = [
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
-    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_stage_ring", "pl_debug_fpexact",
+    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
     "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
 ]
@@ -174,6 +174,7 @@ def lib():
         L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pl_debug_force_generic.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_no_fuse.argtypes = [C.c_void_p, C.c_int]
+        L.pl_debug_inflate_path.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_stage_ring.argtypes = [C.c_void_p, C.c_size_t]
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -607,6 +608,14 @@ Context.residual_decode = _residual_decode
 Context.residual_upsample = _residual_upsample
 Context.force_generic = _force_generic
 Context.no_fuse = _no_fuse
+
+
+def _inflate_path(self, path=0):
+    """0: decoder chosen by the batch size, 1: warp-per-stream kernel, 2: tokenizer + resolver kernels"""
+    check(lib().pl_debug_inflate_path(self.h, int(path)))
+
+
+Context.inflate_path = _inflate_path
 Context.stage_ring = lambda self, min_bytes: check(lib().pl_debug_stage_ring(self.h, min_bytes))
 Context.fpexact = _fpexact
 Context.timing_enable = _timing_enable

@@ -56,6 +56,9 @@ def dem_golden():
     }
     json.dump(out, open(os.path.join(HERE, "dem_dat.json"), "w"))
     print("dem_dat.json: %d tiles, %d blobs kept" % (ntiles, len(keep)))
+    # the whole fixture, byte for byte (554 KB: header, offset table, 145 distinct TIFF/DEFLATE blobs): the GPU box has no
+    # /root/reference, and the device decoders are checked on all 344 tiles (tests/test_gpu_parity.py)
+    open(os.path.join(HERE, "terrain4_DEM.dat"), "wb").write(data)
 
 
 def noise_golden():

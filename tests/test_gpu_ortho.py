@@ -254,8 +254,15 @@ def _ortho_file(channels, max_level=1, seed=3, W=196):
     return tiles, rs.ortho_container(tiles, max_level, W - 4, channels)
 
 
+@pytest.fixture(params=[1, 2], ids=["warp-per-stream", "tokenizer+resolver"])
+def inflate_path(request, ctx):
+    ctx.inflate_path(request.param)
+    yield request.param
+    ctx.inflate_path(0)
+
+
 @pytest.mark.parametrize("channels", [1, 2, 3, 4])
-def test_ortho_decode_batch_matches_oracle_reader(plb, ctx, oracle, channels):
+def test_ortho_decode_batch_matches_oracle_reader(plb, ctx, oracle, channels, inflate_path):
     """pl_ortho_decode_batch (OrthoCPUProducer.cpp:205-232 on the device) against the oracle's reader of the same
     file, byte for byte, for 1..4 channel files; unused channels of the RGBA8 slot are 0"""
     import resid_synth as rs

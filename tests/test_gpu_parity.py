@@ -262,7 +262,32 @@ import resid_synth as rs
 DEM = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dem_dat.json")))
 
 
-def test_residual_decode_reference_fixture(plb, ctx):
+@pytest.fixture(params=[1, 2], ids=["warp-per-stream", "tokenizer+resolver"])
+def inflate_path(request, ctx):
+    """both DEFLATE decoders of pl_residual.cu (the library picks one by batch size: pl_debug_inflate_path)"""
+    ctx.inflate_path(request.param)
+    yield request.param
+    ctx.inflate_path(0)
+
+
+def test_residual_decode_all_344_tiles_of_the_reference_fixture(plb, ctx, inflate_path):
+    """terrain4/DEM.dat whole (tests/golden/terrain4_DEM.dat, md5 in dem_dat.json): every one of its 344 tiles through the
+    device decoder, sha1 of the inflated int16 bytes against the reference file inflated by zlib (make_golden.py)"""
+    import struct
+    data = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "terrain4_DEM.dat"), "rb").read()
+    assert hashlib.md5(data).hexdigest() == DEM["md5"]
+    nt, header = DEM["header"]["ntiles"], DEM["header"]["header_bytes"]
+    offs = struct.unpack_from("<%dI" % (2 * nt), data, 28)
+    blobs = [data[header + offs[2 * t]: header + offs[2 * t + 1]] for t in range(nt)]
+    widths = DEM["tile_width"]
+    pool = ctx.pool(plb.POOL_RESID_I16, 197, nt)
+    ctx.residual_decode(pool, blobs, widths, list(range(nt)))
+    for t, w in enumerate(widths):
+        got = pool.download(t)[:w, :w]
+        assert hashlib.sha1(np.ascontiguousarray(got, "<i2").tobytes()).hexdigest() == DEM["tile_sha1"][t], t
+
+
+def test_residual_decode_reference_fixture(plb, ctx, inflate_path):
     """the reference's own fixture (terrain4/DEM.dat): inflated int16 tiles, sha1 by sha1"""
     ids = sorted(int(t) for t in DEM["blobs"])
     blobs = [base64.b64decode(DEM["blobs"][str(t)]) for t in ids]
@@ -284,7 +309,7 @@ def test_residual_decode_reference_fixture(plb, ctx):
 @pytest.mark.parametrize("level,strategy", [(0, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY),
                                             (6, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_FILTERED),
                                             (6, zlib.Z_FIXED), (6, zlib.Z_RLE), (6, zlib.Z_HUFFMAN_ONLY)])
-def test_residual_decode_deflate_variants(plb, ctx, level, strategy):
+def test_residual_decode_deflate_variants(plb, ctx, level, strategy, inflate_path):
     """stored, fixed-Huffman and dynamic-Huffman blocks; long matches (constant tiles), incompressible noise"""
     rng = np.random.default_rng(level * 10 + strategy)
     tiles = [rs.fractal_tile(rng, 197, 300), np.zeros((197, 197), np.int16),
@@ -299,7 +324,7 @@ def test_residual_decode_deflate_variants(plb, ctx, level, strategy):
         np.testing.assert_array_equal(pool.download(s)[:t.shape[0], :t.shape[0]], t)
 
 
-def test_residual_decode_root_composition_and_errors(plb, ctx):
+def test_residual_decode_root_composition_and_errors(plb, ctx, inflate_path):
     rng = np.random.default_rng(11)
     a, b = rs.fractal_tile(rng, 101, 50), rs.fractal_tile(rng, 101, 10)
     pool = ctx.pool(plb.POOL_RESID_F32, 197, 3)
