@@ -11,10 +11,10 @@ only gathers per-rank counters).  Total work is fixed as N grows -> "strong".
 
   value : device-resident path -- pl_produce_range: the per-tile uniforms are
           generated on the GPU, nothing but (level, Morton range) crosses PCIe.
-  e2e   : the per-tile plugin path -- per-tile uniforms built on the host like
-          ElevationProducer/NormalProducer::doCreateTile do, handed to
-          pl_pair_batch as HOST arrays (copied to the device inside the timed
-          region), per-tile (zmin,zmax) read back.
+  e2e   : the per-tile plugin path -- every tile handed over by identity
+          (level, tx, ty and its slots: pl_tile_id, 32 bytes) as HOST arrays
+          through pl_pair_batch_ids (copied to the device inside the timed
+          region, uniforms expanded there), per-tile (zmin,zmax) read back.
 
   python bench.py [--gpus N --steps K --warmup W] [--impl reference]
   torchrun ... bench.py --gpus N ...          (one rank per GPU)
@@ -139,47 +139,35 @@ class PlanetSweep:
         for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
             pr(self.scenes[f], self.elev, self.norm, level, m0, n, s0, p0, pm0)
 
-    def run_host_requests(self, units, nthreads=0):
-        """e2e: host-built per-tile uniforms, host arrays in, (zmin,zmax) out.  Per batch: build the
-        uniforms (all host threads, in C), hand both arrays to pl_pair_batch (validates, stages, uploads
-        on the copy stream, launches), enqueue the statistics read-back and collect the one enqueued three
-        read-backs earlier -- the reference's TileSamplerZ collects its read-backs a few frames late in
-        the same way (ReadbackManager).  Nothing here waits for the GPU except that collection."""
+    def run_host_ids(self, units):
+        """e2e: what a caller of the plugin path holds per tile -- its quadtree coordinates and the slots its caches
+        handed out, 32 bytes (pl_tile_id) -- as HOST arrays through pl_pair_batch_ids: validated, copied into the
+        pinned staging ring, uploaded on the copy stream beside the kernels of earlier batches; the uniforms of
+        doCreateTile (noise layer / rotation, windows, fp64 patch geometry) are expanded on the device.  Per-tile
+        (zmin, zmax) come back through the asynchronous read-back and are collected three read-backs late -- the
+        reference's TileSamplerZ collects its read-backs a few frames late in the same way (ReadbackManager).
+        Nothing here waits for the GPU except that collection."""
         pl, ctx = self.pl, self.ctx
-        if not hasattr(self, "_req_bufs"):
-            nmax = 4 ** max(self.max_level - 2, 1)
-            self._req_bufs = (np.zeros(nmax, pl.ELEV_REQ_DTYPE), np.zeros(nmax, pl.NORM_REQ_DTYPE))
+        if not hasattr(self, "_id_buf"):
+            self._id_buf = np.zeros(4 ** max(self.max_level - 2, 1), pl.TILE_ID_DTYPE)
         h2d = d2h = 0
         self.stats_checksum = 0.0      # sum of every (zmin, zmax) read back: must not depend on the partition
         pending = []
-        prof = [0.0] * 4 if os.environ.get("PL_E2E_PROFILE") else None
         for f, level, m0, n, s0, p0, pm0 in self.plan.batches(units, self.max_level):
             sc = self.scenes[f]
-            t0 = time.perf_counter()
-            e, q = pl.make_requests_range(sc, level, m0, n, s0, p0, pm0, nthreads=nthreads, out=self._req_bufs)
-            t1 = time.perf_counter()
-            ctx.pair_batch(sc.elev, sc.norm, self.elev, self.norm, e, q)   # copies e, q before it returns
-            t2 = time.perf_counter()
-            h2d += e.nbytes + q.nbytes
-            t3 = t2
+            ids = pl.make_tile_ids_range(level, m0, n, s0, p0, pm0, out=self._id_buf)
+            ctx.pair_batch_ids(sc, self.elev, self.norm, ids)            # copies ids before it returns
+            h2d += ids.nbytes
             if n >= 4096:     # the consumer's readback (TileSamplerZ): 8 bytes per tile, collected three
                 if len(pending) == 3:                                    # read-backs later (ReadbackManager
                     st = ctx.elev_stats_readback_end(pending.pop(0))     # keeps several in flight)
                     d2h += st.nbytes
                     self.stats_checksum += float(st.astype(np.float64).sum())
-                t3 = time.perf_counter()
                 pending.append(ctx.elev_stats_readback_begin(self.elev, s0, n))
-            if prof is not None:
-                t4 = time.perf_counter()
-                for j, dt in enumerate((t1 - t0, t2 - t1, t3 - t2, t4 - t3)):
-                    prof[j] += dt
         for tk in pending:
             st = ctx.elev_stats_readback_end(tk)
             d2h += st.nbytes
             self.stats_checksum += float(st.astype(np.float64).sum())
-        if prof is not None:
-            print("e2e host profile (s): build requests %.3f, pair_batch %.3f, readback wait %.3f, "
-                  "readback begin %.3f" % tuple(prof), file=sys.stderr)
         return h2d, d2h
 
 
@@ -405,19 +393,22 @@ def main():
         ctx.timing_enable(False)
         sweep.set_arith(arith)
 
-        # e2e: host-built requests through the per-tile C ABI, stats read back
+        # e2e: host tile identities through the C ABI (pl_pair_batch_ids), stats read back; `steps` sweeps
         e2e = None
         if not args.no_e2e:
-            sweep.run_host_requests(my_units[:1], nthreads=host_threads)
+            sweep.run_host_ids(my_units[:1])
             barrier()
             ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             ev2.record(stream)
-            h2d, d2h = sweep.run_host_requests(my_units, nthreads=host_threads)
+            h2d = d2h = 0
+            for _ in range(args.steps):
+                a, b = sweep.run_host_ids(my_units)
+                h2d, d2h = h2d + a, d2h + b
             ev3.record(stream)
             barrier()
-            e2e_s = max(time.perf_counter() - t0, 1e-3 * ev2.elapsed_time(ev3))
-            e2e = (e2e_s, h2d, d2h)
+            e2e_s = max(time.perf_counter() - t0, 1e-3 * ev2.elapsed_time(ev3)) / args.steps
+            e2e = (e2e_s, h2d // args.steps, d2h // args.steps)
 
     t = torch.tensor([ms, e2e[0] if e2e else 0.0, other[0]], dtype=torch.float64, device="cuda")
     c = torch.tensor([sweep.stats_checksum if e2e else 0.0], dtype=torch.float64, device="cuda")
@@ -470,7 +461,9 @@ def main():
         if e2e:
             line["e2e"] = {"value": total_pairs / e2e_s_max, "unit": "pairs/s",
                            "h2d_bytes_per_step": int(e2e[1]) * world, "d2h_bytes_per_step": int(e2e[2]) * world,
-                           "path": "host-built per-tile requests -> pl_pair_batch (HOST arrays), stats read back",
+                           "path": "32-byte tile identities (HOST arrays) -> pl_pair_batch_ids (uniforms expanded on the "
+                                   "device) -> fused kernel; per-tile (zmin, zmax) read back asynchronously",
+                           "sweeps_timed": args.steps,
                            "stats_checksum": float(c[0]),
                            "stats_checksum_of": "sum of the (zmin, zmax) of every tile of levels 8..10 read back "
                                                 "in the step: independent of the number of ranks"}

@@ -252,6 +252,21 @@ int pl_pair_batch_dev(pl_ctx *ctx, const pl_elev_scene *escene, const pl_norm_sc
                       pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *dev_ereqs,
                       const pl_norm_req *dev_nreqs);
 
+/* A tile pair by its identity: what a producer KNOWS about the tile it has to create -- its quadtree coordinates and
+ * the slots TileCache handed out -- in 32 bytes.  The uniforms ElevationProducer::doCreateTile / NormalProducer::
+ * doCreateTile derive from them (ElevationProducer.cpp:305-376, NormalProducer.cpp:196-283: noise layer and rotation
+ * through cnoise, parent window, residual window, pixel size; the fp64 patch geometry of the sphere) are expanded ON
+ * THE DEVICE by the code pl_produce_range uses, so 32 instead of 304 bytes per tile cross PCIe and the host does no
+ * per-tile arithmetic at all. */
+typedef struct pl_tile_id {
+    int32_t level, tx, ty;
+    int32_t elev_slot;     /* output slot in the elevation pool                               */
+    int32_t parent_slot;   /* the parent's slot in the elevation pool; ignored at level 0     */
+    int32_t resid_slot;    /* slot in the residual pool, -1: the tile has no residual         */
+    int32_t norm_slot;     /* output slot in the normal pool                                   */
+    int32_t pad_;
+} pl_tile_id;              /* 32 bytes */
+
 typedef struct pl_sweep_scene {
     pl_elev_scene elev;
     pl_norm_scene norm;
@@ -271,6 +286,16 @@ typedef struct pl_sweep_scene {
 int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl_pool *norm,
                      int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,
                      uint64_t parent_morton0);
+/* n tile pairs given by identity (ids: HOST memory, copied inside the call): the uniforms are generated on the device,
+ * then the pair runs exactly as pl_pair_batch would on host-built requests (bit-identical results;
+ * tests/test_gpu_sweep.py).  resid may be NULL; a tile's residual window is (tx % mod, ty % mod) * tileSize of its
+ * residual tile (ElevationProducer.cpp:322-335).  A batch must not contain a tile together with its parent. */
+int pl_pair_batch_ids(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl_pool *norm, pl_pool *resid,
+                      int n, const pl_tile_id *ids);
+/* The identities of a Morton range laid out like pl_produce_range's (host helper: what a caller walking the quadtree
+ * in Morton order hands to pl_pair_batch_ids; the slot of tile m is out_slot0 + (m - morton0) in both pools) */
+int pl_make_tile_ids_range(int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,
+                           uint64_t parent_morton0, pl_tile_id *ids);
 /* The same requests built on the host with nthreads threads (<= 0: all): feeds
  * pl_elevation_batch / pl_normal_batch, and checks the device generator. */
 int pl_make_requests_range(const pl_sweep_scene *scene, int level, uint64_t morton0, int n,

@@ -157,6 +157,106 @@ extern "C" int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *
     return rc;
 }
 
+namespace {
+
+struct GenIdArgs {
+    PerlinView perlin;
+    pl_elev_req *ereq;
+    pl_norm_req *nreq;
+    const pl_tile_id *ids;
+    int tile_w, face, n_amp, sphere, resid_tile_w, n;
+    float root_quad_size;
+    float noise_amp[32];
+};
+
+__global__ void __launch_bounds__(128) gen_requests_ids_kernel(const GenIdArgs g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const pl_tile_id t = g.ids[i];
+    pl_elev_req e;
+    elev_fill_req(g.perlin, g.tile_w, g.root_quad_size, g.noise_amp, g.n_amp, g.face, t.level, t.tx, t.ty, g.resid_tile_w,
+                  t.resid_slot >= 0, &e);
+    e.out_slot = t.elev_slot;
+    e.parent_slot = t.level > 0 ? t.parent_slot : -1;
+    e.resid_slot = t.resid_slot >= 0 ? t.resid_slot : -1;
+    g.ereq[i] = e;
+    pl_norm_req q;
+    norm_fill_req(g.sphere, (double) g.root_quad_size, t.level, t.tx, t.ty, &q);
+    q.out_slot = t.norm_slot;
+    q.elev_slot = t.elev_slot;
+    g.nreq[i] = q;
+}
+
+}  // namespace
+
+extern "C" int pl_pair_batch_ids(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *elev, pl_pool *norm, pl_pool *resid, int n,
+                                 const pl_tile_id *ids)
+{
+    if (!ctx || !sc || !elev || !norm) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (n < 0) return pl_set_error(PL_ERR_ARG, "n < 0");
+    if (n == 0) return PL_OK;
+    if (!ids) return pl_set_error(PL_ERR_ARG, "ids is NULL");
+    if (sc->n_amp < 0 || sc->n_amp > 32) return pl_set_error(PL_ERR_ARG, "n_amp out of range");
+    if (elev->kind != PL_POOL_ELEV_F32x3 || (norm->kind != PL_POOL_NORM_UN8x2 && norm->kind != PL_POOL_NORM_UN8x4))
+        return pl_set_error(PL_ERR_ARG, "pl_pair_batch_ids needs an elevation and a normal pool");
+    if (resid && resid->kind != PL_POOL_RESID_F32 && resid->kind != PL_POOL_RESID_I16)
+        return pl_set_error(PL_ERR_ARG, "resid is not a residual pool");
+    const int rcap = resid ? resid->capacity : 0;
+    for (int i = 0; i < n; ++i) {
+        const pl_tile_id &t = ids[i];
+        if (t.level < 0 || t.level > 24 || t.tx < 0 || t.ty < 0 || t.tx >= (1 << t.level) || t.ty >= (1 << t.level))
+            return pl_set_error(PL_ERR_ARG, "tile %d: (%d, %d, %d) is not a quadtree tile", i, t.level, t.tx, t.ty);
+        if (t.elev_slot < 0 || t.elev_slot >= elev->capacity || t.norm_slot < 0 || t.norm_slot >= norm->capacity ||
+            t.resid_slot >= rcap || (t.level > 0 && (t.parent_slot < 0 || t.parent_slot >= elev->capacity || t.parent_slot == t.elev_slot)))
+            return pl_set_error(PL_ERR_ARG, "tile %d: slot out of range", i);
+    }
+    PL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_perlin(ctx)) != PL_OK) return rc;
+    if ((rc = ensure_gen_buffers(ctx, n)) != PL_OK) return rc;
+    void *dev = nullptr;
+    if ((rc = pl_stage_requests(ctx, ids, sizeof(pl_tile_id) * (size_t) n, &dev)) != PL_OK) return rc;
+    GenIdArgs g;
+    g.perlin.perm = ctx->perlin_perm;
+    g.perlin.g2 = ctx->perlin_g2;
+    g.ereq = ctx->gen_ereq;
+    g.nreq = ctx->gen_nreq;
+    g.ids = static_cast<const pl_tile_id *>(dev);
+    g.tile_w = sc->elev.tile_w;
+    g.face = sc->face;
+    g.n_amp = sc->n_amp;
+    g.sphere = sc->norm.sphere;
+    g.resid_tile_w = resid ? resid->tile_w : 0;
+    g.n = n;
+    g.root_quad_size = sc->root_quad_size;
+    memcpy(g.noise_amp, sc->noise_amp, sizeof(g.noise_amp));
+    pl_timing_begin(ctx, PL_K_GENREQ, n);
+    gen_requests_ids_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    return pl_pair_batch_dev(ctx, &sc->elev, &sc->norm, elev, norm, resid, n, ctx->gen_ereq, ctx->gen_nreq);
+}
+
+extern "C" int pl_make_tile_ids_range(int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,
+                                      uint64_t parent_morton0, pl_tile_id *ids)
+{
+    if (!ids || n < 0 || level < 0 || level > 24) return pl_set_error(PL_ERR_ARG, "bad argument");
+    for (int i = 0; i < n; ++i) {
+        const unsigned long long m = morton0 + (unsigned long long) i;
+        pl_tile_id t;
+        morton_decode(m, &t.tx, &t.ty);
+        t.level = level;
+        t.elev_slot = t.norm_slot = out_slot0 + i;
+        t.parent_slot = level > 0 ? parent_slot0 + (int) ((m >> 2) - parent_morton0) : -1;
+        t.resid_slot = -1;
+        t.pad_ = 0;
+        ids[i] = t;
+    }
+    return PL_OK;
+}
+
 /* the same requests built on the host (all hardware threads): the per-tile
  * plugin path at batch granularity, and the checker of the device generator */
 extern "C" int pl_make_requests_range(const pl_sweep_scene *sc, int level, uint64_t morton0, int n, int out_slot0,

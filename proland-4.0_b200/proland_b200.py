@@ -30,7 +30,7 @@ EXPORTS = [
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
-    "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_produce_range", "pl_make_requests_range",
+    "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
     "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
@@ -102,7 +102,10 @@ NORM_REQ_DTYPE = np.dtype([("out_slot", "i4"), ("elev_slot", "i4"), ("parent_slo
                            ("smooth", "f4"), ("pad_", "i4", (3,))])
 RESID_ENC_DTYPE = np.dtype([("tile_slot", "i4"), ("parent_slot", "i4"), ("approx_slot", "i4"), ("resid_slot", "i4"),
                             ("tile_size", "i4"), ("tx", "i4"), ("ty", "i4"), ("pad_", "i4")])
+TILE_ID_DTYPE = np.dtype([("level", "i4"), ("tx", "i4"), ("ty", "i4"), ("elev_slot", "i4"), ("parent_slot", "i4"),
+                          ("resid_slot", "i4"), ("norm_slot", "i4"), ("pad_", "i4")])
 assert ELEV_REQ_DTYPE.itemsize == 64 and NORM_REQ_DTYPE.itemsize == 240 and RESID_ENC_DTYPE.itemsize == 32
+assert TILE_ID_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -167,6 +170,8 @@ def lib():
         L.pl_pair_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_void_p, C.c_void_p]
         L.pl_pair_batch_dev.argtypes = L.pl_pair_batch.argtypes
+        L.pl_pair_batch_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pl_make_tile_ids_range.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
         L.pl_produce_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]
         L.pl_make_requests_range.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int,
@@ -273,6 +278,13 @@ def make_requests_range(scene, level, morton0, n, out_slot0=0, parent_slot0=0, p
     check(lib().pl_make_requests_range(C.byref(scene), level, morton0, n, out_slot0, parent_slot0,
                                        parent_morton0, _ptr(e), _ptr(q) if normals else None, nthreads))
     return e, q
+
+
+def make_tile_ids_range(level, morton0, n, out_slot0=0, parent_slot0=0, parent_morton0=0, out=None):
+    """tile identities of a Morton range (pl_make_tile_ids_range); out: a preallocated TILE_ID_DTYPE array"""
+    ids = out[:n] if out is not None else np.zeros(n, TILE_ID_DTYPE)
+    check(lib().pl_make_tile_ids_range(level, morton0, n, out_slot0, parent_slot0, parent_morton0, _ptr(ids)))
+    return ids
 
 
 def residual_write_file(path, tiles, min_level, max_level, tile_size, root=(0, 0, 0), scale=1.0, zlib_level=-1):
@@ -444,6 +456,12 @@ class Context:
         assert len(ereqs) == len(nreqs)
         check(lib().pl_pair_batch(self.h, C.byref(escene), C.byref(nscene), elev.h, norm.h,
                                   resid.h if resid else None, len(ereqs), _ptr(ereqs), _ptr(nreqs)))
+
+    def pair_batch_ids(self, scene, elev, norm, ids, resid=None):
+        """elevation + normal tile pairs from 32-byte tile identities (HOST array); the uniforms are expanded on the
+        device (pl_pair_batch_ids)."""
+        ids = np.ascontiguousarray(ids, TILE_ID_DTYPE)
+        check(lib().pl_pair_batch_ids(self.h, C.byref(scene), elev.h, norm.h, resid.h if resid else None, len(ids), _ptr(ids)))
 
     def residual_encode(self, heights, approx, resid, reqs):
         """one level of the residual-pyramid builder (pl_residual_encode_batch);

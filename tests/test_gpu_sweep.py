@@ -114,6 +114,61 @@ def test_subtree_sweep_with_residual_params_d4(plb, ctx, oracle):
         assert np.array_equal(norm.download(s), nrm), (tx, ty)
 
 
+@pytest.mark.parametrize("sphere,arith", [(1, 0), (0, 0), (1, 1)])
+def test_pair_batch_ids_equals_host_built_requests(plb, ctx, sphere, arith):
+    """pl_pair_batch_ids (32-byte tile identities, uniforms expanded on the device) against pl_pair_batch on the
+    host-built requests of the same tiles: elevation and normal tiles bit-identical; with residual tiles on the last
+    level (window origin derived from tx % 2, ty % 2), distinct elevation / normal slots and a shuffled tile order"""
+    amp = [-3250, -1590, -1125, -795, 561, 397] if sphere else [-140, -100, 15, 8, 5, 2.5]
+    kw = dict(noise_amp=amp, face=4 if sphere else 0, root_quad_size=12720000.0 if sphere else 100000.0, sphere=sphere)
+    sc = plb.sweep_scene(want_stats=1, arith=arith, **kw)
+    sc.elev.resid_scale = 0.5
+    L = 4
+    off = [sum(4 ** k for k in range(l)) for l in range(L + 2)]
+    total = off[L + 1]
+    rng = np.random.default_rng(5 + sphere)
+    rtiles = [rs.fractal_tile(rng, 197, 30.0) for _ in range(4)]
+    rpool = ctx.pool(plb.POOL_RESID_I16, 197, len(rtiles))
+    for s_, t in enumerate(rtiles):
+        rpool.upload(s_, t)
+    ctx.noise_init(101)
+    pools = []
+    for use_ids in (False, True):
+        elev = ctx.pool(plb.POOL_ELEV, 101, total)
+        norm = ctx.pool(plb.POOL_NORM2, 97, total + 3)
+        for l in range(L + 1):
+            n = 4 ** l
+            perm = rng.permutation(n) if l == L else np.arange(n)
+            e, q = plb.make_requests_range(sc, l, 0, n, off[l], off[l - 1] if l else 0, 0)
+            ids = plb.make_tile_ids_range(l, 0, n, off[l], off[l - 1] if l else 0, 0)
+            q["out_slot"] += 3                                  # the normal pool hands out other slots than the elevation pool
+            ids["norm_slot"] += 3
+            if l == L:
+                rslot = (e["tx"] // 2 + 3 * (e["ty"] // 2)) % len(rtiles)
+                e["resid_slot"], e["rx"], e["ry"] = rslot, (e["tx"] % 2) * 96, (e["ty"] % 2) * 96
+                ids["resid_slot"] = rslot
+            e, q, ids = e[perm], q[perm], ids[perm]
+            if use_ids:
+                ctx.pair_batch_ids(sc, elev, norm, ids, resid=rpool)
+            else:
+                ctx.pair_batch(sc.elev, sc.norm, elev, norm, e, q, resid=rpool)
+        ctx.sync()
+        pools.append((elev, norm))
+    for s_ in list(range(0, total, 7)) + [total - 1]:
+        assert np.array_equal(pools[0][0].download(s_), pools[1][0].download(s_)), s_
+        assert np.array_equal(pools[0][1].download(s_ + 3), pools[1][1].download(s_ + 3)), s_
+    st0 = ctx.elev_stats_range(pools[0][0], 0, total)
+    st1 = ctx.elev_stats_range(pools[1][0], 0, total)
+    assert np.array_equal(st0, st1)
+    with pytest.raises(plb.PlError):
+        bad = plb.make_tile_ids_range(2, 0, 4, 0, 0, 0)
+        bad["tx"][1] = 4                                        # outside level 2
+        ctx.pair_batch_ids(sc, pools[0][0], pools[0][1], bad)
+    with pytest.raises(plb.PlError):
+        bad = plb.make_tile_ids_range(2, 0, 4, 5, 5, 0)        # a tile that is its own parent
+        ctx.pair_batch_ids(sc, pools[0][0], pools[0][1], bad)
+
+
 def test_elevation_seams_at_scale(plb, ctx):
     """size-independent property at a size the oracle does not reach: the 4 096 tiles of level 6 of config 1's
     terrain (pl_produce_range, fused kernel) -- every pair of neighbouring tiles holds the same zf and zm on the 5
