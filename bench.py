@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--max-level", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of BASELINE configs 1, 3, 4, 5 (tools/configs.py)")
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"],
                     help="arithmetic contract of the normal pass in the timed region (include/proland_b200.h: "
                          "PL_ARITH_FAST = within one unorm8 step of the canonical evaluation, PL_ARITH_EXACT = "
@@ -483,6 +484,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             with torch.cuda.stream(stream):
                 line["other_paths"] = ortho_lines(pl, ctx, torch, stream, peak, peak_kind)
+        if world == 1 and not args.no_configs:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import configs
+            with torch.cuda.stream(stream):
+                line["configs"] = configs.run_all(pl, ctx, torch, stream, peak, peak_kind)
         print(json.dumps(line), flush=True)
 
     ctx.close()

@@ -331,6 +331,18 @@ int pl_residual_decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *bl
                              const int32_t *widths, const int32_t *out_slots,
                              const int32_t *add_slots, float scale);
 
+/* A residual archive resident in device memory: the whole .dat file uploaded once (the reference maps it into the
+ * address space once, ResidualProducer.cpp:70-129), tiles decoded from there.  pl_residual_decode_stored is
+ * pl_residual_decode_batch without the per-batch packing and upload of the blobs: offsets / sizes locate each tile's
+ * TIFF blob inside the archive, host_bytes is the caller's own copy (mapping) of the same file -- the few IFD
+ * bytes of each blob are parsed on the host, the compressed strip is read on the device where it lies. */
+typedef struct pl_blobs pl_blobs;
+int pl_blobs_create(pl_ctx *ctx, const uint8_t *bytes, uint64_t size, pl_blobs **out);
+void pl_blobs_destroy(pl_blobs *blobs);
+int pl_residual_decode_stored(pl_ctx *ctx, pl_pool *out, const pl_blobs *store, const uint8_t *host_bytes, int n,
+                              const uint64_t *offsets, const uint32_t *sizes, const int32_t *widths,
+                              const int32_t *out_slots, const int32_t *add_slots, float scale);
+
 /* A slot argument of the residual entry points may be PL_SLOT_SCRATCH: the hidden extra slot every
  * F32 residual pool carries (the `tmp` array of ResidualProducer::doCreateTile,
  * ResidualProducer.cpp:219). */

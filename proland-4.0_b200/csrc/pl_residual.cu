@@ -1106,9 +1106,18 @@ __global__ void __launch_bounds__(256) residual_encode_kernel(const pl_resid_enc
 
 }  // namespace
 
+/* A residual / ortho archive resident in device memory (pl_blobs_create): the reference maps its .dat files into
+ * the address space once (ResidualProducer.cpp:70-129, util/mfs) and reads tiles from there; here the whole file is
+ * uploaded once and the decoders read the compressed strips in place -- no per-batch packing, no PCIe traffic. */
+struct pl_blobs {
+    pl_ctx *ctx;
+    unsigned char *dev;
+    uint64_t size;
+};
+
 static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, const uint64_t *offsets,
                         const uint32_t *sizes, const int32_t *widths, const int32_t *out_slots,
-                        const int32_t *add_slots, float scale, int *channels_out)
+                        const int32_t *add_slots, float scale, int *channels_out, const pl_blobs *store = nullptr)
 {
     if (!ctx || !out || n < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
     if (n == 0) return PL_OK;
@@ -1133,8 +1142,9 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
         const int as = !add_slots ? -1 : (add_slots[j] == PL_SLOT_SCRATCH ? out->capacity : add_slots[j]);
         if (os < 0 || os > out->capacity || as > out->capacity || (os == out->capacity && out->kind != PL_POOL_RESID_F32))
             return pl_set_error(PL_ERR_ARG, "tile %d: slot out of range", j);
-        packed_off[j] = total;
-        total += ((uint64_t) sizes[j] + 7) & ~7ull;
+        if (store && offsets[j] + sizes[j] > store->size) return pl_set_error(PL_ERR_ARG, "tile %d: blob outside the archive", j);
+        packed_off[j] = store ? offsets[j] : total;     /* resident archive: the strip is read where it lies */
+        if (!store) total += ((uint64_t) sizes[j] + 7) & ~7ull;
         int spp = 0;
         const int rc = parse_tiff(blobs + offsets[j], sizes[j], wj, &jobs[j], packed_off[j], ortho ? 0 : 2, &spp);
         if (rc) return pl_set_error(PL_ERR_CORRUPT, "tile %d: not a single-strip %s TIFF blob of width %d (code %d)", j,
@@ -1158,7 +1168,8 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
     {
         const size_t job_off = (bytes_in + 15) & ~(size_t) 15;
         std::vector<uint8_t> stage(job_off + sizeof(InflateJob) * n + sizeof(StoreJob) * n, 0);
-        for (int j = 0; j < n; ++j) memcpy(stage.data() + packed_off[j], blobs + offsets[j], sizes[j]);
+        if (!store)
+            for (int j = 0; j < n; ++j) memcpy(stage.data() + packed_off[j], blobs + offsets[j], sizes[j]);
         memcpy(stage.data() + job_off, jobs.data(), sizeof(InflateJob) * n);
         memcpy(stage.data() + job_off + sizeof(InflateJob) * n, sjobs.data(), sizeof(StoreJob) * n);
         int rc = pl_stage_requests(ctx, stage.data(), stage.size(), &dev);
@@ -1180,9 +1191,10 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
             PL_CUDA(cudaMalloc(&ctx->resid_scratch, scratch + scratch / 4));
             ctx->resid_scratch_bytes = scratch + scratch / 4;
         }
-        const unsigned char *d_in = static_cast<const unsigned char *>(dev);
-        const InflateJob *d_jobs = reinterpret_cast<const InflateJob *>(d_in + job_off);
-        const StoreJob *d_sjobs = reinterpret_cast<const StoreJob *>(d_in + job_off + sizeof(InflateJob) * n);
+        const unsigned char *d_stage = static_cast<const unsigned char *>(dev);
+        const unsigned char *d_in = store ? store->dev : d_stage;
+        const InflateJob *d_jobs = reinterpret_cast<const InflateJob *>(d_stage + job_off);
+        const StoreJob *d_sjobs = reinterpret_cast<const StoreJob *>(d_stage + job_off + sizeof(InflateJob) * n);
         unsigned char *d_dense = static_cast<unsigned char *>(ctx->resid_scratch);
         int *d_status = reinterpret_cast<int *>(d_dense + off_status);
         TokenInfo *d_info = reinterpret_cast<TokenInfo *>(d_dense + off_info);
@@ -1224,6 +1236,47 @@ static int decode_batch(pl_ctx *ctx, pl_pool *out, int n, const uint8_t *blobs, 
                 return pl_set_error(PL_ERR_CORRUPT, "tile %d: DEFLATE stream is corrupt (inflate code %d)", j, status[j]);
     }
     return PL_OK;
+}
+
+extern "C" int pl_blobs_create(pl_ctx *ctx, const uint8_t *bytes, uint64_t size, pl_blobs **out)
+{
+    if (!ctx || !bytes || !out || size == 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    pl_blobs *b = new pl_blobs();
+    b->ctx = ctx;
+    b->size = size;
+    b->dev = nullptr;
+    /* 16 spare bytes: the bit reader fetches aligned words, the last of which may straddle the end */
+    cudaError_t e = cudaMalloc(&b->dev, size + 16);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->dev + size, 0, 16, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->dev, bytes, size, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (b->dev) cudaFree(b->dev);
+        delete b;
+        return pl_set_error(PL_ERR_CUDA, "pl_blobs_create: %s", cudaGetErrorString(e));
+    }
+    *out = b;
+    return PL_OK;
+}
+
+extern "C" void pl_blobs_destroy(pl_blobs *b)
+{
+    if (!b) return;
+    cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->stream);
+    cudaFree(b->dev);
+    delete b;
+}
+
+extern "C" int pl_residual_decode_stored(pl_ctx *ctx, pl_pool *out, const pl_blobs *store, const uint8_t *host_bytes, int n,
+                                         const uint64_t *offsets, const uint32_t *sizes, const int32_t *widths,
+                                         const int32_t *out_slots, const int32_t *add_slots, float scale)
+{
+    if (!store || store->ctx != ctx) return pl_set_error(PL_ERR_ARG, "the archive belongs to another context");
+    if (out && (out->kind == PL_POOL_ORTHO_UN8x4 || out->kind == PL_POOL_NORM_UN8x4))
+        return pl_set_error(PL_ERR_ARG, "out is not a residual pool");
+    return decode_batch(ctx, out, n, host_bytes, offsets, sizes, widths, out_slots, add_slots, scale, nullptr, store);
 }
 
 extern "C" int pl_debug_inflate_path(pl_ctx *ctx, int path)

@@ -32,7 +32,7 @@ EXPORTS = [
     "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
-    "pl_residual_decode_batch", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
+    "pl_residual_decode_batch", "pl_blobs_create", "pl_blobs_destroy", "pl_residual_decode_stored", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
     "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
 ]
 
@@ -184,6 +184,11 @@ def lib():
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pl_residual_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+        L.pl_blobs_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]
+        L.pl_blobs_destroy.argtypes = [C.c_void_p]
+        L.pl_blobs_destroy.restype = None
+        L.pl_residual_decode_stored.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
         L.pl_residual_upsample.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.pl_residual_write_file.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                              C.c_void_p, C.c_void_p, C.c_int]
@@ -536,6 +541,34 @@ def _residual_decode(self, pool, blobs, widths, out_slots, add_slots=None, scale
                                          C.c_float(scale)))
 
 
+class Blobs:
+    """a residual archive resident in device memory (pl_blobs_create); keeps the host copy for IFD parsing"""
+
+    def __init__(self, ctx, data):
+        self.ctx = ctx
+        self.host = np.frombuffer(bytes(data), np.uint8)
+        h = C.c_void_p()
+        check(lib().pl_blobs_create(ctx.h, _ptr(self.host), len(self.host), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().pl_blobs_destroy(self.h)
+            self.h = None
+
+
+def _residual_decode_stored(self, pool, store, offsets, sizes, widths, out_slots, add_slots=None, scale=1.0):
+    """tiles of a device-resident archive (pl_residual_decode_stored): offsets / sizes of the TIFF blobs inside it"""
+    offs = np.ascontiguousarray(offsets, np.uint64)
+    sizes = np.ascontiguousarray(sizes, np.uint32)
+    widths = np.ascontiguousarray(widths, np.int32)
+    out_slots = np.ascontiguousarray(out_slots, np.int32)
+    add = np.ascontiguousarray(add_slots, np.int32) if add_slots is not None else None
+    check(lib().pl_residual_decode_stored(self.h, pool.h, store.h, _ptr(store.host), len(offs), _ptr(offs), _ptr(sizes),
+                                          _ptr(widths), _ptr(out_slots), _ptr(add) if add is not None else None,
+                                          C.c_float(scale)))
+
+
 def _residual_upsample(self, pool, src_slot, dst_slot, tile_size, tx=0, ty=0):
     check(lib().pl_residual_upsample(self.h, pool.h, src_slot, dst_slot, tile_size, tx, ty))
 
@@ -625,6 +658,8 @@ Context.ortho_batch = _ortho_batch
 Context.residual_decode = _residual_decode
 Context.residual_upsample = _residual_upsample
 Context.force_generic = _force_generic
+Context.residual_decode_stored = _residual_decode_stored
+Context.blobs = lambda self, data: Blobs(self, data)
 Context.no_fuse = _no_fuse
 
 

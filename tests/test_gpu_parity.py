@@ -285,6 +285,17 @@ def test_residual_decode_all_344_tiles_of_the_reference_fixture(plb, ctx, inflat
     for t, w in enumerate(widths):
         got = pool.download(t)[:w, :w]
         assert hashlib.sha1(np.ascontiguousarray(got, "<i2").tobytes()).hexdigest() == DEM["tile_sha1"][t], t
+    # the same file as an archive resident in device memory (pl_blobs_create / pl_residual_decode_stored): tiles located
+    # by the file's own offset table, decoded in place
+    store = ctx.blobs(data)
+    pool2 = ctx.pool(plb.POOL_RESID_I16, 197, nt)
+    ctx.residual_decode_stored(pool2, store, [header + offs[2 * t] for t in range(nt)],
+                               [offs[2 * t + 1] - offs[2 * t] for t in range(nt)], widths, list(range(nt)))
+    for t in range(nt):
+        assert np.array_equal(pool2.download(t), pool.download(t)), t
+    with pytest.raises(plb.PlError):
+        ctx.residual_decode_stored(pool2, store, [len(data) - 10], [100], [197], [0])      # outside the archive
+    store.close()
 
 
 def test_residual_decode_reference_fixture(plb, ctx, inflate_path):

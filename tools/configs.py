@@ -1,0 +1,218 @@
+"""Driver-run records of BASELINE.json's other configs (bench.py calls these at N = 1 after the headline measurement and
+puts them under `configs`; each is also runnable on its own: python tools/configs.py [1 3 4 5]).
+
+  config 1  demo-fractalterrain: flat face, levels 0..8, both arithmetic contracts (tools/fractalterrain.py)
+  config 3  demo-earth-srtm shape: residual decode (device-resident archive and host blobs), the fused kernel's
+            residual variants on the int16 and the float pool, and decode + production back to back
+  config 4  full-subtree sweeps at level 14, d = 6, 8, 10 (tools/subtree_sweep.py)
+  config 5  camera fly-through through the C++ host layer (tools/flythrough.py): tiles/s, p99 frame time
+
+Every record carries its own `roofline` (algorithmic bytes of the dominant kernel / its CUDA-event time; `traffic` = the
+ncu-measured DRAM bytes per pair of the matching capture in profiles/, or null).  Timings are CUDA events on the context's
+stream; nothing here runs under a profiler.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "proland-4.0_b200"), os.path.join(ROOT, "tests"), ROOT, os.path.join(ROOT, "tools")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SRTM_AMP = [0] * 7 + [5, 2.5, 1]          # earth-srtm.xml: no noise down to the residual levels, then a little
+PLANET_SIZE = 12720000.0
+RESID_PAIR_BYTES = {"int16": 212500, "float": 232902}      # 192 098 + the residual window as stored
+
+
+def _events(torch, stream):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def config1(pl, ctx, torch, stream):
+    import fractalterrain as ft
+    out = {}
+    for arith, name in ((pl.ARITH_FAST, "fast"), (pl.ARITH_EXACT, "exact")):
+        out[name] = ft.run(pl, ctx, torch, stream, max_level=8, reps=5, arith=arith)
+    return out
+
+
+def config3(pl, ctx, torch, stream, peak, peak_kind, n_decode=32768, level=8):
+    import resid_synth as rs
+    rng = np.random.default_rng(20240612)
+    distinct = [rs.fractal_tile(rng, 197, 40) for _ in range(64)]
+    blobs64 = [rs.tiff_blob(t, 6) for t in distinct]
+    sizes64 = np.array([len(b) for b in blobs64], np.uint32)
+    offs64 = np.concatenate([[0], np.cumsum((sizes64[:-1] + 15) & ~np.uint32(15), dtype=np.uint64)]).astype(np.uint64)
+    arch = bytearray(int(offs64[-1] + sizes64[-1]))
+    for o, b in zip(offs64, blobs64):
+        arch[int(o):int(o) + len(b)] = b
+    out = {"workload": "config 3 demo-earth-srtm shape: 197 x 197 int16 residual tiles (64 distinct synthetic SRTM-shaped "
+                       "tiles, zlib level 6, cycled), sphere face 2, flip, NEAREST elevation storage",
+           "compression_ratio": float(64 * 197 * 197 * 2 / sizes64.sum())}
+    ctx.noise_init(101)
+    # ---- decode: the archive resident in HBM (the reference maps the file once), tiles located by offset
+    store = ctx.blobs(bytes(arch))
+    idx = np.arange(n_decode) % 64
+    pool = ctx.pool(pl.POOL_RESID_I16, 197, n_decode)
+    args = (pool, store, offs64[idx], sizes64[idx], [197] * n_decode, np.arange(n_decode, dtype=np.int32))
+    ctx.residual_decode_stored(*args)
+    ctx.sync()
+    ctx.timing_collect()
+    ctx.timing_enable(True)
+    e0, e1 = _events(torch, stream)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    reps = 3
+    for _ in range(reps):
+        ctx.residual_decode_stored(*args)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    k_ms = ctx.timing_collect()["residual"][0] / reps
+    ctx.timing_enable(False)
+    assert np.array_equal(pool.download(n_decode - 1)[:197, :197], distinct[(n_decode - 1) % 64])
+    out["decode_resident"] = {
+        "tiles": n_decode, "tiles_per_s_kernels": n_decode / (k_ms * 1e-3), "tiles_per_s_call": n_decode / wall,
+        "kernel_ms": k_ms, "decoded_GBps": n_decode * 197 * 197 * 2 / (k_ms * 1e-3) / 1e9,
+        "compressed_GBps": float(sizes64[idx].sum()) / (k_ms * 1e-3) / 1e9,
+        "path": "pl_residual_decode_stored: tokenizer (lane per stream) + resolver (warp per stream) kernels, int16 pool",
+        "roofline": {"bound": "latency", "note": "a DEFLATE stream is one serial chain: the tokenizer is bound by the "
+                     "per-symbol dependency chain times the streams resident per SM, not by HBM (DESIGN 3.3)",
+                     "achieved": n_decode * (197 * 197 * 2 + float(sizes64.mean())) / (k_ms * 1e-3) / 1e9, "peak": peak,
+                     "unit": "GB/s", "frac": n_decode * (197 * 197 * 2 + float(sizes64.mean())) / (k_ms * 1e-3) / 1e9 / peak,
+                     "peak_kind": peak_kind, "traffic": None}}
+    pool.close()
+    # ---- decode from HOST blobs (packing + upload inside the call), the warp-per-stream decoder's batch size
+    nh = 4096
+    blobs = [blobs64[i % 64] for i in range(nh)]
+    hpool = ctx.pool(pl.POOL_RESID_I16, 197, nh)
+    ctx.residual_decode(hpool, blobs, [197] * nh, list(range(nh)))
+    ctx.sync()
+    t0 = time.perf_counter()
+    ctx.residual_decode(hpool, blobs, [197] * nh, list(range(nh)))
+    ctx.sync()
+    out["decode_host_blobs"] = {"tiles": nh, "tiles_per_s_call": nh / (time.perf_counter() - t0),
+                                "path": "pl_residual_decode_batch: blobs packed and uploaded inside the call"}
+    # ---- the fused kernel with residuals, one level-`level` batch; then decode + production back to back
+    off = [sum(4 ** k for k in range(l)) for l in range(level + 2)]
+    n = 4 ** level
+    nres = n // 4
+    elev = ctx.pool(pl.POOL_ELEV, 101, off[level + 1])
+    norm = ctx.pool(pl.POOL_NORM2, 97, off[level + 1])
+    for arith, aname in ((pl.ARITH_FAST, "fast"), (pl.ARITH_EXACT, "exact")):
+        sc = pl.sweep_scene(noise_amp=SRTM_AMP, face=2, root_quad_size=PLANET_SIZE, sphere=1, flip=1,
+                            elev_filter=pl.FILTER_NEAREST, want_stats=1, arith=arith)
+        sc.elev.resid_scale = 1.0
+        for l in range(level):      # ancestors: fractal only
+            ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+        ids = pl.make_tile_ids_range(level, 0, n, off[level], off[level - 1], 0)
+        # one residual tile per 2 x 2 tiles
+        ids["resid_slot"] = (ids["tx"] // 2) + (ids["ty"] // 2) * (1 << (level - 1))
+        ridx = np.arange(nres) % 64
+        for kind, name in ((pl.POOL_RESID_I16, "int16"), (pl.POOL_RESID_F32, "float")):
+            rpool = ctx.pool(kind, 197, nres)
+            dargs = (rpool, store, offs64[ridx], sizes64[ridx], [197] * nres, np.arange(nres, dtype=np.int32))
+            ctx.residual_decode_stored(*dargs)
+            ctx.pair_batch_ids(sc, elev, norm, ids, resid=rpool)      # warm-up
+            ctx.sync()
+            ctx.timing_collect()
+            ctx.timing_enable(True)
+            reps = 5
+            for _ in range(reps):
+                ctx.pair_batch_ids(sc, elev, norm, ids, resid=rpool)
+            ms = ctx.timing_collect()["pair"][0] / reps
+            gbs = RESID_PAIR_BYTES[name] * n / (ms * 1e-3) / 1e9
+            rec = {"pairs": n, "pairs_per_s": n / (ms * 1e-3), "kernel_ms": ms,
+                   "roofline": {"bound": "hbm", "kernel": "pair (residual variant)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                "frac": gbs / peak, "bytes_per_pair": RESID_PAIR_BYTES[name], "peak_kind": peak_kind, "traffic": None}}
+            # decode INSIDE the timed region: the residual tiles of the batch, then the batch
+            e0, e1 = _events(torch, stream)
+            ctx.timing_collect()
+            e0.record(stream)
+            for _ in range(reps):
+                ctx.residual_decode_stored(*dargs)
+                ctx.pair_batch_ids(sc, elev, norm, ids, resid=rpool)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            kt = ctx.timing_collect()
+            ctx.timing_enable(False)
+            tot = e0.elapsed_time(e1) / reps
+            rec["with_decode"] = {"pairs_per_s": n / (tot * 1e-3), "ms": tot, "residual_tiles": nres,
+                                  "decode_kernel_ms": kt["residual"][0] / reps, "pair_kernel_ms": kt["pair"][0] / reps,
+                                  "fraction_of_kernel_only": ms / tot}
+            out["pairs_%s_pool_%s" % (name, aname)] = rec
+            rpool.close()
+    norm.close()
+    elev.close()
+    store.close()
+    hpool.close()
+    return out
+
+
+def config4(pl, ctx, torch, stream, peak, peak_kind, ds=(6, 8, 10)):
+    import subtree_sweep as ss
+    import bench
+    out = {}
+    ss.run_sweep(pl, ctx, 6)
+    for d in ds:
+        e0, e1 = _events(torch, stream)
+        ctx.timing_collect()
+        ctx.timing_enable(True)
+        e0.record(stream)
+        n, fp, plan = ss.run_sweep(pl, ctx, d)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        kt = ctx.timing_collect()
+        ctx.timing_enable(False)
+        ms = e0.elapsed_time(e1)
+        pair_ms, launches, tiles = kt["pair"]
+        gbs = bench.PAIR_BYTES * tiles / (pair_ms * 1e-3) / 1e9
+        out["d%d" % d] = {"workload": "all level-14 descendants of one level-%d tile (+ ancestors): %d pairs, flat face 0, "
+                                      "PL_ARITH_EXACT" % (14 - d, n),
+                          "pairs": n, "pairs_per_s": n / (ms * 1e-3), "ms": ms, "launches": int(2 * launches),
+                          "roofline": {"bound": "hbm", "kernel": "pair", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                       "frac": gbs / peak, "bytes_per_pair": bench.PAIR_BYTES, "peak_kind": peak_kind,
+                                       "share_of_sweep": pair_ms / ms, "traffic_per_pair": bench.TRAFFIC.get("pair_flat")},
+                          "fingerprint_xor": fp["xor"]}
+    return out
+
+
+def config5(frames=200):
+    import flythrough as fl
+    rec = fl.run(frames=frames, asynchronous=True)
+    sync = fl.run(frames=frames, asynchronous=False)
+    rec["synchronous"] = {k: sync[k] for k in ("tiles_made", "tiles_per_s", "frame_ms_p50", "frame_ms_p99", "tiles_per_launch")}
+    return rec
+
+
+def run_all(pl, ctx, torch, stream, peak, peak_kind, which=(1, 3, 4, 5)):
+    out = {}
+    for k, fn in ((1, lambda: config1(pl, ctx, torch, stream)), (3, lambda: config3(pl, ctx, torch, stream, peak, peak_kind)),
+                  (4, lambda: config4(pl, ctx, torch, stream, peak, peak_kind)), (5, config5)):
+        if k not in which:
+            continue
+        t0 = time.perf_counter()
+        try:
+            out["config%d" % k] = fn()
+        except Exception as ex:     # a sub-record must not take the headline line with it
+            out["config%d" % k] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        ctx.sync()
+        out["config%d" % k]["seconds"] = time.perf_counter() - t0
+    return out
+
+
+if __name__ == "__main__":
+    import torch
+    import proland_b200 as pl
+    import bench
+    which = tuple(int(a) for a in sys.argv[1:]) or (1, 3, 4, 5)
+    peak, kind = bench.peaks()
+    with pl.Context(0) as ctx:
+        stream = torch.cuda.Stream()
+        ctx.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            print(json.dumps(run_all(pl, ctx, torch, stream, peak, kind, which), indent=1))
