@@ -183,6 +183,13 @@ int pl_elev_stats_range(pl_ctx *ctx, pl_pool *elev, int slot0, int n, float *out
  * (TileSamplerZ.cpp:253-351).  At most 4 read-backs can be in flight. */
 int pl_elev_stats_readback_begin(pl_ctx *ctx, pl_pool *elev, int slot0, int n, int *ticket);
 int pl_elev_stats_readback_end(pl_ctx *ctx, int ticket, float *out);
+/* TileSamplerZ's frame read-back (core/sources/proland/terrain/TileSamplerZ.cpp:253-351): the z range of up to 64 tiles in
+ * arbitrary slots and, when cam_slot >= 0, the zm texel (cam_x, cam_y) of that slot -- the ground height under the
+ * camera.  Collected with pl_elev_stats_readback_end: [(h, h) of the camera texel], then (zmin, zmax) per slot.
+ * pl_elev_stats_readback_ready: 1 once the result has arrived (the collection will not wait), 0 before. */
+int pl_elev_zreadback_begin(pl_ctx *ctx, pl_pool *elev, int n, const int32_t *slots, int cam_slot, int cam_x, int cam_y,
+                            int *ticket);
+int pl_elev_stats_readback_ready(pl_ctx *ctx, int ticket);
 
 /* ----------------------------------------------------------------- normals */
 

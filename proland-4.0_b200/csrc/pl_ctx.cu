@@ -91,6 +91,7 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     if (ctx->gen_ereq) cudaFree(ctx->gen_ereq);
     if (ctx->gen_nreq) cudaFree(ctx->gen_nreq);
     if (ctx->resid_scratch) cudaFree(ctx->resid_scratch);
+    if (ctx->zgather) cudaFree(ctx->zgather);
     for (auto &t : *ctx->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto &e : *ctx->event_pool) cudaEventDestroy(e);
     delete ctx->timed;
@@ -768,6 +769,81 @@ extern "C" int pl_elev_stats_readback_begin(pl_ctx *ctx, pl_pool *elev, int slot
     rb.busy = 1;
     *ticket = k;
     return PL_OK;
+}
+
+/* TileSamplerZ's frame read-back (core/.../terrain/TileSamplerZ.cpp:253-351): the z range of up to kZTiles tiles in
+ * ARBITRARY slots -- the tiles a frame picked from its needReadback set -- and the zm texel under the camera, gathered by
+ * one small kernel and copied back asynchronously like pl_elev_stats_readback_begin.  Result pairs, in this order:
+ * [(h, h) of the camera texel, when cam_slot >= 0], then (zmin, zmax) of slots[0..n). */
+namespace {
+constexpr int kZTiles = 64;
+struct ZGather { int n; int cam_slot, cam_x, cam_y; int slots[kZTiles]; };
+__global__ void z_gather_kernel(const ZGather g, const float2 *stats, const float *elev, size_t slot_elems, size_t plane, int pitch,
+                                float2 *out)
+{
+    const int i = threadIdx.x;
+    const int c = g.cam_slot >= 0 ? 1 : 0;
+    if (i == 0 && c) {
+        const float h = elev[(size_t) g.cam_slot * slot_elems + 2 * plane + (size_t) g.cam_y * pitch + g.cam_x];
+        out[0] = make_float2(h, h);
+    }
+    if (i < g.n) out[c + i] = stats[g.slots[i]];
+}
+}  // namespace
+
+extern "C" int pl_elev_zreadback_begin(pl_ctx *ctx, pl_pool *elev, int n, const int32_t *slots, int cam_slot, int cam_x, int cam_y,
+                                       int *ticket)
+{
+    if (!ctx || !elev || !ticket || n < 0 || n > kZTiles || (n > 0 && !slots)) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (elev->kind != PL_POOL_ELEV_F32x3) return pl_set_error(PL_ERR_ARG, "not an elevation pool");
+    ZGather g;
+    g.n = n;
+    g.cam_slot = cam_slot >= 0 ? cam_slot : -1;
+    g.cam_x = cam_x;
+    g.cam_y = cam_y;
+    for (int i = 0; i < n; ++i) {
+        if (slots[i] < 0 || slots[i] >= elev->capacity) return pl_set_error(PL_ERR_ARG, "slot out of range");
+        g.slots[i] = slots[i];
+    }
+    if (cam_slot >= elev->capacity || (cam_slot >= 0 && (cam_x < 0 || cam_y < 0 || cam_x >= elev->tile_w || cam_y >= elev->tile_w)))
+        return pl_set_error(PL_ERR_ARG, "camera texel out of range");
+    PL_CUDA(cudaSetDevice(ctx->device));
+    int k = -1;
+    for (int i = 0; i < pl_ctx::kReadbacks; ++i)
+        if (!ctx->readback[i].busy) { k = i; break; }
+    if (k < 0) return pl_set_error(PL_ERR_ARG, "all %d read-backs are in flight: collect one first", (int) pl_ctx::kReadbacks);
+    pl_ctx::Readback &rb = ctx->readback[k];
+    if (!rb.done) PL_CUDA(cudaEventCreateWithFlags(&rb.done, cudaEventDisableTiming));
+    const int pairs = n + (cam_slot >= 0 ? 1 : 0);
+    const size_t bytes = sizeof(float2) * (size_t) (kZTiles + 1);
+    if (bytes > rb.cap) {
+        if (rb.pinned) cudaFreeHost(rb.pinned);
+        rb.pinned = nullptr;
+        rb.cap = 0;
+        PL_CUDA(cudaMallocHost(&rb.pinned, bytes + 4096));
+        rb.cap = bytes + 4096;
+    }
+    if (!ctx->zgather) PL_CUDA(cudaMalloc(&ctx->zgather, sizeof(float2) * (kZTiles + 1) * pl_ctx::kReadbacks));
+    float2 *dev = static_cast<float2 *>(ctx->zgather) + (size_t) k * (kZTiles + 1);
+    if (pairs) {
+        z_gather_kernel<<<1, kZTiles, 0, ctx->stream>>>(g, elev->stats, reinterpret_cast<const float *>(elev->base),
+                                                       elev->slot_bytes / sizeof(float), elev->plane_elems, elev->pitch, dev);
+        PL_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        PL_CUDA(cudaMemcpyAsync(rb.pinned, dev, sizeof(float2) * (size_t) pairs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PL_CUDA(cudaEventRecord(rb.done, ctx->stream));
+    rb.n = pairs;
+    rb.busy = 1;
+    *ticket = k;
+    return PL_OK;
+}
+
+/* 1 when the read-back behind `ticket` has arrived (pl_elev_stats_readback_end will not wait), 0 when not, < 0: error */
+extern "C" int pl_elev_stats_readback_ready(pl_ctx *ctx, int ticket)
+{
+    if (!ctx || ticket < 0 || ticket >= pl_ctx::kReadbacks || !ctx->readback[ticket].busy) return -1;
+    return cudaEventQuery(ctx->readback[ticket].done) == cudaSuccess ? 1 : 0;
 }
 
 extern "C" int pl_elev_stats_readback_end(pl_ctx *ctx, int ticket, float *out)

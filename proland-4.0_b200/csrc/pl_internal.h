@@ -92,6 +92,7 @@ struct pl_ctx {
     struct Readback { void *pinned; size_t cap; cudaEvent_t done; int n; int busy; };
     enum { kReadbacks = 4 };
     Readback readback[kReadbacks];
+    void *zgather;               /* device staging of pl_elev_zreadback_begin */
 };
 
 int pl_set_error(int code, const char *fmt, ...);

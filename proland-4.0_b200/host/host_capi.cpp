@@ -21,6 +21,7 @@
 #include "proland/resource/ResourceManager.h"
 #include "proland/terrain/TerrainQuad.h"
 #include "proland/terrain/TileSampler.h"
+#include "proland/terrain/TileSamplerZ.h"
 
 using namespace proland;
 
@@ -427,6 +428,54 @@ void *plh_sampler_create(const char *name, void *prod, int async, int store_pare
     PLH_CATCH(NULL)
 }
 
+/* a TileSamplerZ (<tileSamplerZ sampler= producer=>): also feeds TerrainQuad::zmin / zmax and the ground height under the
+ * camera from the z ranges of the elevation tiles it holds */
+void *plh_sampler_z_create(const char *name, void *prod, int async, int store_parent)
+{
+    PLH_TRY
+    TileSamplerZ *s = new TileSamplerZ(name, static_cast<TileProducer *>(prod));
+    s->setStoreParent(store_parent != 0);
+    s->setAsynchronous(async != 0);
+    s->acquire();
+    return static_cast<TileSampler *>(s);
+    PLH_CATCH(NULL)
+}
+
+int plh_sampler_z_counts(void *sampler, unsigned long long out[3])
+{
+    TileSamplerZ *z = dynamic_cast<TileSamplerZ *>(static_cast<TileSampler *>(sampler));
+    if (z == NULL) return -1;
+    z->getCounts(out);
+    return 0;
+}
+
+/* TerrainNode::groundHeightAtCamera and nextGroundHeightAtCamera; set >= 0: overwrite both first (tests) */
+void plh_ground_height(float out[2], int reset)
+{
+    if (reset) TerrainNode::groundHeightAtCamera = TerrainNode::nextGroundHeightAtCamera = 0.0f;
+    out[0] = TerrainNode::groundHeightAtCamera;
+    out[1] = TerrainNode::nextGroundHeightAtCamera;
+}
+
+static void list_quads_z(TerrainQuad *q, float *out, int max_quads, int *n)
+{
+    if (*n < max_quads) {
+        float *o = out + 5 * (*n);
+        o[0] = (float) q->level; o[1] = (float) q->tx; o[2] = (float) q->ty; o[3] = q->zmin; o[4] = q->zmax;
+    }
+    ++*n;
+    if (!q->isLeaf())
+        for (int i = 0; i < 4; ++i) list_quads_z(q->children[i].get(), out, max_quads, n);
+}
+
+/* pre-order (level, tx, ty, zmin, zmax) as floats */
+int plh_terrain_quads_z(void *node, float *out, int max_quads)
+{
+    int n = 0;
+    list_quads_z(static_cast<TerrainNode *>(node)->root.get(), out, max_quads, &n);
+    return n;
+}
+
 void plh_sampler_destroy(void *sampler)
 {
     if (sampler) {
@@ -444,8 +493,10 @@ int plh_frame_update(void *scheduler, void *node, void **samplers, int n)
     PLH_TRY
     ptr<TaskGraph> frame = new TaskGraph();
     int tasks = 0;
+    static unsigned int frameNumber = 0;      /* SceneManager::getFrameNumber() */
+    ++frameNumber;
     for (int i = 0; i < n; ++i) {
-        ptr<TaskGraph> g = static_cast<TileSampler *>(samplers[i])->update(static_cast<TerrainNode *>(node)->root);
+        ptr<TaskGraph> g = static_cast<TileSampler *>(samplers[i])->update(static_cast<TerrainNode *>(node)->root, frameNumber);
         TaskGraph::TaskIterator it = g->getAllTasks();
         while (it.hasNext()) {
             frame->addTask(it.next());

@@ -8,6 +8,7 @@ namespace proland
 {
 
 float TerrainNode::groundHeightAtCamera = 0.0f;
+float TerrainNode::nextGroundHeightAtCamera = 0.0f;
 
 TerrainQuad::TerrainQuad(TerrainNode *owner, const TerrainQuad *parent, int tx, int ty, double ox, double oy, double l,
                          float zmin, float zmax) :

@@ -60,6 +60,8 @@ public:
     int maxLevel;
     /* height of the ground under the camera (TerrainNode::groundHeightAtCamera, fed by TileSamplerZ) */
     static float groundHeightAtCamera;
+    /* the value groundHeightAtCamera will have at the next frame (TerrainNode.h:118) */
+    static float nextGroundHeightAtCamera;
 
     /* root quad [-size, size]^2 like <terrainNode size= zmin= zmax= splitFactor= maxLevel=> */
     TerrainNode(float size, float zmin, float zmax, float splitFactor, int maxLevel);

@@ -10,6 +10,10 @@ TileSampler::Tree::Tree(Tree *parent) : newTree(true), needTile(false), parent(p
     children[0] = children[1] = children[2] = children[3] = NULL;
 }
 
+TileSampler::Tree::~Tree()
+{
+}
+
 TileSampler::TileSampler(const std::string &name, ptr<TileProducer> producer) :
     Object("TileSampler"), name(name), producer(producer), root(NULL), storeLeaf(true), storeParent(true), async(false),
     held(0)
@@ -59,8 +63,9 @@ bool TileSampler::needTile(ptr<TerrainQuad> q)
     return need;
 }
 
-ptr<TaskGraph> TileSampler::update(ptr<TerrainQuad> q)
+ptr<TaskGraph> TileSampler::update(ptr<TerrainQuad> q, unsigned int frameNumber)
 {
+    (void) frameNumber;
     ptr<TaskGraph> result = new TaskGraph();
     if (!async && storeLeaf && root != NULL) {
         /* spare capacity goes to the children of the new leaves (TileSampler.cpp:312-315) */

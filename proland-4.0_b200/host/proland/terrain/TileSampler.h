@@ -36,14 +36,15 @@ public:
     /* async: tiles below the root are only taken when already in the cache, else prefetched */
     void setAsynchronous(bool v);
 
-    /* one frame; the returned graph holds the tasks of the needed tiles that are not done */
-    ptr<TaskGraph> update(ptr<TerrainQuad> root);
+    /* one frame; the returned graph holds the tasks of the needed tiles that are not done.  frameNumber:
+     * SceneManager::getFrameNumber() of the reference's update(scene, root) (used by TileSamplerZ) */
+    virtual ptr<TaskGraph> update(ptr<TerrainQuad> root, unsigned int frameNumber = 0);
     /* tiles currently held (users taken by this sampler) */
     int getTileCount() const { return held; }
     /* drops every tile (call before the producer's cache goes away) */
     void release();
 
-private:
+protected:
     struct Tree
     {
         bool newTree;
@@ -52,6 +53,7 @@ private:
         TileCache::Tile *t;
         Tree *children[4];
         explicit Tree(Tree *parent);
+        virtual ~Tree();
     };
 
     std::string name;
@@ -62,10 +64,10 @@ private:
     bool async;
     int held;
 
-    bool needTile(ptr<TerrainQuad> q);
-    void recursiveDelete(Tree *t);
+    virtual bool needTile(ptr<TerrainQuad> q);
+    virtual void recursiveDelete(Tree *t);
     void putTiles(Tree **t, ptr<TerrainQuad> q);
-    void getTiles(Tree *parent, Tree **t, ptr<TerrainQuad> q, ptr<TaskGraph> result);
+    virtual void getTiles(Tree *parent, Tree **t, ptr<TerrainQuad> q, ptr<TaskGraph> result);
     void prefetch(Tree *t, ptr<TerrainQuad> q, int &prefetchCount);
 };
 

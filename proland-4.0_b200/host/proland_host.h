@@ -72,6 +72,10 @@ float plh_split_distance(float split_factor, float viewport_width, float fov_rad
 int plh_terrain_update(void *node, double x, double y, double z, float split_dist, float dist_factor);
 int plh_terrain_quads(void *node, int *out, int max_quads);   /* pre-order (level, tx, ty, leaf) */
 void *plh_sampler_create(const char *name, void *prod, int async, int store_parent);
+void *plh_sampler_z_create(const char *name, void *prod, int async, int store_parent);
+int plh_sampler_z_counts(void *sampler, unsigned long long out[3]);   /* read-backs issued, applied, tiles waiting */
+void plh_ground_height(float out[2], int reset);   /* TerrainNode::groundHeightAtCamera, nextGroundHeightAtCamera */
+int plh_terrain_quads_z(void *node, float *out, int max_quads);   /* pre-order (level, tx, ty, zmin, zmax) */
 void plh_sampler_destroy(void *sampler);
 int plh_sampler_tile_count(void *sampler);
 int plh_frame_update(void *scheduler, void *node, void **samplers, int n);

@@ -29,7 +29,7 @@ EXPORTS = [
     "pl_pool_export", "pl_pool_attach_peers", "pl_pool_push_to_peers",
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
-    "pl_elev_stats_readback_end", "pl_norm_make_req", "pl_normal_batch",
+    "pl_elev_stats_readback_end", "pl_elev_zreadback_begin", "pl_elev_stats_readback_ready", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_blobs_create", "pl_blobs_destroy", "pl_residual_decode_stored", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",

@@ -30,7 +30,7 @@ EXPORTS = [
     "plh_debug_log", "plh_debug_log_lines", "plh_quiet_errors", "plh_upsample_variant", "plh_test_scene",
     "plh_test_scene_close", "plh_test_producer", "plh_test_cache", "plh_test_scheduler", "plh_test_calls",
     "plh_test_begin_end", "plh_terrain_create", "plh_terrain_destroy", "plh_split_distance", "plh_terrain_update",
-    "plh_terrain_quads", "plh_sampler_create", "plh_sampler_destroy", "plh_sampler_tile_count", "plh_frame_update",
+    "plh_terrain_quads", "plh_terrain_quads_z", "plh_sampler_z_create", "plh_sampler_z_counts", "plh_ground_height", "plh_sampler_create", "plh_sampler_destroy", "plh_sampler_tile_count", "plh_frame_update",
 ]
 
 
@@ -52,7 +52,7 @@ def lib():
         L.plh_last_error.restype = C.c_char_p
         for name in ("plh_open", "plh_producer", "plh_cache", "plh_scheduler", "plh_producer_cache", "plh_cache_scheduler",
                      "plh_get_tile", "plh_find_tile", "plh_test_scene", "plh_test_producer", "plh_test_cache",
-                     "plh_test_scheduler", "plh_terrain_create", "plh_sampler_create"):
+                     "plh_test_scheduler", "plh_terrain_create", "plh_sampler_create", "plh_sampler_z_create"):
             getattr(L, name).restype = vp
         L.plh_producer_type.restype = C.c_char_p
         L.plh_producer_task_type.restype = C.c_char_p
@@ -92,6 +92,11 @@ def lib():
         L.plh_terrain_update.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_float, C.c_float]
         L.plh_terrain_quads.argtypes = [vp, vp, i]
         L.plh_sampler_create.argtypes = [C.c_char_p, vp, i, i]
+        L.plh_sampler_z_create.argtypes = [C.c_char_p, vp, i, i]
+        L.plh_sampler_z_counts.argtypes = [vp, vp]
+        L.plh_ground_height.argtypes = [vp, i]
+        L.plh_ground_height.restype = None
+        L.plh_terrain_quads_z.argtypes = [vp, vp, i]
         L.plh_sampler_destroy.argtypes = [vp]
         L.plh_sampler_tile_count.argtypes = [vp]
         L.plh_frame_update.argtypes = [vp, vp, vp, i]
@@ -338,6 +343,13 @@ class Terrain:
         lib().plh_terrain_quads(self.h, out, n)
         return [tuple(out[4 * k:4 * k + 4]) for k in range(n)]
 
+    def quads_z(self):
+        """pre-order (level, tx, ty, zmin, zmax): the z ranges a TileSamplerZ has read back so far"""
+        n = lib().plh_terrain_quads_z(self.h, None, 0)
+        out = (C.c_float * (5 * n))()
+        lib().plh_terrain_quads_z(self.h, out, n)
+        return [(int(out[5 * k]), int(out[5 * k + 1]), int(out[5 * k + 2]), out[5 * k + 3], out[5 * k + 4]) for k in range(n)]
+
     def close(self):
         if self.h:
             lib().plh_terrain_destroy(self.h)
@@ -360,6 +372,27 @@ class Sampler:
         if self.h:
             lib().plh_sampler_destroy(self.h)
             self.h = None
+
+
+class SamplerZ(Sampler):
+    """TileSamplerZ: a Sampler of elevation tiles that feeds TerrainQuad zmin / zmax and the ground height under the camera"""
+
+    def __init__(self, name, producer, asynchronous=False, store_parent=True):
+        self.h = lib().plh_sampler_z_create(name.encode(), producer.h, int(asynchronous), int(store_parent))
+        if not self.h:
+            raise HostError(_err())
+
+    def counts(self):
+        out = (C.c_ulonglong * 3)()
+        lib().plh_sampler_z_counts(self.h, out)
+        return tuple(out)      # read-backs issued, applied, tiles waiting
+
+
+def ground_height(reset=False):
+    """(TerrainNode::groundHeightAtCamera, nextGroundHeightAtCamera)"""
+    out = (C.c_float * 2)()
+    lib().plh_ground_height(out, int(reset))
+    return out[0], out[1]
 
 
 def frame_update(scheduler, terrain, samplers):
