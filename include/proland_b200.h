@@ -165,6 +165,10 @@ void pl_elev_make_req(int tile_w, float root_quad_size, const float *noise_amp, 
                       int face, int level, int tx, int ty, int resid_tile_w, int has_resid,
                       pl_elev_req *req);
 
+/* Requests handed over as HOST arrays are validated (slots, noise indices, dx / dy in {0, tileSize / 2}, the residual
+ * window inside its tile with rx a multiple of 4); the *_dev variants trust the caller.  A batch must not contain both a
+ * tile and its parent (or a tile whose parent_slot is another request's out_slot): tiles of a launch are produced
+ * concurrently -- produce level by level, as TileProducer's task graph orders a tile behind its parent. */
 /* The batched upsampleShader: n tiles, one CTA per tile.  reqs is HOST memory
  * (copied to the device inside the call).  resid may be NULL. */
 int pl_elevation_batch(pl_ctx *ctx, const pl_elev_scene *scene, pl_pool *elev,

@@ -686,16 +686,28 @@ extern "C" int pl_elevation_batch_dev(pl_ctx *ctx, const pl_elev_scene *sc, pl_p
     return pl_launch_elevation(ctx, sc, elev, resid, n, dev_reqs);
 }
 
-static int check_elev_reqs(const pl_pool *elev, const pl_pool *resid, int n, const pl_elev_req *reqs)
+/* everything a kernel derives an address from: slots, noise indices, the parent window (dx, dy) and the residual window
+ * (rx, ry; the specialised kernel reads it with 16- / 8-byte loads: rx must be a multiple of 4) */
+static inline bool elev_req_bad(const pl_elev_req &q, const pl_pool *elev, const pl_pool *resid)
 {
     const int rcap = resid ? resid->capacity : 0;
-    for (int i = 0; i < n; ++i) {
-        const pl_elev_req &q = reqs[i];
-        if (q.out_slot < 0 || q.out_slot >= elev->capacity || q.parent_slot >= elev->capacity ||
-            q.resid_slot >= rcap || q.noise_r < 0 || q.noise_r > 3 || q.noise_l < 0 || q.noise_l > 5 ||
-            q.parent_slot == q.out_slot)
-            return pl_set_error(PL_ERR_ARG, "request %d: slot / noise index out of range", i);
-    }
+    const int half = (elev->tile_w - 5) / 2;
+    if (q.out_slot < 0 || q.out_slot >= elev->capacity || q.parent_slot < -1 || q.parent_slot >= elev->capacity ||
+        q.resid_slot < -1 || q.resid_slot >= rcap || q.noise_r < 0 || q.noise_r > 3 || q.noise_l < 0 || q.noise_l > 5 ||
+        q.parent_slot == q.out_slot)
+        return true;
+    if ((q.dx != 0 && q.dx != half) || (q.dy != 0 && q.dy != half)) return true;
+    if (q.resid_slot >= 0 &&
+        (q.rx < 0 || q.ry < 0 || q.rx + elev->tile_w > resid->tile_w || q.ry + elev->tile_w > resid->tile_w || (q.rx & 3) != 0))
+        return true;
+    return false;
+}
+
+static int check_elev_reqs(const pl_pool *elev, const pl_pool *resid, int n, const pl_elev_req *reqs)
+{
+    for (int i = 0; i < n; ++i)
+        if (elev_req_bad(reqs[i], elev, resid))
+            return pl_set_error(PL_ERR_ARG, "request %d: slot, noise index or window out of range", i);
     return PL_OK;
 }
 
@@ -941,14 +953,12 @@ extern "C" int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
     rc = stage_acquire(ctx, sizeof(pl_elev_req) * (size_t) n, sizeof(pl_norm_req) * (size_t) n, &tk, &pe, &pn);
     if (rc) return rc;
     std::atomic<int> bad(n);
-    const int rcap = resid ? resid->capacity : 0;
     parallel_chunks(n, 4096, [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
             const pl_elev_req &e = ereqs[i];
             const pl_norm_req &q = nreqs[i];
             int kind = 0;
-            if (e.out_slot < 0 || e.out_slot >= elev->capacity || e.parent_slot >= elev->capacity || e.resid_slot >= rcap ||
-                e.noise_r < 0 || e.noise_r > 3 || e.noise_l < 0 || e.noise_l > 5 || e.parent_slot == e.out_slot)
+            if (elev_req_bad(e, elev, resid))
                 kind = 1;
             else if (q.out_slot < 0 || q.out_slot >= norm->capacity || q.elev_slot < 0 || q.elev_slot >= elev->capacity ||
                      q.parent_slot >= norm->capacity || (q.parent_slot >= 0 && q.parent_slot == q.out_slot))
@@ -968,9 +978,7 @@ extern "C" int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
         const int i = bad.load();
         /* re-derive the kind for the first bad request (threads may have raced on bad_kind) */
         const pl_elev_req &e = ereqs[i];
-        const bool ebad = e.out_slot < 0 || e.out_slot >= elev->capacity || e.parent_slot >= elev->capacity || e.resid_slot >= rcap ||
-                          e.noise_r < 0 || e.noise_r > 3 || e.noise_l < 0 || e.noise_l > 5 || e.parent_slot == e.out_slot;
-        if (ebad) return pl_set_error(PL_ERR_ARG, "request %d: slot / noise index out of range", i);
+        if (elev_req_bad(e, elev, resid)) return pl_set_error(PL_ERR_ARG, "request %d: slot, noise index or window out of range", i);
         if (nreqs[i].elev_slot != e.out_slot && nreqs[i].elev_slot >= 0 && nreqs[i].elev_slot < elev->capacity &&
             nreqs[i].out_slot >= 0 && nreqs[i].out_slot < norm->capacity)
             return pl_set_error(PL_ERR_ARG, "request %d: the normal request does not read the elevation tile of the same index", i);

@@ -758,15 +758,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_warp_kernel(int n, 
                 const unsigned int dist = kDistBase[ds] + br_take(b, kDistExtra[ds]);
                 bad |= dist > pos ? 2 : 0;
                 __syncwarp();   /* lane 0's literals are in the ring */
-                if (dist < (unsigned int) kRing) {
-                    /* overlapping matches repeat their first `dist` bytes, all of which exist already */
+                if (dist <= (unsigned int) (kRing - 258)) {
+                    /* source and destination are both inside the ring and share none of its bytes (a distance closer
+                     * to the ring size would have one lane overwrite the ring byte another lane is about to read:
+                     * those take the HBM branch below).  Overlapping matches repeat their first `dist` bytes, all of
+                     * which exist already */
                     if (dist >= len) {
                         for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = ring[(pos - dist + k) & M];
                     } else {
                         for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = ring[(pos - dist + (k % dist)) & M];
                     }
                 } else if (!bad) {
-                    /* the source lies at least kRing - 258 bytes behind pos: flushed long ago (dist > len) */
+                    /* the source lies at least kRing - 2 * 258 bytes behind pos: flushed long ago (dist > len) */
                     for (unsigned int k = lane; k < len; k += 32) ring[(pos + k) & M] = dst[pos - dist + k];
                 }
                 pos += len;

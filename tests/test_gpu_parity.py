@@ -421,6 +421,17 @@ def test_elevation_with_residuals(plb, ctx, oracle, kind, fused):
     for t, (e, n) in ref.items():
         assert np.array_equal(elev.download(slot_of[t]), e), t
         assert np.array_equal(norm.download(slot_of[t]), n), t
+    # host arrays are validated: a window outside the residual / parent tile, a misaligned one, a bad residual slot
+    l2 = [i for i in range(len(reqs)) if reqs["resid_slot"][i] >= 0] or [0]
+    for field, value in (("rx", 100), ("rx", 2), ("ry", -1), ("ry", 97), ("dx", 3), ("dy", 96), ("resid_slot", -2), ("parent_slot", -5)):
+        bad = reqs.copy()
+        bad["resid_slot"][l2[0]] = max(int(bad["resid_slot"][l2[0]]), 0)
+        bad[field][l2[0]] = value
+        with pytest.raises(plb.PlError):
+            if fused:
+                ctx.pair_batch(es, ns, elev, norm, bad, nreqs, resid=rpool)
+            else:
+                ctx.elevation_batch(es, elev, bad, resid=rpool)
 
 
 @pytest.mark.parametrize("sphere,parent_filter", [(0, 1), (1, 1), (1, 0)])
