@@ -303,6 +303,22 @@ int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl
  * residual tile (ElevationProducer.cpp:322-335).  A batch must not contain a tile together with its parent. */
 int pl_pair_batch_ids(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl_pool *norm, pl_pool *resid,
                       int n, const pl_tile_id *ids);
+/* Several consecutive levels of a subtree in ONE launch: the chain root -> leaves of a small sweep is otherwise a
+ * sequence of launches of 1, 4, 16, .. tiles, each waiting for the level before it to drain (config 4, d = 6: 30
+ * launches for 5 469 pairs).  Here the tiles of all ranges are CTAs of one grid, ordered by level; a tile of range
+ * k >= 1 waits, inside the kernel, for the ready flag its parent (a tile of range k - 1, a CTA with a lower index) sets
+ * once its elevation planes are stored -- children start while the parent still computes its normals.
+ * Contract: ranges[k].level == ranges[k-1].level + 1, every parent of ranges[k] is a tile of ranges[k-1]
+ * (parent_slot0 / parent_morton0 of range k are out_slot0 / morton0 of range k - 1); the parents of ranges[0] are
+ * finished tiles.  Each range is laid out like a pl_produce_range call; results are bit-identical to those calls. */
+typedef struct pl_level_range {
+    int32_t level, n;
+    uint64_t morton0;
+    int32_t out_slot0, parent_slot0;
+    uint64_t parent_morton0;
+} pl_level_range;
+int pl_produce_levels(pl_ctx *ctx, const pl_sweep_scene *scene, pl_pool *elev, pl_pool *norm, int nranges,
+                      const pl_level_range *ranges);
 /* The identities of a Morton range laid out like pl_produce_range's (host helper: what a caller walking the quadtree
  * in Morton order hands to pl_pair_batch_ids; the slot of tile m is out_slot0 + (m - morton0) in both pools) */
 int pl_make_tile_ids_range(int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,

@@ -444,6 +444,8 @@ extern "C" int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, p
 
     if (kind == PL_POOL_ELEV_F32x3) {
         PL_CUDA(cudaMalloc(&p->stats, sizeof(float2) * capacity));
+        PL_CUDA(cudaMalloc(&p->ready, sizeof(int) * capacity));
+        PL_CUDA(cudaMemset(p->ready, 0, sizeof(int) * capacity));
         PL_CUDA(cudaMemsetAsync(p->stats, 0, sizeof(float2) * capacity, ctx->stream));
         /* parent window staged by TMA: (tileSize/2 + 6) texels each way, the
          * inner extent rounded up to 4 floats (16-byte box rows) */
@@ -480,6 +482,7 @@ extern "C" void pl_pool_destroy(pl_pool *p)
     for (int i = 0; i < p->npeers; ++i) cudaIpcCloseMemHandle(p->peer_base[i]);
     if (p->base) cudaFree(p->base);
     if (p->stats) cudaFree(p->stats);
+    if (p->ready) cudaFree(p->ready);
     delete p;
 }
 

@@ -296,6 +296,8 @@ int pl_elev_fill_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_po
     a.noise = ctx->noise_rot;
     a.reqs = dev_reqs;
     a.stats = elev->stats;
+    a.ready = nullptr;
+    a.epoch = 0;
     a.W = elev->tile_w;
     a.pitch = elev->pitch;
     a.plane = (int) elev->plane_elems;

@@ -23,6 +23,8 @@ struct ElevArgs {
     const __half *noise;
     const pl_elev_req *reqs;
     float2 *stats;
+    int *ready;              /* pl_produce_levels: per-slot ready flags, NULL otherwise */
+    int epoch;
     int W, pitch, plane;
     int grid, flip, noise_mode, no_clamp, want_stats;
     int box_w, box_h, nk;
@@ -59,6 +61,33 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, ui
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t) tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+/* pl_produce_levels: tiles of several quadtree levels in ONE launch.  A tile whose request says so (pad_[0] != 0)
+ * waits until its parent -- a CTA with a lower block index of the same launch -- has published its elevation planes:
+ * the parent's threads fence their stores, meet, and one of them releases ready[slot] = epoch; the child's thread 0
+ * acquires it, orders the generic-proxy view before its TMA copy (fence.proxy.async) and the CTA proceeds. */
+__device__ __forceinline__ void levels_wait_parent(const ElevArgs &a, const pl_elev_req &rq, const int tid)
+{
+    if (a.ready == nullptr) return;
+    if (tid == 0 && rq.pad_[0] != 0 && rq.parent_slot >= 0) {
+        const int *flag = a.ready + rq.parent_slot;
+        int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v != a.epoch) __nanosleep(64);
+        } while (v != a.epoch);
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncthreads();
+}
+/* after the elevation planes of the tile have been stored: every thread calls this (contains a barrier) */
+__device__ __forceinline__ void levels_publish(const ElevArgs &a, const pl_elev_req &rq, const int tid)
+{
+    if (a.ready == nullptr) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.ready + rq.out_slot), "r"(a.epoch) : "memory");
 }
 
 __device__ __forceinline__ int floordiv(int a, int b) { int q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
@@ -429,7 +458,7 @@ __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const Elev
             const int kx = q % NK - 1, ky = q / NK - 1;
             const int px = min(max(2 + G * kx + rq.dx, 0), W - 1);   /* CLAMP_TO_EDGE */
             const int py = min(max(2 + G * ky + rq.dy, 0), W - 1);
-            lat[q] = __ldg(pzm + py * GEO::PITCH + px);
+            lat[q] = __ldcg(pzm + py * GEO::PITCH + px);   /* L2: the parent may have been finished by another CTA of this launch */
         }
     } else {
         for (int q = tid; q < GEO::BOX_W * GEO::BOX_H; q += NT) { winA[q] = 0.0f; winB[q] = 0.0f; }

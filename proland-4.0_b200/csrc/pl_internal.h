@@ -36,6 +36,7 @@ struct pl_pool {
     size_t tile_bytes;  /* reference layout */
     uint8_t *base;      /* device */
     float2 *stats;      /* ELEV only: per-slot (zmin, zmax) */
+    int *ready;         /* ELEV only: per-slot epoch of the pl_produce_levels call that finished the tile's elevation planes */
     /* peer copies of this pool on the other GPUs of the box (pl_pool_attach_peers): device pointers into
      * their memory, mapped through CUDA IPC; kernels that push finished tiles store to them over NVLink */
     enum { kMaxPeers = 7 };
@@ -67,6 +68,7 @@ struct pl_ctx {
     int gen_cap;
     int force_generic;   /* tests: run the runtime-geometry kernels even for the shipped geometry */
     int no_fuse;         /* tests / profiling: pl_produce_range launches the two passes separately */
+    int levels_epoch;    /* pl_produce_levels: the value a finished tile's ready flag takes in the current call */
     int inflate_path;    /* tests / profiling: 0 = by batch size, 1 = warp-per-stream decoder, 2 = tokenizer + resolver */
     /* per-launch CUDA-event timing (pl_timing_*): events on the launching stream */
     int timing;
@@ -128,6 +130,8 @@ int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_poo
 /* fused elevation + normal pass (pl_pair.cu): one CTA per tile pair */
 bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, const pl_pool *elev,
                        const pl_pool *norm);
+int pl_launch_pair_levels(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm, int n,
+                           const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch);
 int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
                    pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs);
 

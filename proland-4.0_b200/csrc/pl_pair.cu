@@ -80,11 +80,13 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
     plnorm::normal_uv_tables<TW - 4, kPairThreads>(ulut, tid);
     __syncthreads();
     if (FAST && SPHERE) plnorm::normal_reg_qtab(rowtab, nrq, tid);   /* visible after the elevation phase's barriers */
+    plelev::levels_wait_parent(ea, erq, tid);                        /* pl_produce_levels: the parent is a CTA of this launch */
 
     /* elevation: planes to HBM, zm also to shared memory */
     unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
     const bool reg_form = FAST && !PUSH && plnorm::normal_reg_ok(nrq, SPHERE);
     plelev::elevation_tile<TW, TG, RESID, kPairThreads, true>(&tm, ea, erq, work, &bar, 0, zs, tid, reg_form);
+    plelev::levels_publish(ea, erq, tid);   /* children may start while this CTA computes its normals */
     __syncthreads();   /* zm plane complete; the elevation scratch is free */
 
     /* normals from the shared zm plane */
@@ -137,14 +139,34 @@ bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
 
 /* n tile pairs: normal request i must describe the normal tile of elevation request i
  * (nreq[i].elev_slot == ereq[i].out_slot) */
+static int launch_pair_any(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
+                           pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch);
+
 int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
                    pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs)
+{
+    return launch_pair_any(ctx, esc, nsc, elev, norm, resid, n, dev_ereqs, dev_nreqs, 0);
+}
+
+/* tiles of several levels in one launch, ordered by level: requests with pad_[0] != 0 wait for their parent's ready flag */
+int pl_launch_pair_levels(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm, int n,
+                          const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch)
+{
+    return launch_pair_any(ctx, esc, nsc, elev, norm, nullptr, n, dev_ereqs, dev_nreqs, epoch);
+}
+
+static int launch_pair_any(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
+                           pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch)
 {
     PL_CUDA(cudaSetDevice(ctx->device));
     plelev::ElevArgs ea;
     plnorm::NormArgs na;
     int rc = pl_elev_fill_args(ctx, esc, elev, resid, dev_ereqs, ea);
     if (rc) return rc;
+    if (epoch != 0) {
+        ea.ready = elev->ready;
+        ea.epoch = epoch;
+    }
     if ((rc = pl_norm_fill_args(ctx, nsc, norm, elev, dev_nreqs, na)) != PL_OK) return rc;
     const int rk = !resid ? 0 : (resid->kind == PL_POOL_RESID_F32 ? 1 : 2);
     return rk == 0 ? launch_pair<0>(ctx, elev, ea, na, n) : (rk == 1 ? launch_pair<1>(ctx, elev, ea, na, n) : launch_pair<2>(ctx, elev, ea, na, n));

@@ -239,6 +239,97 @@ extern "C" int pl_pair_batch_ids(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool 
     return pl_pair_batch_dev(ctx, &sc->elev, &sc->norm, elev, norm, resid, n, ctx->gen_ereq, ctx->gen_nreq);
 }
 
+/* ---- several levels of a subtree in ONE launch (pl_produce_levels) ------------------------------------------ */
+namespace {
+
+constexpr int kMaxLevelRanges = 24;
+struct GenLevelsArgs {
+    GenArgs base;                       /* scene, buffers */
+    int nranges;
+    int first[kMaxLevelRanges + 1];     /* first request of every range */
+    int level[kMaxLevelRanges];
+    unsigned long long morton0[kMaxLevelRanges], parent_morton0[kMaxLevelRanges];
+    int out_slot0[kMaxLevelRanges], parent_slot0[kMaxLevelRanges];
+};
+
+__global__ void __launch_bounds__(128) gen_requests_levels_kernel(const GenLevelsArgs g)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.first[g.nranges]) return;
+    int r = 0;
+    while (i >= g.first[r + 1]) ++r;
+    GenArgs a = g.base;
+    a.level = g.level[r];
+    a.morton0 = g.morton0[r];
+    a.parent_morton0 = g.parent_morton0[r];
+    a.out_slot0 = g.out_slot0[r];
+    a.parent_slot0 = g.parent_slot0[r];
+    a.ereq = g.base.ereq + g.first[r];
+    a.nreq = g.base.nreq + g.first[r];
+    gen_one(a, i - g.first[r]);
+    /* ranges after the first wait for their parents, which are tiles of this launch */
+    if (r > 0) a.ereq[i - g.first[r]].pad_[0] = 1;
+}
+
+}  // namespace
+
+extern "C" int pl_produce_levels(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *elev, pl_pool *norm, int nranges,
+                                 const pl_level_range *ranges)
+{
+    if (!ctx || !ranges || !norm) return pl_set_error(PL_ERR_ARG, "NULL argument");
+    if (nranges < 1 || nranges > kMaxLevelRanges) return pl_set_error(PL_ERR_ARG, "1 .. %d level ranges per call", kMaxLevelRanges);
+    GenLevelsArgs g;
+    long long total = 0;
+    for (int r = 0; r < nranges; ++r) {
+        const pl_level_range &q = ranges[r];
+        int rc = check_range(sc, elev, norm, q.level, q.morton0, q.n, q.out_slot0, q.parent_slot0, q.parent_morton0);
+        if (rc) return rc;
+        if (q.n < 1) return pl_set_error(PL_ERR_ARG, "range %d is empty", r);
+        if (r > 0) {
+            /* the contract that makes the launch deadlock-free: the parents of range r are tiles of range r - 1 */
+            const pl_level_range &p = ranges[r - 1];
+            const uint64_t p_first = q.morton0 >> 2, p_last = (q.morton0 + q.n - 1) >> 2;
+            if (q.level != p.level + 1 || p_first < p.morton0 || p_last >= p.morton0 + (uint64_t) p.n ||
+                q.parent_morton0 != p.morton0 || q.parent_slot0 != p.out_slot0)
+                return pl_set_error(PL_ERR_ARG, "range %d: its parents are not the tiles of range %d", r, r - 1);
+        }
+        g.first[r] = (int) total;
+        g.level[r] = q.level;
+        g.morton0[r] = q.morton0;
+        g.parent_morton0[r] = q.parent_morton0;
+        g.out_slot0[r] = q.out_slot0;
+        g.parent_slot0[r] = q.parent_slot0;
+        total += q.n;
+        if (total > (1ll << 30)) return pl_set_error(PL_ERR_ARG, "too many tiles");
+    }
+    g.first[nranges] = (int) total;
+    g.nranges = nranges;
+    /* output slots of different ranges must not overlap (each is checked against its own parents by check_range) */
+    for (int r = 0; r < nranges; ++r)
+        for (int q = 0; q < r; ++q)
+            if (ranges[r].out_slot0 < ranges[q].out_slot0 + ranges[q].n && ranges[q].out_slot0 < ranges[r].out_slot0 + ranges[r].n)
+                return pl_set_error(PL_ERR_ARG, "ranges %d and %d share output slots", q, r);
+    if (!pl_pair_supported(ctx, &sc->elev, &sc->norm, elev, norm))
+        return pl_set_error(PL_ERR_ARG, "pl_produce_levels needs the shipped geometry (101 / 97, grid 4, RG8): use pl_produce_range");
+    const int n = (int) total;
+    PL_CUDA(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_perlin(ctx)) != PL_OK) return rc;
+    if ((rc = ensure_gen_buffers(ctx, n)) != PL_OK) return rc;
+    g.base.perlin.perm = ctx->perlin_perm;
+    g.base.perlin.g2 = ctx->perlin_g2;
+    g.base.ereq = ctx->gen_ereq;
+    g.base.nreq = ctx->gen_nreq;
+    fill_gen_args(g.base, sc, 0, 0, n, 0, 0, 0);
+    pl_timing_begin(ctx, PL_K_GENREQ, n);
+    gen_requests_levels_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g);
+    pl_timing_end(ctx);
+    PL_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    ctx->levels_epoch = ctx->levels_epoch == 0x7fffffff ? 1 : ctx->levels_epoch + 1;
+    return pl_launch_pair_levels(ctx, &sc->elev, &sc->norm, elev, norm, n, ctx->gen_ereq, ctx->gen_nreq, ctx->levels_epoch);
+}
+
 extern "C" int pl_make_tile_ids_range(int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,
                                       uint64_t parent_morton0, pl_tile_id *ids)
 {

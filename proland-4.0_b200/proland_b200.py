@@ -30,7 +30,7 @@ EXPORTS = [
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_elev_zreadback_begin", "pl_elev_stats_readback_ready", "pl_norm_make_req", "pl_normal_batch",
-    "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
+    "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_produce_levels", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_blobs_create", "pl_blobs_destroy", "pl_residual_decode_stored", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
     "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
@@ -105,7 +105,9 @@ RESID_ENC_DTYPE = np.dtype([("tile_slot", "i4"), ("parent_slot", "i4"), ("approx
 TILE_ID_DTYPE = np.dtype([("level", "i4"), ("tx", "i4"), ("ty", "i4"), ("elev_slot", "i4"), ("parent_slot", "i4"),
                           ("resid_slot", "i4"), ("norm_slot", "i4"), ("pad_", "i4")])
 assert ELEV_REQ_DTYPE.itemsize == 64 and NORM_REQ_DTYPE.itemsize == 240 and RESID_ENC_DTYPE.itemsize == 32
-assert TILE_ID_DTYPE.itemsize == 32
+LEVEL_RANGE_DTYPE = np.dtype([("level", "i4"), ("n", "i4"), ("morton0", "u8"), ("out_slot0", "i4"), ("parent_slot0", "i4"),
+                              ("parent_morton0", "u8")])
+assert TILE_ID_DTYPE.itemsize == 32 and LEVEL_RANGE_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -171,6 +173,7 @@ def lib():
                                     C.c_int, C.c_void_p, C.c_void_p]
         L.pl_pair_batch_dev.argtypes = L.pl_pair_batch.argtypes
         L.pl_pair_batch_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pl_produce_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.pl_make_tile_ids_range.argtypes = [C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p]
         L.pl_produce_range.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                        C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint64]
@@ -461,6 +464,14 @@ class Context:
         assert len(ereqs) == len(nreqs)
         check(lib().pl_pair_batch(self.h, C.byref(escene), C.byref(nscene), elev.h, norm.h,
                                   resid.h if resid else None, len(ereqs), _ptr(ereqs), _ptr(nreqs)))
+
+    def produce_levels(self, scene, elev, norm, ranges):
+        """consecutive levels of a subtree in one launch (pl_produce_levels); ranges: (level, morton0, n, out_slot0,
+        parent_slot0, parent_morton0) tuples, each laid out like a produce_range call"""
+        arr = np.zeros(len(ranges), LEVEL_RANGE_DTYPE)
+        for k, (level, m0, n, s0, p0, pm0) in enumerate(ranges):
+            arr[k] = (level, n, m0, s0, p0, pm0)
+        check(lib().pl_produce_levels(self.h, C.byref(scene), elev.h, norm.h, len(arr), _ptr(arr)))
 
     def pair_batch_ids(self, scene, elev, norm, ids, resid=None):
         """elevation + normal tile pairs from 32-byte tile identities (HOST array); the uniforms are expanded on the

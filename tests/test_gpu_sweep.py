@@ -169,6 +169,36 @@ def test_pair_batch_ids_equals_host_built_requests(plb, ctx, sphere, arith):
         ctx.pair_batch_ids(sc, pools[0][0], pools[0][1], bad)
 
 
+@pytest.mark.parametrize("d,unit_depth,arith", [(6, 7, 0), (6, 7, 1), (8, 6, 0)])
+def test_produce_levels_equals_the_level_by_level_sweep(plb, ctx, d, unit_depth, arith):
+    """pl_produce_levels (all levels of a chain / unit in ONE launch, parent -> child dependency resolved inside the
+    kernel through ready flags) against the same sweep as one pl_produce_range per level: every leaf statistic and sampled
+    elevation + normal tiles bit-identical, over several repetitions (a missed dependency would read a half-written
+    parent)"""
+    import subtree_sweep as ss
+    import sweep
+    plan = sweep.SubtreeSweep(14 - d, (1 << (14 - d)) // 3, (1 << (14 - d)) // 5, d, unit_depth)
+    first = plan.root_morton << (2 * d)
+    want = [first, first + 4 ** d // 3, first + 4 ** d - 1]
+    kw = dict(scene_kw=dict(arith=arith), unit_depth=unit_depth)
+    keep0 = {"want": want}
+    n0, fp0, _ = ss.run_sweep(plb, ctx, d, keep=keep0, **kw)
+    for rep in range(4):
+        keep1 = {"want": want}
+        launches = ctx.launches
+        n1, fp1, _ = ss.run_sweep(plb, ctx, d, keep=keep1, levels=True, **kw)
+        assert n1 == n0 and fp1 == fp0, rep
+        for m in want:
+            assert np.array_equal(keep0[m][0], keep1[m][0]) and np.array_equal(keep0[m][1], keep1[m][1]), (rep, m)
+        if plan.k == 0:
+            assert ctx.launches - launches == 2      # one request generation + one pair launch for all 15 levels
+    with pytest.raises(plb.PlError):                 # the contract: the parents of a range are the tiles of the range before
+        sc = plb.sweep_scene(noise_amp=FRACTAL, face=0, root_quad_size=100000.0, sphere=0)
+        e, nrm = ctx.pool(plb.POOL_ELEV, 101, 32), ctx.pool(plb.POOL_NORM2, 97, 32)
+        ctx.noise_init(101)
+        ctx.produce_levels(sc, e, nrm, [(0, 0, 1, 0, 0, 0), (2, 0, 16, 1, 0, 0)])
+
+
 def test_elevation_seams_at_scale(plb, ctx):
     """size-independent property at a size the oracle does not reach: the 4 096 tiles of level 6 of config 1's
     terrain (pl_produce_range, fused kernel) -- every pair of neighbouring tiles holds the same zf and zm on the 5

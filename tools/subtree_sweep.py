@@ -23,9 +23,12 @@ FRACTAL = [-140, -100, -15, -8, 5, 2.5, 1.5, 1, 0.5, 0.25, 0.1, 0.05]
 LEAF_LEVEL = 14
 
 
-def run_sweep(pl, ctx, d, rank=0, world=1, unit_depth=7, root=None, scene_kw=None, keep=None):
+def run_sweep(pl, ctx, d, rank=0, world=1, unit_depth=7, root=None, scene_kw=None, keep=None, levels=False, pools=None):
     """Produces rank `rank`'s share; returns (tiles produced, fingerprint dict).  keep: optional dict
-    filled with {(level, tx, ty): (elev, norm)} for the leaf tiles whose Morton index is in keep['want']."""
+    filled with {(level, tx, ty): (elev, norm)} for the leaf tiles whose Morton index is in keep['want'].
+    levels: the chain + top tree, and every unit, as ONE launch each (pl_produce_levels: the level-to-level dependency
+    is resolved inside the kernel) instead of one pl_produce_range per level.
+    pools: (elev, norm) of at least plan.capacity slots to produce into (kept open); default: created and closed here."""
     import sweep
     root_level = LEAF_LEVEL - d
     tx, ty = root if root is not None else ((1 << root_level) // 3, (1 << root_level) // 5)
@@ -33,13 +36,24 @@ def run_sweep(pl, ctx, d, rank=0, world=1, unit_depth=7, root=None, scene_kw=Non
     kw = dict(noise_amp=FRACTAL, face=0, root_quad_size=100000.0, sphere=0, want_stats=1)
     kw.update(scene_kw or {})
     sc = pl.sweep_scene(**kw)
-    elev = ctx.pool(pl.POOL_ELEV, 101, plan.capacity)
-    norm = ctx.pool(pl.POOL_NORM2, 97, plan.capacity)
-    ctx.noise_init(101)
+    if pools is None:
+        elev = ctx.pool(pl.POOL_ELEV, 101, plan.capacity)
+        norm = ctx.pool(pl.POOL_NORM2, 97, plan.capacity)
+        ctx.noise_init(101)
+    else:
+        elev, norm = pools
     produced = 0
-    for level, m0, n, s0, p0, pm0 in plan.prologue():
-        ctx.produce_range(sc, elev, norm, level, m0, n, s0, p0, pm0)
-        produced += n
+    carry = []       # levels mode, k == 0: the chain and the single unit are one consecutive run of levels
+    if levels:
+        carry = list(plan.prologue())
+        produced += sum(b[2] for b in carry)
+        if plan.k > 0:
+            ctx.produce_levels(sc, elev, norm, carry)
+            carry = []
+    else:
+        for level, m0, n, s0, p0, pm0 in plan.prologue():
+            ctx.produce_range(sc, elev, norm, level, m0, n, s0, p0, pm0)
+            produced += n
     slot0, nleaf = plan.leaf_region()
     fp_sum, fp_lo, fp_hi, fp_xor = 0.0, np.inf, -np.inf, np.uint32(0)
     def fold(st):
@@ -50,9 +64,15 @@ def run_sweep(pl, ctx, d, rank=0, world=1, unit_depth=7, root=None, scene_kw=Non
 
     pending = []      # TileSamplerZ's readback, 8 bytes per leaf tile: enqueued behind the unit's kernels,
     for unit in plan.units_of_rank(rank, world):          # collected two units later (ReadbackManager)
-        for level, m0, n, s0, p0, pm0 in plan.unit_batches(unit):
-            ctx.produce_range(sc, elev, norm, level, m0, n, s0, p0, pm0)
-            produced += n
+        if levels:
+            ub = list(plan.unit_batches(unit))
+            ctx.produce_levels(sc, elev, norm, carry + ub)
+            carry = []
+            produced += sum(b[2] for b in ub)
+        else:
+            for level, m0, n, s0, p0, pm0 in plan.unit_batches(unit):
+                ctx.produce_range(sc, elev, norm, level, m0, n, s0, p0, pm0)
+                produced += n
         if len(pending) == 2:
             fold(ctx.elev_stats_readback_end(pending.pop(0)))
         pending.append(ctx.elev_stats_readback_begin(elev, slot0, nleaf))
@@ -65,8 +85,9 @@ def run_sweep(pl, ctx, d, rank=0, world=1, unit_depth=7, root=None, scene_kw=Non
     for tk in pending:
         fold(ctx.elev_stats_readback_end(tk))
     ctx.sync()
-    elev.close()
-    norm.close()
+    if pools is None:
+        elev.close()
+        norm.close()
     return produced, dict(sum=fp_sum, lo=fp_lo, hi=fp_hi, xor=int(fp_xor)), plan
 
 
