@@ -389,12 +389,13 @@ int pl_residual_upsample(pl_ctx *ctx, pl_pool *pool, int src_slot, int dst_slot,
  * The upsample is ResidualProducer::upsample's (same taps, same CPU evaluation order), so the
  * approximation equals, bit for bit, what the run-time producer reconstructs from the file.
  * heights / approx: F32 residual pools (tiles of tile_size + 5 texels in the lower-left corner of the
- * slot, heights already divided by the file's scale); resid: an I16 residual pool.  The approximation of a
- * level-0 tile is the tile itself (getApproxTile :420-431): upload it to the approx pool.
+ * slot, heights already divided by the file's scale); resid: an I16 residual pool.  parent_slot = -1 is the
+ * level-0 rule (produceTile :567-578, getApproxTile :420-431): stored int16 = short(roundf(heights)), and the
+ * approximation is the height tile itself, unrounded.
  * max_residual / max_err (n floats each, or NULL): max |residual before rounding|, max |heights - approximation|. */
 typedef struct pl_resid_enc_req {
     int32_t tile_slot;      /* heights pool: the tile to encode                    */
-    int32_t parent_slot;    /* approx pool: the parent's approximation             */
+    int32_t parent_slot;    /* approx pool: the parent's approximation; -1: level 0 */
     int32_t approx_slot;    /* approx pool: receives this tile's approximation     */
     int32_t resid_slot;     /* resid pool: receives the int16 residuals            */
     int32_t tile_size;      /* min(topLevelSize << level, tileSize)                */
@@ -403,6 +404,36 @@ typedef struct pl_resid_enc_req {
 } pl_resid_enc_req;         /* 32 bytes */
 int pl_residual_encode_batch(pl_ctx *ctx, pl_pool *heights, pl_pool *approx, pl_pool *resid, int n,
                              const pl_resid_enc_req *reqs, float *max_residual, float *max_err);
+
+/* ---- the height pyramid of the residual builder (the step before pl_residual_encode_batch) ------------------
+ * HeightMipmap's base level, mipmap levels and cube-face stitching (preprocess/terrain/HeightMipmap.cpp:67-81, 149-254,
+ * 327-372, 404-412; Preprocess.cpp:512-585 preprocessSphericalDem).  The six base-level grids ((base_size + 1)^2 int16
+ * samples each, row-major; base_size = top_level_size << maxLevel) stay resident on the device; a height tile of any
+ * level is gathered from them: level l = the base level decimated, samples near a cube corner collapse onto the corner,
+ * samples past an edge come from the neighbouring face under setCube's rotation (nfaces = 6), or are clamped
+ * (nfaces = 1: a flat DEM, AbstractTileCache.cpp:73-92).
+ *   pl_height_cube_create       from host grids (faces[0..nfaces): hm1..hm6 of setCube)
+ *   pl_height_cube_from_latlon  SphericalHeightFunction (Preprocess.cpp:406-445): the six grids from an equirectangular
+ *                               source map (src_w x src_h floats, bilinear in lon / lat), computed on the device
+ *   pl_height_cube_from_plane   PlaneHeightFunction (Preprocess.cpp:335-366): the one grid of a flat DEM (preprocessDem)
+ *   pl_height_tiles             HeightMipmap::getTile for n (face, level, tx, ty): (ts + 5)^2 heights / scale into slot
+ *                               out_slot of an F32 residual pool, ts = min(top_level_size << level, tile_size) */
+typedef struct pl_height_cube pl_height_cube;
+typedef struct pl_height_req {
+    int32_t face, level, tx, ty;
+    int32_t out_slot;
+    int32_t pad_[3];
+} pl_height_req;             /* 32 bytes */
+int pl_height_cube_create(pl_ctx *ctx, int base_size, int nfaces, const int16_t *const *faces, pl_height_cube **out);
+int pl_height_cube_from_latlon(pl_ctx *ctx, int base_size, const float *src, int src_w, int src_h, pl_height_cube **out);
+int pl_height_cube_from_plane(pl_ctx *ctx, int base_size, const float *src, int src_w, int src_h, pl_height_cube **out);
+/* how many base samples pl_height_cube_from_latlon has recomputed with the host's libm so far (the samples whose int16
+ * truncation the device's atan2 / acos could not decide) */
+uint64_t pl_debug_height_unsure(const pl_ctx *ctx);
+int pl_height_cube_download(pl_ctx *ctx, const pl_height_cube *cube, int face, int16_t *out);
+void pl_height_cube_destroy(pl_height_cube *cube);
+int pl_height_tiles(pl_ctx *ctx, const pl_height_cube *cube, pl_pool *heights, int top_level_size, int tile_size,
+                    float scale, int n, const pl_height_req *reqs);
 
 /* HeightMipmap::generate + produceTile (HeightMipmap.cpp:99-130, 561-655): write a residual file in the
  * format ResidualProducer reads -- header, offset table per tile id, one little-endian TIFF/DEFLATE blob

@@ -248,12 +248,23 @@ int orc_ortho_cpu_read(const uint8_t *file, size_t size, int level, int tx, int 
 long orc_ortho_quadtree(int W, int face, int maxLevel, const float *noiseAmp, int nAmp, const float noiseColor[4],
                         const float rootNoiseColor[4], int hsv, float scale, const uint8_t *noise, uint8_t *out);
 
-#ifdef __cplusplus
-}
-#endif
+/* the height pyramid of a cube: HeightMipmap::getTileHeight / getTile with setCube's stitching, the six cube
+ * projections and SphericalHeightFunction (orc_preprocess.c) */
+float orc_hm_height(const short *const *faces, int nfaces, int B, int maxLevel, int level, int face, int x, int y);
+void orc_hm_get_tile(const short *const *faces, int nfaces, int B, int maxLevel, int topLevelSize, int tileSize, float scale,
+                     int level, int face, int tx, int ty, float *tile);
+void orc_cube_projection(int face, int x, int y, int w, double *sx, double *sy, double *sz);
+short orc_spherical_base_sample(const float *src, int sw, int sh, int face, int x, int y, int B);
+void orc_spherical_base_grid(const float *src, int sw, int sh, int face, int B, short *out);
+void orc_plane_base_grid(const float *src, int sw, int sh, int B, short *out);
+
 /* ---------------------------------------------------------------- preprocess
  * the residual-pyramid builder, one tile of one level (HeightMipmap.cpp:449-559), orc_preprocess.c */
 void orc_hm_encode_tile(const float *parentTile, const float *tile, int n, int tileSize, int tx, int ty,
                         short *resid, float *approx, float *maxR, float *maxErr);
+
+#ifdef __cplusplus
+}
+#endif
 
 #endif

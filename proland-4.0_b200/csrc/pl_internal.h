@@ -53,6 +53,7 @@ struct pl_ctx {
     cudaStream_t own_stream;
     cudaStream_t stream;
     uint64_t launches;
+    uint64_t height_unsure;   /* pl_height_cube_from_latlon: base samples redone with the host's libm (pl_heights.cu) */
     /* noise (createDemNoise), 4 rotations x 6 layers of fp16 */
     int noise_w;
     int noise_pitch;

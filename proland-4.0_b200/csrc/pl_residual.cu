@@ -1077,7 +1077,8 @@ __global__ void __launch_bounds__(256) residual_encode_kernel(const pl_resid_enc
     __shared__ float red_r[8], red_e[8];
     const pl_resid_enc_req J = jobs[blockIdx.x];
     const float *tile = reinterpret_cast<const float *>(hbase + (size_t) J.tile_slot * hslot);
-    const float *parent = reinterpret_cast<const float *>(abase + (size_t) J.parent_slot * aslot);
+    const bool root = J.parent_slot < 0;      /* level 0: stored as short(roundf(h)), its own approximation (produceTile :567-578) */
+    const float *parent = reinterpret_cast<const float *>(abase + (size_t) (root ? 0 : J.parent_slot) * aslot);
     float *approx = reinterpret_cast<float *>(abase + (size_t) J.approx_slot * aslot);
     short *resid = reinterpret_cast<short *>(rbase + (size_t) J.resid_slot * rslot);
     const int w = J.tile_size + 5;
@@ -1085,12 +1086,12 @@ __global__ void __launch_bounds__(256) residual_encode_kernel(const pl_resid_enc
     float mr = 0.0f, me = 0.0f;
     for (int k = threadIdx.x; k < w * w; k += blockDim.x) {
         const int j = k / w, i = k - j * w;
-        const float z = hm_predict(parent, apitch, i, j, px, py);
+        const float z = root ? 0.0f : hm_predict(parent, apitch, i, j, px, py);
         const float t = tile[i + j * hpitch];
         const float diff = t - z;
         mr = fmaxf(fabsf(diff), mr);
         const short q = (short) (int) roundf(diff);          /* short(roundf(residual)): half away from zero */
-        const float a = z + (float) q;
+        const float a = root ? t : z + (float) q;           /* getApproxTile(0) is the height tile itself (:420-431) */
         me = fmaxf(fabsf(t - a), me);
         resid[i + j * rpitch] = q;
         approx[i + j * apitch] = a;
@@ -1351,7 +1352,7 @@ extern "C" int pl_residual_encode_batch(pl_ctx *ctx, pl_pool *heights, pl_pool *
         if (q.tile_size < 2 || q.tile_size % 2 != 0 || q.tile_size + 5 > heights->tile_w || q.tile_size + 5 > approx->tile_w ||
             q.tile_size + 5 > resid->tile_w || q.tx < 0 || q.ty < 0)
             return pl_set_error(PL_ERR_ARG, "request %d: tile size %d does not fit the pools", j, q.tile_size);
-        if (q.tile_slot < 0 || q.tile_slot >= heights->capacity || q.parent_slot < 0 || q.parent_slot >= approx->capacity ||
+        if (q.tile_slot < 0 || q.tile_slot >= heights->capacity || q.parent_slot < -1 || q.parent_slot >= approx->capacity ||
             q.approx_slot < 0 || q.approx_slot >= approx->capacity || q.resid_slot < 0 || q.resid_slot >= resid->capacity ||
             q.approx_slot == q.parent_slot)
             return pl_set_error(PL_ERR_ARG, "request %d: slot out of range", j);

@@ -16,6 +16,7 @@
 #include "proland/dem/ResidualProducer.h"
 #include "proland/ortho/OrthoCPUProducer.h"
 #include "proland/ortho/OrthoProducer.h"
+#include "proland/preprocess/terrain/Preprocess.h"
 #include "proland/producer/TileCache.h"
 #include "proland/producer/TileProducer.h"
 #include "proland/resource/ResourceManager.h"
@@ -113,6 +114,17 @@ struct TestScene
 };
 
 static Logger g_debug("DEBUG");
+
+/* an InputMap over a caller's float array (row 0 first), the way a user subclasses it (Preprocess.h:58-154) */
+class ArrayInputMap : public InputMap
+{
+public:
+    ArrayInputMap(const float *data, int w, int h, int tile) : InputMap(w, h, 1, tile), data(data) {}
+    virtual vec4f getValue(int x, int y) { return vec4f(data[(size_t) y * width + x], 0, 0, 0); }
+
+private:
+    const float *data;
+};
 
 }  // namespace
 
@@ -509,6 +521,19 @@ int plh_frame_update(void *scheduler, void *node, void **samplers, int n)
 }
 
 /* ---------------------------------------------------------------- CPU-only test double */
+
+int plh_preprocess_dem(const float *src, int src_w, int src_h, int min_tile_size, int tile_size, int max_level, const char *dst_folder,
+                       float residual_scale, int spherical)
+{
+    PLH_TRY
+    int tile = 256;
+    while (tile > 1 && (src_w % tile != 0 || src_h % tile != 0)) tile /= 2;
+    ArrayInputMap map(src, src_w, src_h, tile);
+    if (spherical) preprocessSphericalDem(&map, min_tile_size, tile_size, max_level, dst_folder, "", residual_scale);
+    else preprocessDem(&map, min_tile_size, tile_size, max_level, dst_folder, "", residual_scale);
+    return 0;
+    PLH_CATCH(-1)
+}
 
 void *plh_test_scene(int capacity, int tile_size, int max_level, int prefetch_rate, int prefetch_queue)
 {

@@ -32,6 +32,15 @@
 namespace ork
 {
 
+/* ork/math/vec4.h: what the preprocessing interface needs of it (InputMap::getValue returns one) */
+template <typename T> struct vec4
+{
+    T x, y, z, w;
+    vec4() : x(0), y(0), z(0), w(0) {}
+    vec4(T x, T y, T z, T w) : x(x), y(y), z(z), w(w) {}
+};
+typedef vec4<float> vec4f;
+
 class Object
 {
 public:

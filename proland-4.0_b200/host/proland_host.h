@@ -79,6 +79,10 @@ int plh_terrain_quads_z(void *node, float *out, int max_quads);   /* pre-order (
 void plh_sampler_destroy(void *sampler);
 int plh_sampler_tile_count(void *sampler);
 int plh_frame_update(void *scheduler, void *node, void **samplers, int n);
+/* proland::preprocessDem / preprocessSphericalDem (Preprocess.cpp:512-585) over a float array: writes dst_folder/DEM.dat
+ * or DEM1..6.dat; 0 or -1 (plh_last_error) */
+int plh_preprocess_dem(const float *src, int src_w, int src_h, int min_tile_size, int tile_size, int max_level, const char *dst_folder,
+                       float residual_scale, int spherical);
 
 /* CPU-only scene with a recording producer (cache / task / scheduler logic without a device) */
 void *plh_test_scene(int capacity, int tile_size, int max_level, int prefetch_rate, int prefetch_queue);

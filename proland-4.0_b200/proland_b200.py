@@ -33,6 +33,7 @@ EXPORTS = [
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_produce_levels", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
     "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_blobs_create", "pl_blobs_destroy", "pl_residual_decode_stored", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
+    "pl_height_cube_create", "pl_height_cube_from_latlon", "pl_height_cube_from_plane", "pl_debug_height_unsure", "pl_height_cube_download", "pl_height_cube_destroy", "pl_height_tiles",
     "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
 ]
 
@@ -108,6 +109,8 @@ assert ELEV_REQ_DTYPE.itemsize == 64 and NORM_REQ_DTYPE.itemsize == 240 and RESI
 LEVEL_RANGE_DTYPE = np.dtype([("level", "i4"), ("n", "i4"), ("morton0", "u8"), ("out_slot0", "i4"), ("parent_slot0", "i4"),
                               ("parent_morton0", "u8")])
 assert TILE_ID_DTYPE.itemsize == 32 and LEVEL_RANGE_DTYPE.itemsize == 32
+HEIGHT_REQ_DTYPE = np.dtype([("face", "i4"), ("level", "i4"), ("tx", "i4"), ("ty", "i4"), ("out_slot", "i4"), ("pad_", "i4", (3,))])
+assert HEIGHT_REQ_DTYPE.itemsize == 32
 
 _lib = None
 
@@ -197,6 +200,15 @@ def lib():
                                              C.c_void_p, C.c_void_p, C.c_int]
         L.pl_residual_encode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                                C.c_void_p, C.c_void_p]
+        L.pl_height_cube_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+        L.pl_height_cube_from_latlon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pl_height_cube_from_plane.argtypes = L.pl_height_cube_from_latlon.argtypes
+        L.pl_debug_height_unsure.argtypes = [C.c_void_p]
+        L.pl_debug_height_unsure.restype = C.c_uint64
+        L.pl_height_cube_download.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.pl_height_cube_destroy.argtypes = [C.c_void_p]
+        L.pl_height_cube_destroy.restype = None
+        L.pl_height_tiles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
         L.pl_ortho_noise_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pl_ortho_noise_host.argtypes = [C.c_int, C.c_void_p]
         L.pl_ortho_make_req.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -489,9 +501,56 @@ class Context:
                                              _ptr(mr), _ptr(me)))
         return mr, me
 
+    def height_cube(self, faces):
+        """the base-level grids of a residual builder on the device: faces = 1 (flat DEM) or 6 (setCube order hm1..hm6)
+        int16 arrays of (B + 1, B + 1) samples (pl_height_cube_create)"""
+        faces = [np.ascontiguousarray(f, np.int16) for f in faces]
+        B = faces[0].shape[0] - 1
+        assert all(f.shape == (B + 1, B + 1) for f in faces)
+        ptrs = (C.c_void_p * len(faces))(*[f.ctypes.data for f in faces])
+        h = C.c_void_p()
+        check(lib().pl_height_cube_create(self.h, B, len(faces), ptrs, C.byref(h)))
+        return HeightCube(self, h, B, len(faces))
+
+    def height_cube_from_latlon(self, src, base_size):
+        """SphericalHeightFunction on the device: six base grids from an equirectangular float map (pl_height_cube_from_latlon)"""
+        src = np.ascontiguousarray(src, np.float32)
+        h = C.c_void_p()
+        check(lib().pl_height_cube_from_latlon(self.h, base_size, _ptr(src), src.shape[1], src.shape[0], C.byref(h)))
+        return HeightCube(self, h, base_size, 6)
+
+    def height_cube_from_plane(self, src, base_size):
+        """PlaneHeightFunction on the device: the base grid of a flat DEM (pl_height_cube_from_plane)"""
+        src = np.ascontiguousarray(src, np.float32)
+        h = C.c_void_p()
+        check(lib().pl_height_cube_from_plane(self.h, base_size, _ptr(src), src.shape[1], src.shape[0], C.byref(h)))
+        return HeightCube(self, h, base_size, 1)
+
     def normal_batch_dev(self, scene, norm, elev, n, dev_ptr):
         check(lib().pl_normal_batch_dev(self.h, C.byref(scene), norm.h, elev.h, n,
                                         C.c_void_p(dev_ptr)))
+
+
+class HeightCube:
+    """pl_height_cube: the resident base level of HeightMipmap (one flat DEM or the six faces of a cube)"""
+
+    def __init__(self, ctx, h, B, nfaces):
+        self.ctx, self.h, self.B, self.nfaces = ctx, h, B, nfaces
+
+    def download(self, face):
+        out = np.empty((self.B + 1, self.B + 1), np.int16)
+        check(lib().pl_height_cube_download(self.ctx.h, self.h, face, _ptr(out)))
+        return out
+
+    def tiles(self, heights, top_level_size, tile_size, reqs, scale=1.0):
+        """HeightMipmap::getTile for a batch of (face, level, tx, ty, out_slot) (pl_height_tiles)"""
+        reqs = np.ascontiguousarray(reqs, HEIGHT_REQ_DTYPE)
+        check(lib().pl_height_tiles(self.ctx.h, self.h, heights.h, top_level_size, tile_size, scale, len(reqs), _ptr(reqs)))
+
+    def close(self):
+        if self.h:
+            lib().pl_height_cube_destroy(self.h)
+            self.h = None
 
 
 def _produce_range(self, scene, elev, norm, level, morton0, n, out_slot0, parent_slot0=0,

@@ -31,7 +31,17 @@ EXPORTS = [
     "plh_test_scene_close", "plh_test_producer", "plh_test_cache", "plh_test_scheduler", "plh_test_calls",
     "plh_test_begin_end", "plh_terrain_create", "plh_terrain_destroy", "plh_split_distance", "plh_terrain_update",
     "plh_terrain_quads", "plh_terrain_quads_z", "plh_sampler_z_create", "plh_sampler_z_counts", "plh_ground_height", "plh_sampler_create", "plh_sampler_destroy", "plh_sampler_tile_count", "plh_frame_update",
+    "plh_preprocess_dem",
 ]
+
+
+def preprocess_dem(src, min_tile_size, tile_size, max_level, dst_folder, residual_scale=1.0, spherical=False):
+    """proland::preprocessDem / preprocessSphericalDem on a (h, w) float32 map -> dst_folder/DEM.dat or DEM1..6.dat"""
+    import numpy as np
+    src = np.ascontiguousarray(src, np.float32)
+    if lib().plh_preprocess_dem(src.ctypes.data, src.shape[1], src.shape[0], min_tile_size, tile_size, max_level,
+                                os.fsencode(dst_folder), residual_scale, 1 if spherical else 0) != 0:
+        raise HostError(_err())
 
 
 class HostError(RuntimeError):
@@ -67,6 +77,7 @@ def lib():
                      "plh_test_cache", "plh_test_scheduler"):
             getattr(L, name).argtypes = [vp]
         L.plh_set_root_quad_size.argtypes = [vp, C.c_float]
+        L.plh_preprocess_dem.argtypes = [vp, i, i, i, i, i, C.c_char_p, C.c_float, i]
         for name in ("plh_producer_info", "plh_producer_counts", "plh_cache_stats", "plh_scheduler_stats", "plh_residual_info",
                      "plh_test_begin_end"):
             getattr(L, name).argtypes = [vp, vp]

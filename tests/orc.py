@@ -13,6 +13,7 @@ ORC_DIR = os.path.join(ROOT, "oracle")
 ORC_SO = os.path.join(ORC_DIR, "liborc.so")
 REF_SO = os.path.join(ORC_DIR, "_ref", "libref_noise.so")
 GLSL_SO = os.path.join(ORC_DIR, "_ref", "libref_glsl.so")
+HM_SO = os.path.join(ORC_DIR, "_ref", "libref_hm.so")
 STRICT_SO = os.path.join(ORC_DIR, "liborc_strict.so")
 
 c_float_p = C.POINTER(C.c_float)
@@ -139,6 +140,32 @@ def glsl():
             return None
         _glsl = C.CDLL(GLSL_SO)
     return _glsl
+
+
+_hm = None
+
+
+def hm():
+    """The reference's own residual builder (preprocess/terrain/*.cpp compiled unchanged over the Ork / libtiff shims:
+    oracle/_ref/libref_hm.so, oracle/Makefile), or None when oracle/_ref was not built."""
+    global _hm
+    if _hm is None:
+        if not os.path.exists(HM_SO):
+            return None
+        H = C.CDLL(HM_SO)
+        for f in (H.ref_preprocess_spherical_dem, H.ref_preprocess_dem):
+            f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_float]
+        _hm = H
+    return _hm
+
+
+def ref_preprocess_dem(src, min_tile_size, tile_size, max_level, dst, tmp, scale=1.0, spherical=False):
+    """proland::preprocessDem / preprocessSphericalDem of the reference itself -> dst/DEM.dat or dst/DEM1..6.dat"""
+    src = np.ascontiguousarray(src, np.float32)
+    f = hm().ref_preprocess_spherical_dem if spherical else hm().ref_preprocess_dem
+    rc = f(src.ctypes.data, src.shape[1], src.shape[0], min_tile_size, tile_size, max_level, os.fsencode(dst), os.fsencode(tmp), scale)
+    if rc != 0:
+        raise RuntimeError("the reference's preprocess failed")
 
 
 def _fp(a):
@@ -352,6 +379,62 @@ def hm_encode_tile(parent, tile, tile_size, tx, ty):
     L.orc_hm_encode_tile(parent.ctypes.data, tile.ctypes.data, n, tile_size, tx, ty, resid.ctypes.data,
                          approx.ctypes.data, C.byref(mr), C.byref(me))
     return resid, approx, mr.value, me.value
+
+
+def _face_ptrs(faces):
+    faces = [np.ascontiguousarray(f, np.int16) for f in faces]
+    return faces, (C.c_void_p * len(faces))(*[f.ctypes.data for f in faces])
+
+
+def hm_height(faces, max_level, level, face, x, y):
+    """HeightMipmap::getTileHeight with setCube's stitching (orc_preprocess.c); faces: 1 or 6 (B + 1, B + 1) int16 grids"""
+    faces, ptrs = _face_ptrs(faces)
+    L = lib()
+    L.orc_hm_height.restype = C.c_float
+    L.orc_hm_height.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    return L.orc_hm_height(ptrs, len(faces), faces[0].shape[0] - 1, max_level, level, face, x, y)
+
+
+def hm_get_tile(faces, max_level, top_level_size, tile_size, level, face, tx, ty, scale=1.0):
+    """HeightMipmap::getTile -> (tileSize + 5, tileSize + 5) float32, the tile in the lower-left (ts + 5)^2"""
+    faces, ptrs = _face_ptrs(faces)
+    n = tile_size + 5
+    out = np.zeros((n, n), np.float32)
+    L = lib()
+    L.orc_hm_get_tile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_void_p]
+    L.orc_hm_get_tile(ptrs, len(faces), faces[0].shape[0] - 1, max_level, top_level_size, tile_size, scale, level, face, tx, ty,
+                      out.ctypes.data)
+    return out
+
+
+def cube_projection(face, x, y, w):
+    """projection1..6 of Preprocess.cpp:155-213 -> (sx, sy, sz)"""
+    L = lib()
+    L.orc_cube_projection.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    v = (C.c_double * 3)()
+    L.orc_cube_projection(face, x, y, w, C.byref(v, 0), C.byref(v, 8), C.byref(v, 16))
+    return tuple(v)
+
+
+def spherical_base(src, face, B):
+    """the base grid of one cube face from an equirectangular map: (short) SphericalHeightFunction::getHeight(x, y)"""
+    src = np.ascontiguousarray(src, np.float32)
+    L = lib()
+    L.orc_spherical_base_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    out = np.empty((B + 1, B + 1), np.int16)
+    L.orc_spherical_base_grid(src.ctypes.data, src.shape[1], src.shape[0], face, B, out.ctypes.data)
+    return out
+
+
+def plane_base(src, B):
+    """the base grid of a flat DEM: (short) PlaneHeightFunction::getHeight(x, y)"""
+    src = np.ascontiguousarray(src, np.float32)
+    L = lib()
+    L.orc_plane_base_grid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    out = np.empty((B + 1, B + 1), np.int16)
+    L.orc_plane_base_grid(src.ctypes.data, src.shape[1], src.shape[0], B, out.ctypes.data)
+    return out
 
 
 # --------------------------------------------------------------- driver ----
