@@ -148,9 +148,89 @@ def config3(pl, ctx, torch, stream, peak, peak_kind, n_decode=32768, level=8):
             rpool.close()
     norm.close()
     elev.close()
-    store.close()
     hpool.close()
+    try:
+        out["planet_sweep"] = config3_sweep(pl, ctx, torch, stream, peak, peak_kind, store, offs64, sizes64)
+    except Exception as ex:
+        out["planet_sweep"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    store.close()
     return out
+
+
+def config3_sweep(pl, ctx, torch, stream, peak, peak_kind, store, offs64, sizes64, max_level=10, resid_levels=6, reps=2):
+    """Config 3 as SURVEY 8d defines it: the cube-face quadtree of a planet whose residual files end at a finite level
+    (stored level 8 = elevation levels 0..6), fractal amplification below.  The residual tiles of the whole sweep (one per
+    2 x 2 elevation tiles, 1366 per face) are decoded in ONE batch INSIDE the timed region, then the 6 faces are swept
+    breadth-first through the recycling pool (plan: sweep.py); tiles of levels 0..resid_levels read their residual window."""
+    import sweep as plan
+    _, cap = plan.region_offsets(max_level)
+    elev = ctx.pool(pl.POOL_ELEV, 101, cap)
+    norm = ctx.pool(pl.POOL_NORM2, 97, cap)
+    level_base = [0, 1]
+    for l in range(2, resid_levels + 2):
+        level_base.append(level_base[-1] + 4 ** (l - 2))
+    per_face = level_base[resid_levels + 1]
+    nres = 6 * per_face
+    rpool = ctx.pool(pl.POOL_RESID_I16, 197, nres)
+    ridx = np.arange(nres) % len(sizes64)
+    dargs = (rpool, store, offs64[ridx], sizes64[ridx], [197] * nres, np.arange(nres, dtype=np.int32))
+    amp = SRTM_AMP + [0.5] * max(0, max_level + 1 - len(SRTM_AMP))
+    scenes = {}
+    for f in range(1, 7):
+        sc = pl.sweep_scene(noise_amp=amp, face=f, root_quad_size=PLANET_SIZE, sphere=1, flip=1, elev_filter=pl.FILTER_NEAREST,
+                            want_stats=1, arith=pl.ARITH_FAST)
+        sc.elev.resid_scale = 1.0
+        scenes[f] = sc
+    units = plan.planet_units()
+    pairs = plan.pairs_in_units(units, max_level, True)
+    id_buf = np.zeros(4 ** max(resid_levels, 1), pl.TILE_ID_DTYPE)
+    resid_pairs = 0
+
+    def sweep():
+        nonlocal resid_pairs
+        resid_pairs = 0
+        ctx.residual_decode_stored(*dargs)
+        for f, level, m0, n, s0, p0, pm0 in plan.batches(units, max_level):
+            if level <= resid_levels:
+                ids = pl.make_tile_ids_range(level, m0, n, s0, p0, pm0, out=id_buf)
+                ids["resid_slot"] = (f - 1) * per_face + level_base[level] + ((m0 + np.arange(n)) >> 2 if level else 0)
+                ctx.pair_batch_ids(scenes[f], elev, norm, ids, resid=rpool)
+                resid_pairs += n
+            else:
+                ctx.produce_range(scenes[f], elev, norm, level, m0, n, s0, p0, pm0)
+
+    sweep()
+    ctx.sync()
+    ctx.timing_collect()
+    ctx.timing_enable(True)
+    e0, e1 = _events(torch, stream)
+    e0.record(stream)
+    for _ in range(reps):
+        sweep()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    kt = ctx.timing_collect()
+    ctx.timing_enable(False)
+    ms = e0.elapsed_time(e1) / reps
+    pair_ms = kt["pair"][0] / reps
+    dec_ms = kt["residual"][0] / reps
+    nbytes = (pairs - resid_pairs) * 192098 + resid_pairs * RESID_PAIR_BYTES["int16"]
+    st = ctx.elev_stats_readback_end(ctx.elev_stats_readback_begin(elev, 0, plan.ROOT_SLOTS))
+    rec = {"workload": "config 3 as a planet sweep: 6 cube faces, levels 0..%d, %d pairs; residual files end at elevation level %d "
+                       "(%d pairs read a residual window, %d residual tiles of 197 x 197 int16 decoded in one batch inside the timed "
+                       "region), fractal amplification below; flip, NEAREST elevation storage, sphere normals, PL_ARITH_FAST"
+                       % (max_level, pairs, resid_levels, resid_pairs, nres),
+           "pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3), "ms_per_sweep": ms, "decode_kernel_ms": dec_ms,
+           "pair_kernel_ms": pair_ms, "decode_tiles_per_s": nres / (dec_ms * 1e-3) if dec_ms else None,
+           "fraction_of_kernel_only": pair_ms / ms,
+           "roofline": {"bound": "hbm", "kernel": "pair", "achieved": nbytes / (pair_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": nbytes / (pair_ms * 1e-3) / 1e9 / peak, "frac_with_decode_in_the_denominator": nbytes / (ms * 1e-3) / 1e9 / peak,
+                        "bytes_per_pair": nbytes / pairs, "peak_kind": peak_kind, "traffic": None},
+           "fingerprint": {"root_stats_sum": float(st.astype(np.float64).sum())}}
+    rpool.close()
+    norm.close()
+    elev.close()
+    return rec
 
 
 def config4(pl, ctx, torch, stream, peak, peak_kind, ds=(6, 8, 10)):
