@@ -17,7 +17,7 @@ void BatchScheduler::setWaveHook(WaveHook hook)
 }
 
 BatchScheduler::BatchScheduler(int prefetchRate, int prefetchQueue) :
-    Scheduler("BatchScheduler"), prefetchRate(prefetchRate), prefetchQueue(prefetchQueue), frame(0), waves(0), executed(0)
+    Scheduler("BatchScheduler"), prefetchRate(prefetchRate), prefetchQueue(prefetchQueue), frame(0), waves(0), executed(0), lastNodes(0)
 {
 }
 
@@ -51,27 +51,44 @@ namespace
 struct Node
 {
     Task *task;
+    void *context;              /* Task::getContext, read once per flattened view (the sort key of a wave) */
     std::vector<Task *> deps;   /* tasks or graphs this task waits for, over all graphs that hold it */
 };
 
-/* the primitive tasks below the roots, in the order the graphs list them (hashed lookup: the view is
- * rebuilt every wave of every frame) */
+/* stamps handed to Task::schedViewStamp / schedMemoStamp: never 0, never reused */
+static unsigned long long g_stamp = 0;
+
+/* the primitive tasks below the roots, in the order the graphs list them.  A task knows its slot in the current view
+ * (Task::schedSlot, valid while Task::schedViewStamp equals the view's stamp): no look-up table */
 struct Flat
 {
     std::vector<Node> nodes;
-    std::unordered_map<Task *, size_t> index;
-    std::unordered_set<Task *> seenGraphs;
+    unsigned long long stamp;       /* of this view */
+    unsigned long long madeAt;      /* TaskGraph::editCount() when the view was made */
+
+    Flat() : stamp(++g_stamp), madeAt(~0ull) {}
 
     Node &operator[](Task *t)
     {
-        std::unordered_map<Task *, size_t>::iterator i = index.find(t);
-        if (i != index.end()) {
-            return nodes[i->second];
+        if (t->schedViewStamp == stamp) {
+            return nodes[t->schedSlot];
         }
-        index.insert(std::make_pair(t, nodes.size()));
+        t->schedViewStamp = stamp;
+        t->schedSlot = nodes.size();
         nodes.push_back(Node());
         nodes.back().task = t;
+        nodes.back().context = NULL;
         return nodes.back();
+    }
+
+    /* first visit of a graph in this view? */
+    bool enter(Task *g)
+    {
+        if (g->schedViewStamp == stamp) {
+            return false;
+        }
+        g->schedViewStamp = stamp;
+        return true;
     }
 };
 
@@ -83,7 +100,7 @@ void flatten(Task *t, Flat &nodes)
         n.task = t;
         return;
     }
-    if (!nodes.seenGraphs.insert(t).second) {
+    if (!nodes.enter(t)) {
         return;
     }
     TaskGraph *g = static_cast<TaskGraph *>(t);
@@ -112,22 +129,61 @@ void flatten(Task *t, Flat &nodes)
     }
 }
 
-bool byContext(Task *a, Task *b)
+bool byContext(const Node *a, const Node *b)
 {
-    void *ca = a->getContext(), *cb = b->getContext();
-    return ca != cb ? ca < cb : a < b;
+    return a->context != b->context ? a->context < b->context : a->task < b->task;
 }
+
+/* is a dependency (a task or a graph) done?  A graph is done when all its tasks are (TaskGraph::isDone walks them,
+ * sub-graphs included: a tile's graph holds its parent's, which holds its parent's ...); within one wave nothing
+ * completes, so the answer per graph is remembered for the wave */
+struct DoneMemo
+{
+    unsigned long long stamp;
+
+    DoneMemo() : stamp(++g_stamp) {}
+
+    bool operator()(Task *t)
+    {
+        if (!t->isTaskGraph()) {
+            return t->isDone();
+        }
+        if (t->schedMemoStamp == stamp) {
+            return t->schedMemo;
+        }
+        bool done = true;
+        const TaskGraph::TaskSet &ts = static_cast<TaskGraph *>(t)->taskSet();
+        for (TaskGraph::TaskSet::const_iterator c = ts.begin(); c != ts.end() && done; ++c) {
+            done = (*this)(c->get());
+        }
+        t->schedMemoStamp = stamp;
+        t->schedMemo = done;
+        return done;
+    }
+};
 
 }  // namespace
 
-static void initAll(const std::vector<ptr<Task> > &roots, std::set<Task *> &initialized)
+static void rebuild(const std::vector<ptr<Task> > &roots, Flat &nodes)
+{
+    const size_t hint = nodes.nodes.size();
+    nodes = Flat();
+    nodes.nodes.reserve(hint);
+    for (size_t i = 0; i < roots.size(); ++i) {
+        flatten(roots[i].get(), nodes);
+    }
+    nodes.madeAt = TaskGraph::editCount();
+}
+
+/* Task::init of every primitive task below the roots that is not in `initialized` yet; initialising a task may add
+ * tasks (CreateTile::start acquires the tiles it is made from): the view is rebuilt and the pass repeated while the
+ * graphs keep changing (TaskGraph::editCount).  Leaves `nodes` current. */
+static void initAll(const std::vector<ptr<Task> > &roots, std::set<Task *> &initialized, Flat &nodes)
 {
     for (;;) {
-        Flat nodes;
-        for (size_t i = 0; i < roots.size(); ++i) {
-            flatten(roots[i].get(), nodes);
+        if (nodes.madeAt != TaskGraph::editCount()) {
+            rebuild(roots, nodes);
         }
-        bool any = false;
         /* keep the tasks alive: an init may drop the last other reference to a sibling */
         std::vector<ptr<Task> > todo;
         for (std::vector<Node>::iterator n = nodes.nodes.begin(); n != nodes.nodes.end(); ++n) {
@@ -137,9 +193,8 @@ static void initAll(const std::vector<ptr<Task> > &roots, std::set<Task *> &init
         }
         for (size_t i = 0; i < todo.size(); ++i) {
             todo[i]->init(initialized);
-            any = true;
         }
-        if (!any) {
+        if (todo.empty() || nodes.madeAt == TaskGraph::editCount()) {
             break;
         }
     }
@@ -163,20 +218,23 @@ void BatchScheduler::run(ptr<Task> task)
      * flattened view visits every graph once; initialising a task may add tasks (CreateTile::start acquires
      * the tiles it is made from), so flatten again until nothing new appears. */
     std::set<Task *> initialized;
-    initAll(roots, initialized);
+    Flat nodes;
+    nodes.nodes.reserve(lastNodes);
+    initAll(roots, initialized, nodes);
 
     for (;;) {
-        /* flatten again every wave: finishing a task releases its inputs, restarting one re-acquires
-         * them, both edit the graphs */
-        Flat nodes;
-        for (size_t i = 0; i < roots.size(); ++i) {
-            flatten(roots[i].get(), nodes);
+        /* the flattened view is rebuilt only when some graph was edited since it was made (restarting a task
+         * re-acquires its inputs and edits its graph; finishing one only releases tiles): TaskGraph::editCount */
+        if (nodes.madeAt != TaskGraph::editCount()) {
+            rebuild(roots, nodes);
         }
         /* done tasks that completed before one of their inputs changed are stale */
         bool restarted = false;
         for (std::vector<Node>::iterator n = nodes.nodes.begin(); n != nodes.nodes.end(); ++n) {
             Task *t = n->task;
             if (!t->isDone()) continue;
+            /* a task completed in this run carries this run's date: none of its inputs can have changed LATER */
+            if (t->getCompletionDate() == frame) continue;
             for (size_t d = 0; d < n->deps.size(); ++d) {
                 if (n->deps[d]->getChangeDate() > t->getCompletionDate()) {
                     t->setIsDone(false, 0, Task::DATA_CHANGED);
@@ -188,31 +246,37 @@ void BatchScheduler::run(ptr<Task> task)
         }
         if (restarted) {
             /* restarted tasks re-acquire their input tiles (CreateTile::init -> start) */
-            initAll(roots, initialized);
+            initAll(roots, initialized, nodes);
             continue;
         }
 
-        std::vector<Task *> ready;
+        std::vector<Node *> readyNodes;
         size_t open = 0;
+        DoneMemo isDone;
         for (std::vector<Node>::iterator n = nodes.nodes.begin(); n != nodes.nodes.end(); ++n) {
             if (n->task->isDone()) continue;
             ++open;
             bool ok = true;
             for (size_t d = 0; d < n->deps.size() && ok; ++d) {
-                ok = n->deps[d]->isDone();
+                ok = isDone(n->deps[d]);
             }
-            if (ok) ready.push_back(n->task);
+            if (ok) {
+                if (n->context == NULL) n->context = n->task->getContext();
+                readyNodes.push_back(&*n);
+            }
         }
         if (open == 0) {
             break;
         }
-        if (ready.empty()) {
+        if (readyNodes.empty()) {
             if (Logger::ERROR_LOGGER != NULL) {
                 Logger::ERROR_LOGGER->logf("SCHEDULER", "%d tasks left but none can run (dependency cycle)", (int) open);
             }
             throw std::logic_error("BatchScheduler: dependency cycle");
         }
-        std::sort(ready.begin(), ready.end(), byContext);
+        std::sort(readyNodes.begin(), readyNodes.end(), byContext);
+        std::vector<Task *> ready(readyNodes.size());
+        for (size_t i = 0; i < readyNodes.size(); ++i) ready[i] = readyNodes[i]->task;
 
         /* keep the tasks alive while they run */
         std::vector<ptr<Task> > hold(ready.begin(), ready.end());
@@ -235,6 +299,7 @@ void BatchScheduler::run(ptr<Task> task)
         ++waves;
         executed += ready.size();
     }
+    lastNodes = nodes.nodes.size();
     for (size_t i = 0; i < roots.size(); ++i) {
         if (roots[i]->isTaskGraph()) {
             /* a graph has no run(); record its completion */

@@ -52,6 +52,7 @@ private:
     std::deque<ptr<Task> > prefetch;
     unsigned int frame;
     unsigned long waves, executed;
+    size_t lastNodes;      /* size of the last flattened view: the next one reserves as much */
 };
 
 }  // namespace ork

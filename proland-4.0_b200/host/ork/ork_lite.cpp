@@ -36,7 +36,8 @@ void Logger::logf(const char *topic, const char *fmt, ...)
 }
 
 Task::Task(const char *type, bool gpuTask, unsigned int deadline) :
-    Object(type), done(false), completionDate(0), changeDate(0), lastReason(DATA_NEEDED), gpuTask(gpuTask), deadline(deadline)
+    Object(type), schedViewStamp(0), schedSlot(0), schedMemoStamp(0), schedMemo(false), done(false), completionDate(0), changeDate(0),
+    lastReason(DATA_NEEDED), gpuTask(gpuTask), deadline(deadline)
 {
 }
 
@@ -57,6 +58,8 @@ void Task::setIsDone(bool d, unsigned int t, reason r)
         lastReason = r;
     }
 }
+
+unsigned long long TaskGraph::edits = 0;
 
 TaskGraph::TaskGraph() : Task("TaskGraph", false, 0)
 {
@@ -132,11 +135,13 @@ void TaskGraph::init(std::set<Task *> &initialized)
 
 void TaskGraph::addTask(ptr<Task> t)
 {
+    ++edits;
     tasks.insert(t);
 }
 
 void TaskGraph::removeTask(ptr<Task> t)
 {
+    ++edits;
     TaskSet gone;
     removeAndGetDependencies(t, gone);
     std::map<Task *, std::set<Task *> >::iterator inv = inverse.find(t.get());
@@ -152,12 +157,14 @@ void TaskGraph::removeTask(ptr<Task> t)
 
 void TaskGraph::addDependency(ptr<Task> src, ptr<Task> dst)
 {
+    ++edits;
     dependencies[src.get()].insert(dst);
     inverse[dst.get()].insert(src.get());
 }
 
 void TaskGraph::removeDependency(ptr<Task> src, ptr<Task> dst)
 {
+    ++edits;
     std::map<Task *, TaskSet>::iterator d = dependencies.find(src.get());
     if (d != dependencies.end()) {
         d->second.erase(dst);
@@ -185,12 +192,14 @@ void TaskGraph::removeAndGetDependencies(ptr<Task> src, TaskSet &deletedDependen
 
 void TaskGraph::clearDependencies()
 {
+    ++edits;
     dependencies.clear();
     inverse.clear();
 }
 
 void TaskGraph::cleanup()
 {
+    ++edits;
     dependencies.clear();
     inverse.clear();
     tasks.clear();

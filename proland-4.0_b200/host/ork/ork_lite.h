@@ -163,6 +163,14 @@ public:
 
     virtual bool isTaskGraph() const { return false; }
 
+    /* scratch of the scheduler that is flattening the graphs this task sits in (one scheduler thread at a time):
+     * the task's slot in the current flattened view and a per-wave memo, each valid for one stamp -- instead of hash
+     * tables keyed by the task's address, rebuilt every view */
+    mutable unsigned long long schedViewStamp;
+    mutable size_t schedSlot;
+    mutable unsigned long long schedMemoStamp;
+    mutable bool schedMemo;
+
 protected:
     bool done;
     unsigned int completionDate;
@@ -220,6 +228,9 @@ public:
 
     /* direct access for schedulers */
     const TaskSet &taskSet() const { return tasks; }
+    /* counts the structural edits (tasks or dependencies added / removed) of ALL graphs: a scheduler that keeps a
+     * flattened view across waves rebuilds it only when this moved */
+    static unsigned long long editCount() { return edits; }
     const TaskSet *dependenciesOf(Task *t) const;
 
 protected:
@@ -227,6 +238,7 @@ protected:
     void cleanup();
 
 private:
+    static unsigned long long edits;
     TaskSet tasks;
     std::map<Task *, TaskSet> dependencies;          /* src -> what it needs */
     std::map<Task *, std::set<Task *> > inverse;     /* dst -> who needs it */

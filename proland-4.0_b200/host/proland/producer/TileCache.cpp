@@ -63,6 +63,10 @@ void TileCache::init(ptr<TileStorage> storage, std::string name, ptr<Scheduler> 
     this->queries = 0;
     this->misses = 0;
     this->name = name;
+    if (storage != NULL) {
+        usedTiles.reserve(2 * (size_t) storage->getCapacity());
+        unusedTiles.reserve(2 * (size_t) storage->getCapacity());
+    }
 }
 
 TileCache::~TileCache()
@@ -84,7 +88,7 @@ TileCache::~TileCache()
             Logger::WARNING_LOGGER->logf("CACHE", "%s: %d tiles still in use when the cache is deleted", name.c_str(),
                                          (int) usedTiles.size());
         }
-        for (std::map<Tile::TId, Tile *>::iterator i = usedTiles.begin(); i != usedTiles.end(); ++i) {
+        for (TileMap<Tile *>::type::iterator i = usedTiles.begin(); i != usedTiles.end(); ++i) {
             storage->deleteSlot(i->second->data);
             delete i->second;
         }
@@ -118,12 +122,12 @@ TileCache::Tile *TileCache::findTile(int producerId, int level, int tx, int ty, 
     assert(producers.find(producerId) != producers.end());
     std::lock_guard<std::recursive_mutex> lock(mutex);
     const Tile::TId id = Tile::getTId(producerId, level, tx, ty);
-    std::map<Tile::TId, Tile *>::iterator u = usedTiles.find(id);
+    TileMap<Tile *>::type::iterator u = usedTiles.find(id);
     if (u != usedTiles.end()) {
         return u->second;
     }
     if (includeCache) {
-        std::map<Tile::TId, Order::iterator>::iterator c = unusedTiles.find(id);
+        TileMap<Order::iterator>::type::iterator c = unusedTiles.find(id);
         if (c != unusedTiles.end()) {
             return *(c->second);
         }
@@ -150,7 +154,7 @@ ptr<Task> TileCache::makeTask(int producerId, const Tile::TId &id, int level, in
                               unsigned int deadline, bool *reused)
 {
     ptr<Task> task;
-    std::map<Tile::TId, Task *>::iterator d = deletedTiles.find(id);
+    TileMap<Task *>::type::iterator d = deletedTiles.find(id);
     *reused = d != deletedTiles.end();
     if (*reused) {
         task = d->second;
@@ -180,13 +184,13 @@ TileCache::Tile *TileCache::getTile(int producerId, int level, int tx, int ty, u
     std::lock_guard<std::recursive_mutex> lock(mutex);
     const Tile::TId id = Tile::getTId(producerId, level, tx, ty);
     Tile *t = NULL;
-    std::map<Tile::TId, Tile *>::iterator u = usedTiles.find(id);
+    TileMap<Tile *>::type::iterator u = usedTiles.find(id);
     if (u != usedTiles.end()) {
         t = u->second;
     } else {
         ++queries;
         bool reused = false;
-        std::map<Tile::TId, Order::iterator>::iterator c = unusedTiles.find(id);
+        TileMap<Order::iterator>::type::iterator c = unusedTiles.find(id);
         if (c != unusedTiles.end()) {
             /* still in storage: just back to the used set */
             t = *(c->second);
@@ -258,7 +262,7 @@ int TileCache::putTile(Tile *t)
     t->users -= 1;
     if (t->users == 0) {
         const Tile::TId id = t->getTId();
-        std::map<Tile::TId, Tile *>::iterator u = usedTiles.find(id);
+        TileMap<Tile *>::type::iterator u = usedTiles.find(id);
         assert(u != usedTiles.end() && u->second == t);
         usedTiles.erase(u);
         assert(unusedTiles.find(id) == unusedTiles.end());
@@ -271,13 +275,13 @@ void TileCache::invalidateTiles(int producerId)
 {
     std::lock_guard<std::recursive_mutex> lock(mutex);
     const unsigned int deadline = 1u << 31u;
-    for (std::map<Tile::TId, Tile *>::iterator i = usedTiles.begin(); i != usedTiles.end(); ++i) {
+    for (TileMap<Tile *>::type::iterator i = usedTiles.begin(); i != usedTiles.end(); ++i) {
         if (i->second->producerId == producerId) rerun(i->second->task, Task::DATA_CHANGED, deadline);
     }
     for (Order::iterator j = unusedTilesOrder.begin(); j != unusedTilesOrder.end(); ++j) {
         if ((*j)->producerId == producerId) rerun((*j)->task, Task::DATA_CHANGED, deadline);
     }
-    for (std::map<Tile::TId, Task *>::iterator k = deletedTiles.begin(); k != deletedTiles.end(); ++k) {
+    for (TileMap<Task *>::type::iterator k = deletedTiles.begin(); k != deletedTiles.end(); ++k) {
         if (k->first.first == producerId) rerun(k->second, Task::DATA_CHANGED, deadline);
     }
 }
@@ -287,11 +291,11 @@ void TileCache::invalidateTile(int producerId, int level, int tx, int ty)
     std::lock_guard<std::recursive_mutex> lock(mutex);
     const Tile::TId id = Tile::getTId(producerId, level, tx, ty);
     const unsigned int deadline = 1u << 31u;
-    std::map<Tile::TId, Tile *>::iterator u = usedTiles.find(id);
+    TileMap<Tile *>::type::iterator u = usedTiles.find(id);
     if (u != usedTiles.end()) rerun(u->second->task, Task::DATA_CHANGED, deadline);
-    std::map<Tile::TId, Order::iterator>::iterator c = unusedTiles.find(id);
+    TileMap<Order::iterator>::type::iterator c = unusedTiles.find(id);
     if (c != unusedTiles.end()) rerun((*(c->second))->task, Task::DATA_CHANGED, deadline);
-    std::map<Tile::TId, Task *>::iterator k = deletedTiles.find(id);
+    TileMap<Task *>::type::iterator k = deletedTiles.find(id);
     if (k != deletedTiles.end()) rerun(k->second, Task::DATA_CHANGED, deadline);
 }
 

@@ -17,6 +17,7 @@
 #include <list>
 #include <map>
 #include <mutex>
+#include <unordered_map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -97,15 +98,29 @@ protected:
 
 private:
     typedef std::list<Tile *> Order;
+    /* the reference keeps its tiles in std::map keyed by the nested-pair TId (TileCache.h:271-289): every lookup is a
+     * tree descent of four-int comparisons.  Same key, hashed: one 64-bit mix of (producer, level, tx, ty) */
+    struct TIdHash
+    {
+        size_t operator()(const Tile::TId &id) const
+        {
+            unsigned long long h = ((unsigned long long) (unsigned int) id.first << 56) ^ ((unsigned long long) (unsigned int) id.second.first << 48) ^
+                                   ((unsigned long long) (unsigned int) id.second.second.first << 24) ^ (unsigned int) id.second.second.second;
+            h ^= h >> 29;
+            h *= 0x9E3779B97F4A7C15ull;
+            return (size_t) (h ^ (h >> 32));
+        }
+    };
+    template <typename V> struct TileMap { typedef std::unordered_map<Tile::TId, V, TIdHash> type; };
 
     int nextProducerId;
     std::map<int, TileProducer *> producers;
     ptr<TileStorage> storage;
     ptr<Scheduler> scheduler;
-    std::map<Tile::TId, Tile *> usedTiles;
-    std::map<Tile::TId, Order::iterator> unusedTiles;
+    TileMap<Tile *>::type usedTiles;
+    TileMap<Order::iterator>::type unusedTiles;
     Order unusedTilesOrder;               /* front = least recently used */
-    std::map<Tile::TId, Task *> deletedTiles;
+    TileMap<Task *>::type deletedTiles;
     int queries;
     int misses;
     std::recursive_mutex mutex;
