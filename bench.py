@@ -297,6 +297,7 @@ def main():
     ap.add_argument("--max-level", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1: skip the `gather` record (tools/gather_tiles.py)")
     ap.add_argument("--no-configs", action="store_true", help="skip the sub-records of BASELINE configs 1, 3, 4, 5 (tools/configs.py)")
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"],
                     help="arithmetic contract of the normal pass in the timed region (include/proland_b200.h: "
@@ -418,6 +419,19 @@ def main():
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
     ms_max, e2e_s_max, other_ms_max = float(t[0]), float(t[1]), float(t[2])
 
+    # N > 1: gathering finished tiles and statistics (the one use the north star has for NCCL), and the same gather
+    # without a collective -- the fused kernel's PUSH variant storing its normal tiles into the peers' pools
+    gather = None
+    if world > 1 and not args.no_gather:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import gather_tiles
+        sweep.elev.close()      # the gather lays its own pools out for a whole quadtree
+        sweep.norm.close()
+        try:
+            gather = gather_tiles.gather_record(ctx, torch, dist, stream, rank, world)
+        except Exception as ex:         # a sub-record must not take the headline line with it
+            gather = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank == 0:
         peak, peak_kind = peaks()
         secs = ms_max * 1e-3
@@ -468,6 +482,13 @@ def main():
                            "stats_checksum": float(c[0]),
                            "stats_checksum_of": "sum of the (zmin, zmax) of every tile of levels 8..10 read back "
                                                 "in the step: independent of the number of ranks"}
+        if gather is not None:
+            g = dict(gather)
+            if "normals" in g:
+                g["normals_GBps_per_rank"] = g["normals"]["GBps_per_rank"]
+                g["identical_on_every_rank"] = bool(g.get("identical_to_single_gpu")) and \
+                    bool(g.get("push_from_the_kernel", {}).get("identical_on_every_rank", False))
+            line["gather"] = g
         if world == 1 and not args.no_cpu_baseline:
             n, dt, (csum, clo, chi) = cpu_sample(7)
             line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": os.cpu_count(),

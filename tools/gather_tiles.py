@@ -51,33 +51,13 @@ class _DeviceBytes:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-def main():
-    import torch
-    import torch.distributed as dist
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--level", type=int, default=7)
-    ap.add_argument("--reps", type=int, default=5)
-    a = ap.parse_args()
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    sys.stdout.flush()
-    saved = os.dup(1)
-    os.dup2(2, 1)                   # NCCL's version banner goes to stderr: stdout is the one JSON line
-    try:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist.all_reduce(torch.zeros(1, device="cuda"))
-        torch.cuda.synchronize()
-    finally:
-        sys.stdout.flush()
-        ctypes.CDLL(None).fflush(None)          # the banner sits in C stdio's buffer when stdout is a pipe
-        os.dup2(saved, 1)
-        os.close(saved)
-    L = a.level
+def gather_record(ctx, torch, dist, stream, rank, world, level=7, reps=5):
+    """the gather measurements on an existing context / stream (bench.py calls this at N > 1); -> the record on rank 0,
+    None elsewhere.  Collective: every rank of the group must call it."""
+    line = None
+    L = level
     off = [(4 ** l - 1) // 3 for l in range(L + 2)]
-    with pl.Context(local) as ctx:
-        stream = torch.cuda.Stream()
-        ctx.set_stream(stream.cuda_stream)
+    if True:
         elev = ctx.pool(pl.POOL_ELEV, 101, off[L + 1])
         norm = ctx.pool(pl.POOL_NORM2, 97, off[L + 1])
         ctx.noise_init(101)
@@ -97,11 +77,11 @@ def main():
             ctx.sync()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for _ in range(a.reps):
+            for _ in range(reps):
                 produce(rank, world)
             e1.record(stream)
             torch.cuda.synchronize()
-            prod_ms = e0.elapsed_time(e1) / a.reps
+            prod_ms = e0.elapsed_time(e1) / reps
 
             m0, n = rank_range(L, rank, world)
             results = {}
@@ -112,22 +92,22 @@ def main():
                 dist.all_gather_into_tensor(out, inp)
                 torch.cuda.synchronize()
                 e0.record(stream)
-                for _ in range(a.reps):
+                for _ in range(reps):
                     dist.all_gather_into_tensor(out, inp)
                 e1.record(stream)
                 torch.cuda.synchronize()
-                results[name] = e0.elapsed_time(e1) / a.reps
+                results[name] = e0.elapsed_time(e1) / reps
             for name, pool in (("normals", norm), ("elevations", elev)):
                 full = slab(pool)
                 part = full[m0 * pool.slot_bytes:(m0 + n) * pool.slot_bytes]
                 dist.all_gather_into_tensor(full, part)          # in place: a rank's share is already where it belongs
                 torch.cuda.synchronize()
                 e0.record(stream)
-                for _ in range(a.reps):
+                for _ in range(reps):
                     dist.all_gather_into_tensor(full, part)
                 e1.record(stream)
                 torch.cuda.synchronize()
-                results[name] = e0.elapsed_time(e1) / a.reps
+                results[name] = e0.elapsed_time(e1) / reps
             t = torch.tensor([prod_ms] + [results[k] for k in ("stats", "normals", "elevations")], dtype=torch.float64,
                              device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -163,13 +143,13 @@ def main():
                 torch.cuda.synchronize()
                 pushed_ok = bool(torch.equal(slab(norm), got_n))        # every rank holds the whole level again
                 e0.record(stream)
-                for _ in range(a.reps):
+                for _ in range(reps):
                     produce(rank, world)
                 e1.record(stream)
                 torch.cuda.synchronize()
                 dist.barrier()
                 norm.push_to_peers(False)
-                tp = torch.tensor([e0.elapsed_time(e1) / a.reps, 0.0 if pushed_ok else 1.0], dtype=torch.float64, device="cuda")
+                tp = torch.tensor([e0.elapsed_time(e1) / reps, 0.0 if pushed_ok else 1.0], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tp, op=dist.ReduceOp.MAX)
                 push = (float(tp[0]), float(tp[1]) == 0.0)
         if rank == 0:
@@ -192,8 +172,43 @@ def main():
                     "production_ms": push[0], "extra_ms_vs_plain_production": push[0] - float(t[0]),
                     "all_gather_of_the_normals_ms": float(t[2]), "bytes_sent_per_rank": sent,
                     "identical_on_every_rank": push[1]}
+    dist.barrier()              # nobody still reads a peer's pool
+    torch.cuda.synchronize()
+    norm.close()
+    elev.close()
+    return line
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--level", type=int, default=7)
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)                   # NCCL's version banner goes to stderr: stdout is the one JSON line
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.all_reduce(torch.zeros(1, device="cuda"))
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        ctypes.CDLL(None).fflush(None)          # the banner sits in C stdio's buffer when stdout is a pipe
+        os.dup2(saved, 1)
+        os.close(saved)
+    with pl.Context(local) as ctx:
+        stream = torch.cuda.Stream()
+        ctx.set_stream(stream.cuda_stream)
+        line = gather_record(ctx, torch, dist, stream, rank, world, a.level, a.reps)
+        if rank == 0:
             print(json.dumps(line), flush=True)
     dist.destroy_process_group()
+
 
 
 if __name__ == "__main__":
