@@ -43,8 +43,11 @@ NORM_BYTES = 99 * 99 * 4 + 97 * 97 * 2           # normal kernel: own zm read + 
 PAIR_BYTES = ELEV_BYTES + NORM_BYTES             # 192 098
 METRIC = "elevation+normal tile pairs/sec"
 # dram__bytes_read.sum + dram__bytes_write.sum per tile of one `ncu --set full` capture (profiles/README.md):
-# 16384 level-8 tiles in one launch
-TRAFFIC = {"pair": 155752, "elevation": 136520, "normal": 59565}
+# 16384 level-8 planet tiles in one launch.  pair: the kernel of the timed contract -- PL_ARITH_FAST
+# profiles/pair_r2x_fast_ncu_raw.csv (233.36 MB read + 2 361.59 MB written), PL_ARITH_EXACT profiles/pair_r1w_ncu_raw.csv;
+# the residual variants (config 3) and the flat scene (config 1) have no capture of their own: their records say null
+TRAFFIC = {"pair": 158382, "elevation": 136520, "normal": 59565}
+TRAFFIC_EXACT_PAIR = 155752
 ARITH_NOTE = {"fast": "PL_ARITH_FAST: elevation tiles bit-identical to the oracle; a normal byte within ONE unorm8 step of "
                       "the canonical evaluation (tests/test_gpu_fast.py bounds how many differ by the reference's own "
                       "non-contracted reading)",
@@ -439,6 +442,7 @@ def main():
         # dominant kernel = the one with the largest share of the step (the fused elevation+normal
         # kernel on this path; the separate passes appear when fusion is off)
         per_tile = {"pair": PAIR_BYTES, "elevation": ELEV_BYTES, "normal": NORM_BYTES}
+        traffic = dict(TRAFFIC, pair=TRAFFIC["pair"] if args.arith == "fast" else TRAFFIC_EXACT_PAIR)
         roof = {}
         for k in per_tile:
             tot_ms, n_launch, n_tiles = kt[k]
@@ -449,8 +453,8 @@ def main():
             roof[k] = {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
                        "frac": gbs / peak,
                        # measured DRAM bytes (ncu --set full, profiles/) scaled to the average launch of this run
-                       "traffic": TRAFFIC[k] * per_launch if TRAFFIC.get(k) else None,
-                       "traffic_per_pair": TRAFFIC.get(k), "algorithmic_bytes_per_launch": per_tile[k] * per_launch,
+                       "traffic": traffic[k] * per_launch if traffic.get(k) else None,
+                       "traffic_per_pair": traffic.get(k), "algorithmic_bytes_per_launch": per_tile[k] * per_launch,
                        "tiles_per_launch": per_launch, "launches": n_launch,
                        "avg_launch_ms": tot_ms / max(n_launch, 1), "share_of_step": tot_ms / ms_max,
                        "bytes_per_tile": per_tile[k], "peak_kind": peak_kind}
