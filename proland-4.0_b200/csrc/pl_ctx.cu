@@ -66,7 +66,7 @@ extern "C" void pl_ctx_destroy(pl_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
-    if (ctx->noise_rot) cudaFree(ctx->noise_rot);
+    for (int i = 0; i < ctx->n_noise; ++i) cudaFree(ctx->noise_tabs[i].rot);
     if (ctx->ortho_noise_rot) cudaFree(ctx->ortho_noise_rot);
     for (auto &rb : ctx->readback) {
         if (rb.pinned) cudaFreeHost(rb.pinned);
@@ -623,6 +623,10 @@ extern "C" int pl_noise_init(pl_ctx *ctx, int tile_w, float *host_out)
     if (tile_w < 11 || tile_w > 1024) return pl_set_error(PL_ERR_ARG, "bad noise tile_w %d", tile_w);
     PL_CUDA(cudaSetDevice(ctx->device));
     const int W = tile_w;
+    const bool have = ctx->noise_for(W) != nullptr;
+    if (have && !host_out) return PL_OK;      /* cached per width */
+    if (!have && ctx->n_noise == (int) (sizeof(ctx->noise_tabs) / sizeof(ctx->noise_tabs[0])))
+        return pl_set_error(PL_ERR_ARG, "too many distinct noise tile widths in one context");
     std::vector<float> n6((size_t) 6 * W * W);
     pl_host_dem_noise(W, n6.data());
     /* the reference uploads the array as R16F: round to nearest even */
@@ -631,6 +635,7 @@ extern "C" int pl_noise_init(pl_ctx *ctx, int tile_w, float *host_out)
         h6[i] = __float2half_rn(n6[i]);
         if (host_out) host_out[i] = __half2float(h6[i]);
     }
+    if (have) return PL_OK;                   /* host_out filled; the device table exists */
     const int pitch = pl_round_up(W + 1, 8);
     std::vector<__half> rot((size_t) 24 * W * pitch, __float2half_rn(0.0f));
     for (int r = 0; r < 4; ++r)
@@ -647,17 +652,18 @@ extern "C" int pl_noise_init(pl_ctx *ctx, int tile_w, float *host_out)
                     }
                     rot[((size_t) (r * 6 + l) * W + y) * pitch + pl_noise_col(x)] = h6[(size_t) l * W * W + sx + (size_t) sy * W];
                 }
-    if (ctx->noise_rot) {
-        PL_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(ctx->noise_rot);
-        ctx->noise_rot = nullptr;
+    __half *dev = nullptr;
+    PL_CUDA(cudaMalloc(&dev, rot.size() * sizeof(__half)));
+    cudaError_t e = cudaMemcpyAsync(dev, rot.data(), rot.size() * sizeof(__half), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(dev);
+        return pl_set_error(PL_ERR_CUDA, "pl_noise_init: %s", cudaGetErrorString(e));
     }
-    PL_CUDA(cudaMalloc(&ctx->noise_rot, rot.size() * sizeof(__half)));
-    PL_CUDA(cudaMemcpyAsync(ctx->noise_rot, rot.data(), rot.size() * sizeof(__half), cudaMemcpyHostToDevice,
-                            ctx->stream));
-    PL_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->noise_w = W;
-    ctx->noise_pitch = pitch;
+    pl_ctx::NoiseTable &t = ctx->noise_tabs[ctx->n_noise++];
+    t.w = W;
+    t.pitch = pitch;
+    t.rot = dev;
     return PL_OK;
 }
 
@@ -674,7 +680,7 @@ static int check_elev_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, 
     if (resid && (resid->tile_w - 5) % (sc->tile_w - 5) != 0)
         return pl_set_error(PL_ERR_ARG, "residual tile size %d is not a multiple of %d", resid->tile_w - 5, sc->tile_w - 5);
     if (sc->grid <= 0) return pl_set_error(PL_ERR_ARG, "grid must be > 0");
-    if (ctx->noise_w != sc->tile_w)
+    if (!ctx->noise_for(sc->tile_w))
         return pl_set_error(PL_ERR_ARG, "pl_noise_init(ctx, %d) has not been called", sc->tile_w);
     return PL_OK;
 }

@@ -293,7 +293,9 @@ int pl_elev_fill_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_po
 {
     a.elev = reinterpret_cast<float *>(elev->base);
     a.resid = resid ? resid->base : nullptr;
-    a.noise = ctx->noise_rot;
+    const pl_ctx::NoiseTable *nt = ctx->noise_for(sc->tile_w);
+    if (!nt) return pl_set_error(PL_ERR_ARG, "pl_noise_init(ctx, %d) has not been called", sc->tile_w);
+    a.noise = nt->rot;
     a.reqs = dev_reqs;
     a.stats = elev->stats;
     a.ready = nullptr;
@@ -311,8 +313,8 @@ int pl_elev_fill_args(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_po
     /* lattice indices k in [-1, floor((W-3+g)/2g)] */
     a.nk = (a.W - 3 + a.grid) / (2 * a.grid) + 2;
     if (a.nk > 255) return pl_set_error(PL_ERR_ARG, "grid %d too fine for tile_w %d", a.grid, a.W);
-    a.noise_pitch = ctx->noise_pitch;
-    a.noise_plane = ctx->noise_w * ctx->noise_pitch;
+    a.noise_pitch = nt->pitch;
+    a.noise_plane = nt->w * nt->pitch;
     a.resid_pitch = resid ? resid->pitch : 0;
     a.resid_slot_elems = resid ? (long long) (resid->slot_bytes / (resid->kind == PL_POOL_RESID_F32 ? 4 : 2)) : 0;
     a.resid_scale = sc->resid_scale;

@@ -54,10 +54,18 @@ struct pl_ctx {
     cudaStream_t stream;
     uint64_t launches;
     uint64_t height_unsure;   /* pl_height_cube_from_latlon: base samples redone with the host's libm (pl_heights.cu) */
-    /* noise (createDemNoise), 4 rotations x 6 layers of fp16 */
-    int noise_w;
-    int noise_pitch;
-    __half *noise_rot;
+    /* noise (createDemNoise), 4 rotations x 6 layers of fp16: one table per tile width, as the reference's
+     * demNoiseFactory caches one texture per width (ElevationProducer.cpp:135) -- producers of different tile sizes
+     * share a context */
+    struct NoiseTable { int w, pitch; __half *rot; };
+    NoiseTable noise_tabs[8];
+    int n_noise;
+    const NoiseTable *noise_for(int w) const
+    {
+        for (int i = 0; i < n_noise; ++i)
+            if (noise_tabs[i].w == w) return &noise_tabs[i];
+        return nullptr;
+    }
     /* ortho noise (createOrthoNoise), 4 rotations x 6 layers of RGBA8 */
     int ortho_noise_w;
     uint32_t *ortho_noise_rot;

@@ -177,8 +177,20 @@ __device__ __forceinline__ unsigned int br_byte_pos(const BitReader &b) { return
 
 /* The tables of a canonical prefix code from lens[0..n) (one lane, serial): symbols sorted by (length, value), and
  * lim[] / off[] as described at LaneTables.  Returns false for an over-subscribed code. */
+/* zlib's rule (inftrees.c inflate_table), which is what the reference's libtiff decodes with: an over-subscribed code
+ * is an error; an INCOMPLETE one too, except a literal/length or distance code whose longest (i.e. only) length is 1 bit,
+ * or one with no symbols at all; the code-length code (`codes`) must be complete */
+__device__ __forceinline__ bool code_is_acceptable(int left, const unsigned short *count, bool codes)
+{
+    if (left == 0) return true;
+    int maxl = 0;
+    for (int l = 1; l < 16; ++l)
+        if (count[l]) maxl = l;
+    return maxl == 0 || (!codes && maxl == 1);
+}
+
 __device__ bool build_code(const unsigned char *lens, int n, unsigned short *count, unsigned short *lim, short *off,
-                           unsigned short *sym)
+                           unsigned short *sym, bool codes = false)
 {
     for (int l = 0; l < 16; ++l) count[l] = 0;
     for (int s = 0; s < n; ++s) count[lens[s]]++;
@@ -188,6 +200,7 @@ __device__ bool build_code(const unsigned char *lens, int n, unsigned short *cou
         left -= count[l];
         if (left < 0) return false;
     }
+    if (!code_is_acceptable(left, count, codes)) return false;
     /* canonical codes in order of (length, value): code = first code of the length + rank */
     unsigned int code = 0, idx = 0;
     for (int l = 1; l < 16; ++l) {
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(kTokLanes) inflate_tokens_kernel(int n, const 
                         for (int s = 0; s < 19; ++s) lens[s] = 0;
                         for (int k = 0; k < ncode; ++k) lens[kClOrder[k]] = (unsigned char) br_bits(b, 3);
                         /* the code-length code reuses the literal tables (its codes have at most 7 bits) */
-                        if (!build_code(lens, 19, T.cnt, T.lim, T.off, T.lit_sym)) err = INF_BAD_CODE;
+                        if (!build_code(lens, 19, T.cnt, T.lim, T.off, T.lit_sym, true)) err = INF_BAD_CODE;
                     }
                     int idx = 0, prev_len = 0;
                     while (!err && idx < nlen + ndist) {
@@ -407,7 +420,8 @@ __global__ void __launch_bounds__(kTokLanes) inflate_tokens_kernel(int n, const 
                 /* distance lengths follow the literal/length lengths in lens[]; incomplete distance codes (a single
                  * distance code) are legal, over-subscription is not */
                 if (!err) {
-                    if (!build_code(lens + (type == 1 ? 288 : nlen), ndist, T.cnt, T.lim, T.off, T.dist_sym)) err = INF_BAD_CODE;
+                    /* the fixed distance code has 32 five-bit codes (30 and 31 never valid in data): complete */
+                    if (!build_code(lens + (type == 1 ? 288 : nlen), type == 1 ? 32 : ndist, T.cnt, T.lim, T.off, T.dist_sym)) err = INF_BAD_CODE;
                     load_code(DC, T.lim, T.off);
                     if (!build_code(lens, nlen, T.cnt, T.lim, T.off, T.lit_sym)) err = INF_BAD_CODE;
                     load_code(LC, T.lim, T.off);
@@ -497,7 +511,7 @@ struct WarpTables {
  * lens[0..n) (all 32 lanes; lane 0 does the short serial parts).  Returns false for an
  * over-subscribed code. */
 __device__ bool build_code(const unsigned char *lens, int n, unsigned short *count, unsigned short *sym,
-                           unsigned short *lut, int lut_bits, int lane)
+                           unsigned short *lut, int lut_bits, int lane, bool codes = false)
 {
     __shared__ unsigned short next_code_sh[kWarpsPerCta][16];
     __shared__ unsigned short offs_sh[kWarpsPerCta][16];
@@ -513,6 +527,7 @@ __device__ bool build_code(const unsigned char *lens, int n, unsigned short *cou
             left -= count[l];
             if (left < 0) ok = false;
         }
+        if (ok && !code_is_acceptable(left, count, codes)) ok = false;
         unsigned int code = 0;
         offs[1] = 0;
         next_code[0] = 0;
@@ -685,7 +700,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_warp_kernel(int n, 
             }
             __syncwarp();
             /* the code-length code reuses the literal tables (7-bit codes fit the first-level table) */
-            if (!build_code(T.lens, 19, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane)) { err = INF_BAD_CODE; break; }
+            if (!build_code(T.lens, 19, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane, true)) { err = INF_BAD_CODE; break; }
             {
                 /* the 19 code-length lengths are in use through the tables only, which are already
                  * built, so lens[] is overwritten (by lane 0; every lane tracks the previous length) */
@@ -725,7 +740,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_warp_kernel(int n, 
         __syncwarp();
         {
             const unsigned char *dl = T.lens + (type == 1 ? 288 : nlen);
-            const bool okd = build_code(dl, ndist, T.dist_count, T.dist_sym, T.dist_lut, kDistBits, lane);
+            /* the fixed distance code has 32 five-bit codes (30 and 31 never valid in data): complete */
+            const bool okd = build_code(dl, type == 1 ? 32 : ndist, T.dist_count, T.dist_sym, T.dist_lut, kDistBits, lane);
             const bool okl = build_code(T.lens, nlen, T.lit_count, T.lit_sym, T.lit_lut, kLitBits, lane);
             /* incomplete distance codes (a single distance code) are legal; over-subscription is not */
             if (!okd || !okl) { err = INF_BAD_CODE; break; }

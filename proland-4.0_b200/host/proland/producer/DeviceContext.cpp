@@ -72,6 +72,8 @@ DeviceContext::~DeviceContext()
 
 void DeviceContext::ensureNoise(int tileWidth)
 {
+    /* the library keeps one table per width (demNoiseFactory caches one texture per width,
+     * ElevationProducer.cpp:135): producers of different tile sizes can share this context */
     if (noiseWidth != tileWidth) {
         check(pl_noise_init(ctx, tileWidth, NULL));
         noiseWidth = tileWidth;

@@ -26,6 +26,8 @@ int GPUTileStorage::GPUSlot::getHeight()
 void GPUTileStorage::GPUSlot::setSubImage(const void *pixels, size_t bytes)
 {
     GPUTileStorage *s = static_cast<GPUTileStorage *>(getOwner());
+    /* kernels queued earlier in this wave that read or write the slot go first (getImage flushes likewise) */
+    s->getContext()->flush();
     DeviceContext::check(pl_pool_upload(s->getPool(), l, pixels, bytes));
 }
 

@@ -12,6 +12,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _cuda_device_present():
+    """a CUDA driver with at least one device (no torch import: this runs at collection time)"""
+    import ctypes
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+        n = ctypes.c_int(0)
+        return cu.cuInit(0) == 0 and cu.cuDeviceGetCount(ctypes.byref(n)) == 0 and n.value > 0
+    except OSError:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """without a GPU the tests marked `gpu` are skipped, not failed: `pytest tests` is then the CPU suite.  (The product has no
+    CPU fallback: what is skipped is the test, nothing runs elsewhere.)"""
+    if _cuda_device_present():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def oracle():
     import orc

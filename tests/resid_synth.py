@@ -15,12 +15,60 @@ import zlib
 import numpy as np
 
 
-def tiff_blob(tile, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, compression=32946):
-    """tile: (w, w) int16 -> TIFF bytes"""
+def hand_made_zlib_stream(complete):
+    """a zlib stream of ONE dynamic block holding the two literals 'A' 'A' (one int16 texel 0x4141), its bits written by
+    hand.  complete=False: the literal/length code has only the lengths {65: 2, 256: 2} -- an INCOMPLETE code, which zlib
+    (and therefore the reference's libtiff) rejects ("invalid literal/lengths set"); complete=True adds symbol 66 with
+    length 1, which makes the same stream valid."""
+    bits = []
+
+    def put(value, n):               # n bits, least significant first (header fields, extra bits)
+        bits.extend((value >> k) & 1 for k in range(n))
+
+    def code(value, n):              # a Huffman code, most significant bit first
+        bits.extend((value >> (n - 1 - k)) & 1 for k in range(n))
+
+    put(1, 1)                        # BFINAL
+    put(2, 2)                        # BTYPE = dynamic
+    put(0, 5)                        # HLIT: 257 literal/length codes
+    put(0, 5)                        # HDIST: 1 distance code
+    # code-length code: symbols 18 (1 bit), 0, 1 or 2 (2 bits each): complete.  HCLEN covers the order up to that symbol
+    order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    third = 2 if not complete else 1
+    cl = {18: 1, 0: 2, third: 2}
+    ncl = 16 if not complete else 18
+    put(ncl - 4, 4)
+    for sym in order[:ncl]:
+        put(cl.get(sym, 0), 3)
+    # canonical code-length codes: 18 -> 0; then by symbol value among the 2-bit ones
+    two = sorted(k for k in cl if cl[k] == 2)
+    cc = {18: (0, 1), two[0]: (2, 2), two[1]: (3, 2)}
+
+    def zeros(n):                    # n zeros, 11 <= n <= 138, by symbol 18
+        code(*cc[18])
+        put(n - 11, 7)
+
+    if not complete:                 # lengths: 65 zeros, 2, 190 zeros, 2 | distance: 0
+        zeros(65); code(*cc[2]); zeros(138); zeros(52); code(*cc[2]); code(*cc[0])
+        lit = {65: (0, 2), 256: (1, 2)}
+    else:                            # lengths {65: 1, 66: 0 ..., 256: 1}: a complete 1-bit code
+        zeros(65); code(*cc[1]); zeros(138); zeros(52); code(*cc[1]); code(*cc[0])
+        lit = {65: (0, 1), 256: (1, 1)}
+    code(*lit[65]); code(*lit[65]); code(*lit[256])
+    while len(bits) % 8:
+        bits.append(0)
+    body = bytes(sum(b << k for k, b in enumerate(bits[i:i + 8])) for i in range(0, len(bits), 8))
+    return b"\x78\x9c" + body + struct.pack(">I", zlib.adler32(b"AA"))
+
+
+def tiff_blob(tile, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, compression=32946, strip=None):
+    """tile: (w, w) int16 -> TIFF bytes (strip: a ready-made compressed strip to wrap instead)"""
     tile = np.ascontiguousarray(tile, "<i2")
     w = tile.shape[0]
     raw = tile.tobytes()
-    if compression == 1:
+    if strip is not None:
+        pass
+    elif compression == 1:
         strip = raw
     else:
         co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)

@@ -57,6 +57,16 @@ def test_shader_variants(plb, ctx, oracle, noise_mode, flip, no_clamp):
          no_clamp=no_clamp)
 
 
+def test_noise_tables_are_kept_per_tile_width(plb, ctx, oracle):
+    """demNoiseFactory caches one texture per tile width (ElevationProducer.cpp:135): initialising the noise of another
+    width must not take the first producer's table away"""
+    ctx.noise_init(101)
+    other = ctx.noise_init(53)
+    assert other.shape == (6, 53, 53)
+    assert np.array_equal(ctx.noise_init(101), oracle.dem_noise(101).reshape(6, 101, 101))
+    assert _run(plb, ctx, oracle, 2, noise_amp=FRACTAL) == 21          # still served from the 101-wide table
+
+
 def test_generic_geometry_kernels(plb, ctx, oracle):
     """the runtime-geometry kernels (used for tile sizes other than 101/97) on the same case"""
     ctx.force_generic(True)
@@ -357,6 +367,23 @@ def test_residual_decode_root_composition_and_errors(plb, ctx, inflate_path):
     assert e.value.code == plb.PL_ERR_CORRUPT
     with pytest.raises(plb.PlError) as e:
         ctx.residual_decode(pool, [good], [53], [2])           # width mismatch
+    assert e.value.code == plb.PL_ERR_CORRUPT
+
+
+def test_residual_decode_rejects_what_zlib_rejects(plb, ctx, inflate_path):
+    """an INCOMPLETE literal/length code is an error in zlib (inftrees.c: "invalid literal/lengths set"), i.e. in the
+    reference's TIFFReadEncodedStrip; the same hand-written stream with a complete code decodes.  Both decoders."""
+    import zlib
+    good, bad = rs.hand_made_zlib_stream(True), rs.hand_made_zlib_stream(False)
+    assert zlib.decompress(good) == b"AA"
+    with pytest.raises(zlib.error):
+        zlib.decompress(bad)
+    one = np.zeros((1, 1), np.int16)
+    pool = ctx.pool(plb.POOL_RESID_I16, 197, 1)
+    ctx.residual_decode(pool, [rs.tiff_blob(one, strip=good)], [1], [0])
+    assert pool.download(0)[0, 0] == 0x4141
+    with pytest.raises(plb.PlError) as e:
+        ctx.residual_decode(pool, [rs.tiff_blob(one, strip=bad)], [1], [0])
     assert e.value.code == plb.PL_ERR_CORRUPT
 
 
