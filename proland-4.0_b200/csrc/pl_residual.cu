@@ -73,7 +73,8 @@ enum {
     INF_OVERRUN_IN = 4,
     INF_OVERRUN_OUT = 5,
     INF_BAD_DISTANCE = 6,
-    INF_SHORT = 7
+    INF_SHORT = 7,
+    INF_BAD_CHECKSUM = 8
 };
 
 /* A canonical prefix code is decoded WITHOUT a look-up table: with v = the next 15 bits of the stream, first bit on
@@ -174,7 +175,16 @@ __device__ __forceinline__ bool br_overrun(const BitReader &b)
 }
 /* strip offset of the next unread byte (call at a byte boundary) */
 __device__ __forceinline__ unsigned int br_byte_pos(const BitReader &b) { return b.merged - (unsigned int) (b.cnt >> 3); }
-
+/* the 4-byte big-endian Adler-32 behind the last block (RFC 1950); false: the strip ends before it */
+__device__ __forceinline__ bool br_trailer(BitReader &b, unsigned int *adler)
+{
+    br_drop(b, b.cnt & 7);
+    const unsigned int p = br_byte_pos(b);
+    if (p + 4 > b.end) return false;
+    *adler = ((unsigned int) __ldg(b.src + p) << 24) | ((unsigned int) __ldg(b.src + p + 1) << 16) |
+             ((unsigned int) __ldg(b.src + p + 2) << 8) | (unsigned int) __ldg(b.src + p + 3);
+    return true;
+}
 /* The tables of a canonical prefix code from lens[0..n) (one lane, serial): symbols sorted by (length, value), and
  * lim[] / off[] as described at LaneTables.  Returns false for an over-subscribed code. */
 /* zlib's rule (inftrees.c inflate_table), which is what the reference's libtiff decodes with: an over-subscribed code
@@ -295,6 +305,8 @@ struct TokenInfo {
     unsigned int out_len;    /* bytes they expand to */
     int status;
     int stored;              /* 1: uncompressed strip, no tokens: the resolver copies the strip */
+    unsigned int adler;      /* the zlib trailer (Adler-32 of the output, RFC 1950): the resolver checks it, */
+    int has_adler;           /* as inflate() does at the end of the stream; 0 for uncompressed strips */
 };
 
 /* ---- kernel 1: Huffman decoding, one lane per stream -------------------------------------------------- */
@@ -472,6 +484,7 @@ __global__ void __launch_bounds__(kTokLanes) inflate_tokens_kernel(int n, const 
     TokenInfo ti;
     if (J.compression == 1) {
         ti.ntok = 0; ti.out_len = J.in_len; ti.stored = 1;
+        ti.adler = 0; ti.has_adler = 0;
         ti.status = J.in_len == cap ? INF_OK : INF_SHORT;
     } else {
         if (!err && lit_n) {
@@ -479,6 +492,8 @@ __global__ void __launch_bounds__(kTokLanes) inflate_tokens_kernel(int n, const 
             else tok[ntok++] = (lit_n << 30) | lit_acc;
         }
         if (!err && pos != cap) err = INF_SHORT;
+        ti.adler = 0; ti.has_adler = 1;
+        if (!err && !br_trailer(b, &ti.adler)) err = INF_OVERRUN_IN;
         ti.ntok = ntok; ti.out_len = pos; ti.status = err; ti.stored = 0;
     }
     info[job] = ti;
@@ -629,7 +644,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_warp_kernel(int n, 
 
     if (J.compression == 1) {   /* uncompressed strip */
         for (unsigned int k = lane; k < min(J.in_len, cap); k += 32) dst[k] = __ldg(src + k);
-        if (lane == 0) { TokenInfo ti; ti.ntok = 0; ti.out_len = cap; ti.status = J.in_len == cap ? INF_OK : INF_SHORT; ti.stored = 2; info[job] = ti; }
+        if (lane == 0) { TokenInfo ti; ti.ntok = 0; ti.out_len = cap; ti.status = J.in_len == cap ? INF_OK : INF_SHORT; ti.stored = 2; ti.adler = 0; ti.has_adler = 0; info[job] = ti; }
         return;
     }
 
@@ -812,7 +827,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) inflate_warp_kernel(int n, 
         flush_ring(ring, dst, flushed, r16, lane);
         for (unsigned int k = r16 + lane; k < rest; k += 32) dst[flushed + k] = ring[(flushed + k) & M];
     }
-    if (lane == 0) { TokenInfo ti; ti.ntok = 0; ti.out_len = pos; ti.status = err; ti.stored = 2; info[job] = ti; }
+    unsigned int adler = 0;
+    if (!err && !br_trailer(b, &adler)) err = INF_OVERRUN_IN;
+    if (lane == 0) { TokenInfo ti; ti.ntok = 0; ti.out_len = pos; ti.status = err; ti.stored = 2; ti.adler = adler; ti.has_adler = 1; info[job] = ti; }
 }
 
 }  // namespace warpinf
@@ -832,7 +849,7 @@ constexpr int kResolveWarps = 4;
 constexpr int kWarpPathBelow = 6000;     /* batches smaller than this take the warp-per-stream decoder (see warpinf) */
 
 template <int STORE>
-__global__ void __launch_bounds__(kResolveWarps * 32) lz_resolve_kernel(int n, const InflateJob *jobs, const unsigned char *in,
+__global__ void __launch_bounds__(kResolveWarps * 32, 16) lz_resolve_kernel(int n, const InflateJob *jobs, const unsigned char *in,
                                                                         const unsigned int *tokens, size_t tok_stride,
                                                                         const TokenInfo *info, unsigned char *dense, size_t dense_stride,
                                                                         int *status, const StoreJob *sjobs, unsigned char *pool,
@@ -912,26 +929,44 @@ __global__ void __launch_bounds__(kResolveWarps * 32) lz_resolve_kernel(int n, c
         if (!err && pos != ti.out_len) err = INF_SHORT;
     }
     err = (int) __reduce_max_sync(0xffffffffu, (unsigned int) err);   /* any lane's error is the stream's */
-    if (lane == 0) status[job] = err;
-    if (err) return;
+    if (err) {
+        if (lane == 0) status[job] = err;
+        return;
+    }
     __syncwarp();
 
-    /* the finished tile -> the pool (ResidualProducer.cpp:321-338; OrthoCPUProducer.cpp:226-231) */
+    /* the finished tile -> the pool (ResidualProducer.cpp:321-338; OrthoCPUProducer.cpp:226-231).  The same pass sums
+     * the Adler-32 of the bytes it reads (s1 = 1 + sum b_i, s2 = len + sum (len - i) b_i, mod 65521): what inflate()
+     * checks at the end of a zlib stream and TIFFReadEncodedStrip fails on.  A tile whose checksum is wrong is reported
+     * corrupt; its slot holds the undefined bytes of a failed decode. */
     const StoreJob S = sjobs[job];
     const int w = S.width;
+    const unsigned int len = ti.out_len;
+    unsigned long long s1 = 0, s2 = 0;
+    unsigned int covered = 0;                  /* bytes of the dense stream the store pass has read */
     if (STORE == STORE_ORTHO) {
         uint32_t *o = reinterpret_cast<uint32_t *>(pool + (size_t) S.out_slot * slot_bytes);
         const int ch = S.channels;
         for (int k = lane; k < w * w; k += 32) {
             uint32_t t = 0;
-            for (int c = 0; c < ch; ++c) t |= (uint32_t) __ldcg(dst + (size_t) k * ch + c) << (8 * c);
+            for (int c = 0; c < ch; ++c) {
+                const unsigned int i = (unsigned int) k * ch + c, v = __ldcg(dst + i);
+                t |= v << (8 * c);
+                s1 += v;
+                s2 += (unsigned long long) (len - i) * v;
+            }
             o[k] = t;
         }
+        covered = (unsigned int) (w * w * ch);
     } else {
-        const short *src = reinterpret_cast<const short *>(dst);
+        const unsigned short *src = reinterpret_cast<const unsigned short *>(dst);
+        int j = lane / w, i = lane - j * w;          /* texel k = i + j w, advanced without a division per texel */
         for (int k = lane; k < w * w; k += 32) {
-            const int j = k / w, i = k - j * w;
-            const short z = __ldcg(src + k);
+            const unsigned int zu = __ldcg(src + k);
+            const short z = (short) zu;
+            const unsigned int lo = zu & 255u, hi = zu >> 8;
+            s1 += lo + hi;
+            s2 += (unsigned long long) (len - 2u * (unsigned int) k) * (lo + hi) - hi;
             if (STORE == STORE_F32) {
                 float *o = reinterpret_cast<float *>(pool + (size_t) S.out_slot * slot_bytes);
                 const float zs = (float) z * scale;
@@ -945,8 +980,26 @@ __global__ void __launch_bounds__(kResolveWarps * 32) lz_resolve_kernel(int n, c
                 short *o = reinterpret_cast<short *>(pool + (size_t) S.out_slot * slot_bytes);
                 o[(size_t) j * pitch + i] = z;
             }
+            i += 32;
+            while (i >= w) { i -= w; ++j; }
         }
+        covered = 2u * (unsigned int) (w * w);
     }
+    if (ti.has_adler) {
+        for (unsigned int i = covered + lane; i < len; i += 32) {      /* a stream longer than the tile (not the case for valid files) */
+            const unsigned int v = __ldcg(dst + i);
+            s1 += v;
+            s2 += (unsigned long long) (len - i) * v;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+        }
+        const unsigned int adler = (unsigned int) (((s2 + len) % 65521ull) << 16) | (unsigned int) ((s1 + 1ull) % 65521ull);
+        if (covered > len || adler != ti.adler) err = INF_BAD_CHECKSUM;
+    }
+    if (lane == 0) status[job] = err;
 }
 
 /* ResidualProducer::upsample (ResidualProducer.cpp:342-384): the (ts + 5)^2 tile of the next root

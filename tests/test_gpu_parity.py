@@ -385,6 +385,24 @@ def test_residual_decode_rejects_what_zlib_rejects(plb, ctx, inflate_path):
     with pytest.raises(plb.PlError) as e:
         ctx.residual_decode(pool, [rs.tiff_blob(one, strip=bad)], [1], [0])
     assert e.value.code == plb.PL_ERR_CORRUPT
+    # the Adler-32 trailer (RFC 1950) is verified like inflate() does: a structurally valid stream whose checksum is
+    # wrong, or missing, fails
+    for strip in (good[:-1] + bytes([good[-1] ^ 1]), good[:-4]):
+        with pytest.raises(zlib.error):
+            zlib.decompress(strip)
+        with pytest.raises(plb.PlError) as e:
+            ctx.residual_decode(pool, [rs.tiff_blob(one, strip=strip)], [1], [0])
+        assert e.value.code == plb.PL_ERR_CORRUPT
+    rng = np.random.default_rng(3)
+    tile = rs.fractal_tile(rng, 197, 80)
+    co = zlib.compressobj(6)
+    strip = bytearray(co.compress(tile.tobytes()) + co.flush())
+    ctx.residual_decode(pool, [rs.tiff_blob(tile, strip=bytes(strip))], [197], [0])
+    assert np.array_equal(pool.download(0), tile)
+    strip[-2] ^= 0x10
+    with pytest.raises(plb.PlError) as e:
+        ctx.residual_decode(pool, [rs.tiff_blob(tile, strip=bytes(strip))], [197], [0])
+    assert e.value.code == plb.PL_ERR_CORRUPT
 
 
 @pytest.mark.parametrize("fused", [False, True])
