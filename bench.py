@@ -491,7 +491,8 @@ def main():
             if "normals" in g:
                 g["normals_GBps_per_rank"] = g["normals"]["GBps_per_rank"]
                 g["identical_on_every_rank"] = bool(g.get("identical_to_single_gpu")) and \
-                    bool(g.get("push_from_the_kernel", {}).get("identical_on_every_rank", False))
+                    bool(g.get("push_from_the_kernel", {}).get("identical_on_every_rank", False)) and \
+                    bool(g.get("multicast_push_from_the_kernel", {"identical_on_every_rank": True})["identical_on_every_rank"])
             line["gather"] = g
         if world == 1 and not args.no_cpu_baseline:
             n, dt, (csum, clo, chi) = cpu_sample(7)

@@ -115,6 +115,21 @@ int pl_pool_export(pl_pool *pool, void *handle64);
 int pl_pool_attach_peers(pl_pool *pool, int n, const void *handles, int self);
 int pl_pool_push_to_peers(pl_pool *pool, int on);
 
+/* The same push through ONE store: an NVLink multicast object (cuMulticastCreate) every rank binds its pool's memory to;
+ * a store to the object's mapping is replicated by the NVSwitch into the same offset of every bound pool, so one copy of a
+ * tile leaves the producing GPU instead of one per peer.  The pools come from pl_pool_create_shared (VMM allocator, same
+ * kind / tile_w / capacity on every rank; otherwise identical to pl_pool_create).  Order, one process per GPU:
+ *   rank 0: pl_pool_mc_create(pool, n, &fd) -- fd is a POSIX file descriptor naming the object; the CALLER hands it to the
+ *           other ranks (SCM_RIGHTS over a Unix socket; the library does no inter-process transport) -- the others:
+ *           pl_pool_mc_import(pool, their copy of fd, n); every rank: pl_pool_mc_add_device; BARRIER; every rank:
+ *           pl_pool_mc_bind; BARRIER; pl_pool_push_to_peers(pool, 2) selects the multicast push (1: unicast, 0: off).
+ * The file descriptors may be closed after the import.  PL_ERR_ARG when the device has no multicast support. */
+int pl_pool_create_shared(pl_ctx *ctx, int kind, int tile_w, int capacity, pl_pool **out);
+int pl_pool_mc_create(pl_pool *pool, int n_devices, int *fd_out);
+int pl_pool_mc_import(pl_pool *pool, int fd, int n_devices);
+int pl_pool_mc_add_device(pl_pool *pool);
+int pl_pool_mc_bind(pl_pool *pool);
+
 /* ------------------------------------------------------------------- noise */
 
 /* createDemNoise (ElevationProducer.cpp:50-133): builds the six W x W layers

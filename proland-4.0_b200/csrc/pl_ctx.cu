@@ -381,6 +381,16 @@ static int elem_bytes(int kind)
     }
 }
 
+static thread_local bool g_pool_shared = false;
+
+extern "C" int pl_pool_create_shared(pl_ctx *ctx, int kind, int tile_w, int capacity, pl_pool **out)
+{
+    g_pool_shared = true;
+    const int rc = pl_pool_create(ctx, kind, tile_w, capacity, out);
+    g_pool_shared = false;
+    return rc;
+}
+
 extern "C" int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, pl_pool **out)
 {
     if (!ctx || !out) return pl_set_error(PL_ERR_ARG, "pl_pool_create: NULL argument");
@@ -431,7 +441,17 @@ extern "C" int pl_pool_create(pl_ctx *ctx, int kind, int tile_w, int capacity, p
     /* F32 residual pools carry one hidden scratch slot (index capacity, PL_SLOT_SCRATCH): the
      * temporary of the root-level composition, ResidualProducer.cpp:218-228 */
     const size_t nslots = (size_t) capacity + (kind == PL_POOL_RESID_F32 ? 1 : 0);
-    cudaError_t e = cudaMalloc(&p->base, p->slot_bytes * nslots);
+    cudaError_t e = cudaSuccess;
+    if (g_pool_shared) {
+        /* pl_pool_create_shared: the memory comes from the VMM allocator with a shareable handle (pl_multicast.cu) */
+        const int rc = pl_vmm_alloc(p, p->slot_bytes * nslots);
+        if (rc) {
+            delete p;
+            return rc;
+        }
+    } else {
+        e = cudaMalloc(&p->base, p->slot_bytes * nslots);
+    }
     if (e != cudaSuccess) {
         const size_t want = p->slot_bytes * nslots;
         delete p;
@@ -480,7 +500,8 @@ extern "C" void pl_pool_destroy(pl_pool *p)
     cudaSetDevice(p->ctx->device);
     cudaStreamSynchronize(p->ctx->stream);
     for (int i = 0; i < p->npeers; ++i) cudaIpcCloseMemHandle(p->peer_base[i]);
-    if (p->base) cudaFree(p->base);
+    if (p->vmm) pl_vmm_free(p);
+    else if (p->base) cudaFree(p->base);
     if (p->stats) cudaFree(p->stats);
     if (p->ready) cudaFree(p->ready);
     delete p;
@@ -494,6 +515,7 @@ extern "C" int pl_pool_export(pl_pool *p, void *handle64)
     static_assert(sizeof(cudaIpcMemHandle_t) == PL_IPC_HANDLE_BYTES, "handle size");
     PL_CUDA(cudaSetDevice(p->ctx->device));
     cudaIpcMemHandle_t h;
+    if (p->vmm) return pl_set_error(PL_ERR_ARG, "a shared (VMM) pool has no CUDA IPC handle: use the multicast entry points");
     PL_CUDA(cudaIpcGetMemHandle(&h, p->base));
     memcpy(handle64, &h, sizeof(h));
     return PL_OK;
@@ -520,8 +542,9 @@ extern "C" int pl_pool_push_to_peers(pl_pool *p, int on)
 {
     if (!p) return pl_set_error(PL_ERR_ARG, "pool is NULL");
     if (on && p->kind != PL_POOL_NORM_UN8x2) return pl_set_error(PL_ERR_ARG, "only RG8 normal pools push their tiles");
-    if (on && !p->npeers) return pl_set_error(PL_ERR_ARG, "no peers attached");
-    p->push = on ? 1 : 0;
+    if (on == 2 && p->mc_state != 3) return pl_set_error(PL_ERR_ARG, "the pool is not bound to a multicast object (pl_pool_mc_bind)");
+    if (on != 2 && on && !p->npeers) return pl_set_error(PL_ERR_ARG, "no peers attached");
+    p->push = on == 2 ? 2 : (on ? 1 : 0);
     return PL_OK;
 }
 

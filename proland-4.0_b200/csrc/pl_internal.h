@@ -41,8 +41,16 @@ struct pl_pool {
      * their memory, mapped through CUDA IPC; kernels that push finished tiles store to them over NVLink */
     enum { kMaxPeers = 7 };
     int npeers;
-    int push;              /* NORM pools: the fused kernel also stores every tile into the peers */
+    int push;              /* NORM pools: the fused kernel also stores every tile into the peers (1: unicast, 2: multicast) */
     uint8_t *peer_base[kMaxPeers];
+    /* NVLink multicast (pl_multicast.cu): the pool's memory is a VMM allocation bound to a multicast object shared by
+     * the ranks of the box; a store to mc_base + offset lands at base + offset on EVERY GPU of the group */
+    int vmm;                               /* base comes from cuMemCreate / cuMemMap (pl_pool_create_shared) */
+    size_t vmm_size;
+    unsigned long long vmm_handle;         /* CUmemGenericAllocationHandle of the pool's memory */
+    unsigned long long mc_handle;          /* ... of the multicast object (0: none) */
+    int mc_devices, mc_state;              /* 1: object known, 2: device added, 3: bound and mapped */
+    uint8_t *mc_base;
     CUtensorMap tm_parent; /* ELEV only: 3-D map over the zf/zc/zm planes, box = parent window */
     int box_w, box_h;
 };
@@ -107,6 +115,9 @@ struct pl_ctx {
 };
 
 int pl_set_error(int code, const char *fmt, ...);
+/* pl_multicast.cu: a pool's memory on the VMM allocator (pl_pool_create_shared) */
+int pl_vmm_alloc(pl_pool *p, size_t bytes);
+void pl_vmm_free(pl_pool *p);
 #define PL_CUDA(call)                                                                       \
     do {                                                                                    \
         cudaError_t e_ = (call);                                                            \

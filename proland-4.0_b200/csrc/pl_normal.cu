@@ -271,8 +271,14 @@ int pl_norm_fill_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_po
     a.max_rows = a.W - (a.nbands - 1) * kBandRows;
     a.fast = sc->arith == PL_ARITH_FAST;
     a.norm_slot_bytes = (long long) norm->slot_bytes;
-    a.npeers = norm->push ? norm->npeers : 0;
+    a.npeers = norm->push == 1 ? norm->npeers : 0;
     for (int p = 0; p < a.npeers; ++p) a.peer_delta[p] = (long long) (norm->peer_base[p] - norm->base);
+    if (norm->push == 2) {
+        /* multicast: ONE store through the multicast mapping reaches the slot on every GPU of the group (this one
+         * included), replicated by the NVLink switch instead of one unicast store per peer */
+        a.npeers = 1;
+        a.peer_delta[0] = (long long) (norm->mc_base - norm->base);
+    }
     return PL_OK;
 }
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "pl_pool_destroy", "pl_pool_capacity", "pl_pool_tile_w", "pl_pool_tile_bytes",
     "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload",
     "pl_pool_export", "pl_pool_attach_peers", "pl_pool_push_to_peers",
+    "pl_pool_create_shared", "pl_pool_mc_create", "pl_pool_mc_import", "pl_pool_mc_add_device", "pl_pool_mc_bind",
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_elev_zreadback_begin", "pl_elev_stats_readback_ready", "pl_norm_make_req", "pl_normal_batch",
@@ -150,6 +151,11 @@ def lib():
         L.pl_pool_export.argtypes = [C.c_void_p, C.c_void_p]
         L.pl_pool_attach_peers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.pl_pool_push_to_peers.argtypes = [C.c_void_p, C.c_int]
+        L.pl_pool_create_shared.argtypes = L.pl_pool_create.argtypes
+        L.pl_pool_mc_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.pl_pool_mc_import.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.pl_pool_mc_add_device.argtypes = [C.c_void_p]
+        L.pl_pool_mc_bind.argtypes = [C.c_void_p]
         L.pl_pool_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.pl_pool_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.pl_noise_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -336,11 +342,12 @@ def morton_decode(m):
 # ------------------------------------------------------------------- context
 
 class Pool:
-    def __init__(self, ctx, kind, tile_w, capacity):
+    def __init__(self, ctx, kind, tile_w, capacity, shared=False):
         self.ctx = ctx
         self.kind = kind
         h = C.c_void_p()
-        check(lib().pl_pool_create(ctx.h, kind, tile_w, capacity, C.byref(h)))
+        # shared: the memory comes from the VMM allocator and can be bound to an NVLink multicast object (pl_pool_mc_*)
+        check((lib().pl_pool_create_shared if shared else lib().pl_pool_create)(ctx.h, kind, tile_w, capacity, C.byref(h)))
         self.h = h
         self.tile_w = tile_w
         self.capacity = capacity
@@ -364,7 +371,23 @@ class Pool:
         check(lib().pl_pool_attach_peers(self.h, len(hs), _ptr(hs), self_rank))
 
     def push_to_peers(self, on=True):
+        """True / 1: one unicast store per attached peer; 2: one store through the multicast mapping; False: off"""
         check(lib().pl_pool_push_to_peers(self.h, int(on)))
+
+    def mc_create(self, n_devices):
+        """rank 0: the multicast object of the group -> a file descriptor to hand to the other ranks (pl_pool_mc_create)"""
+        fd = C.c_int(-1)
+        check(lib().pl_pool_mc_create(self.h, n_devices, C.byref(fd)))
+        return fd.value
+
+    def mc_import(self, fd, n_devices):
+        check(lib().pl_pool_mc_import(self.h, fd, n_devices))
+
+    def mc_add_device(self):
+        check(lib().pl_pool_mc_add_device(self.h))
+
+    def mc_bind(self):
+        check(lib().pl_pool_mc_bind(self.h))
 
     def _shape_dtype(self):
         W = self.tile_w
@@ -406,8 +429,8 @@ class Context:
     def __exit__(self, *a):
         self.close()
 
-    def pool(self, kind, tile_w, capacity):
-        p = Pool(self, kind, tile_w, capacity)
+    def pool(self, kind, tile_w, capacity, shared=False):
+        p = Pool(self, kind, tile_w, capacity, shared)
         self._pools.append(p)
         return p
 

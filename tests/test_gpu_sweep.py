@@ -266,6 +266,38 @@ def test_gather_and_push_between_two_gpus():
     assert out.stdout.strip().startswith("{"), "stdout must be the JSON line only"
     assert line["identical_to_single_gpu"] is True
     assert line["push_from_the_kernel"]["identical_on_every_rank"] is True
+    # the multicast push (pl_pool_create_shared + pl_pool_mc_*): one store, every GPU's pool
+    assert line["multicast_push_from_the_kernel"]["identical_on_every_rank"] is True
+
+
+def test_shared_pool_behaves_like_a_pool_and_checks_the_multicast_order(plb, ctx, oracle):
+    """a pool on the VMM allocator (pl_pool_create_shared) is an ordinary pool for production and transfers; the
+    multicast entry points refuse to be called out of order (the two-GPU behaviour is in
+    test_gather_and_push_between_two_gpus)"""
+    norm = ctx.pool(plb.POOL_NORM2, 97, 32, shared=True)
+    plain = ctx.pool(plb.POOL_NORM2, 97, 32)
+    elev = ctx.pool(plb.POOL_ELEV, 101, 32)
+    ctx.noise_init(101)
+    sc = plb.sweep_scene(noise_amp=[-140, -100, -15], face=0, root_quad_size=100000.0, sphere=0, want_stats=1)
+    for pool in (norm, plain):
+        ctx.produce_range(sc, elev, pool, 0, 0, 1, 0, 0, 0)
+        ctx.produce_range(sc, elev, pool, 1, 0, 4, 1, 0, 0)
+        ctx.produce_range(sc, elev, pool, 2, 0, 16, 5, 1, 0)
+    ctx.sync()
+    for s in range(21):
+        assert np.array_equal(norm.download(s), plain.download(s)), s
+    with pytest.raises(plb.PlError):                      # no CUDA IPC handle for VMM memory
+        norm.export()
+    with pytest.raises(plb.PlError):                      # nothing bound yet
+        norm.push_to_peers(2)
+    with pytest.raises(plb.PlError):                      # no object yet
+        norm.mc_add_device()
+    with pytest.raises(plb.PlError):
+        norm.mc_bind()
+    with pytest.raises(plb.PlError):                      # an ordinary pool cannot join a multicast group
+        plain.mc_create(2)
+    with pytest.raises(plb.PlError):                      # a group of one is not a group
+        norm.mc_create(1)
 
 
 def test_peer_api_errors_on_one_gpu(plb, ctx):

@@ -46,6 +46,44 @@ def rank_range(level, rank, world):
     return rank * n, n
 
 
+def share_fd(dist, rank, world, fd, key):
+    """hands rank 0's file descriptor to every other rank of the box: SCM_RIGHTS over an abstract Unix socket (the C ABI
+    leaves the inter-process transport to the caller).  -> the local descriptor"""
+    import socket
+    name = "\0proland-b200-mc-%s-%s" % (os.environ.get("MASTER_PORT", "0"), key)
+    if rank == 0:
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(name)
+        srv.listen(world)
+    dist.barrier()                       # the socket is listening
+    if rank == 0:
+        for _ in range(world - 1):
+            conn, _ = srv.accept()
+            socket.send_fds(conn, [b"fd"], [fd])
+            conn.recv(1)                 # the peer has the descriptor
+            conn.close()
+        srv.close()
+        return fd
+    c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    c.connect(name)
+    _, fds, _, _ = socket.recv_fds(c, 16, 1)
+    c.send(b"k")
+    c.close()
+    return fds[0]
+
+
+def multicast_group(dist, pool, rank, world, key="norm"):
+    """binds a shared pool (ctx.pool(..., shared=True)) of every rank to one NVLink multicast object"""
+    fd = share_fd(dist, rank, world, pool.mc_create(world) if rank == 0 else -1, key)
+    if rank != 0:
+        pool.mc_import(fd, world)
+    os.close(fd)
+    pool.mc_add_device()
+    dist.barrier()                       # every device is added: binding may start
+    pool.mc_bind()
+    dist.barrier()
+
+
 class _DeviceBytes:
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -63,7 +101,7 @@ def gather_record(ctx, torch, dist, stream, rank, world, level=7, reps=5):
         ctx.noise_init(101)
         sc = pl.sweep_scene(noise_amp=PLANET, face=3, root_quad_size=12720000.0, sphere=1, want_stats=1)
 
-        def produce(r, w):
+        def produce(r, w, norm=norm):
             for l in range(L + 1):
                 m0, n = rank_range(l, r, w)
                 ctx.produce_range(sc, elev, norm, l, m0, n, off[l] + m0, off[l - 1] + (m0 >> 2) if l else 0, m0 >> 2)
@@ -152,6 +190,42 @@ def gather_record(ctx, torch, dist, stream, rank, world, level=7, reps=5):
                 tp = torch.tensor([e0.elapsed_time(e1) / reps, 0.0 if pushed_ok else 1.0], dtype=torch.float64, device="cuda")
                 dist.all_reduce(tp, op=dist.ReduceOp.MAX)
                 push = (float(tp[0]), float(tp[1]) == 0.0)
+
+            # ---- and through ONE store per 16 bytes: a pool on the VMM allocator, bound on every rank to one NVLink
+            # multicast object; the switch replicates the store into every GPU's pool (pl_pool_mc_*, pl_multicast.cu)
+            mcast = None
+            if world > 1 and os.environ.get("PL_NO_MULTICAST") is None:
+                try:
+                    normm = ctx.pool(pl.POOL_NORM2, 97, off[L + 1], shared=True)
+                    have = 1.0
+                except pl.PlError:
+                    normm, have = None, 0.0
+                hv = torch.tensor([have], dtype=torch.float64, device="cuda")
+                dist.all_reduce(hv, op=dist.ReduceOp.MIN)
+                if float(hv[0]) == 1.0:
+                    multicast_group(dist, normm, rank, world)
+                    slab(normm).zero_()
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    normm.push_to_peers(2)
+                    produce(rank, world, normm)
+                    ctx.sync()
+                    dist.barrier()
+                    torch.cuda.synchronize()
+                    mc_ok = bool(torch.equal(slab(normm), got_n))
+                    e0.record(stream)
+                    for _ in range(reps):
+                        produce(rank, world, normm)
+                    e1.record(stream)
+                    torch.cuda.synchronize()
+                    dist.barrier()
+                    normm.push_to_peers(False)
+                    tm = torch.tensor([e0.elapsed_time(e1) / reps, 0.0 if mc_ok else 1.0], dtype=torch.float64, device="cuda")
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                    mcast = (float(tm[0]), float(tm[1]) == 0.0)
+                    dist.barrier()
+                if normm is not None:
+                    normm.close()
         if rank == 0:
             tiles = 4 ** L
             recv = lambda pool_bytes: (world - 1) / world * tiles * pool_bytes
@@ -172,6 +246,13 @@ def gather_record(ctx, torch, dist, stream, rank, world, level=7, reps=5):
                     "production_ms": push[0], "extra_ms_vs_plain_production": push[0] - float(t[0]),
                     "all_gather_of_the_normals_ms": float(t[2]), "bytes_sent_per_rank": sent,
                     "identical_on_every_rank": push[1]}
+            if mcast:
+                line["multicast_push_from_the_kernel"] = {
+                    "what": "the same, one store per 16 bytes through an NVLink multicast mapping of the normal pools (cuMulticast: "
+                            "the switch replicates it into every GPU's pool)",
+                    "production_ms": mcast[0], "extra_ms_vs_plain_production": mcast[0] - float(t[0]),
+                    "bytes_sent_per_rank": sum(rank_range(l, 0, world)[1] for l in range(L + 1)) * 97 * 97 * 2,
+                    "identical_on_every_rank": mcast[1]}
     dist.barrier()              # nobody still reads a peer's pool
     torch.cuda.synchronize()
     norm.close()
