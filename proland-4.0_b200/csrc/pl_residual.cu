@@ -915,11 +915,17 @@ __global__ void __launch_bounds__(kResolveWarps * 32, 16) lz_resolve_kernel(int 
                         }
                     }
                 }
-                /* runs: pass values down the lanes until every byte of the step is known (a source lane is always lower) */
+                /* runs: pass values down the lanes until every byte of the step is known (a source lane is always
+                 * lower).  Pointer jumping: a lane whose source is itself still waiting adopts the source's source, so a
+                 * chain of depth d (a run of distance 1 is 32 deep) resolves in log2 d + 1 rounds instead of d */
                 while (__any_sync(0xffffffffu, !done)) {
                     const unsigned int v = __shfl_sync(0xffffffffu, val, from);
                     const int d = __shfl_sync(0xffffffffu, done ? 1 : 0, from);
-                    if (!done && d) { val = v; done = true; }
+                    const int f2 = __shfl_sync(0xffffffffu, from, from);
+                    if (!done) {
+                        if (d) { val = v; done = true; }
+                        else from = f2;
+                    }
                 }
                 if (active) dst[pos + q] = (unsigned char) val;
                 __syncwarp();
