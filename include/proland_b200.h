@@ -350,6 +350,10 @@ int pl_debug_force_generic(pl_ctx *ctx, int on);
 /* tests / profiling: make pl_produce_range and pl_pair_batch[_dev] launch the elevation and the normal
  * pass as two kernels instead of the fused one (same results, bit for bit) */
 int pl_debug_no_fuse(pl_ctx *ctx, int on);
+/* tests / profiling: the fused kernel never uses its slim layout (launches whose tiles all take the register form of the
+ * FAST normal pass: 4 CTAs per SM; by default flat scenes only, where it pays); on = -1: use it on spheres too.  Results are
+ * the same bit for bit */
+int pl_debug_no_slim(pl_ctx *ctx, int on);
 /* tests / profiling: which DEFLATE decoder pl_residual_decode_batch / pl_ortho_decode_batch run: 0 = chosen by the batch
  * size (default), 1 = the warp-per-stream kernel (small batches), 2 = the tokenizer + resolver pair (large batches) */
 int pl_debug_inflate_path(pl_ctx *ctx, int path);

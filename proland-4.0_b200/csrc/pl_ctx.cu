@@ -172,6 +172,14 @@ extern "C" int pl_debug_no_fuse(pl_ctx *ctx, int on)
     return PL_OK;
 }
 
+extern "C" int pl_debug_no_slim(pl_ctx *ctx, int on)
+{
+    if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
+    ctx->no_slim = on > 0 ? 1 : 0;
+    ctx->slim_sphere = on < 0 ? 1 : 0;
+    return PL_OK;
+}
+
 extern "C" int pl_timing_enable(pl_ctx *ctx, int on)
 {
     if (!ctx) return pl_set_error(PL_ERR_ARG, "ctx is NULL");
@@ -954,6 +962,13 @@ extern "C" int pl_normal_batch(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *no
 /* ------------------------------------------------------------ tile pairs */
 
 
+int pl_check_pair_pools(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm, pl_pool *resid, int n)
+{
+    int rc = check_elev_args(ctx, esc, elev, resid, n);
+    if (rc) return rc;
+    return check_norm_args(ctx, nsc, norm, elev, n);
+}
+
 extern "C" int pl_pair_batch_dev(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev,
                                  pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *dev_ereqs,
                                  const pl_norm_req *dev_nreqs)
@@ -985,10 +1000,15 @@ extern "C" int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
     rc = stage_acquire(ctx, sizeof(pl_elev_req) * (size_t) n, sizeof(pl_norm_req) * (size_t) n, &tk, &pe, &pn);
     if (rc) return rc;
     std::atomic<int> bad(n);
+    std::atomic<int> not_reg(0);      /* some tile does not qualify for the register form (plnorm::normal_reg_ok, restated) */
+    const bool sphere = nsc->sphere != 0;
     parallel_chunks(n, 4096, [&](int lo, int hi) {
         for (int i = lo; i < hi; ++i) {
             const pl_elev_req &e = ereqs[i];
             const pl_norm_req &q = nreqs[i];
+            const bool reg = sphere ? q.smooth == 1.0f
+                                    : (q.w2t[0] == 1.0f && q.w2t[1] == 0.0f && q.w2t[2] == 0.0f && q.w2t[3] == 0.0f && q.w2t[4] == 1.0f && q.w2t[5] == 0.0f);
+            if (!reg) not_reg.store(1, std::memory_order_relaxed);
             int kind = 0;
             if (elev_req_bad(e, elev, resid))
                 kind = 1;
@@ -1018,5 +1038,7 @@ extern "C" int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
     }
     void *de = nullptr, *dn = nullptr;
     if ((rc = stage_commit(ctx, tk, &de, &dn)) != PL_OK) return rc;
+    if (pl_pair_supported(ctx, esc, nsc, elev, norm))
+        return pl_launch_pair(ctx, esc, nsc, elev, norm, resid, n, (const pl_elev_req *) de, (const pl_norm_req *) dn, not_reg.load() == 0);
     return pl_pair_batch_dev(ctx, esc, nsc, elev, norm, resid, n, (const pl_elev_req *) de, (const pl_norm_req *) dn);
 }

@@ -179,7 +179,20 @@ __device__ __forceinline__ plf2::F2 amp_of2(const QuadCtx &k, plf2::F2 sx, plf2:
  * fp32 operation of the canonical order is issued ONCE for both quads as a packed fp32x2 instruction:
  * lane .x = quad A (columns 4ip, 4ip+1), lane .y = quad B (columns 4ip+2, 4ip+3).
  * TAIL: only the first row of the quads exists (row TW-1). */
-template <class GEO, int NZ, int RESID, bool TAIL, bool ZS>
+/* two adjacent floats of shared memory that do NOT start on an 8-byte boundary, as one register pair: two 4-byte loads
+ * straight into the halves of the pair, at a constant byte offset from one shared-space address per quad pair.  Written
+ * as PTX so that the compiler does not reuse the halves of neighbouring 8-byte loads instead (it then rebuilds the pair
+ * with MOVs: + 5 % instructions, measured) */
+template <int OFF>
+__device__ __forceinline__ plf2::F2 lds_pair_at(const uint32_t a)
+{
+    float x, y;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(a), "n"(OFF));
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(y) : "r"(a), "n"(OFF + 4));
+    return make_float2(x, y);
+}
+
+template <class GEO, int NZ, int RESID, bool TAIL, bool ZS, bool WB = true>
 __device__ __forceinline__ void do_quad2(const QuadCtx &k, const int ip, const int j, float &lo, float &hi)
 {
     using namespace plf2;
@@ -237,13 +250,18 @@ __device__ __forceinline__ void do_quad2(const QuadCtx &k, const int ip, const i
 
     /* cz[c][r] = parent.zf[bx + r, by + c] -> z<c><r> = (quad A, quad B): quad B's taps are quad A's one
      * window column further right, so even r are aligned pairs of winA, odd r aligned pairs of winB */
-    const float *wa = k.winA + j * BW + i, *wb = k.winB + j * BW + i;
+    /* WB = false (the slim layout of the fused kernel, pl_pair.cu): no second copy of the window; the odd pairs are two
+     * 4-byte loads into one register pair instead of one 8-byte load -- 8 more LDS per quad pair, 12 KB less shared memory */
+    const float *wa = k.winA + j * BW + i, *wb = WB ? k.winB + j * BW + i : wa + 1;
+    const uint32_t sa = WB ? 0u : smem_u32(wa);
 #define LDP(p) (*reinterpret_cast<const F2 *>(p))
-    const F2 z00 = LDP(wa), z01 = LDP(wb), z02 = LDP(wa + 2), z03 = LDP(wb + 2);
-    const F2 z10 = LDP(wa + BW), z11 = LDP(wb + BW), z12 = LDP(wa + BW + 2), z13 = LDP(wb + BW + 2);
-    const F2 z20 = LDP(wa + 2 * BW), z21 = LDP(wb + 2 * BW), z22 = LDP(wa + 2 * BW + 2), z23 = LDP(wb + 2 * BW + 2);
+#define LDO(row, col) (WB ? LDP(wb + (row) * BW + (col)) : lds_pair_at<4 * ((row) * BW + (col) + 1)>(sa))
+    const F2 z00 = LDP(wa), z01 = LDO(0, 0), z02 = LDP(wa + 2), z03 = LDO(0, 2);
+    const F2 z10 = LDP(wa + BW), z11 = LDO(1, 0), z12 = LDP(wa + BW + 2), z13 = LDO(1, 2);
+    const F2 z20 = LDP(wa + 2 * BW), z21 = LDO(2, 0), z22 = LDP(wa + 2 * BW + 2), z23 = LDO(2, 2);
     F2 z30 = bc(0.0f), z31 = bc(0.0f), z32 = bc(0.0f), z33 = bc(0.0f);
-    if (!TAIL) { z30 = LDP(wa + 3 * BW); z31 = LDP(wb + 3 * BW); z32 = LDP(wa + 3 * BW + 2); z33 = LDP(wb + 3 * BW + 2); }
+    if (!TAIL) { z30 = LDP(wa + 3 * BW); z31 = LDO(3, 0); z32 = LDP(wa + 3 * BW + 2); z33 = LDO(3, 2); }
+#undef LDO
 #undef LDP
 
     /* noise term scale per texel: T<x><y> */
@@ -380,27 +398,27 @@ __device__ __forceinline__ void do_quad2(const QuadCtx &k, const int ip, const i
     }
 }
 
-template <class GEO, int NZ, int RESID, int NT, bool ZS>
+template <class GEO, int NZ, int RESID, int NT, bool ZS, bool WB = true>
 __device__ __forceinline__ void tile_loop(const QuadCtx &k, const int tid, float &lo, float &hi)
 {
     constexpr int QP = GEO::QW / 2, QH = GEO::QH;   /* quad pairs per row pair, full row pairs */
     constexpr int DJ = NT / QP, DI = NT - DJ * QP;   /* one stride of NT items in (row pair, quad pair) */
     int j = tid / QP, ip = tid - j * QP;
     while (j < QH) {
-        do_quad2<GEO, NZ, RESID, false, ZS>(k, ip, j, lo, hi);
+        do_quad2<GEO, NZ, RESID, false, ZS, WB>(k, ip, j, lo, hi);
         ip += DI; j += DJ;
         if (ip >= QP) { ip -= QP; j += 1; }
     }
-    if (tid < QP) do_quad2<GEO, NZ, RESID, true, ZS>(k, tid, QH, lo, hi);
+    if (tid < QP) do_quad2<GEO, NZ, RESID, true, ZS, WB>(k, tid, QH, lo, hi);
 }
 
 /* Shared memory one tile needs (all threads of the CTA pass the same pointers). */
-template <int TW, int TG>
+template <int TW, int TG, bool WB = true>
 struct ElevSmem {
     using GEO = Geo<TW, TG>;
     static constexpr int WIN = GEO::BOX_H * GEO::BOX_W;          /* floats per window copy */
     static constexpr int LAT = GEO::NK * GEO::NK;
-    static constexpr int FLOATS = 2 * WIN + ((LAT + 3) & ~3) + 2 * GEO::QW + 2 * 32;   /* windows, lattice, luts, reduction */
+    static constexpr int FLOATS = (WB ? 2 : 1) * WIN + ((LAT + 3) & ~3) + 2 * GEO::QW + 2 * 32;   /* window(s), lattice, luts, reduction */
     static_assert(WIN % 4 == 0, "the second window copy is written as float4");
 };
 
@@ -409,10 +427,10 @@ struct ElevSmem {
  * current phase parity is `parity`.  All NT threads of the CTA call this; it contains __syncthreads(). */
 /* defer_stats: the caller has a barrier of its own right after this call: the per-warp statistics are left in shared
  * memory and the caller finishes them with elevation_stats_finish after that barrier (one barrier less per tile) */
-template <int TW, int TG, int NT>
+template <int TW, int TG, int NT, bool WB = true>
 __device__ __forceinline__ void elevation_stats_finish(const ElevArgs &a, const pl_elev_req &rq, const float *smem)
 {
-    using SM = ElevSmem<TW, TG>;
+    using SM = ElevSmem<TW, TG, WB>;
     const float *red_lo = smem + SM::FLOATS - 64, *red_hi = red_lo + 32;
     float lo = red_lo[0], hi = red_hi[0];
 #pragma unroll
@@ -420,18 +438,18 @@ __device__ __forceinline__ void elevation_stats_finish(const ElevArgs &a, const 
     a.stats[rq.out_slot] = make_float2(lo, hi);
 }
 
-template <int TW, int TG, int RESID, int NT, bool ZS>
+template <int TW, int TG, int RESID, int NT, bool ZS, bool WB = true>
 __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const ElevArgs &a, const pl_elev_req &rq, float *smem,
                                                uint64_t *bar, const uint32_t parity, float *zms, const int tid,
                                                const bool defer_stats = false)
 {
     using GEO = Geo<TW, TG>;
-    using SM = ElevSmem<TW, TG>;
+    using SM = ElevSmem<TW, TG, WB>;
     constexpr int W = GEO::W, G = GEO::G, NK = GEO::NK, QW = GEO::QW;
     static_assert(QW % 2 == 0 && GEO::BOX_W % 4 == 0 && GEO::BOX_W >= QW + 4, "quad pairs read aligned float pairs inside a window row");
     float *winA = smem;
-    float *winB = winA + SM::WIN;
-    float *lat = winB + SM::WIN;
+    float *winB = winA + SM::WIN;                       /* WB only */
+    float *lat = winA + (WB ? 2 : 1) * SM::WIN;
     int *lutx = reinterpret_cast<int *>(lat + ((SM::LAT + 3) & ~3));
     int *luty = lutx + QW;
     float *red_lo = reinterpret_cast<float *>(luty + QW), *red_hi = red_lo + 32;   /* = smem + SM::FLOATS - 64 (elevation_stats_finish) */
@@ -461,11 +479,12 @@ __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const Elev
             lat[q] = __ldcg(pzm + py * GEO::PITCH + px);   /* L2: the parent may have been finished by another CTA of this launch */
         }
     } else {
-        for (int q = tid; q < GEO::BOX_W * GEO::BOX_H; q += NT) { winA[q] = 0.0f; winB[q] = 0.0f; }
+        for (int q = tid; q < GEO::BOX_W * GEO::BOX_H; q += NT) { winA[q] = 0.0f; if (WB) winB[q] = 0.0f; }
         for (int q = tid; q < NK * NK; q += NT) lat[q] = 0.0f;
     }
     __syncthreads();
-    if (has_parent) {
+    if (has_parent && !WB) mbar_wait(bar, parity);
+    if (has_parent && WB) {
         mbar_wait(bar, parity);
         /* the window a second time, one texel to the right: packed loads of odd window columns become
          * aligned pairs of the copy.  (A second TMA load at dx + 1 is not possible: without swizzle the
@@ -482,7 +501,7 @@ __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const Elev
 
     QuadCtx k;
     k.winA = winA;
-    k.winB = winB;
+    k.winB = WB ? winB : winA;
     k.lat = lat;
     k.lutx = lutx;
     k.luty = luty;
@@ -514,10 +533,10 @@ __device__ __forceinline__ void elevation_tile(const CUtensorMap *tm, const Elev
     /* tile-uniform noise variant; rs == 0 adds exactly 0 in every variant */
     const int nz = rq.rs == 0.0f ? NZ_NONE : (a.noise_mode == PL_NOISE_PLAIN ? NZ_PLAIN : (rq.rs < 0.0f ? NZ_NEG : NZ_SLOPE));
     switch (nz) {
-    case NZ_NONE: tile_loop<GEO, NZ_NONE, RESID, NT, ZS>(k, tid, lo, hi); break;
-    case NZ_PLAIN: tile_loop<GEO, NZ_PLAIN, RESID, NT, ZS>(k, tid, lo, hi); break;
-    case NZ_NEG: tile_loop<GEO, NZ_NEG, RESID, NT, ZS>(k, tid, lo, hi); break;
-    default: tile_loop<GEO, NZ_SLOPE, RESID, NT, ZS>(k, tid, lo, hi); break;
+    case NZ_NONE: tile_loop<GEO, NZ_NONE, RESID, NT, ZS, WB>(k, tid, lo, hi); break;
+    case NZ_PLAIN: tile_loop<GEO, NZ_PLAIN, RESID, NT, ZS, WB>(k, tid, lo, hi); break;
+    case NZ_NEG: tile_loop<GEO, NZ_NEG, RESID, NT, ZS, WB>(k, tid, lo, hi); break;
+    default: tile_loop<GEO, NZ_SLOPE, RESID, NT, ZS, WB>(k, tid, lo, hi); break;
     }
 
     if (k.want_stats) {

@@ -85,6 +85,8 @@ struct pl_ctx {
     int gen_cap;
     int force_generic;   /* tests: run the runtime-geometry kernels even for the shipped geometry */
     int no_fuse;         /* tests / profiling: pl_produce_range launches the two passes separately */
+    int no_slim;         /* tests / profiling: the fused kernel never uses its slim (4 CTAs per SM) layout */
+    int slim_sphere;     /* tests / profiling: ... and uses it on spheres too (pl_debug_no_slim(ctx, -1)) */
     int levels_epoch;    /* pl_produce_levels: the value a finished tile's ready flag takes in the current call */
     int inflate_path;    /* tests / profiling: 0 = by batch size, 1 = warp-per-stream decoder, 2 = tokenizer + resolver */
     /* per-launch CUDA-event timing (pl_timing_*): events on the launching stream */
@@ -147,13 +149,16 @@ int pl_launch_elevation(pl_ctx *ctx, const pl_elev_scene *sc, pl_pool *elev, pl_
 int pl_launch_normal(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_pool *elev,
                      int n, const pl_norm_req *dev_reqs);
 
+int pl_check_pair_pools(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm, pl_pool *resid, int n);
 /* fused elevation + normal pass (pl_pair.cu): one CTA per tile pair */
 bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, const pl_pool *elev,
                        const pl_pool *norm);
 int pl_launch_pair_levels(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm, int n,
-                           const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch);
+                           const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch, bool all_reg = false);
+/* all_reg: the caller knows that every tile of the launch qualifies for the register form of the FAST normal pass
+ * (norm_level_all_reg / plnorm::normal_reg_ok): the fused kernel may use its slim layout (4 CTAs per SM) */
 int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
-                   pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs);
+                   pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, bool all_reg = false);
 
 int pl_launch_ortho(pl_ctx *ctx, const pl_ortho_scene *sc, pl_pool *ortho, pl_pool *resid, int n,
                     const pl_ortho_req *dev_reqs);

@@ -31,19 +31,24 @@ int pl_norm_fill_args(pl_ctx *ctx, const pl_norm_scene *sc, pl_pool *norm, pl_po
 namespace {
 
 
-template <int TW, int TG>
+/* SLIM: the layout of launches in which EVERY tile takes the register form of the normal pass (PL_ARITH_FAST, the host
+ * checks it per launch): no position planes, the elevation phase without its second window copy, 28 floats of corner
+ * values instead of the banded form's row table -- 55.6 KB, FOUR CTAs per SM instead of three (71.7 KB). */
+template <int TW, int TG, bool SLIM = false>
 struct PairSmem {
     using EG = plelev::Geo<TW, TG>;
     using NG = plnorm::NGeo<TW - 4>;
     static constexpr int GUARD = 24;                                           /* floats in front of the zm plane (>= 4; makes ZM a multiple of 128 bytes) */
     static constexpr int ZM = GUARD + EG::PLANE;                               /* floats: guard + zm plane */
-    static constexpr int ELEV = plelev::ElevSmem<TW, TG>::FLOATS;
-    static constexpr int POS = 3 * NG::POS_PLANE;
+    static constexpr int ELEV = plelev::ElevSmem<TW, TG, !SLIM>::FLOATS;
+    static constexpr int POS = SLIM ? 0 : 3 * NG::POS_PLANE;
     static constexpr int WORK = ((ELEV > POS ? ELEV : POS) + 3) & ~3;           /* elevation scratch, then positions */
-    static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT + NG::ROWTAB) * 4;
+    static constexpr int QTAB = SLIM ? 32 : NG::ROWTAB;
+    static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT + QTAB) * 4;
     static_assert(EG::PITCH == NG::EPITCH && EG::PLANE == NG::EPLANE, "both passes agree on the plane layout");
     static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
-    static_assert(ELEV - 64 >= plnorm::RGeo<TW - 4, 224>::TAB && NG::ROWTAB >= 28, "row tables of the register form fit in front of the statistics");
+    static_assert(ELEV - 64 >= plnorm::RGeo<TW - 4, 224>::TAB && QTAB >= 28, "row tables of the register form fit in front of the statistics");
+    static_assert(!SLIM || BYTES + 1280 <= 233472 / 4, "four CTAs per SM");
 };
 
 /* threads of a CTA: 256 under PL_ARITH_EXACT; 224 under PL_ARITH_FAST -- 7 warps x 3 CTAs leave 96 registers per
@@ -51,11 +56,12 @@ struct PairSmem {
  * 663 quad pairs of an elevation tile are 3 passes of 224 threads (97 % of the lanes busy) as they are 3 passes of 256 */
 template <bool FAST> struct PairThreads { static constexpr int N = FAST ? 224 : 256; };
 
-template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false>
-__global__ void __launch_bounds__(PairThreads<FAST>::N, 3)
+template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false, bool SLIM = false>
+__global__ void __launch_bounds__(PairThreads<FAST>::N, SLIM ? 4 : 3)
 tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
 {
-    using SM = PairSmem<TW, TG>;
+    static_assert(!SLIM || (FAST && !PUSH), "the slim layout serves the register form only");
+    using SM = PairSmem<TW, TG, SLIM>;
     constexpr int kPairThreads = PairThreads<FAST>::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *zs = reinterpret_cast<float *>(smem_raw) + SM::GUARD;   /* zm plane behind the guard floats */
@@ -84,8 +90,8 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
 
     /* elevation: planes to HBM, zm also to shared memory */
     unsigned short *out = reinterpret_cast<unsigned short *>(na.norm + (size_t) nrq.out_slot * na.norm_slot_bytes);
-    const bool reg_form = FAST && !PUSH && plnorm::normal_reg_ok(nrq, SPHERE);
-    plelev::elevation_tile<TW, TG, RESID, kPairThreads, true>(&tm, ea, erq, work, &bar, 0, zs, tid, reg_form);
+    const bool reg_form = SLIM || (FAST && !PUSH && plnorm::normal_reg_ok(nrq, SPHERE));
+    plelev::elevation_tile<TW, TG, RESID, kPairThreads, true, !SLIM>(&tm, ea, erq, work, &bar, 0, zs, tid, reg_form);
     plelev::levels_publish(ea, erq, tid);   /* children may start while this CTA computes its normals */
     __syncthreads();   /* zm plane complete; the elevation scratch is free */
 
@@ -94,17 +100,34 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
         /* the register form: no position planes, no barriers; its row tables live in the elevation scratch (the
          * first RGeo::TAB floats of it: the per-warp statistics at its end stay intact and are finished here,
          * behind the barrier above instead of one of their own) */
-        if (tid == kPairThreads - 32 && ea.want_stats) plelev::elevation_stats_finish<TW, TG, kPairThreads>(ea, erq, work);
+        if (tid == kPairThreads - 32 && ea.want_stats) plelev::elevation_stats_finish<TW, TG, kPairThreads, !SLIM>(ea, erq, work);
         plnorm::normal_tile_reg<TW - 4, SPHERE, LINEAR, kPairThreads>(zs, work, rowtab, ulut, nrq, out, tid);
         return;
     }
-    plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH, FAST>(zs, work, ulut, nrq, out, tid, &na, rowtab);
+    if (!SLIM) plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH, FAST>(zs, work, ulut, nrq, out, tid, &na, rowtab);
 }
 
 template <int RESID>
-int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const plnorm::NormArgs &na, int n)
+int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const plnorm::NormArgs &na, int n, bool all_reg = false)
 {
     using SM = PairSmem<101, 4>;
+    if (all_reg && na.fast && na.npeers == 0 && !ctx->no_slim && (!na.sphere || ctx->slim_sphere)) {
+        /* every tile of the launch qualifies for the register form (the caller checked): the slim layout, 4 CTAs per SM.
+         * Flat scenes gain 6.6 % (0.583 -> 0.547 ms per 16 384 pairs); on the sphere the 72-register budget of 4 CTAs
+         * spills (40 bytes of stack) and the time does not move (0.757 ms either way): spheres keep the 3-CTA layout
+         * unless pl_debug_no_slim(ctx, -1) asks for the slim one (tests) */
+        using SL = PairSmem<101, 4, true>;
+        void (*slim)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
+            na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true, false, true, true> : tile_pair_kernel<101, 4, RESID, true, false, false, true, true>)
+                      : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true, false, true, true> : tile_pair_kernel<101, 4, RESID, false, false, false, true, true>);
+        PL_CUDA(cudaFuncSetAttribute(slim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SL::BYTES));
+        pl_timing_begin(ctx, PL_K_PAIR, n);
+        slim<<<n, PairThreads<true>::N, SL::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
+        pl_timing_end(ctx);
+        PL_CUDA(cudaGetLastError());
+        ctx->launches += 1;
+        return PL_OK;
+    }
     void (*kern)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
         na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true> : tile_pair_kernel<101, 4, RESID, true, false>)
                   : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true> : tile_pair_kernel<101, 4, RESID, false, false>);
@@ -140,23 +163,23 @@ bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
 /* n tile pairs: normal request i must describe the normal tile of elevation request i
  * (nreq[i].elev_slot == ereq[i].out_slot) */
 static int launch_pair_any(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
-                           pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch);
+                           pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch, bool all_reg);
 
 int pl_launch_pair(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
-                   pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs)
+                   pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, bool all_reg)
 {
-    return launch_pair_any(ctx, esc, nsc, elev, norm, resid, n, dev_ereqs, dev_nreqs, 0);
+    return launch_pair_any(ctx, esc, nsc, elev, norm, resid, n, dev_ereqs, dev_nreqs, 0, all_reg);
 }
 
 /* tiles of several levels in one launch, ordered by level: requests with pad_[0] != 0 wait for their parent's ready flag */
 int pl_launch_pair_levels(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm, int n,
-                          const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch)
+                          const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch, bool all_reg)
 {
-    return launch_pair_any(ctx, esc, nsc, elev, norm, nullptr, n, dev_ereqs, dev_nreqs, epoch);
+    return launch_pair_any(ctx, esc, nsc, elev, norm, nullptr, n, dev_ereqs, dev_nreqs, epoch, all_reg);
 }
 
 static int launch_pair_any(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_scene *nsc, pl_pool *elev, pl_pool *norm,
-                           pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch)
+                           pl_pool *resid, int n, const pl_elev_req *dev_ereqs, const pl_norm_req *dev_nreqs, int epoch, bool all_reg)
 {
     PL_CUDA(cudaSetDevice(ctx->device));
     plelev::ElevArgs ea;
@@ -169,5 +192,5 @@ static int launch_pair_any(pl_ctx *ctx, const pl_elev_scene *esc, const pl_norm_
     }
     if ((rc = pl_norm_fill_args(ctx, nsc, norm, elev, dev_nreqs, na)) != PL_OK) return rc;
     const int rk = !resid ? 0 : (resid->kind == PL_POOL_RESID_F32 ? 1 : 2);
-    return rk == 0 ? launch_pair<0>(ctx, elev, ea, na, n) : (rk == 1 ? launch_pair<1>(ctx, elev, ea, na, n) : launch_pair<2>(ctx, elev, ea, na, n));
+    return rk == 0 ? launch_pair<0>(ctx, elev, ea, na, n, all_reg) : (rk == 1 ? launch_pair<1>(ctx, elev, ea, na, n, all_reg) : launch_pair<2>(ctx, elev, ea, na, n, all_reg));
 }

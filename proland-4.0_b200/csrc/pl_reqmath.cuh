@@ -236,6 +236,20 @@ PL_HD void norm_fill_req(int sphere, double root_quad_size, int level, int tx, i
     req->smooth = t * t * fmaf(-2.0f, t, 3.0f);
 }
 
+/* does EVERY tile of `level` qualify for the register form of the FAST normal pass (plnorm::normal_reg_ok)?  Spheres: the
+ * smoothstep factor of norm_fill_req is exactly 1 (it depends on the level only); flat scenes: the tangent frame norm_fill_req
+ * writes is the identity.  The host decides per launch with this; the expressions are norm_fill_req's. */
+PL_HD bool norm_level_all_reg(int sphere, double root_quad_size, int level)
+{
+    if (!sphere) return true;
+    const double D = root_quad_size, R = D / 2.0;
+    const float Rf = (float) R, dz = (float) (D / (double) (1 << level));
+    const float e0 = Rf / 32.0f, e1 = Rf / 64.0f;
+    float t = (dz - e0) / (e1 - e0);
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    return t * t * fmaf(-2.0f, t, 3.0f) == 1.0f;
+}
+
 /* Morton (Z-order) index <-> (tx, ty): the four children of a quad are
  * (2tx,2ty), (2tx+1,2ty), (2tx,2ty+1), (2tx+1,2ty+1) in that order
  * (TileSampler.cpp:416-461), i.e. x in the even bits */

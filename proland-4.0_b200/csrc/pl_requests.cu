@@ -150,7 +150,8 @@ extern "C" int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *
     ctx->launches += 1;
     /* request i of both arrays describes tile i: the fused kernel applies */
     if (norm && pl_pair_supported(ctx, &sc->elev, &sc->norm, elev, norm))
-        return pl_launch_pair(ctx, &sc->elev, &sc->norm, elev, norm, nullptr, n, ctx->gen_ereq, ctx->gen_nreq);
+        return pl_launch_pair(ctx, &sc->elev, &sc->norm, elev, norm, nullptr, n, ctx->gen_ereq, ctx->gen_nreq,
+                              norm_level_all_reg(sc->norm.sphere, sc->root_quad_size, level));
     rc = pl_elevation_batch_dev(ctx, &sc->elev, elev, nullptr, n, ctx->gen_ereq);
     if (rc) return rc;
     if (norm) rc = pl_normal_batch_dev(ctx, &sc->norm, norm, elev, n, ctx->gen_nreq);
@@ -203,8 +204,10 @@ extern "C" int pl_pair_batch_ids(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool 
     if (resid && resid->kind != PL_POOL_RESID_F32 && resid->kind != PL_POOL_RESID_I16)
         return pl_set_error(PL_ERR_ARG, "resid is not a residual pool");
     const int rcap = resid ? resid->capacity : 0;
+    int min_level = 99;
     for (int i = 0; i < n; ++i) {
         const pl_tile_id &t = ids[i];
+        min_level = t.level < min_level ? t.level : min_level;
         if (t.level < 0 || t.level > 24 || t.tx < 0 || t.ty < 0 || t.tx >= (1 << t.level) || t.ty >= (1 << t.level))
             return pl_set_error(PL_ERR_ARG, "tile %d: (%d, %d, %d) is not a quadtree tile", i, t.level, t.tx, t.ty);
         if (t.elev_slot < 0 || t.elev_slot >= elev->capacity || t.norm_slot < 0 || t.norm_slot >= norm->capacity ||
@@ -236,6 +239,12 @@ extern "C" int pl_pair_batch_ids(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool 
     pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
+    /* the smoothstep factor only grows with the level: the shallowest tile of the batch decides for all */
+    if (pl_pair_supported(ctx, &sc->elev, &sc->norm, elev, norm)) {
+        if ((rc = pl_check_pair_pools(ctx, &sc->elev, &sc->norm, elev, norm, resid, n)) != PL_OK) return rc;
+        return pl_launch_pair(ctx, &sc->elev, &sc->norm, elev, norm, resid, n, ctx->gen_ereq, ctx->gen_nreq,
+                              norm_level_all_reg(sc->norm.sphere, sc->root_quad_size, min_level));
+    }
     return pl_pair_batch_dev(ctx, &sc->elev, &sc->norm, elev, norm, resid, n, ctx->gen_ereq, ctx->gen_nreq);
 }
 
@@ -327,7 +336,9 @@ extern "C" int pl_produce_levels(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool 
     PL_CUDA(cudaGetLastError());
     ctx->launches += 1;
     ctx->levels_epoch = ctx->levels_epoch == 0x7fffffff ? 1 : ctx->levels_epoch + 1;
-    return pl_launch_pair_levels(ctx, &sc->elev, &sc->norm, elev, norm, n, ctx->gen_ereq, ctx->gen_nreq, ctx->levels_epoch);
+    bool all_reg = true;
+    for (int r = 0; r < nranges; ++r) all_reg = all_reg && norm_level_all_reg(sc->norm.sphere, sc->root_quad_size, ranges[r].level);
+    return pl_launch_pair_levels(ctx, &sc->elev, &sc->norm, elev, norm, n, ctx->gen_ereq, ctx->gen_nreq, ctx->levels_epoch, all_reg);
 }
 
 extern "C" int pl_make_tile_ids_range(int level, uint64_t morton0, int n, int out_slot0, int parent_slot0,

@@ -32,7 +32,7 @@ EXPORTS = [
     "pl_elevation_batch_dev", "pl_elev_stats_download", "pl_elev_stats_range", "pl_elev_stats_readback_begin",
     "pl_elev_stats_readback_end", "pl_elev_zreadback_begin", "pl_elev_stats_readback_ready", "pl_norm_make_req", "pl_normal_batch",
     "pl_normal_batch_dev", "pl_pair_batch", "pl_pair_batch_dev", "pl_pair_batch_ids", "pl_produce_levels", "pl_make_tile_ids_range", "pl_produce_range", "pl_make_requests_range",
-    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
+    "pl_debug_download_requests", "pl_debug_force_generic", "pl_debug_no_fuse", "pl_debug_no_slim", "pl_debug_inflate_path", "pl_debug_stage_ring", "pl_debug_fpexact",
     "pl_residual_decode_batch", "pl_blobs_create", "pl_blobs_destroy", "pl_residual_decode_stored", "pl_residual_upsample", "pl_residual_encode_batch", "pl_residual_write_file",
     "pl_height_cube_create", "pl_height_cube_from_latlon", "pl_height_cube_from_plane", "pl_debug_height_unsure", "pl_height_cube_download", "pl_height_cube_destroy", "pl_height_tiles",
     "pl_ortho_noise_init", "pl_ortho_noise_host", "pl_ortho_make_req", "pl_ortho_make_requests_range", "pl_ortho_batch", "pl_ortho_batch_dev", "pl_ortho_decode_batch", "pl_ortho_produce_range",
@@ -191,6 +191,7 @@ def lib():
         L.pl_debug_download_requests.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.pl_debug_force_generic.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_no_fuse.argtypes = [C.c_void_p, C.c_int]
+        L.pl_debug_no_slim.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_inflate_path.argtypes = [C.c_void_p, C.c_int]
         L.pl_debug_stage_ring.argtypes = [C.c_void_p, C.c_size_t]
         L.pl_debug_fpexact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -612,6 +613,11 @@ def _no_fuse(self, on=True):
     check(lib().pl_debug_no_fuse(self.h, int(on)))
 
 
+def _no_slim(self, on=True):
+    """the fused kernel keeps its 3-CTA layout even when every tile takes the register form (same results)."""
+    check(lib().pl_debug_no_slim(self.h, int(on)))
+
+
 def _fpexact(self, a, b):
     a = np.ascontiguousarray(a, np.float32)
     b = np.ascontiguousarray(b, np.float32)
@@ -754,6 +760,7 @@ Context.force_generic = _force_generic
 Context.residual_decode_stored = _residual_decode_stored
 Context.blobs = lambda self, data: Blobs(self, data)
 Context.no_fuse = _no_fuse
+Context.no_slim = _no_slim
 
 
 def _inflate_path(self, path=0):

@@ -77,3 +77,41 @@ def test_fast_sweep_levels_0_5(plb, ctx, oracle, fused):
         q = oracle.normal_uniforms(l, tx, ty, rootQuadSize=12720000.0, sphere=1, elev_filter=1)
         sbad += int(np.count_nonzero(oracle.pack_unorm8(oracle.normal_tile(q, e, L=oracle.strict()), 2) != n))
     _check(len(ref), worst, bad, nbytes, sbad)
+
+
+@pytest.mark.parametrize("sphere", [0, 1])
+def test_slim_layout_is_byte_identical_to_the_regular_one(plb, ctx, sphere):
+    """launches whose tiles all take the register form run the fused kernel in its slim layout (no second window copy, no
+    position planes: 4 CTAs per SM; by default on flat scenes, forced here on spheres too): the same elevation planes,
+    statistics and normal bytes as the regular layout, on a whole level with slope noise, through produce_range, the
+    identity entry point and host-built requests"""
+    level, n = 8, 1024
+    kw = dict(noise_amp=gc.PLANET, face=3, root_quad_size=12720000.0, sphere=1) if sphere else \
+        dict(noise_amp=gc.FRACTAL + [2, 1, 1], face=0, root_quad_size=100000.0, sphere=0)
+    sc = plb.sweep_scene(want_stats=1, arith=plb.ARITH_FAST, **kw)
+    ctx.noise_init(101)
+    elev = ctx.pool(plb.POOL_ELEV, 101, 2 * n + n // 4)
+    norm = ctx.pool(plb.POOL_NORM2, 97, 2 * n + n // 4)
+    ctx.no_slim(1)
+    ctx.produce_range(sc, elev, norm, level - 1, 0, n // 4, 2 * n, 0, 0)          # parents (from zero grandparents)
+    got = {}
+    for mode, base in ((1, 0), (-1, n)):                                           # regular layout, then slim
+        ctx.no_slim(mode)
+        ctx.produce_range(sc, elev, norm, level, 0, n, base, 2 * n, 0)
+        ctx.sync()
+        got[mode] = ([elev.download(base + s) for s in range(0, n, 37)], [norm.download(base + s) for s in range(0, n, 37)],
+                     ctx.elev_stats_range(elev, base, n))
+    for a, b in zip(got[1][0], got[-1][0]):
+        assert np.array_equal(a, b)
+    for a, b in zip(got[1][1], got[-1][1]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(got[1][2], got[-1][2])
+    # the identity entry point takes the same decision per batch
+    ids = plb.make_tile_ids_range(level, 0, n, n, 2 * n, 0)
+    ids["norm_slot"] = np.arange(n)                                                # normals over the regular run's slots
+    ctx.pair_batch_ids(sc, elev, norm, ids)
+    ctx.sync()
+    for k, s in enumerate(range(0, n, 37)):
+        assert np.array_equal(norm.download(s), got[1][1][k])
+        assert np.array_equal(elev.download(n + s), got[1][0][k])
+    ctx.no_slim(0)
