@@ -61,12 +61,13 @@ void Task::setIsDone(bool d, unsigned int t, reason r)
 
 unsigned long long TaskGraph::edits = 0;
 
-TaskGraph::TaskGraph() : Task("TaskGraph", false, 0)
+TaskGraph::TaskGraph() : Task("TaskGraph", false, 0), index(NULL)
 {
 }
 
 TaskGraph::~TaskGraph()
 {
+    delete index;
 }
 
 bool TaskGraph::isDone()
@@ -133,10 +134,57 @@ void TaskGraph::init(std::set<Task *> &initialized)
     }
 }
 
+bool TaskGraph::contains(Task *t) const
+{
+    if (index != NULL) {
+        return index->find(t) != index->end();
+    }
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        if (tasks[i].get() == t) return true;
+    }
+    return false;
+}
+
+TaskGraph::Needs *TaskGraph::needsOf(Task *src)
+{
+    for (size_t i = 0; i < dependencies.size(); ++i) {
+        if (dependencies[i].src == src) return &dependencies[i];
+    }
+    return NULL;
+}
+
+const TaskGraph::Needs *TaskGraph::needsOf(Task *src) const
+{
+    return const_cast<TaskGraph *>(this)->needsOf(src);
+}
+
+TaskGraph::NeededBy *TaskGraph::neededBy(Task *dst)
+{
+    for (size_t i = 0; i < inverse.size(); ++i) {
+        if (inverse[i].dst == dst) return &inverse[i];
+    }
+    return NULL;
+}
+
+const TaskGraph::NeededBy *TaskGraph::neededBy(Task *dst) const
+{
+    return const_cast<TaskGraph *>(this)->neededBy(dst);
+}
+
 void TaskGraph::addTask(ptr<Task> t)
 {
+    if (contains(t.get())) {
+        return;
+    }
     ++edits;
-    tasks.insert(t);
+    tasks.push_back(t);
+    if (index != NULL) {
+        index->insert(t.get());
+    } else if (tasks.size() > (size_t) kIndexAbove) {
+        index = new std::unordered_set<Task *>();
+        index->reserve(4 * tasks.size());
+        for (size_t i = 0; i < tasks.size(); ++i) index->insert(tasks[i].get());
+    }
 }
 
 void TaskGraph::removeTask(ptr<Task> t)
@@ -144,49 +192,82 @@ void TaskGraph::removeTask(ptr<Task> t)
     ++edits;
     TaskSet gone;
     removeAndGetDependencies(t, gone);
-    std::map<Task *, std::set<Task *> >::iterator inv = inverse.find(t.get());
-    if (inv != inverse.end()) {
-        std::set<Task *> users = inv->second;
-        for (std::set<Task *>::iterator u = users.begin(); u != users.end(); ++u) {
-            dependencies[*u].erase(t);
+    if (NeededBy *nb = neededBy(t.get())) {
+        const std::vector<Task *> users = nb->src;
+        for (size_t u = 0; u < users.size(); ++u) {
+            if (Needs *n = needsOf(users[u])) {
+                for (size_t k = 0; k < n->dst.size(); ++k) {
+                    if (n->dst[k].get() == t.get()) {
+                        n->dst.erase(n->dst.begin() + k);
+                        break;
+                    }
+                }
+            }
         }
-        inverse.erase(t.get());
+        nb = neededBy(t.get());
+        inverse.erase(inverse.begin() + (nb - &inverse[0]));
     }
-    tasks.erase(t);
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        if (tasks[i].get() == t.get()) {
+            tasks.erase(tasks.begin() + i);
+            break;
+        }
+    }
+    if (index != NULL) index->erase(t.get());
 }
 
 void TaskGraph::addDependency(ptr<Task> src, ptr<Task> dst)
 {
     ++edits;
-    dependencies[src.get()].insert(dst);
-    inverse[dst.get()].insert(src.get());
+    Needs *n = needsOf(src.get());
+    if (n == NULL) {
+        dependencies.push_back(Needs());
+        n = &dependencies.back();
+        n->src = src.get();
+    }
+    bool have = false;
+    for (size_t k = 0; k < n->dst.size() && !have; ++k) have = n->dst[k].get() == dst.get();
+    if (!have) n->dst.push_back(dst);
+    NeededBy *nb = neededBy(dst.get());
+    if (nb == NULL) {
+        inverse.push_back(NeededBy());
+        nb = &inverse.back();
+        nb->dst = dst.get();
+    }
+    if (std::find(nb->src.begin(), nb->src.end(), src.get()) == nb->src.end()) nb->src.push_back(src.get());
 }
 
 void TaskGraph::removeDependency(ptr<Task> src, ptr<Task> dst)
 {
     ++edits;
-    std::map<Task *, TaskSet>::iterator d = dependencies.find(src.get());
-    if (d != dependencies.end()) {
-        d->second.erase(dst);
-        if (d->second.empty()) dependencies.erase(d);
+    if (Needs *n = needsOf(src.get())) {
+        for (size_t k = 0; k < n->dst.size(); ++k) {
+            if (n->dst[k].get() == dst.get()) {
+                n->dst.erase(n->dst.begin() + k);
+                break;
+            }
+        }
+        if (n->dst.empty()) dependencies.erase(dependencies.begin() + (n - &dependencies[0]));
     }
-    std::map<Task *, std::set<Task *> >::iterator i = inverse.find(dst.get());
-    if (i != inverse.end()) {
-        i->second.erase(src.get());
-        if (i->second.empty()) inverse.erase(i);
+    if (NeededBy *nb = neededBy(dst.get())) {
+        std::vector<Task *>::iterator i = std::find(nb->src.begin(), nb->src.end(), src.get());
+        if (i != nb->src.end()) nb->src.erase(i);
+        if (nb->src.empty()) inverse.erase(inverse.begin() + (nb - &inverse[0]));
     }
 }
 
 void TaskGraph::removeAndGetDependencies(ptr<Task> src, TaskSet &deletedDependencies)
 {
-    std::map<Task *, TaskSet>::iterator d = dependencies.find(src.get());
-    if (d == dependencies.end()) {
+    const Needs *n = needsOf(src.get());
+    if (n == NULL) {
         return;
     }
-    TaskSet deps = d->second;
-    for (TaskSet::iterator i = deps.begin(); i != deps.end(); ++i) {
-        deletedDependencies.insert(*i);
-        removeDependency(src, *i);
+    const TaskSet deps = n->dst;
+    for (size_t i = 0; i < deps.size(); ++i) {
+        bool have = false;
+        for (size_t k = 0; k < deletedDependencies.size() && !have; ++k) have = deletedDependencies[k].get() == deps[i].get();
+        if (!have) deletedDependencies.push_back(deps[i]);
+        removeDependency(src, deps[i]);
     }
 }
 
@@ -203,19 +284,21 @@ void TaskGraph::cleanup()
     dependencies.clear();
     inverse.clear();
     tasks.clear();
+    delete index;
+    index = NULL;
 }
 
 TaskGraph::TaskIterator TaskGraph::getAllTasks() const
 {
-    return TaskIterator(std::vector<ptr<Task> >(tasks.begin(), tasks.end()));
+    return TaskIterator(tasks);
 }
 
 TaskGraph::TaskIterator TaskGraph::getFirstTasks() const
 {
     std::vector<ptr<Task> > v;
-    for (TaskSet::const_iterator i = tasks.begin(); i != tasks.end(); ++i) {
-        std::map<Task *, TaskSet>::const_iterator d = dependencies.find(i->get());
-        if (d == dependencies.end() || d->second.empty()) v.push_back(*i);
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        const Needs *n = needsOf(tasks[i].get());
+        if (n == NULL || n->dst.empty()) v.push_back(tasks[i]);
     }
     return TaskIterator(v);
 }
@@ -223,34 +306,32 @@ TaskGraph::TaskIterator TaskGraph::getFirstTasks() const
 TaskGraph::TaskIterator TaskGraph::getLastTasks() const
 {
     std::vector<ptr<Task> > v;
-    for (TaskSet::const_iterator i = tasks.begin(); i != tasks.end(); ++i) {
-        std::map<Task *, std::set<Task *> >::const_iterator d = inverse.find(i->get());
-        if (d == inverse.end() || d->second.empty()) v.push_back(*i);
+    for (size_t i = 0; i < tasks.size(); ++i) {
+        const NeededBy *nb = neededBy(tasks[i].get());
+        if (nb == NULL || nb->src.empty()) v.push_back(tasks[i]);
     }
     return TaskIterator(v);
 }
 
 TaskGraph::TaskIterator TaskGraph::getDependencies(ptr<Task> t) const
 {
-    std::map<Task *, TaskSet>::const_iterator d = dependencies.find(t.get());
-    if (d == dependencies.end()) return TaskIterator();
-    return TaskIterator(std::vector<ptr<Task> >(d->second.begin(), d->second.end()));
+    const Needs *n = needsOf(t.get());
+    return n == NULL ? TaskIterator() : TaskIterator(n->dst);
 }
 
 TaskGraph::TaskIterator TaskGraph::getInverseDependencies(ptr<Task> t) const
 {
     std::vector<ptr<Task> > v;
-    std::map<Task *, std::set<Task *> >::const_iterator d = inverse.find(t.get());
-    if (d != inverse.end()) {
-        for (std::set<Task *>::const_iterator i = d->second.begin(); i != d->second.end(); ++i) v.push_back(ptr<Task>(*i));
+    if (const NeededBy *nb = neededBy(t.get())) {
+        for (size_t i = 0; i < nb->src.size(); ++i) v.push_back(ptr<Task>(nb->src[i]));
     }
     return TaskIterator(v);
 }
 
 const TaskGraph::TaskSet *TaskGraph::dependenciesOf(Task *t) const
 {
-    std::map<Task *, TaskSet>::const_iterator d = dependencies.find(t);
-    return d == dependencies.end() ? NULL : &d->second;
+    const Needs *n = needsOf(t);
+    return n == NULL ? NULL : &n->dst;
 }
 
 }  // namespace ork

@@ -23,6 +23,7 @@
 #include <set>
 #include <string>
 #include <typeinfo>
+#include <unordered_set>
 #include <vector>
 
 #ifndef PROLAND_API
@@ -186,7 +187,10 @@ private:
 class TaskGraph : public Task
 {
 public:
-    typedef std::set<ptr<Task> > TaskSet;
+    /* unique tasks in insertion order.  Ork keeps std::set / std::map here; a tile's graph holds two or three tasks and one
+     * or two dependencies, and every container node was a heap allocation per tile: flat vectors, searched linearly, with a
+     * hash index only for graphs that grow large (a frame's root graph) */
+    typedef std::vector<ptr<Task> > TaskSet;
 
     /* Ork's iterator flavour: hasNext()/next() over a snapshot */
     class TaskIterator
@@ -238,10 +242,20 @@ protected:
     void cleanup();
 
 private:
+    struct Needs { Task *src; TaskSet dst; };                    /* src -> what it needs */
+    struct NeededBy { Task *dst; std::vector<Task *> src; };      /* dst -> who needs it */
     static unsigned long long edits;
     TaskSet tasks;
-    std::map<Task *, TaskSet> dependencies;          /* src -> what it needs */
-    std::map<Task *, std::set<Task *> > inverse;     /* dst -> who needs it */
+    std::unordered_set<Task *> *index;                            /* of `tasks`, once there are more than kIndexAbove */
+    std::vector<Needs> dependencies;
+    std::vector<NeededBy> inverse;
+    enum { kIndexAbove = 16 };
+
+    bool contains(Task *t) const;
+    Needs *needsOf(Task *src);
+    const Needs *needsOf(Task *src) const;
+    NeededBy *neededBy(Task *dst);
+    const NeededBy *neededBy(Task *dst) const;
 };
 
 class Scheduler : public Object

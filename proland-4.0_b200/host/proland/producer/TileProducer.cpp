@@ -194,12 +194,12 @@ TileProducer::~TileProducer()
 {
     assert(cache != NULL);
     cache->producers.erase(id);
-    for (size_t i = 0; i < tasks.size(); ++i) {
-        CreateTile *t = dynamic_cast<CreateTile *>(tasks[i]);
+    for (std::unordered_set<Task *>::iterator i = tasks.begin(); i != tasks.end(); ++i) {
+        CreateTile *t = dynamic_cast<CreateTile *>(*i);
         if (t != NULL) {
             t->owner = NULL;
         } else {
-            dynamic_cast<CreateTileTaskGraph *>(tasks[i])->owner = NULL;
+            dynamic_cast<CreateTileTaskGraph *>(*i)->owner = NULL;
         }
     }
     layers.clear();
@@ -398,10 +398,10 @@ ptr<Task> TileProducer::createTile(int level, int tx, int ty, TileStorage::Slot 
         throw;
     }
     std::lock_guard<std::mutex> lock(mutex);
-    tasks.push_back(t.get());
+    tasks.insert(t.get());
     if (r.get() != t.get()) {
         assert(r.cast<CreateTileTaskGraph>() != NULL);
-        tasks.push_back(r.get());
+        tasks.insert(r.get());
     }
     return r;
 }
@@ -429,10 +429,7 @@ void TileProducer::cacheFull(const char *producerType)
 void TileProducer::removeCreateTile(Task *t)
 {
     std::lock_guard<std::mutex> lock(mutex);
-    std::vector<Task *>::iterator i = std::find(tasks.begin(), tasks.end(), t);
-    if (i != tasks.end()) {
-        tasks.erase(i);
-    }
+    tasks.erase(t);
 }
 
 }  // namespace proland
