@@ -48,40 +48,80 @@ def rank_range(level, rank, world):
 
 def share_fd(dist, rank, world, fd, key):
     """hands rank 0's file descriptor to every other rank of the box: SCM_RIGHTS over an abstract Unix socket (the C ABI
-    leaves the inter-process transport to the caller).  -> the local descriptor"""
+    leaves the inter-process transport to the caller).  -> the local descriptor.  Every rank reaches the barrier whatever
+    happens; a failure surfaces as OSError on the ranks it concerns (sockets time out instead of waiting for ever)."""
     import socket
     name = "\0proland-b200-mc-%s-%s" % (os.environ.get("MASTER_PORT", "0"), key)
+    srv, err = None, None
     if rank == 0:
-        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        srv.bind(name)
-        srv.listen(world)
-    dist.barrier()                       # the socket is listening
+        try:
+            srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            srv.bind(name)
+            srv.listen(world)
+            srv.settimeout(30.0)
+        except OSError as e:
+            err = e
+    dist.barrier()                       # the socket is listening (or rank 0 failed: the peers' connect is refused)
     if rank == 0:
-        for _ in range(world - 1):
-            conn, _ = srv.accept()
-            socket.send_fds(conn, [b"fd"], [fd])
-            conn.recv(1)                 # the peer has the descriptor
-            conn.close()
-        srv.close()
+        if err is not None:
+            raise err
+        try:
+            for _ in range(world - 1):
+                conn, _ = srv.accept()
+                conn.settimeout(30.0)
+                socket.send_fds(conn, [b"fd"], [fd])
+                conn.recv(1)             # the peer has the descriptor
+                conn.close()
+        finally:
+            srv.close()
         return fd
     c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    c.connect(name)
-    _, fds, _, _ = socket.recv_fds(c, 16, 1)
-    c.send(b"k")
-    c.close()
+    c.settimeout(30.0)
+    try:
+        c.connect(name)
+        _, fds, _, _ = socket.recv_fds(c, 16, 1)
+        c.send(b"k")
+    finally:
+        c.close()
+    if not fds:
+        raise OSError("no file descriptor received")
     return fds[0]
 
 
 def multicast_group(dist, pool, rank, world, key="norm"):
-    """binds a shared pool (ctx.pool(..., shared=True)) of every rank to one NVLink multicast object"""
-    fd = share_fd(dist, rank, world, pool.mc_create(world) if rank == 0 else -1, key)
-    if rank != 0:
-        pool.mc_import(fd, world)
-    os.close(fd)
-    pool.mc_add_device()
-    dist.barrier()                       # every device is added: binding may start
-    pool.mc_bind()
-    dist.barrier()
+    """binds a shared pool (ctx.pool(..., shared=True)) of every rank to one NVLink multicast object.  Every stage ends
+    with an agreement over the ranks (all_reduce MIN of a success flag, which is also the barrier the C ABI asks for): if a
+    stage fails anywhere, ALL ranks give the group up together instead of waiting for each other.  -> True when bound"""
+    import torch
+
+    def agreed(ok):
+        t = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return float(t[0]) == 1.0
+
+    fd, ok = -1, True
+    try:
+        if rank == 0:
+            fd = pool.mc_create(world)
+    except pl.PlError:
+        ok = False
+    if not agreed(ok):
+        return False
+    try:
+        fd = share_fd(dist, rank, world, fd, key)
+        if rank != 0:
+            pool.mc_import(fd, world)
+        os.close(fd)
+        pool.mc_add_device()
+    except (pl.PlError, OSError):
+        ok = False
+    if not agreed(ok):                   # every device is added: binding may start
+        return False
+    try:
+        pool.mc_bind()
+    except pl.PlError:
+        ok = False
+    return agreed(ok)
 
 
 class _DeviceBytes:
@@ -202,8 +242,7 @@ def gather_record(ctx, torch, dist, stream, rank, world, level=7, reps=5):
                     normm, have = None, 0.0
                 hv = torch.tensor([have], dtype=torch.float64, device="cuda")
                 dist.all_reduce(hv, op=dist.ReduceOp.MIN)
-                if float(hv[0]) == 1.0:
-                    multicast_group(dist, normm, rank, world)
+                if float(hv[0]) == 1.0 and multicast_group(dist, normm, rank, world):
                     slab(normm).zero_()
                     torch.cuda.synchronize()
                     dist.barrier()
