@@ -181,11 +181,43 @@ __device__ __forceinline__ int row_shift(int g) { return ((g + 3) >> 1) & 1; }
  *   - normalisation by MUFU.RSQ, folded with the unorm8 scale into the tangent-frame product:
  *         byte = round(127.5 * rsqrt(n.n) * dot(w2t_row, n) + 127.5)
  *     (no IEEE square root, no reciprocal, no clamp: |t| <= 1 + 1e-6 keeps the magic-add rounding inside 0..255) */
-template <int TW, bool SPHERE, bool LINEAR, int NT, bool PUSH = false, bool FAST = false>
+/* the coarse normal of an RGBA8 texel (normalShader.glsl:100-114): the parent tile's normal at the two coarse mesh
+ * vertices around (x, y), averaged, unpacked and -- on a sphere -- rotated by parentToTangentFrame; without a parent
+ * (normalOSL.x = -1) the fine normal (tx, ty) itself.  -> b | a << 8, the texel's upper two bytes.  Same operations, same
+ * order as the runtime-geometry kernel (pl_normal.cu). */
+__device__ __forceinline__ unsigned int coarse_normal_ba(const NormArgs &a, const pl_norm_req &rq, const int W, const bool sphere,
+                                                         const int x, const int y, const float tx, const float ty)
+{
+    float ncx = tx, ncy = ty;
+    if (rq.parent_slot >= 0) {
+        const uchar4 *parent = reinterpret_cast<const uchar4 *>(a.norm + (size_t) rq.parent_slot * a.norm_slot_bytes);
+        const int g = a.grid;
+        const float offx = (float) rq.ptx * ((float) W / 2.0f) + 0.25f, offy = (float) rq.pty * ((float) W / 2.0f) + 0.25f;
+        const float2 nc0 = fetch_parent_xy(parent, W, a.parent_linear != 0, (float) (g * floordiv(x + g, 2 * g)) + offx,
+                                           (float) (g * floordiv(y, 2 * g)) + offy);
+        const float2 nc1 = fetch_parent_xy(parent, W, a.parent_linear != 0, (float) (g * floordiv(x, 2 * g)) + offx,
+                                           (float) (g * floordiv(y + g, 2 * g)) + offy);
+        ncx = fmaf((nc0.x + nc1.x) * 0.5f, 2.0f, -1.0f);
+        ncy = fmaf((nc0.y + nc1.y) * 0.5f, 2.0f, -1.0f);
+        if (sphere) {
+            const float ncz = sqrtf(1.0f - fmaf(ncy, ncy, ncx * ncx));
+            const float qx = dot3(rq.p2t[0], rq.p2t[1], rq.p2t[2], ncx, ncy, ncz);
+            const float qy = dot3(rq.p2t[3], rq.p2t[4], rq.p2t[5], ncx, ncy, ncz);
+            ncx = qx;
+            ncy = qy;
+        }
+    }
+    return unorm8(fmaf(ncx, 0.5f, 0.5f)) | (unorm8(fmaf(ncy, 0.5f, 0.5f)) << 8);
+}
+
+/* C4: an RGBA8 normal storage (tileSDF.z = 1): `out` addresses 4-byte texels (r, g, b, a) = (fine.xy, coarse.xy); the
+ * exact arithmetic only (FAST = false) */
+template <int TW, bool SPHERE, bool LINEAR, int NT, bool PUSH = false, bool FAST = false, bool C4 = false>
 __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const float *ulut, const pl_norm_req &rq,
                                             unsigned short *out, const int tid, const NormArgs *peers = nullptr,
                                             float *rowtab = nullptr)
 {
+    static_assert(!C4 || (!FAST && !PUSH), "RGBA8 normals: exact arithmetic, no push");
     using namespace plf2;
     using GEO = NGeo<TW>;
     constexpr int W = GEO::W, GWP = GEO::GWP, EPITCH = GEO::EPITCH, UL = GEO::ULUT;
@@ -460,13 +492,28 @@ __device__ __forceinline__ void normal_tile(const float *zs, float *pos, const f
                 const unsigned int gx = __float_as_uint(g.x + 12582912.0f), gy = __float_as_uint(g.y + 12582912.0f);
                 rg[half][0] = __byte_perm(rx, gx, 0x0040u);
                 rg[half][1] = __byte_perm(ry, gy, 0x0040u);
+                if (C4) {
+                    /* the coarse normal in the upper two bytes; texels outside the tile are not stored */
+                    const int yy = y_begin + 2 * k + half;
+                    const int x0c = min(max(x, 0), W - 1), x1c = min(x + 1, W - 1), yc = min(yy, W - 1);
+                    rg[half][0] = (rg[half][0] & 0xffffu) | (coarse_normal_ba(*peers, rq, W, SPHERE, x0c, yc, tx.x, ty.x) << 16);
+                    rg[half][1] = (rg[half][1] & 0xffffu) | (coarse_normal_ba(*peers, rq, W, SPHERE, x1c, yc, tx.y, ty.y) << 16);
+                }
             }
-            unsigned short *o = ob - odd;
             const bool px0 = x >= 0, px1 = x + 1 < W, py1 = ry + 1 < rows;
-            if (px0) o[0] = (unsigned short) rg[0][0];
-            if (px1) o[1] = (unsigned short) rg[0][1];
-            if (px0 && py1) o[W] = (unsigned short) rg[1][0];
-            if (px1 && py1) o[W + 1] = (unsigned short) rg[1][1];
+            if (C4) {
+                unsigned int *o = reinterpret_cast<unsigned int *>(out) + (y_begin + 2 * k) * W + x;
+                if (px0) o[0] = rg[0][0];
+                if (px1) o[1] = rg[0][1];
+                if (px0 && py1) o[W] = rg[1][0];
+                if (px1 && py1) o[W + 1] = rg[1][1];
+            } else {
+                unsigned short *o = ob - odd;
+                if (px0) o[0] = (unsigned short) rg[0][0];
+                if (px1) o[1] = (unsigned short) rg[0][1];
+                if (px0 && py1) o[W] = (unsigned short) rg[1][0];
+                if (px1 && py1) o[W + 1] = (unsigned short) rg[1][1];
+            }
         }
     }
     if (PUSH) {

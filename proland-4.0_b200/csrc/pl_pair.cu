@@ -56,11 +56,12 @@ struct PairSmem {
  * 663 quad pairs of an elevation tile are 3 passes of 224 threads (97 % of the lanes busy) as they are 3 passes of 256 */
 template <bool FAST> struct PairThreads { static constexpr int N = FAST ? 224 : 256; };
 
-template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false, bool SLIM = false>
+template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false, bool SLIM = false, bool C4 = false>
 __global__ void __launch_bounds__(PairThreads<FAST>::N, SLIM ? 4 : 3)
 tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
 {
     static_assert(!SLIM || (FAST && !PUSH), "the slim layout serves the register form only");
+    static_assert(!C4 || (!FAST && !PUSH && !SLIM), "RGBA8 normals (fine + parent coarse normal): exact arithmetic, no push");
     using SM = PairSmem<TW, TG, SLIM>;
     constexpr int kPairThreads = PairThreads<FAST>::N;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -104,14 +105,14 @@ tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs 
         plnorm::normal_tile_reg<TW - 4, SPHERE, LINEAR, kPairThreads>(zs, work, rowtab, ulut, nrq, out, tid);
         return;
     }
-    if (!SLIM) plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH, FAST>(zs, work, ulut, nrq, out, tid, &na, rowtab);
+    if (!SLIM) plnorm::normal_tile<TW - 4, SPHERE, LINEAR, kPairThreads, PUSH, FAST, C4>(zs, work, ulut, nrq, out, tid, &na, rowtab);
 }
 
 template <int RESID>
 int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const plnorm::NormArgs &na, int n, bool all_reg = false)
 {
     using SM = PairSmem<101, 4>;
-    if (all_reg && na.fast && na.npeers == 0 && !ctx->no_slim && (!na.sphere || ctx->slim_sphere)) {
+    if (all_reg && na.fast && na.npeers == 0 && na.channels != 4 && !ctx->no_slim && (!na.sphere || ctx->slim_sphere)) {
         /* every tile of the launch qualifies for the register form (the caller checked): the slim layout, 4 CTAs per SM.
          * Flat scenes gain 6.6 % (0.583 -> 0.547 ms per 16 384 pairs); on the sphere the 72-register budget of 4 CTAs
          * spills (40 bytes of stack) and the time does not move (0.757 ms either way): spheres keep the 3-CTA layout
@@ -131,9 +132,15 @@ int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const pl
     void (*kern)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
         na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true> : tile_pair_kernel<101, 4, RESID, true, false>)
                   : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true> : tile_pair_kernel<101, 4, RESID, false, false>);
-    if (na.fast && na.npeers == 0)
+    if (na.fast && na.npeers == 0 && na.channels != 4)
         kern = na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true, false, true> : tile_pair_kernel<101, 4, RESID, true, false, false, true>)
                          : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true, false, true> : tile_pair_kernel<101, 4, RESID, false, false, false, true>);
+    if (na.channels == 4) {
+        /* RGBA8 normal storage: fine normal + the parent's coarse normal (normalShader.glsl:100-114); exact arithmetic */
+        if (na.npeers > 0) return pl_set_error(PL_ERR_ARG, "pushing tiles to peers is built for RG8 normal pools");
+        kern = na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true, false, false, false, true> : tile_pair_kernel<101, 4, RESID, true, false, false, false, false, true>)
+                         : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true, false, false, false, true> : tile_pair_kernel<101, 4, RESID, false, false, false, false, false, true>);
+    }
     if (na.npeers > 0) {
         /* finished normal tiles also go to the peer GPUs (fractal scenes: the variants without residuals) */
         if (RESID != 0) return pl_set_error(PL_ERR_ARG, "pushing tiles to peers is built for scenes without residuals");
@@ -142,7 +149,7 @@ int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const pl
     }
     PL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SM::BYTES));
     pl_timing_begin(ctx, PL_K_PAIR, n);
-    const int threads = na.fast && na.npeers == 0 ? PairThreads<true>::N : PairThreads<false>::N;
+    const int threads = na.fast && na.npeers == 0 && na.channels != 4 ? PairThreads<true>::N : PairThreads<false>::N;
     kern<<<n, threads, SM::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
     pl_timing_end(ctx);
     PL_CUDA(cudaGetLastError());
@@ -157,7 +164,7 @@ bool pl_pair_supported(const pl_ctx *ctx, const pl_elev_scene *esc, const pl_nor
                        const pl_pool *norm)
 {
     return !ctx->force_generic && !ctx->no_fuse && elev->tile_w == 101 && esc->grid == 4 && norm->tile_w == 97 &&
-           nsc->elev_border == 2 && norm->kind == PL_POOL_NORM_UN8x2;
+           nsc->elev_border == 2 && (norm->kind == PL_POOL_NORM_UN8x2 || norm->kind == PL_POOL_NORM_UN8x4);
 }
 
 /* n tile pairs: normal request i must describe the normal tile of elevation request i

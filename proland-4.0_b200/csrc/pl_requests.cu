@@ -32,6 +32,7 @@ struct GenArgs {
     int level, n;
     unsigned long long morton0, parent_morton0;
     int out_slot0, parent_slot0;
+    int norm4;              /* RGBA8 normal pool: the normal request names the parent's normal tile (same slot numbering) */
 };
 
 __host__ __device__ __forceinline__ void gen_one(const GenArgs &g, int i)
@@ -49,6 +50,7 @@ __host__ __device__ __forceinline__ void gen_one(const GenArgs &g, int i)
         norm_fill_req(g.sphere, (double) g.root_quad_size, g.level, tx, ty, &q);
         q.out_slot = g.out_slot0 + i;
         q.elev_slot = g.out_slot0 + i;
+        if (g.norm4) q.parent_slot = e.parent_slot;      /* normalOSL: the parent's normal tile sits in the parent's slot */
         g.nreq[i] = q;
     }
 }
@@ -123,6 +125,7 @@ void fill_gen_args(GenArgs &g, const pl_sweep_scene *sc, int level, uint64_t mor
     g.parent_morton0 = parent_morton0;
     g.out_slot0 = out_slot0;
     g.parent_slot0 = parent_slot0;
+    g.norm4 = 0;
 }
 
 }  // namespace
@@ -143,6 +146,7 @@ extern "C" int pl_produce_range(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool *
     g.ereq = ctx->gen_ereq;
     g.nreq = norm ? ctx->gen_nreq : nullptr;
     fill_gen_args(g, sc, level, morton0, n, out_slot0, parent_slot0, parent_morton0);
+    g.norm4 = norm && norm->kind == PL_POOL_NORM_UN8x4;
     pl_timing_begin(ctx, PL_K_GENREQ, n);
     gen_requests_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(g);
     pl_timing_end(ctx);
@@ -318,7 +322,9 @@ extern "C" int pl_produce_levels(pl_ctx *ctx, const pl_sweep_scene *sc, pl_pool 
         for (int q = 0; q < r; ++q)
             if (ranges[r].out_slot0 < ranges[q].out_slot0 + ranges[q].n && ranges[q].out_slot0 < ranges[r].out_slot0 + ranges[r].n)
                 return pl_set_error(PL_ERR_ARG, "ranges %d and %d share output slots", q, r);
-    if (!pl_pair_supported(ctx, &sc->elev, &sc->norm, elev, norm))
+    /* RGBA8 normals read the PARENT's normal tile, which a parent of the same launch publishes too late (the ready flag goes
+     * up behind its elevation planes): level by level only */
+    if (!pl_pair_supported(ctx, &sc->elev, &sc->norm, elev, norm) || norm->kind != PL_POOL_NORM_UN8x2)
         return pl_set_error(PL_ERR_ARG, "pl_produce_levels needs the shipped geometry (101 / 97, grid 4, RG8): use pl_produce_range");
     const int n = (int) total;
     PL_CUDA(cudaSetDevice(ctx->device));

@@ -479,10 +479,13 @@ def test_elevation_with_residuals(plb, ctx, oracle, kind, fused):
                 ctx.elevation_batch(es, elev, bad, resid=rpool)
 
 
+@pytest.mark.parametrize("path", ["two passes", "fused", "produce_range"])
 @pytest.mark.parametrize("sphere,parent_filter", [(0, 1), (1, 1), (1, 0)])
-def test_rgba8_normals_with_parent_coarse_normal(plb, ctx, oracle, sphere, parent_filter):
+def test_rgba8_normals_with_parent_coarse_normal(plb, ctx, oracle, sphere, parent_filter, path):
     """4-channel normal storages (tileSDF.z = 1, normalShader.glsl:100-119): .zw = the parent
-    tile's normal at the coarse mesh vertices, rotated by parentToTangentFrame on a sphere."""
+    tile's normal at the coarse mesh vertices, rotated by parentToTangentFrame on a sphere.  Through the runtime-geometry
+    normal kernel (two passes), the fused elevation + normal kernel (pl_pair_batch: its RGBA8 variant) and
+    pl_produce_range (device-generated requests naming the parent's normal tile)."""
     W, rq = 101, 12720000.0 if sphere else 100000.0
     amp = PLANET if sphere else FRACTAL
     tiles = [t for l in range(3) for t in qt.level_tiles(l)]
@@ -500,9 +503,20 @@ def test_rgba8_normals_with_parent_coarse_normal(plb, ctx, oracle, sphere, paren
             reqs["out_slot"][i] = nreqs["out_slot"][i] = nreqs["elev_slot"][i] = slot[t]
             if level > 0:
                 reqs["parent_slot"][i] = nreqs["parent_slot"][i] = slot[(level - 1, t[1] // 2, t[2] // 2)]
-        ctx.elevation_batch(es, elev, reqs)
-        ctx.normal_batch(ns, norm, elev, nreqs)
+        if path == "two passes":
+            ctx.elevation_batch(es, elev, reqs)
+            ctx.normal_batch(ns, norm, elev, nreqs)
+        elif path == "fused":
+            ctx.pair_batch(es, ns, elev, norm, reqs, nreqs)
+        else:     # slots of qt.level_tiles are row-major per level; produce_range numbers them in Morton order
+            sc = plb.sweep_scene(noise_amp=amp, face=3 if sphere else 0, root_quad_size=rq, sphere=sphere, want_stats=0)
+            sc.norm.parent_filter = parent_filter
+            off = [0, 1, 5]
+            ctx.produce_range(sc, elev, norm, level, 0, 4 ** level, off[level], off[level - 1] if level else 0, 0)
     ctx.sync()
+    if path == "produce_range":
+        off = [0, 1, 5]
+        slot = {(l, tx, ty): off[l] + plb.morton_encode(tx, ty) for (l, tx, ty) in tiles}
     ref = {}
     for t in tiles:
         level, tx, ty = t
