@@ -1,7 +1,9 @@
 """Feasibility probe for the multicast push: N processes, one per GPU of one box, share ONE NVLink multicast
 object through a POSIX file descriptor passed over a pipe (SCM_RIGHTS); every process binds its own VMM allocation to it;
 process 0 stores through the multicast mapping (mc_store.cubin: multimem.st = STG to the multicast address) and every
-process finds the words in its own memory.   python tools/microbench/mc_push_probe.py [N]"""
+process finds the words in its own memory.
+    nvcc -gencode arch=compute_100a,code=sm_100a -cubin -o tools/microbench/mc_store.cubin tools/microbench/mc_store.cu
+    python tools/microbench/mc_push_probe.py [N]"""
 import multiprocessing as mp
 import multiprocessing.reduction as red
 import os
