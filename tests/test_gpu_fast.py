@@ -79,13 +79,15 @@ def test_fast_sweep_levels_0_5(plb, ctx, oracle, fused):
     _check(len(ref), worst, bad, nbytes, sbad)
 
 
-@pytest.mark.parametrize("sphere", [0, 1])
-def test_slim_layout_is_byte_identical_to_the_regular_one(plb, ctx, sphere):
+@pytest.mark.parametrize("sphere,level", [(0, 8), (1, 8), (1, 7), (1, 6)])
+def test_slim_layout_is_byte_identical_to_the_regular_one(plb, ctx, sphere, level):
     """launches whose tiles all take the register form run the fused kernel in its slim layout (no second window copy, no
     position planes: 4 CTAs per SM; by default on flat scenes, forced here on spheres too): the same elevation planes,
     statistics and normal bytes as the regular layout, on a whole level with slope noise, through produce_range, the
-    identity entry point and host-built requests"""
-    level, n = 8, 1024
+    identity entry point and host-built requests.  Planet level 7 is the first whose quads are R/64 wide (smoothstep factor
+    exactly 1: the host's per-launch criterion says "register form"), level 6 the last that is not (the slim layout must
+    not be chosen: both runs take the regular one)"""
+    n = 1024
     kw = dict(noise_amp=gc.PLANET, face=3, root_quad_size=12720000.0, sphere=1) if sphere else \
         dict(noise_amp=gc.FRACTAL + [2, 1, 1], face=0, root_quad_size=100000.0, sphere=0)
     sc = plb.sweep_scene(want_stats=1, arith=plb.ARITH_FAST, **kw)
