@@ -245,34 +245,41 @@ def config4(pl, ctx, torch, stream, peak, peak_kind, ds=(6, 8, 10)):
         plan = sweep.SubtreeSweep(14 - d, (1 << (14 - d)) // 3, (1 << (14 - d)) // 5, d, 7)
         pools = (ctx.pool(pl.POOL_ELEV, 101, plan.capacity), ctx.pool(pl.POOL_NORM2, 97, plan.capacity))
         rec = {}
-        for levels, key in ((False, "launch_per_level"), (True, "launch_per_subtree")):
-            ss.run_sweep(pl, ctx, d, pools=pools, levels=levels)      # warm-up
-            ctx.sync()
-            e0, e1 = _events(torch, stream)
-            ctx.timing_collect()
-            ctx.timing_enable(True)
-            l0 = ctx.launches
-            reps = 5 if d <= 8 else 2
-            e0.record(stream)
-            for _ in range(reps):
-                n, fp, _ = ss.run_sweep(pl, ctx, d, pools=pools, levels=levels)
-            e1.record(stream)
-            torch.cuda.synchronize()
-            kt = ctx.timing_collect()
-            ctx.timing_enable(False)
-            ms = e0.elapsed_time(e1) / reps
-            pair_ms, launches, tiles = kt["pair"]
-            gbs = bench.PAIR_BYTES * tiles / (pair_ms * 1e-3) / 1e9
-            rec[key] = {"pairs_per_s": n / (ms * 1e-3), "ms": ms, "launches": int((ctx.launches - l0) // reps),
-                        "roofline": {"bound": "hbm", "kernel": "pair", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                                     "frac": gbs / peak, "bytes_per_pair": bench.PAIR_BYTES, "peak_kind": peak_kind,
-                                     "share_of_sweep": pair_ms / reps / ms, "traffic_per_pair": bench.TRAFFIC.get("pair_flat")},
-                        "fingerprint_xor": fp["xor"]}
-        rec["workload"] = ("all level-14 descendants of one level-%d tile (+ ancestors): %d pairs, flat face 0, PL_ARITH_EXACT; "
+        for arith, aname in ((pl.ARITH_FAST, "fast"), (pl.ARITH_EXACT, "exact")):
+            sub = {}
+            for levels, key in ((False, "launch_per_level"), (True, "launch_per_subtree")):
+                kw = dict(scene_kw=dict(arith=arith))
+                ss.run_sweep(pl, ctx, d, pools=pools, levels=levels, **kw)      # warm-up
+                ctx.sync()
+                e0, e1 = _events(torch, stream)
+                ctx.timing_collect()
+                ctx.timing_enable(True)
+                l0 = ctx.launches
+                reps = 5 if d <= 8 else 2
+                e0.record(stream)
+                for _ in range(reps):
+                    n, fp, _ = ss.run_sweep(pl, ctx, d, pools=pools, levels=levels, **kw)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                kt = ctx.timing_collect()
+                ctx.timing_enable(False)
+                ms = e0.elapsed_time(e1) / reps
+                pair_ms, launches, tiles = kt["pair"]
+                gbs = bench.PAIR_BYTES * tiles / (pair_ms * 1e-3) / 1e9
+                sub[key] = {"pairs_per_s": n / (ms * 1e-3), "ms": ms, "launches": int((ctx.launches - l0) // reps),
+                            "roofline": {"bound": "hbm", "kernel": "pair", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                         "frac": gbs / peak, "bytes_per_pair": bench.PAIR_BYTES, "peak_kind": peak_kind,
+                                         "share_of_sweep": pair_ms / reps / ms, "traffic_per_pair": None},
+                            "fingerprint_xor": fp["xor"]}
+            sub["identical"] = bool(sub["launch_per_level"]["fingerprint_xor"] == sub["launch_per_subtree"]["fingerprint_xor"])
+            rec[aname] = sub
+        # the elevation statistics are bit-exact under both contracts: one fingerprint
+        rec["identical"] = bool(rec["fast"]["identical"] and rec["exact"]["identical"] and
+                                rec["fast"]["launch_per_level"]["fingerprint_xor"] == rec["exact"]["launch_per_level"]["fingerprint_xor"])
+        rec["workload"] = ("all level-14 descendants of one level-%d tile (+ ancestors): %d pairs, flat face 0, both arithmetic contracts; "
                            "launch_per_level = one pl_produce_range per level, launch_per_subtree = pl_produce_levels (the chain / a "
                            "unit in one launch, parent -> child dependency resolved inside the kernel)" % (14 - d, n))
         rec["pairs"] = n
-        rec["identical"] = bool(rec["launch_per_level"]["fingerprint_xor"] == rec["launch_per_subtree"]["fingerprint_xor"])
         out["d%d" % d] = rec
         pools[0].close()
         pools[1].close()
