@@ -153,8 +153,60 @@ def config3(pl, ctx, torch, stream, peak, peak_kind, n_decode=32768, level=8):
         out["planet_sweep"] = config3_sweep(pl, ctx, torch, stream, peak, peak_kind, store, offs64, sizes64)
     except Exception as ex:
         out["planet_sweep"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    try:
+        out["every_tile_with_residuals_level9"] = config3_every_tile_large(pl, ctx, torch, stream, peak, peak_kind, store, offs64, sizes64)
+    except Exception as ex:
+        out["every_tile_with_residuals_level9"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
     store.close()
     return out
+
+
+def config3_every_tile_large(pl, ctx, torch, stream, peak, peak_kind, store, offs64, sizes64, level=9, reps=2):
+    """The worst case at a batch size the two-kernel decoder is built for: EVERY tile of one level-`level` batch of a sphere face
+    reads a residual window (one 197 x 197 int16 tile per 2 x 2 elevation tiles), its residual tiles decoded inside the timed
+    region, int16 pool, PL_ARITH_FAST."""
+    off = [sum(4 ** k for k in range(l)) for l in range(level + 2)]
+    n = 4 ** level
+    nres = n // 4
+    elev = ctx.pool(pl.POOL_ELEV, 101, off[level + 1])
+    norm = ctx.pool(pl.POOL_NORM2, 97, off[level + 1])
+    rpool = ctx.pool(pl.POOL_RESID_I16, 197, nres)
+    sc = pl.sweep_scene(noise_amp=SRTM_AMP, face=2, root_quad_size=PLANET_SIZE, sphere=1, flip=1,
+                        elev_filter=pl.FILTER_NEAREST, want_stats=1, arith=pl.ARITH_FAST)
+    sc.elev.resid_scale = 1.0
+    for l in range(level):      # ancestors: fractal only
+        ctx.produce_range(sc, elev, norm, l, 0, 4 ** l, off[l], off[l - 1] if l else 0, 0)
+    ids = pl.make_tile_ids_range(level, 0, n, off[level], off[level - 1], 0)
+    ids["resid_slot"] = (ids["tx"] // 2) + (ids["ty"] // 2) * (1 << (level - 1))
+    ridx = np.arange(nres) % len(sizes64)
+    dargs = (rpool, store, offs64[ridx], sizes64[ridx], [197] * nres, np.arange(nres, dtype=np.int32))
+    ctx.residual_decode_stored(*dargs)
+    ctx.pair_batch_ids(sc, elev, norm, ids, resid=rpool)
+    ctx.sync()
+    e0, e1 = _events(torch, stream)
+    ctx.timing_collect()
+    ctx.timing_enable(True)
+    e0.record(stream)
+    for _ in range(reps):
+        ctx.residual_decode_stored(*dargs)
+        ctx.pair_batch_ids(sc, elev, norm, ids, resid=rpool)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    kt = ctx.timing_collect()
+    ctx.timing_enable(False)
+    tot = e0.elapsed_time(e1) / reps
+    pair_ms, dec_ms = kt["pair"][0] / reps, kt["residual"][0] / reps
+    gbs = RESID_PAIR_BYTES["int16"] * n / (pair_ms * 1e-3) / 1e9
+    rec = {"workload": "every one of the %d level-%d tiles of a sphere face reads a residual window; its %d residual tiles (197 x 197 "
+                       "int16, zlib 6) decoded inside the timed region by the two-kernel decoder" % (n, level, nres),
+           "pairs": n, "pairs_per_s": n / (tot * 1e-3), "ms": tot, "residual_tiles": nres, "decode_kernel_ms": dec_ms,
+           "pair_kernel_ms": pair_ms, "decode_tiles_per_s": nres / (dec_ms * 1e-3), "fraction_of_kernel_only": pair_ms / tot,
+           "roofline": {"bound": "hbm", "kernel": "pair (residual variant)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                        "frac": gbs / peak, "bytes_per_pair": RESID_PAIR_BYTES["int16"], "peak_kind": peak_kind, "traffic": None}}
+    rpool.close()
+    norm.close()
+    elev.close()
+    return rec
 
 
 def config3_sweep(pl, ctx, torch, stream, peak, peak_kind, store, offs64, sizes64, max_level=10, resid_levels=6, reps=2):
