@@ -100,6 +100,8 @@ void *pl_pool_device_ptr(pl_pool *pool);
  * interleaved bytes for normals; dense floats / int16 for residuals. */
 int pl_pool_download(pl_pool *pool, int slot, void *host, size_t bytes);
 int pl_pool_upload(pl_pool *pool, int slot, const void *host, size_t bytes);
+/* n consecutive slots, same layout per tile, one device-to-host copy (bytes = n * pl_pool_tile_bytes) */
+int pl_pool_download_range(pl_pool *pool, int slot0, int n, void *host, size_t bytes);
 
 /* Peers: the copies of a pool on the other GPUs of one box (one process per GPU).  pl_pool_export gives the
  * PL_IPC_HANDLE_BYTES-byte CUDA IPC handle of the pool's memory; after the processes have exchanged them (any

@@ -608,6 +608,50 @@ extern "C" int pl_pool_download(pl_pool *p, int slot, void *host, size_t bytes)
     return PL_OK;
 }
 
+/* n consecutive slots in ONE device-to-host copy, then the reference layout per tile on the host (threads): the bulk form of
+ * pl_pool_download for callers that read whole levels back (the residual builder) */
+extern "C" int pl_pool_download_range(pl_pool *p, int slot0, int n, void *host, size_t bytes)
+{
+    if (!p || n < 0) return pl_set_error(PL_ERR_ARG, "bad argument");
+    if (n == 0) return PL_OK;
+    if (!host) return pl_set_error(PL_ERR_ARG, "host is NULL");
+    if (slot0 < 0 || (long long) slot0 + n > p->capacity) return pl_set_error(PL_ERR_ARG, "slots [%d, %d) out of range", slot0, slot0 + n);
+    if (bytes != p->tile_bytes * (size_t) n) return pl_set_error(PL_ERR_ARG, "buffer of %zu bytes, %d tiles of %zu bytes expected", bytes, n, p->tile_bytes);
+    PL_CUDA(cudaSetDevice(p->ctx->device));
+    std::vector<uint8_t> stage(p->slot_bytes * (size_t) n);
+    PL_CUDA(cudaMemcpyAsync(stage.data(), p->base + (size_t) slot0 * p->slot_bytes, stage.size(), cudaMemcpyDeviceToHost, p->ctx->stream));
+    PL_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    const int W = p->tile_w;
+    uint8_t *out = static_cast<uint8_t *>(host);
+    parallel_chunks(n, 8, [&](int lo, int hi) {
+        for (int t = lo; t < hi; ++t) {
+            const uint8_t *src = stage.data() + (size_t) t * p->slot_bytes;
+            uint8_t *dst = out + (size_t) t * p->tile_bytes;
+            switch (p->kind) {
+            case PL_POOL_ELEV_F32x3: {
+                const float *planes = reinterpret_cast<const float *>(src);
+                float *o = reinterpret_cast<float *>(dst);
+                for (int y = 0; y < W; ++y)
+                    for (int x = 0; x < W; ++x)
+                        for (int c = 0; c < 3; ++c)
+                            o[(size_t) (x + y * W) * 3 + c] = planes[c * p->plane_elems + (size_t) y * p->pitch + x];
+                break;
+            }
+            case PL_POOL_RESID_F32:
+            case PL_POOL_RESID_I16: {
+                const size_t eb = p->kind == PL_POOL_RESID_F32 ? 4 : 2;
+                for (int y = 0; y < W; ++y) memcpy(dst + (size_t) y * W * eb, src + (size_t) y * p->pitch * eb, W * eb);
+                break;
+            }
+            default:
+                memcpy(dst, src, p->tile_bytes);
+                break;
+            }
+        }
+    });
+    return PL_OK;
+}
+
 extern "C" int pl_pool_upload(pl_pool *p, int slot, const void *host, size_t bytes)
 {
     int rc = check_slot(p, slot, bytes);

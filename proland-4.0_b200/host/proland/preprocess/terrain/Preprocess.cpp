@@ -4,6 +4,9 @@
 #include <cerrno>
 #include <cstdint>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include <fcntl.h>
@@ -47,6 +50,19 @@ vec4f InputMap::get(int x, int y)
 
 namespace
 {
+
+/* PLH_PREPROCESS_TIMING=1: where the builder's wall time goes, on stderr */
+struct Phase
+{
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    explicit Phase(const char *name) : name(name), t0(std::chrono::steady_clock::now()) {}
+    ~Phase()
+    {
+        static const bool on = getenv("PLH_PREPROCESS_TIMING") != NULL;
+        if (on) fprintf(stderr, "[preprocess] %-28s %8.1f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 bool fexists(const string &name)
 {
@@ -118,7 +134,7 @@ void generateFace(pl_ctx *ctx, pl_height_cube *cube, Pools &pools, int face, int
     const int nTilesTotal = minLevel + ((1 << (max(maxLevel - minLevel, 0) * 2 + 2)) - 1) / 3;
     vector<int16_t> tiles;
     vector<uint64_t> offsets((size_t) nTilesTotal + 1, 0);
-    vector<int16_t> slot((size_t) n * n);
+    vector<int16_t> level_tiles;      /* the residual tiles of a level, n x n each, read back in one copy */
     vector<pl_height_req> hreqs;
     vector<pl_resid_enc_req> ereqs;
     size_t tileId = 0;
@@ -153,16 +169,20 @@ void generateFace(pl_ctx *ctx, pl_height_cube *cube, Pools &pools, int face, int
         }
         DeviceContext::check(pl_residual_encode_batch(ctx, pools.heights, pools.approx, pools.resid, count, ereqs.data(), NULL, NULL));
         /* tiles in id order: levels below minLevel first, then row-major per level (ResidualProducer::getTileId) */
+        level_tiles.resize((size_t) count * n * n);
+        DeviceContext::check(pl_pool_download_range(pools.resid, 0, count, level_tiles.data(), sizeof(int16_t) * level_tiles.size()));
+        const int w = ts + 5;
+        tiles.reserve(tiles.size() + (size_t) count * w * w);
         for (int k = 0; k < count; ++k) {
-            DeviceContext::check(pl_pool_download(pools.resid, k, slot.data(), sizeof(int16_t) * slot.size()));
-            const int w = ts + 5;
+            const int16_t *slot = level_tiles.data() + (size_t) k * n * n;
             offsets[tileId] = tiles.size();
-            for (int j = 0; j < w; ++j) tiles.insert(tiles.end(), slot.begin() + (size_t) j * n, slot.begin() + (size_t) j * n + w);
+            for (int j = 0; j < w; ++j) tiles.insert(tiles.end(), slot + (size_t) j * n, slot + (size_t) j * n + w);
             ++tileId;
         }
     }
     offsets[tileId] = tiles.size();
     assert((int) tileId == nTilesTotal);
+    Phase pw("  of which: write the file");
     DeviceContext::check(pl_residual_write_file(file.c_str(), minLevel, maxLevel, tileSize, 0, 0, 0, scale, tiles.data(), offsets.data(), -1));
 }
 
@@ -173,13 +193,19 @@ void preprocess(InputMap *src, int dstMinTileSize, int dstTileSize, int dstMaxLe
     ptr<DeviceContext> dc = DeviceContext::get();
     dc->flush();
     pl_ctx *ctx = dc->handle();
-    const vector<float> map = readMap(src);
+    vector<float> map;
+    {
+        Phase ph("read the source map");
+        map = readMap(src);
+    }
     CubeHolder holder;
+    Phase *ph = new Phase("base level grids");
     if (nfaces == 6) {
         DeviceContext::check(pl_height_cube_from_latlon(ctx, dstSize, map.data(), src->width, src->height, &holder.cube));
     } else {
         DeviceContext::check(pl_height_cube_from_plane(ctx, dstSize, map.data(), src->width, src->height, &holder.cube));
     }
+    delete ph;
     const int last = (dstSize / dstTileSize) * (dstSize / dstTileSize);
     Pools pools;
     DeviceContext::check(pl_pool_create(ctx, PL_POOL_RESID_F32, dstTileSize + 5, last, &pools.heights));
@@ -189,6 +215,7 @@ void preprocess(InputMap *src, int dstMinTileSize, int dstTileSize, int dstMaxLe
         string file = dstFolder + "/DEM";
         if (nfaces == 6) file += char('1' + f);
         file += ".dat";
+        Phase pf("one face: tiles + file");
         generateFace(ctx, holder.cube, pools, f, dstMinTileSize, dstSize, dstTileSize, residualScale, file);
     }
     DeviceContext::check(pl_sync(ctx));

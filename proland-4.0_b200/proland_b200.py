@@ -25,7 +25,7 @@ EXPORTS = [
     "pl_ctx_stream", "pl_sync", "pl_ctx_launch_count", "pl_device_sm_count", "pl_timing_enable",
     "pl_timing_collect", "pl_pool_create",
     "pl_pool_destroy", "pl_pool_capacity", "pl_pool_tile_w", "pl_pool_tile_bytes",
-    "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload",
+    "pl_pool_slot_bytes", "pl_pool_device_ptr", "pl_pool_download", "pl_pool_upload", "pl_pool_download_range",
     "pl_pool_export", "pl_pool_attach_peers", "pl_pool_push_to_peers",
     "pl_pool_create_shared", "pl_pool_mc_create", "pl_pool_mc_import", "pl_pool_mc_add_device", "pl_pool_mc_bind",
     "pl_noise_init", "pl_noise_select", "pl_cnoise2", "pl_elev_make_req", "pl_elevation_batch",
@@ -157,6 +157,7 @@ def lib():
         L.pl_pool_mc_add_device.argtypes = [C.c_void_p]
         L.pl_pool_mc_bind.argtypes = [C.c_void_p]
         L.pl_pool_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.pl_pool_download_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.pl_pool_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
         L.pl_noise_init.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.pl_noise_select.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
@@ -400,6 +401,13 @@ class Pool:
         shape, dt = self._shape_dtype()
         out = np.empty(shape, dt)
         check(lib().pl_pool_download(self.h, slot, _ptr(out), out.nbytes))
+        return out
+
+    def download_range(self, slot0, n):
+        """n consecutive slots in one copy (pl_pool_download_range) -> (n,) + the tile shape"""
+        shape, dt = self._shape_dtype()
+        out = np.empty((n,) + shape, dt)
+        check(lib().pl_pool_download_range(self.h, slot0, n, _ptr(out), out.nbytes))
         return out
 
     def upload(self, slot, arr):

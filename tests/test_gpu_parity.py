@@ -67,6 +67,20 @@ def test_noise_tables_are_kept_per_tile_width(plb, ctx, oracle):
     assert _run(plb, ctx, oracle, 2, noise_amp=FRACTAL) == 21          # still served from the 101-wide table
 
 
+def test_pool_download_range_equals_per_slot_downloads(plb, ctx):
+    rng = np.random.default_rng(5)
+    for kind, w in ((plb.POOL_RESID_I16, 197), (plb.POOL_RESID_F32, 101), (plb.POOL_NORM2, 97), (plb.POOL_ELEV, 101)):
+        pool = ctx.pool(kind, w, 7)
+        shape, dt = pool._shape_dtype()
+        for s in range(7):
+            pool.upload(s, (rng.random(shape) * 200 - 50).astype(dt))
+        got = pool.download_range(2, 4)
+        for k in range(4):
+            assert np.array_equal(got[k], pool.download(2 + k)), (kind, k)
+        with pytest.raises(plb.PlError):
+            pool.download_range(5, 3)
+
+
 def test_generic_geometry_kernels(plb, ctx, oracle):
     """the runtime-geometry kernels (used for tile sizes other than 101/97) on the same case"""
     ctx.force_generic(True)
