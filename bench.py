@@ -176,17 +176,52 @@ class PlanetSweep:
 
 # -------------------------------------------------------------- CPU baseline
 
-def cpu_sample(max_level, face=1, nthreads=0):
-    """The oracle (CPU restatement of the reference's GLSL path, OpenMP over the
-    tiles of a level) on one face of the same planet, levels 0..max_level."""
+def cpu_sample(max_level, face=1, nthreads=0, engine="port"):
+    """One face of the same planet, levels 0..max_level, on the host cores (OpenMP over the tiles of a level).
+    engine "port": the oracle (CPU restatement of the reference's GLSL path); "reference": the reference's OWN shader text
+    compiled unchanged as C++ (oracle/_ref/libref_glsl.so; per-tile uniforms from the oracle: the reference's host code
+    needs Ork) -- None when oracle/_ref is not there."""
     import orc
     orc.build()
     scene = orc.make_scene(W=101, gridMeshSize=24, rootQuadSize=PLANET_SIZE, face=face, flip=0,
                            noise_mode=1, no_clamp=0, noiseAmp=PLANET_AMP, sphere=1, elev_filter=1)
     t0 = time.perf_counter()
-    n, checksum, lo, hi = orc.produce_quadtree(scene, max_level, nthreads)
+    r = orc.produce_quadtree(scene, max_level, nthreads) if engine == "port" else orc.glsl_produce_quadtree(scene, max_level, nthreads)
+    if r is None:
+        return None
+    n, checksum, lo, hi = r
     dt = time.perf_counter() - t0
     return n, dt, (checksum, lo, hi)
+
+
+def cpu_arm(nthreads, steps=1, warmup=0):
+    """the CPU arm of the bench: the oracle port on one face, levels 0..7 per step -> (pairs, seconds, kind, sample text).
+    The port is the FASTER of the two CPU implementations of the path this repo can run (see glsl_reference_sample): the
+    conservative denominator for a speed-up."""
+    level = 7
+    for _ in range(min(warmup, 1)):
+        cpu_sample(5, nthreads=nthreads)
+    t_total, n_total = 0.0, 0
+    for _ in range(max(steps, 1)):
+        n, dt, _ = cpu_sample(level, nthreads=nthreads)
+        t_total += dt
+        n_total += n
+    sample = "face 1 of the planet, levels 0..%d (%d pairs) per step, the oracle port, %d OpenMP threads" % (level, n_total // max(steps, 1), nthreads)
+    return n_total, t_total, "port", sample
+
+
+def glsl_reference_sample(nthreads, level=5):
+    """the reference's OWN shader text (upsampleShader.glsl, normalShader.glsl compiled unchanged as C++ behind the shim:
+    oracle/_ref/libref_glsl.so) on a smaller sample of the same workload -- reported beside the port, not used as the
+    denominator: the shim's vector classes and texture emulation make it ~10 x slower than the port, which says more about the
+    shim than about the reference.  None when oracle/_ref is not there."""
+    r = cpu_sample(level, nthreads=nthreads, engine="reference")
+    if r is None:
+        return None
+    n, dt, _ = r
+    return {"value": n / dt, "unit": "pairs/s", "cores": nthreads, "kind": "reference",
+            "sample": "face 1 of the planet, levels 0..%d (%d pairs), the reference's own upsampleShader.glsl / normalShader.glsl "
+                      "compiled unchanged as C++ (oracle/_ref/libref_glsl.so), uniforms from the oracle, %d OpenMP threads" % (level, n, nthreads)}
 
 
 def gpu_fingerprint(pl, ctx, max_level, face=1):
@@ -258,32 +293,25 @@ def host_cores():
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's algorithm for the path on the box's host cores (the oracle port, OpenMP over
-    the tiles of a level).  One step = face 1 of the same planet, levels 0..7: 21 845 pairs, 98 % of them in levels
-    5..7 (1 024 / 4 096 / 16 384 independent tiles per level: saturates any core count up to a few hundred)."""
+    """--impl reference: the reference's algorithm for the path on the box's host cores, all of them (the oracle port, OpenMP
+    over the tiles of a level).  One step = face 1 of the same planet, levels 0..7: 21 845 pairs, 98 % of them in levels
+    5..7 (1 024 / 4 096 / 16 384 independent tiles per level: saturates any core count up to a few hundred).  The line also
+    carries `reference_glsl`: the reference's own shader text compiled as C++, timed on a smaller sample."""
     if rank != 0:
         return
     cores = host_cores()
-    level = 7
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(5, nthreads=cores)
-    t_total, n_total = 0.0, 0
-    for _ in range(args.steps):
-        n, dt, _ = cpu_sample(level, nthreads=cores)
-        t_total += dt
-        n_total += n
+    n_total, t_total, kind, sample = cpu_arm(cores, args.steps, args.warmup)
     value = n_total / t_total
-    sample = ("face 1 of the planet, levels 0..%d (%d pairs) per step, %d OpenMP threads"
-              % (level, n_total // max(args.steps, 1), cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "demo-fractalplanet: 6 faces, levels 0..10, 8388606 pairs "
                                    "(bounded CPU sample per step)", "tile_w": 101, "normal_w": 97},
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind,
                              "sample": sample},
             "threads": cores, "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+            "reference_glsl": glsl_reference_sample(cores),
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -496,10 +524,10 @@ def main():
             line["gather"] = g
         if world == 1 and not args.no_cpu_baseline:
             n, dt, (csum, clo, chi) = cpu_sample(7)
-            line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": os.cpu_count(),
-                                    "kind": "port",
+            line["cpu_baseline"] = {"value": n / dt, "unit": "pairs/s", "cores": host_cores(), "kind": "port",
                                     "sample": "face 1 of the same planet, levels 0..7 (%d pairs), oracle "
-                                              "with OpenMP over the tiles of a level" % n}
+                                              "with OpenMP over the tiles of a level" % n,
+                                    "reference_glsl": glsl_reference_sample(host_cores())}
             # the oracle run doubles as the checker: same tiles on the GPU, same checksum of checksums
             gsum, glo, ghi = gpu_fingerprint(pl, ctx, 7)
             line["parity"] = {"tiles": n, "vs": "oracle (cpu_baseline sample)",

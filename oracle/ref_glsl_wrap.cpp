@@ -22,6 +22,10 @@
 #include <cstdint>
 #include <cstring>
 #include "../orc.h"
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "glsl_shim.h"
 
 namespace glsl {
@@ -305,6 +309,68 @@ int ref_glsl_ortho_tile(int variant, const orc_ortho_params *p, const uint8_t *p
     case 1: run_ortho_ex(a); return 0;
     }
     return -1;
+}
+
+/* The quadtree of a scene, produced by the reference's own shader text: per tile the uniforms of ElevationProducer /
+ * NormalProducer::doCreateTile (the restatement's: orc_elev_uniforms / orc_normal_uniforms, liborc.so -- the reference's
+ * host code needs Ork), then upsampleShader.glsl (demo variant: slope noise, clamp or NO_CLAMP) and normalShader.glsl (demo)
+ * over every fragment, then the RG8 packing.  Tiles of a level in parallel (OpenMP; the shader globals are thread_local).
+ * The same signature and results layout as orc_produce_quadtree: bench.py's `--impl reference` arm and cpu_baseline run
+ * this when oracle/_ref exists (kind "reference"); scenes without residuals. */
+long ref_glsl_produce_quadtree(const orc_scene *s, int maxLevel, int nthreads, double *checksum, float *zmin, float *zmax)
+{
+    const int W = s->W, NW = W - 4;
+    const size_t esz = (size_t) W * W * 3;
+    if (s->resid != NULL || s->noise_mode != 1) return -1;        /* the demo variant: slope-modulated noise */
+    std::vector<float> noise((size_t) 6 * W * W);
+    orc_dem_noise_r16f(W, noise.data());
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    std::vector<float> prev, cur;
+    long produced = 0;
+    double sum = 0.0;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int level = 0; level <= maxLevel; ++level) {
+        const long n = 1L << level, count = n * n;
+        cur.assign(esz * (size_t) count, 0.0f);
+        double lsum = 0.0;
+        float llo = INFINITY, lhi = -INFINITY;
+#pragma omp parallel
+        {
+            std::vector<float> data((size_t) NW * NW * 4);
+            std::vector<uint8_t> norm((size_t) NW * NW * 2);
+#pragma omp for schedule(dynamic, 4) reduction(+ : lsum) reduction(min : llo) reduction(max : lhi)
+            for (long t = 0; t < count; ++t) {
+                const int tx = (int) (t % n), ty = (int) (t / n);
+                const float *parent = level > 0 ? prev.data() + esz * ((size_t) (tx / 2) + (size_t) (ty / 2) * (n / 2)) : NULL;
+                float *e = cur.data() + esz * (size_t) t;
+                orc_elev_params ep;
+                orc_elev_uniforms(W, s->gridMeshSize, s->rootQuadSize, s->flip, s->noiseAmp, s->nAmp, s->face, level, tx, ty, 0, 0,
+                                  s->noise_mode, s->no_clamp, &ep);
+                ref_glsl_upsample_tile(s->no_clamp ? 4 : 3, &ep, parent, s->elev_filter, NULL, noise.data(), 8, e);
+                orc_norm_params np;
+                orc_normal_uniforms(NW, s->gridMeshSize, 2, 0, W, 2, s->elev_filter, ORC_FILTER_LINEAR, (double) s->rootQuadSize,
+                                    s->sphere, level, tx, ty, &np);
+                ref_glsl_normal_tile(2, &np, e, NULL, 8, data.data());
+                orc_pack_unorm8(NW, 2, data.data(), norm.data());
+                float a, b;
+                orc_tile_minmax(W, e, &a, &b);
+                lsum += (double) a + (double) b;
+                llo = fminf(llo, a);
+                lhi = fmaxf(lhi, b);
+            }
+        }
+        produced += count;
+        sum += lsum;
+        lo = fminf(lo, llo);
+        hi = fmaxf(hi, lhi);
+        prev.swap(cur);
+    }
+    if (checksum) *checksum = sum;
+    if (zmin) *zmin = lo;
+    if (zmax) *zmax = hi;
+    return produced;
 }
 
 } /* extern "C" */

@@ -471,6 +471,18 @@ def produce_quadtree(scene, max_level, nthreads=0):
     return n, cs.value, lo.value, hi.value
 
 
+def glsl_produce_quadtree(scene, max_level, nthreads=0):
+    """the same quadtree by the reference's own shader text (oracle/_ref/libref_glsl.so, ref_glsl_produce_quadtree);
+    None when oracle/_ref was not built"""
+    G = glsl()
+    if G is None or not hasattr(G, "ref_glsl_produce_quadtree"):
+        return None
+    G.ref_glsl_produce_quadtree.restype = C.c_long
+    cs, lo, hi = C.c_double(), C.c_float(), C.c_float()
+    n = G.ref_glsl_produce_quadtree(C.byref(scene), max_level, nthreads, C.byref(cs), C.byref(lo), C.byref(hi))
+    return (n, cs.value, lo.value, hi.value) if n > 0 else None
+
+
 # ---------------------------------------------------------------- ortho ----
 
 def _u8(a):

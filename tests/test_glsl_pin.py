@@ -112,3 +112,16 @@ def test_ortho_canonical_within_one_step_of_the_glsl(oracle):
         nbad += int(np.count_nonzero(d)); ntot += d.size
         parent = tc
     assert nbad < 1e-4 * ntot
+
+
+def test_glsl_quadtree_driver_agrees_with_the_port(oracle):
+    """bench.py's `reference_glsl` datum: a whole quadtree by the reference's shader text (ref_glsl_produce_quadtree, OpenMP)
+    against the oracle port's -- same tile count, per-tile (zmin + zmax) checksum within the contraction tolerance"""
+    if oracle.glsl() is None:
+        pytest.skip("oracle/_ref/libref_glsl.so not built (reference checkout absent)")
+    scene = oracle.make_scene(W=101, gridMeshSize=24, rootQuadSize=12720000.0, face=3, flip=0, noise_mode=1, no_clamp=0,
+                              noiseAmp=gc.PLANET, sphere=1, elev_filter=1)
+    n, cs, lo, hi = oracle.produce_quadtree(scene, 3, 2)
+    got = oracle.glsl_produce_quadtree(scene, 3, 2)
+    assert got is not None and got[0] == n == 85
+    assert abs(got[1] - cs) <= 1e-6 * abs(cs) and abs(got[2] - lo) <= 1e-5 * (hi - lo) and abs(got[3] - hi) <= 1e-5 * (hi - lo)
