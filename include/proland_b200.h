@@ -273,7 +273,9 @@ int pl_normal_batch_dev(pl_ctx *ctx, const pl_norm_scene *scene, pl_pool *norm, 
  * (TileProducer.cpp:199-217 -> ElevationProducer.cpp:280-405, NormalProducer.cpp:164-289).  Request i of
  * both arrays describes tile i: nreqs[i].elev_slot == ereqs[i].out_slot.  Results are bit-identical to
  * pl_elevation_batch followed by pl_normal_batch; geometries the fused kernel does not cover (tile
- * sizes other than 101/97, RGBA8 normals) run as those two passes. */
+ * sizes other than 101/97) run as those two passes.  RGBA8 normal pools (NORM_UN8x4: fine + the parent's coarse normal,
+ * normalShader.glsl:100-114) are served by the fused kernel in exact arithmetic: nreqs[i].parent_slot names the parent's
+ * NORMAL tile, which -- like the parent elevation tile -- must not be produced by the same launch. */
 int pl_pair_batch(pl_ctx *ctx, const pl_elev_scene *escene, const pl_norm_scene *nscene, pl_pool *elev,
                   pl_pool *norm, pl_pool *resid, int n, const pl_elev_req *ereqs, const pl_norm_req *nreqs);
 int pl_pair_batch_dev(pl_ctx *ctx, const pl_elev_scene *escene, const pl_norm_scene *nscene, pl_pool *elev,
