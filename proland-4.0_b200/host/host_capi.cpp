@@ -115,17 +115,6 @@ struct TestScene
 
 static Logger g_debug("DEBUG");
 
-/* an InputMap over a caller's float array (row 0 first), the way a user subclasses it (Preprocess.h:58-154) */
-class ArrayInputMap : public InputMap
-{
-public:
-    ArrayInputMap(const float *data, int w, int h, int tile) : InputMap(w, h, 1, tile), data(data) {}
-    virtual vec4f getValue(int x, int y) { return vec4f(data[(size_t) y * width + x], 0, 0, 0); }
-
-private:
-    const float *data;
-};
-
 }  // namespace
 
 extern "C" {
@@ -526,9 +515,7 @@ int plh_preprocess_dem(const float *src, int src_w, int src_h, int min_tile_size
                        float residual_scale, int spherical)
 {
     PLH_TRY
-    int tile = 256;
-    while (tile > 1 && (src_w % tile != 0 || src_h % tile != 0)) tile /= 2;
-    ArrayInputMap map(src, src_w, src_h, tile);
+    ArrayInputMap map(src, src_w, src_h);
     if (spherical) preprocessSphericalDem(&map, min_tile_size, tile_size, max_level, dst_folder, "", residual_scale);
     else preprocessDem(&map, min_tile_size, tile_size, max_level, dst_folder, "", residual_scale);
     return 0;

@@ -48,6 +48,33 @@ vec4f InputMap::get(int x, int y)
     return getValue(max(min(x, width - 1), 0), max(min(y, height - 1), 0));
 }
 
+int ArrayInputMap::tileFor(int width, int height)
+{
+    int tile = 256;
+    while (tile > 1 && (width % tile != 0 || height % tile != 0)) tile /= 2;
+    return tile;
+}
+
+ArrayInputMap::ArrayInputMap(const float *data, int width, int height) :
+    InputMap(width, height, 1, tileFor(width, height)), data(data)
+{
+}
+
+vec4f ArrayInputMap::getValue(int x, int y)
+{
+    return vec4f(data[(size_t) y * width + x], 0, 0, 0);
+}
+
+float *ArrayInputMap::getValues(int x, int y)
+{
+    /* rows of the array are rows of the tile: no per-pixel virtual call */
+    float *v = new float[(size_t) tileSize * tileSize];
+    for (int j = 0; j < tileSize; ++j) {
+        memcpy(v + (size_t) j * tileSize, data + (size_t) (y + j) * width + x, sizeof(float) * tileSize);
+    }
+    return v;
+}
+
 namespace
 {
 

@@ -42,6 +42,20 @@ public:
     vec4f get(int x, int y);
 };
 
+/* An InputMap over a float array the caller keeps alive (row 0 first, one channel): what the reference's preprocess examples
+ * subclass InputMap for.  Not in the reference; the tile size is the largest power of two <= 256 dividing both extents. */
+class ArrayInputMap : public InputMap
+{
+public:
+    ArrayInputMap(const float *data, int width, int height);
+    virtual vec4f getValue(int x, int y);
+    virtual float *getValues(int x, int y);
+
+private:
+    const float *data;
+    static int tileFor(int width, int height);
+};
+
 /* Preprocess.cpp:512-533 */
 PROLAND_API void preprocessDem(InputMap *src, int dstMinTileSize, int dstTileSize, int dstMaxLevel,
     const string &dstFolder, const string &tmpFolder, float residualScale);
