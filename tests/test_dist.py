@@ -77,3 +77,42 @@ def test_gather_partition_covers_every_level_once():
                 assert (c0, cn) == (4 * m0, 4 * n)
         for level in range(ls):
             assert all(gt.rank_range(level, r, world) == (0, 4 ** level) for r in range(world))
+
+
+def _fd_worker(rank, world, port, q):
+    import importlib.util
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec = importlib.util.spec_from_file_location("gather_tiles", os.path.join(ROOT, "tools", "gather_tiles.py"))
+    gt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gt)
+    # rank 0 owns a pipe; its write end travels to the other ranks as a file descriptor (what the multicast object's
+    # descriptor does, tools/gather_tiles.py::share_fd)
+    r_end, w_end = os.pipe() if rank == 0 else (-1, -1)
+    fd = gt.share_fd(dist, rank, world, w_end, "test")
+    os.write(fd, bytes([65 + rank]))
+    dist.barrier()
+    if rank == 0:
+        q.put(sorted(os.read(r_end, 16)))
+    dist.destroy_process_group()
+
+
+def test_share_fd_hands_a_descriptor_to_every_rank():
+    """the transport the multicast push leaves to its caller: SCM_RIGHTS over an abstract Unix socket between the ranks of a
+    box (world 3, gloo): every rank ends up with a descriptor of rank 0's pipe and can write into it"""
+    world = 3
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [65, 66, 67]
