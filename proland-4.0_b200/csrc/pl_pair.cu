@@ -47,7 +47,8 @@ struct PairSmem {
     static constexpr size_t BYTES = (size_t) (ZM + WORK + 2 * NG::ULUT + QTAB) * 4;
     static_assert(EG::PITCH == NG::EPITCH && EG::PLANE == NG::EPLANE, "both passes agree on the plane layout");
     static_assert((ZM * 4) % 128 == 0, "the TMA destination (first window) stays 128-byte aligned");
-    static_assert(ELEV - 64 >= plnorm::RGeo<TW - 4, 224>::TAB && QTAB >= 28, "row tables of the register form fit in front of the statistics");
+    static_assert(ELEV - 64 >= plnorm::RGeo<TW - 4, 224>::TAB && ELEV - 64 >= plnorm::RGeo<TW - 4, 192>::TAB && QTAB >= 28,
+                  "row tables of the register form fit in front of the statistics");
     static_assert(!SLIM || BYTES + 1280 <= 233472 / 4, "four CTAs per SM");
 };
 
@@ -56,14 +57,15 @@ struct PairSmem {
  * 663 quad pairs of an elevation tile are 3 passes of 224 threads (97 % of the lanes busy) as they are 3 passes of 256 */
 template <bool FAST> struct PairThreads { static constexpr int N = FAST ? 224 : 256; };
 
-template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false, bool SLIM = false, bool C4 = false>
-__global__ void __launch_bounds__(PairThreads<FAST>::N, SLIM ? 4 : 3)
+template <int TW, int TG, int RESID, bool SPHERE, bool LINEAR, bool PUSH = false, bool FAST = false, bool SLIM = false, bool C4 = false,
+          int NTHREADS = PairThreads<FAST>::N>
+__global__ void __launch_bounds__(NTHREADS, SLIM ? 4 : 3)
 tile_pair_kernel(const __grid_constant__ CUtensorMap tm, const plelev::ElevArgs ea, const plnorm::NormArgs na)
 {
     static_assert(!SLIM || (FAST && !PUSH), "the slim layout serves the register form only");
     static_assert(!C4 || (!FAST && !PUSH && !SLIM), "RGBA8 normals (fine + parent coarse normal): exact arithmetic, no push");
     using SM = PairSmem<TW, TG, SLIM>;
-    constexpr int kPairThreads = PairThreads<FAST>::N;
+    constexpr int kPairThreads = NTHREADS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *zs = reinterpret_cast<float *>(smem_raw) + SM::GUARD;   /* zm plane behind the guard floats */
     float *work = zs + plelev::Geo<TW, TG>::PLANE;
@@ -112,18 +114,19 @@ template <int RESID>
 int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const plnorm::NormArgs &na, int n, bool all_reg = false)
 {
     using SM = PairSmem<101, 4>;
-    if (all_reg && na.fast && na.npeers == 0 && na.channels != 4 && !ctx->no_slim && (!na.sphere || ctx->slim_sphere)) {
+    if (all_reg && na.fast && na.npeers == 0 && na.channels != 4 && !ctx->no_slim) {
         /* every tile of the launch qualifies for the register form (the caller checked): the slim layout, 4 CTAs per SM.
-         * Flat scenes gain 6.6 % (0.583 -> 0.547 ms per 16 384 pairs); on the sphere the 72-register budget of 4 CTAs
-         * spills (40 bytes of stack) and the time does not move (0.757 ms either way): spheres keep the 3-CTA layout
-         * unless pl_debug_no_slim(ctx, -1) asks for the slim one (tests) */
+         * Flat scenes: 224 threads, 70 registers, + 6.6 % (0.583 -> 0.547 ms per 16 384 pairs).  Spheres: the register form
+         * needs 80 registers, which 4 CTAs of 224 threads do not have (72: spills, no gain) -- 192 threads do (6 warps x 4 =
+         * 24 warps per SM against 21): + 2.1 % (0.757 -> 0.742 ms) */
         using SL = PairSmem<101, 4, true>;
+        /* spheres: 192 threads (6 warps x 4 CTAs leave the 80 registers the register form needs: no spills) */
         void (*slim)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
-            na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true, false, true, true> : tile_pair_kernel<101, 4, RESID, true, false, false, true, true>)
+            na.sphere ? (na.linear ? tile_pair_kernel<101, 4, RESID, true, true, false, true, true, false, 192> : tile_pair_kernel<101, 4, RESID, true, false, false, true, true, false, 192>)
                       : (na.linear ? tile_pair_kernel<101, 4, RESID, false, true, false, true, true> : tile_pair_kernel<101, 4, RESID, false, false, false, true, true>);
         PL_CUDA(cudaFuncSetAttribute(slim, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SL::BYTES));
         pl_timing_begin(ctx, PL_K_PAIR, n);
-        slim<<<n, PairThreads<true>::N, SL::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
+        slim<<<n, na.sphere ? 192 : PairThreads<true>::N, SL::BYTES, ctx->stream>>>(elev->tm_parent, ea, na);
         pl_timing_end(ctx);
         PL_CUDA(cudaGetLastError());
         ctx->launches += 1;
