@@ -114,11 +114,14 @@ template <int RESID>
 int launch_pair(pl_ctx *ctx, pl_pool *elev, const plelev::ElevArgs &ea, const plnorm::NormArgs &na, int n, bool all_reg = false)
 {
     using SM = PairSmem<101, 4>;
-    if (all_reg && na.fast && na.npeers == 0 && na.channels != 4 && !ctx->no_slim) {
+    if (all_reg && na.fast && na.npeers == 0 && na.channels != 4 && !ctx->no_slim && (!na.sphere || na.linear || ctx->slim_sphere)) {
         /* every tile of the launch qualifies for the register form (the caller checked): the slim layout, 4 CTAs per SM.
          * Flat scenes: 224 threads, 70 registers, + 6.6 % (0.583 -> 0.547 ms per 16 384 pairs).  Spheres: the register form
          * needs 80 registers, which 4 CTAs of 224 threads do not have (72: spills, no gain) -- 192 threads do (6 warps x 4 =
-         * 24 warps per SM against 21): + 2.1 % (0.757 -> 0.742 ms) */
+         * 24 warps per SM against 21): + 2.1 % (0.757 -> 0.742 ms) with LINEAR elevation storages; with NEAREST ones the
+         * normal phase is lighter, the extra loads of the window-less elevation phase weigh more and the slim layout LOSES
+         * 1.5 % (0.717 -> 0.728 ms): those keep the regular layout (tools/microbench/slim_compare.py; pl_debug_no_slim(ctx, -1)
+         * forces the slim one) */
         using SL = PairSmem<101, 4, true>;
         /* spheres: 192 threads (6 warps x 4 CTAs leave the 80 registers the register form needs: no spills) */
         void (*slim)(const CUtensorMap, const plelev::ElevArgs, const plnorm::NormArgs) =
