@@ -1,6 +1,7 @@
 #include "ork/BatchScheduler.h"
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <unordered_map>
 #include <unordered_set>
@@ -56,7 +57,7 @@ struct Node
 };
 
 /* stamps handed to Task::schedViewStamp / schedMemoStamp: never 0, never reused */
-static unsigned long long g_stamp = 0;
+static std::atomic<unsigned long long> g_stamp(0);      /* schedulers of different threads draw from one sequence */
 
 /* the primitive tasks below the roots, in the order the graphs list them.  A task knows its slot in the current view
  * (Task::schedSlot, valid while Task::schedViewStamp equals the view's stamp): no look-up table */
