@@ -59,7 +59,7 @@ void Task::setIsDone(bool d, unsigned int t, reason r)
     }
 }
 
-unsigned long long TaskGraph::edits = 0;
+std::atomic<unsigned long long> TaskGraph::edits(0);
 
 TaskGraph::TaskGraph() : Task("TaskGraph", false, 0), index(NULL)
 {

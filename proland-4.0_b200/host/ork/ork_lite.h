@@ -234,7 +234,7 @@ public:
     const TaskSet &taskSet() const { return tasks; }
     /* counts the structural edits (tasks or dependencies added / removed) of ALL graphs: a scheduler that keeps a
      * flattened view across waves rebuilds it only when this moved */
-    static unsigned long long editCount() { return edits; }
+    static unsigned long long editCount() { return edits.load(std::memory_order_relaxed); }
     const TaskSet *dependenciesOf(Task *t) const;
 
 protected:
@@ -244,7 +244,7 @@ protected:
 private:
     struct Needs { Task *src; TaskSet dst; };                    /* src -> what it needs */
     struct NeededBy { Task *dst; std::vector<Task *> src; };      /* dst -> who needs it */
-    static unsigned long long edits;
+    static std::atomic<unsigned long long> edits;
     TaskSet tasks;
     std::unordered_set<Task *> *index;                            /* of `tasks`, once there are more than kIndexAbove */
     std::vector<Needs> dependencies;
